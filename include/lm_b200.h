@@ -1,0 +1,257 @@
+/*
+ * lm_b200.h -- C-ABI of liblm_b200.so, the B200 (sm_100a) implementation of the
+ * data-parallel hot path of aortizt/inverse-eigenvalue-loci-mandelbrot-correspondence.
+ *
+ * The reference is pure Python and has no FFI layer; its boundary is function-level
+ * (SURVEY.md section 8b).  Every entry point below names the reference function
+ * (file:line, relative to the reference checkout) whose arithmetic it replaces.  The
+ * binding a maintainer adds to the reference scripts is a ctypes stub over numpy
+ * buffers.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++ / torch types.
+ *   - every function returns an int32 status: LM_OK (0) or a negative LM_E_* code;
+ *     lm_last_error() returns a thread-local, NUL-terminated description of the last
+ *     failure on the calling thread.
+ *   - "host" entry points take caller-owned, C-contiguous host buffers sized by the
+ *     caller; the library never retains them after return.  "_dev" entry points take
+ *     device pointers on the current CUDA device and a CUstream/cudaStream_t passed as
+ *     void* (NULL = legacy default stream); they enqueue work and do not synchronise.
+ *   - the library keeps one context per process (device workspaces, work-queue
+ *     counters): calls are NOT re-entrant; the Python host serialises them with a lock.
+ *   - there is no CPU fallback: without a usable CUDA device every compute entry point
+ *     returns LM_E_NODEV.
+ */
+#ifndef LM_B200_H
+#define LM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LM_ABI_VERSION 1
+
+/* ---- status codes -------------------------------------------------------------- */
+#define LM_OK           0
+#define LM_E_INVALID   -1   /* bad argument (NULL, negative size, unknown mode ...)     */
+#define LM_E_CUDA      -2   /* CUDA runtime / launch error, see lm_last_error()          */
+#define LM_E_CAP       -3   /* caller-provided output capacity too small                 */
+#define LM_E_NOMEM     -4   /* host or device allocation failed                          */
+#define LM_E_NODEV     -5   /* no CUDA device / wrong architecture                       */
+#define LM_E_NOCONV    -6   /* iterative solver did not converge for some item           */
+#define LM_E_OVERFLOW  -7   /* the reference would raise OverflowError (2**k, k > 1023)  */
+
+/* ---- escape-time modes (K1) ---------------------------------------------------- */
+/* what `field` receives; the dwell outputs are the same in every mode.              */
+#define LM_FIELD_NONE          0
+/* g = log|z_k| * 2^-k at the first k (1-based) with |z_k|^2 > bailout^2, clamped to 0
+ * when negative / non-finite, 0 when no escape.
+ * lucas_equipotential_test_v3.py:124-151 (mandelbrot_parameter_potential).          */
+#define LM_FIELD_GREEN         1
+/* log|z|/2**k, k 0-based at break, test abs(z) > R; ALSO evaluated for orbits that
+ * never escape (k = max_iter-1, |z|>0).  Potentials.py:32-47.                        */
+#define LM_FIELD_POW2_ALWAYS   2
+/* log|z|/(k+1), k 0-based, test abs(z) > R, 0 when no escape.
+ * Laplacian_C-M.py:27-43, Iterative_Variogram_Laplacian.py:114-130.                  */
+#define LM_FIELD_INV_K         3
+/* log|z|/2.0**n, n 1-based first escape (sticky), test abs(z) > R, 0 when no escape;
+ * variograms_construct_mandelbrot.py:148-167 (before its 5-point smoothing).         */
+#define LM_FIELD_POW2_FIRST    4
+
+/* ---- distance-estimator variants (K1b) ----------------------------------------- */
+/* dz0 = 0, dz <- (2 z) dz + 1 then z <- z^2 + c, stop at abs(z) > bailout;
+ * d = |z| log|z| / max(|dz|, 1e-16); 0 when no escape.
+ * construct_stage1_clean.py:50-58.                                                   */
+#define LM_DE_SCALAR           0
+/* dz0 = 1, first escape abs(z) > R captures z and dz;
+ * d = log(max(|z|,1)) |z| / max(|2 z dz|, eps), non-finite -> 0.
+ * variograms_construct_mandelbrot.py:61-88.                                          */
+#define LM_DE_FIRST_ESCAPE     1
+
+/* ---- log-potential variants (K4a) ---------------------------------------------- */
+/* U = (1/N) sum_p log(sqrt(dx^2+dy^2) + eps)         Potentials.py:19-27             */
+#define LM_LOGPOT_SUM_SQRT     0
+/* U = - sum_p log(sqrt(dx^2+dy^2) + eps)/N per term  Laplacian_C-M.py:16-25          */
+#define LM_LOGPOT_NEG_PERTERM  1
+/* U = (1/N) sum_p log(hypot(dx,dy) + eps)            Iterative_Variogram_Laplacian.py:102-112 */
+#define LM_LOGPOT_SUM_HYPOT    2
+/* U = (1/N) sum_p log(1/(|z-p| + eps))               variograms_construct_mandelbrot.py:128-146 */
+#define LM_LOGPOT_LOG_INV      3
+
+/* ---- plain-old-data structs ---------------------------------------------------- */
+typedef struct lm_device_info {
+    int32_t  device;            /* CUDA ordinal                                       */
+    int32_t  cc_major, cc_minor;
+    int32_t  sm_count;
+    int32_t  clock_khz;         /* max SM clock                                       */
+    int32_t  l2_bytes;
+    uint64_t total_mem_bytes;
+    char     name[128];
+} lm_device_info;
+
+typedef struct lm_stats {
+    uint64_t work_units;        /* K1: pixel-iterations = sum min(dwell+1, max_iter)  */
+    uint64_t items;             /* pixels / points / polynomials / cells processed    */
+    float    kernel_ms;         /* device time of the dominant kernel (host entry
+                                   points only; 0 for _dev entry points)              */
+    int32_t  launches;          /* kernels launched by this call                      */
+} lm_stats;
+
+/* ---- context, memory ----------------------------------------------------------- */
+int32_t     lm_abi_version(void);
+const char* lm_last_error(void);
+int32_t     lm_device_count(void);                 /* >=0, or LM_E_* */
+int32_t     lm_set_device(int32_t device);
+int32_t     lm_get_device_info(lm_device_info* out);
+int32_t     lm_device_synchronize(void);
+int32_t     lm_release_workspace(void);            /* frees cached device buffers */
+
+void*   lm_host_alloc(size_t bytes);               /* pinned; NULL on failure */
+int32_t lm_host_free(void* p);
+void*   lm_dev_alloc(size_t bytes);                /* NULL on failure */
+int32_t lm_dev_free(void* p);
+int32_t lm_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes, void* stream);
+int32_t lm_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes, void* stream);
+int32_t lm_stream_synchronize(void* stream);
+
+/* ---- K1: escape-time grid ------------------------------------------------------ */
+/*
+ * Replaces compute_grid + mandelbrot_dwell, mandelbrot_boundary_sample.py:22-39:
+ *   dwell[j*nx+i] = first n in [0,max_iter) with |z_{n+1}|^2 > bailout^2 for
+ *   c = xs[i] + i*ys[j], z_0 = 0, z <- z*z + c, else max_iter.
+ * The recurrence is evaluated in IEEE binary64 without contraction in the reference's
+ * operation order, so dwell is bit-exact.
+ * Any of dwell_i32 / dwell_f64 / field may be NULL (not produced).  `field_mode` is
+ * one of LM_FIELD_*; for LM_FIELD_GREEN the escape test is zr^2+zi^2 > bailout^2, for
+ * the other field modes it is hypot(zr,zi) > bailout, as in the reference functions.
+ * work_units returns the exact pixel-iteration count.
+ */
+int32_t lm_escape_grid_f64(const double* xs, int64_t nx, const double* ys, int64_t ny,
+                           int32_t max_iter, double bailout, int32_t field_mode,
+                           int32_t* dwell_i32, double* dwell_f64, double* field,
+                           lm_stats* stats);
+int32_t lm_escape_grid_f64_dev(const double* xs, int64_t nx, const double* ys, int64_t ny,
+                               int32_t max_iter, double bailout, int32_t field_mode,
+                               int32_t* dwell_i32, double* dwell_f64, double* field,
+                               uint64_t* work_units_dev /* 1 counter, may be NULL */,
+                               void* stream);
+
+/* fp32 variant of the dwell grid (no reference counterpart; validated against the
+ * fp64 kernel by mismatch fraction).                                                 */
+int32_t lm_escape_grid_f32(const double* xs, int64_t nx, const double* ys, int64_t ny,
+                           int32_t max_iter, double bailout,
+                           int32_t* dwell_i32, lm_stats* stats);
+
+/* ---- K1d: escape-time at an arbitrary point list -------------------------------- */
+/*
+ * Replaces batch_potential / mandelbrot_parameter_potential,
+ * lucas_equipotential_test_v3.py:124-162.  it[k] in [1,max_iter]; g, phi as there;
+ * non-escaping points give (0, max_iter, nan+nanj).  Any output may be NULL.
+ */
+int32_t lm_escape_points_f64(const double* c_re, const double* c_im, int64_t n,
+                             int32_t max_iter, double escape_radius,
+                             double* g, int64_t* it, double* phi_re, double* phi_im,
+                             lm_stats* stats);
+
+/* ---- K1b: distance-estimator grid ---------------------------------------------- */
+/* construct_stage1_clean.py:50-58 (LM_DE_SCALAR), variograms_construct_mandelbrot.py:61-88
+ * (LM_DE_FIRST_ESCAPE).  escaped[] (uint8, may be NULL) is the first-escape mask.    */
+int32_t lm_distance_grid_f64(const double* xs, int64_t nx, const double* ys, int64_t ny,
+                             int32_t max_iter, double bailout, double eps, int32_t variant,
+                             double* dist, uint8_t* escaped, lm_stats* stats);
+
+/* ---- K2: level set of the dwell field ------------------------------------------ */
+/*
+ * Replaces plt.contour(xs, ys, Z, levels=[level]) as used by extract_contour,
+ * mandelbrot_boundary_sample.py:41-54 / mandelbrot_boundary_sample_spyder.py:35-43
+ * (contourpy "mpl2014" line semantics).
+ * Input is the int32 dwell grid (host pointer) or, for _dev, a device pointer.
+ * Output: all contour lines in matplotlib's order; line l occupies vertices
+ * [line_offsets[l], line_offsets[l+1]) of verts (x,y interleaved); closed loops repeat
+ * their first vertex.  Returns LM_E_CAP (with *n_verts / *n_lines set to the required
+ * sizes) when a capacity is too small.
+ */
+int32_t lm_contour_level(const int32_t* dwell, const double* xs, int64_t nx,
+                         const double* ys, int64_t ny, double level,
+                         double* verts, int64_t cap_verts, int64_t* n_verts,
+                         int64_t* line_offsets, int64_t cap_lines, int64_t* n_lines,
+                         lm_stats* stats);
+int32_t lm_contour_level_dev(const int32_t* dwell_dev, const double* xs_host, int64_t nx,
+                             const double* ys_host, int64_t ny, double level,
+                             double* verts, int64_t cap_verts, int64_t* n_verts,
+                             int64_t* line_offsets, int64_t cap_lines, int64_t* n_lines,
+                             lm_stats* stats);
+
+/*
+ * Multi-GPU building block: classify the quads of rows [0, ny-1) of a dwell block
+ * (ny rows incl. one halo row) and return the compacted crossing-quad records to the
+ * host; records of several row blocks are concatenated (with row_offset added) and
+ * linked by lm_contour_link.  A record is 4 x int64: {quad = j*nx_quads + i (global),
+ * corner dwell SW|SE<<32, corner dwell NW|NE<<32, reserved}.
+ */
+int32_t lm_contour_classify_dev(const int32_t* dwell_dev, int64_t nx, int64_t ny,
+                                int64_t row_offset, double level,
+                                int64_t* records, int64_t cap_records, int64_t* n_records,
+                                void* stream);
+int32_t lm_contour_link(const int64_t* records, int64_t n_records,
+                        const double* xs, int64_t nx, const double* ys, int64_t ny,
+                        double level,
+                        double* verts, int64_t cap_verts, int64_t* n_verts,
+                        int64_t* line_offsets, int64_t cap_lines, int64_t* n_lines);
+
+/* ---- K3: batched roots of generalized-Lucas characteristic polynomials --------- */
+/*
+ * Replaces np.linalg.eigvals(companion(top row)) in compute_inverse_eigenvalues[_family],
+ * lucas_equipotential_test_v3.py:58-118, construct_points in tci_construct_mandelbrot.py:11-19,
+ * tci_construct_mandelbrot_v002_fixed.py:27-33, construct_stage1_clean.py:34-48,
+ * variograms_construct_mandelbrot.py:48-56, lucas_to_cardioid_v18...py:83-94.
+ * Polynomial k is  x^d - a_1 x^(d-1) - ... - a_d  with d = deg[k] and
+ * a_j = toprows[k*maxdeg + j-1] (zero padded to maxdeg).
+ * Output slot k*maxdeg + r holds root r of polynomial k (r < deg[k]); with invert != 0
+ * the value is 1/lambda and roots with |lambda| <= tol are dropped (slots compacted to
+ * the front; n_kept[k] = number of valid slots).  Unused slots are NaN.
+ * iters (may be NULL) receives the Aberth sweep count per polynomial.
+ * Roots are unordered (the reference's order is LAPACK's); parity is after sorting.
+ */
+int32_t lm_roots_batched(const double* toprows, const int32_t* deg, int64_t npoly,
+                         int32_t maxdeg, int32_t invert, double tol,
+                         double* out_re, double* out_im, int32_t* n_kept, int32_t* iters,
+                         lm_stats* stats);
+
+/* ---- K4: 5-point stencils ------------------------------------------------------ */
+/* lap = (((((-4 U) + U[j-1]) + U[j+1]) + U[:,i-1]) + U[:,i+1]) / (h*h), periodic wrap.
+ * Laplacian_C-M.py:49-59, Iterative_Variogram_Laplacian.py:132-136.  Bit-exact.      */
+int32_t lm_laplacian5_periodic(const double* U, int64_t ny, int64_t nx, double h,
+                               double* out, lm_stats* stats);
+int32_t lm_laplacian5_periodic_dev(const double* U, int64_t ny, int64_t nx, double h,
+                                   double* out, void* stream);
+/* interior 5-point average ((((c+up)+down)+left)+right)/5, border copied.
+ * variograms_construct_mandelbrot.py:169-173.  Bit-exact.                            */
+int32_t lm_smooth5_interior(const double* g, int64_t ny, int64_t nx, double* out,
+                            lm_stats* stats);
+int32_t lm_smooth5_interior_dev(const double* g, int64_t ny, int64_t nx, double* out,
+                                void* stream);
+
+/* ---- K4a: log-potential of a point cloud on a grid ------------------------------ */
+/* Potentials.py:19-27, Laplacian_C-M.py:16-25, Iterative_Variogram_Laplacian.py:102-112,
+ * variograms_construct_mandelbrot.py:128-146 (variant = LM_LOGPOT_*).
+ * Points are accumulated sequentially in input order per grid cell.                  */
+int32_t lm_log_potential(const double* px, const double* py, int64_t npts,
+                         const double* gx, int64_t nx, const double* gy, int64_t ny,
+                         double eps, int32_t variant, double* U, lm_stats* stats);
+
+/* ---- measurement probes -------------------------------------------------------- */
+/* Dependent-free DFMA loop on every SM: FP64 peak (TFLOP/s, 2 flops per DFMA) and a
+ * DMUL/DADD-only variant (the unfused mix K1 needs).  Used by bench.py for the
+ * roofline denominator because MEASURED_PEAKS.json has no FP64 entry.                */
+int32_t lm_probe_fp64_peak(int32_t iters, double* dfma_tflops, double* dmul_dadd_tinstr);
+/* STREAM-style device copy bandwidth in GB/s (read+write bytes). */
+int32_t lm_probe_hbm_copy(size_t bytes, int32_t reps, double* gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LM_B200_H */

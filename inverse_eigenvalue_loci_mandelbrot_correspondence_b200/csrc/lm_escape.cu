@@ -1,0 +1,599 @@
+// lm_escape.cu -- K1: fp64 escape-time kernels (grid and point list) for sm_100a.
+//
+// Reference semantics (bit-exact dwell):
+//   mandelbrot_dwell / compute_grid      mandelbrot_boundary_sample.py:22-39
+//   mandelbrot_parameter_potential       lucas_equipotential_test_v3.py:124-162
+//   escape_potential                     Potentials.py:32-47
+//   mandelbrot_potential                 Laplacian_C-M.py:27-43
+//   escape_potential                     Iterative_Variogram_Laplacian.py:114-130
+//   mandelbrot_escape_potential          variograms_construct_mandelbrot.py:148-167
+//
+// Design (B200-first, FP64-pipe bound -- nothing here is a contraction, so no tensor cores):
+//   * persistent CTAs (one wave, grid = SMs x resident CTAs); every WARP pulls 128-pixel
+//     row segments ("tiles") from a global atomic counter (work stealing) with the next
+//     tile id prefetched one tile ahead;
+//   * lane refill: a lane that finishes its pixel immediately takes the next pixel of
+//     the warp's tile (ballot + popc rank), so divergence near the set boundary never
+//     idles lanes -- all 32 lanes carry live orbits until the global queue drains;
+//   * the recurrence uses __dmul_rn/__dadd_rn/__fma_rn only (and the file is built with
+//     -fmad=false): a=zr*zr, b=zi*zi, p=zr*zi, zr'=(a-b)+cr, zi'=fma(2,p,ci) [== (p+p)+ci
+//     exactly], test fl(a'+b') > bailout^2.  That is 6 FP64-pipe instructions for the
+//     update + 1 DADD for the test;
+//   * "calm" fast path: while every lane has a < T/2 and b < T/2 (checked on the high
+//     words with integer max on the ALU pipe) the sum a+b cannot exceed T, so blocks of
+//     FB iterations run with NO test DADD (6 FP64 instr/iteration) and are rolled back
+//     and re-run carefully if any lane left the calm region;
+//   * results are staged per warp in a shared-memory ring of tiles and leave the SM as
+//     one 128-bit coalesced store per lane per tile; a pixel that is still iterating
+//     when its tile is evicted from the ring patches its own word later.
+//
+// Work unit: pixel_iters = sum over pixels of min(dwell+1, max_iter), counted exactly in
+// the kernel (lm_stats.work_units).
+#include "lm_common.cuh"
+
+#include <math.h>
+#include <string.h>
+
+namespace {
+
+constexpr int TILE = 128;          // pixels per tile (one int4 per lane)
+constexpr int WARPS = 8;           // warps per CTA
+constexpr int CTA_THREADS = WARPS * 32;
+constexpr int RING = 4;            // resident tiles per warp
+constexpr int FB = 4;              // iterations per blind (fast) block
+constexpr int CALM_MIN = 8;        // calm careful iterations required before going blind
+constexpr unsigned FULL = 0xffffffffu;
+
+struct EscapeArgs {
+    const double* xs;              // grid: x coordinates [nx]; points: c_re [nx]
+    const double* ys;              // grid: y coordinates [ny]; points: c_im [nx]
+    long long nx, ny;
+    unsigned long long chunks_per_row, ntiles;
+    int max_iter;
+    double thr2;                   // loop threshold on a+b (bailout^2, slightly lowered for hypot tests)
+    double bailout;                // R
+    unsigned hi_calm;              // high word of thr2/2: a,b below it => no escape possible
+    int* dwell;                    // [ny*nx] or NULL
+    double* dwell_f64;             // [ny*nx] or NULL
+    double* field;                 // grid: [ny*nx] or NULL; points: g
+    long long* it64;               // points only
+    double* phi_re;                // points only
+    double* phi_im;                // points only
+    unsigned long long* tile_counter;
+    unsigned long long* work_counter;   // may be NULL
+    int* overflow_flag;            // set when the reference would raise OverflowError
+    int vec_i32, vec_f64, vec_field;
+};
+
+// one unfused iteration z <- z*z + c given the squares a, b of the current z
+#define LM_STEP6()                                   \
+    do {                                             \
+        const double p__ = __dmul_rn(zr, zi);        \
+        const double t__ = __dsub_rn(a, b);          \
+        zr = __dadd_rn(t__, cr);                     \
+        zi = __fma_rn(2.0, p__, ci);                 \
+        a = __dmul_rn(zr, zr);                       \
+        b = __dmul_rn(zi, zi);                       \
+    } while (0)
+
+__device__ __forceinline__ unsigned hi_word(double x) {
+    return static_cast<unsigned>(__double2hiint(x));
+}
+
+// field value at the end of an orbit.  iters = iterations performed (1-based escape index
+// when escaped, max_iter otherwise); (zr,zi) = z after `iters` iterations.
+template <int FM>
+__device__ __forceinline__ double field_value(double zr, double zi, int iters, bool escaped,
+                                              int* overflow_flag) {
+    if (FM == LM_FIELD_GREEN) {
+        // lucas_equipotential_test_v3.py:142-149: Re(log z) * exp2(-k), clamp
+        if (!escaped) return 0.0;
+        double g = __dmul_rn(log(hypot(zr, zi)), scalbn(1.0, -iters));
+        if (!(g >= 0.0) || isinf(g)) g = 0.0;
+        return g;
+    } else if (FM == LM_FIELD_POW2_ALWAYS) {
+        // Potentials.py:43-46: evaluated whether or not the orbit escaped, k 0-based
+        const double r = hypot(zr, zi);
+        if (!(r > 0.0)) return 0.0;
+        const int k = iters - 1;
+        if (k > 1023) { atomicExch(overflow_flag, 1); return 0.0; }
+        return __dmul_rn(log(r), scalbn(1.0, -k));
+    } else if (FM == LM_FIELD_INV_K) {
+        // Laplacian_C-M.py:41, Iterative_Variogram_Laplacian.py:126
+        if (!escaped) return 0.0;
+        return __ddiv_rn(log(hypot(zr, zi)), static_cast<double>(iters));
+    } else if (FM == LM_FIELD_POW2_FIRST) {
+        // variograms_construct_mandelbrot.py:163
+        if (!escaped) return 0.0;
+        if (iters > 1023) { atomicExch(overflow_flag, 1); return 0.0; }
+        return __dmul_rn(log(hypot(zr, zi)), scalbn(1.0, -iters));
+    }
+    return 0.0;
+}
+
+// POINTS = false : tiles are row segments of the (ny, nx) grid, c = xs[col] + i ys[row]
+// POINTS = true  : one "row" of nx points, c = xs[k] + i ys[k]; outputs g/it/phi written directly
+// FM             : LM_FIELD_* (LM_FIELD_NONE: dwell only)
+// HYPOT          : escape test is hypot(zr,zi) > R (the loop test is a slightly lowered
+//                  a+b threshold, confirmed with hypot in the handler)
+template <bool POINTS, int FM, bool HYPOT>
+__global__ void __launch_bounds__(CTA_THREADS, 3) lm_escape_kernel(const EscapeArgs A) {
+    constexpr bool FIELD = (FM != LM_FIELD_NONE);
+    constexpr int CB = HYPOT ? 1 : 4;          // iterations per careful block
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ long long s_base[WARPS][RING];
+    __shared__ int s_width[WARPS][RING];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+
+    int* s_dwell = reinterpret_cast<int*>(smem_raw) + warp * (RING * TILE);
+    double* s_field = reinterpret_cast<double*>(smem_raw + WARPS * RING * TILE * sizeof(int)) +
+                      warp * (RING * TILE);
+
+    // ---- lane state
+    double zr = 0.0, zi = 0.0, a = 0.0, b = 0.0, cr = 0.0, ci = 0.0;
+    int n = 0;                       // iterations performed on the current pixel
+    bool idle = true;                // lane holds no pixel
+    int my_off = 0;                  // offset of my pixel inside its tile
+    unsigned my_seq = 0;             // sequence number (per warp) of my pixel's tile
+    long long my_g = 0;              // flat output index of my pixel
+    unsigned long long work = 0;     // iterations of finished pixels (this lane)
+
+    // ---- warp state (uniform across lanes)
+    unsigned seq = 0;                // tiles acquired so far
+    int cursor = 0, width = 0;       // next unassigned pixel of the current tile, its size
+    long long base = 0, col0 = 0;    // flat index / first column of the current tile
+    double row_ci = 0.0;
+    bool exhausted = false;
+    int calm = 0;
+    unsigned long long pref = 0;     // prefetched tile id (valid in lane 0)
+    if (lane == 0) pref = atomicAdd(A.tile_counter, 1ULL);
+
+    auto flush_slot = [&](int slot) {
+        __syncwarp();
+        const long long fb = s_base[warp][slot];
+        const int w = s_width[warp][slot];
+        const int* sd = s_dwell + slot * TILE;
+        if (A.dwell) {
+            if (w == TILE && A.vec_i32) {
+                const int4 v = reinterpret_cast<const int4*>(sd)[lane];
+                reinterpret_cast<int4*>(A.dwell + fb)[lane] = v;
+            } else {
+                for (int k = lane; k < w; k += 32) A.dwell[fb + k] = sd[k];
+            }
+        }
+        if (A.dwell_f64) {
+            if (w == TILE && A.vec_f64) {
+                const int2 lo = reinterpret_cast<const int2*>(sd)[lane];
+                const int2 hi = reinterpret_cast<const int2*>(sd)[32 + lane];
+                double2* o = reinterpret_cast<double2*>(A.dwell_f64 + fb);
+                o[lane] = make_double2(static_cast<double>(lo.x), static_cast<double>(lo.y));
+                o[32 + lane] = make_double2(static_cast<double>(hi.x), static_cast<double>(hi.y));
+            } else {
+                for (int k = lane; k < w; k += 32) A.dwell_f64[fb + k] = static_cast<double>(sd[k]);
+            }
+        }
+        if (FIELD && A.field) {
+            const double* sf = s_field + slot * TILE;
+            if (w == TILE && A.vec_field) {
+                double2* o = reinterpret_cast<double2*>(A.field + fb);
+                o[lane] = reinterpret_cast<const double2*>(sf)[lane];
+                o[32 + lane] = reinterpret_cast<const double2*>(sf)[32 + lane];
+            } else {
+                for (int k = lane; k < w; k += 32) A.field[fb + k] = sf[k];
+            }
+        }
+        __syncwarp();
+    };
+
+    // hand pixels to the lanes that need one; acquire tiles as required
+    auto refill = [&](bool need) {
+        bool assigned_any = false;
+        while (true) {
+            const unsigned mask = __ballot_sync(FULL, need);
+            if (mask == 0u) break;
+            if (cursor == width) {
+                if (exhausted) break;
+                const unsigned long long t = __shfl_sync(FULL, pref, 0);
+                if (t >= A.ntiles) { exhausted = true; break; }
+                if (lane == 0) pref = atomicAdd(A.tile_counter, 1ULL);
+                unsigned long long row, chunk;
+                if ((A.ntiles >> 32) == 0ULL) {
+                    const unsigned r32 = static_cast<unsigned>(t) / static_cast<unsigned>(A.chunks_per_row);
+                    row = r32;
+                    chunk = static_cast<unsigned>(t) - r32 * static_cast<unsigned>(A.chunks_per_row);
+                } else {
+                    row = t / A.chunks_per_row;
+                    chunk = t - row * A.chunks_per_row;
+                }
+                col0 = static_cast<long long>(chunk) * TILE;
+                const long long left = A.nx - col0;
+                width = left < TILE ? static_cast<int>(left) : TILE;
+                base = static_cast<long long>(row) * A.nx + col0;
+                if (!POINTS) {
+                    const int slot = seq % RING;
+                    if (seq >= RING) flush_slot(slot);
+                    if (lane == 0) { s_base[warp][slot] = base; s_width[warp][slot] = width; }
+                    row_ci = __ldg(A.ys + row);
+                }
+                cursor = 0;
+                ++seq;
+            }
+            const int rank = __popc(mask & ((1u << lane) - 1u));
+            const int avail = width - cursor;
+            const int cnt = __popc(mask);
+            const int take = cnt < avail ? cnt : avail;
+            if (need && rank < take) {
+                my_off = cursor + rank;
+                my_seq = seq - 1;
+                my_g = base + my_off;
+                cr = __ldg(A.xs + col0 + my_off);
+                ci = POINTS ? __ldg(A.ys + col0 + my_off) : row_ci;
+                zr = 0.0; zi = 0.0; a = 0.0; b = 0.0; n = 0;
+                idle = false;
+                need = false;
+            }
+            cursor += take;
+            assigned_any = true;
+        }
+        if (need) {          // nothing left for this lane: spin on the origin, emit nothing
+            idle = true;
+            cr = 0.0; ci = 0.0; zr = 0.0; zi = 0.0; a = 0.0; b = 0.0; n = 0;
+        }
+        if (assigned_any) calm = 0;
+    };
+
+    refill(true);
+
+    while (true) {
+        if (exhausted && __all_sync(FULL, idle)) break;
+
+        int safe = __reduce_min_sync(FULL, A.max_iter - n);   // >= 1: iterations until the first lane hits max_iter
+        bool done = false;             // this lane escaped inside the current run
+        int n_fin = 0;                 // iterations performed when it escaped
+        double ze_r = 0.0, ze_i = 0.0; // z at the escape (FIELD modes)
+
+        while (true) {
+            if (!HYPOT && safe >= FB && calm >= CALM_MIN) {
+                // ---- blind block: FB iterations without the test DADD
+                const double szr = zr, szi = zi, sa = a, sb = b;
+                unsigned acc = 0u;
+#pragma unroll
+                for (int k = 0; k < FB; ++k) {
+                    LM_STEP6();
+                    acc = max(acc, max(hi_word(a), hi_word(b)));
+                }
+                if (__any_sync(FULL, acc >= A.hi_calm)) {
+                    zr = szr; zi = szi; a = sa; b = sb;     // roll back, redo carefully
+                    calm = 0;
+                } else {
+                    n += FB;
+                    safe -= FB;
+                    if (safe == 0) break;
+                    continue;
+                }
+            }
+            // ---- careful block: up to CB iterations with the exact test, sticky per lane
+            const int cnt = safe < CB ? safe : CB;
+            unsigned acc = 0u;
+#pragma unroll
+            for (int k = 0; k < CB; ++k) {
+                if (k < cnt) {
+                    LM_STEP6();
+                    const double m = __dadd_rn(a, b);
+                    if (m > A.thr2 && !done) {
+                        done = true;
+                        n_fin = n + k + 1;
+                        if (FIELD || HYPOT || POINTS) { ze_r = zr; ze_i = zi; }
+                    }
+                    acc = max(acc, max(hi_word(a), hi_word(b)));
+                }
+            }
+            n += cnt;
+            safe -= cnt;
+            if (!HYPOT) calm = __any_sync(FULL, acc >= A.hi_calm) ? 0 : calm + cnt;
+            if (__any_sync(FULL, done) || safe == 0) break;
+        }
+
+        // ---- handler: retire finished pixels, refill their lanes
+        if (HYPOT && done) {
+            // candidate only: the reference tests abs(z) > R  (CB == 1, so z is still ze)
+            if (!(hypot(ze_r, ze_i) > A.bailout)) done = false;
+        }
+        bool need = false;
+        if (idle) {
+            if (done || n >= A.max_iter) n = 0;
+        } else if (done || n >= A.max_iter) {
+            const int iters = done ? n_fin : A.max_iter;
+            const int dw = done ? n_fin - 1 : A.max_iter;
+            work += static_cast<unsigned long long>(iters);
+            double f = 0.0;
+            if (FIELD) f = field_value<FM>(done ? ze_r : zr, done ? ze_i : zi, iters, done, A.overflow_flag);
+            if (POINTS) {
+                // lucas_equipotential_test_v3.py:140-151
+                if (A.field) A.field[my_g] = f;
+                if (A.it64) A.it64[my_g] = static_cast<long long>(iters);
+                if (A.phi_re || A.phi_im) {
+                    double pr = nan(""), pi = nan("");
+                    if (done) {
+                        // phi = exp(log(z) * 2^-k), principal branch
+                        const double s = scalbn(1.0, -iters);
+                        const double lr = __dmul_rn(log(hypot(ze_r, ze_i)), s);
+                        const double li = __dmul_rn(atan2(ze_i, ze_r), s);
+                        const double e = exp(lr);
+                        double sn, cs;
+                        sincos(li, &sn, &cs);
+                        pr = __dmul_rn(e, cs);
+                        pi = __dmul_rn(e, sn);
+                    }
+                    if (A.phi_re) A.phi_re[my_g] = pr;
+                    if (A.phi_im) A.phi_im[my_g] = pi;
+                }
+            } else {
+                const unsigned age = seq - 1u - my_seq;
+                if (age < static_cast<unsigned>(RING)) {
+                    const int slot = my_seq % RING;
+                    s_dwell[slot * TILE + my_off] = dw;
+                    if (FIELD) s_field[slot * TILE + my_off] = f;
+                } else {               // my tile left the ring: patch my own words
+                    if (A.dwell) A.dwell[my_g] = dw;
+                    if (A.dwell_f64) A.dwell_f64[my_g] = static_cast<double>(dw);
+                    if (FIELD && A.field) A.field[my_g] = f;
+                }
+            }
+            need = true;
+        }
+        refill(need);
+    }
+
+    if (!POINTS) {
+        const unsigned first = seq > static_cast<unsigned>(RING) ? seq - RING : 0u;
+        for (unsigned s = first; s < seq; ++s) flush_slot(static_cast<int>(s % RING));
+    }
+    if (A.work_counter) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) work += __shfl_xor_sync(FULL, work, o);
+        if (lane == 0 && work) atomicAdd(A.work_counter, work);
+    }
+}
+
+size_t smem_bytes(bool points, bool field) {
+    if (points) return 16;
+    size_t b = static_cast<size_t>(WARPS) * RING * TILE * sizeof(int);
+    if (field) b += static_cast<size_t>(WARPS) * RING * TILE * sizeof(double);
+    return b;
+}
+
+template <bool POINTS, int FM, bool HYPOT>
+int32_t launch_one(const EscapeArgs& A, cudaStream_t stream) {
+    auto kern = lm_escape_kernel<POINTS, FM, HYPOT>;
+    const size_t smem = smem_bytes(POINTS, FM != LM_FIELD_NONE);
+    LM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    int per_sm = 0;
+    LM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CTA_THREADS, smem));
+    if (per_sm < 1) return lm::fail(LM_E_CUDA, "escape kernel does not fit on an SM");
+    // no more CTAs than there are tiles for their warps
+    unsigned long long want = (A.ntiles + WARPS - 1) / WARPS;
+    unsigned long long grid = static_cast<unsigned long long>(lm::sm_count()) * per_sm;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    kern<<<static_cast<unsigned>(grid), CTA_THREADS, smem, stream>>>(A);
+    LM_CUDA_TRY(cudaGetLastError());
+    return LM_OK;
+}
+
+int32_t launch_escape(bool points, int field_mode, EscapeArgs& A, cudaStream_t stream) {
+    const bool hypot_test = !(field_mode == LM_FIELD_NONE || field_mode == LM_FIELD_GREEN);
+    const double R = A.bailout;
+    double thr2 = R * R;
+    if (hypot_test) thr2 = thr2 * (1.0 - 1e-9);   // candidate threshold; hypot decides
+    A.thr2 = thr2;
+    {
+        const double half = 0.5 * thr2;
+        long long bits;
+        memcpy(&bits, &half, sizeof(bits));
+        A.hi_calm = static_cast<unsigned>(static_cast<unsigned long long>(bits) >> 32);
+    }
+    if (points) {
+        if (field_mode == LM_FIELD_GREEN) return launch_one<true, LM_FIELD_GREEN, false>(A, stream);
+        return lm::fail(LM_E_INVALID, "points kernel supports LM_FIELD_GREEN only");
+    }
+    switch (field_mode) {
+        case LM_FIELD_NONE:        return launch_one<false, LM_FIELD_NONE, false>(A, stream);
+        case LM_FIELD_GREEN:       return launch_one<false, LM_FIELD_GREEN, false>(A, stream);
+        case LM_FIELD_POW2_ALWAYS: return launch_one<false, LM_FIELD_POW2_ALWAYS, true>(A, stream);
+        case LM_FIELD_INV_K:       return launch_one<false, LM_FIELD_INV_K, true>(A, stream);
+        case LM_FIELD_POW2_FIRST:  return launch_one<false, LM_FIELD_POW2_FIRST, true>(A, stream);
+        default: return lm::fail(LM_E_INVALID, "unknown field_mode %d", field_mode);
+    }
+}
+
+// counters: [0] tile counter, [1] work counter, [2] overflow flag (as 8-byte slots).
+// A small ring of counter blocks lets several launches be in flight on different streams.
+constexpr int COUNTER_BLOCKS = 64;
+int g_counter_next = 0;
+int32_t get_counters(unsigned long long** out, cudaStream_t stream) {
+    void* p = nullptr;
+    int32_t rc = lm::ws_get(lm::WS_COUNTERS, 64 * COUNTER_BLOCKS, &p);
+    if (rc != LM_OK) return rc;
+    unsigned char* blk = static_cast<unsigned char*>(p) + 64 * (g_counter_next++ % COUNTER_BLOCKS);
+    LM_CUDA_TRY(cudaMemsetAsync(blk, 0, 64, stream));
+    *out = reinterpret_cast<unsigned long long*>(blk);
+    return LM_OK;
+}
+
+int32_t check_grid_args(const char* who, const void* xs, int64_t nx, const void* ys, int64_t ny,
+                        int32_t max_iter, double bailout) {
+    LM_REQUIRE(xs && ys, "%s: xs/ys is NULL", who);
+    LM_REQUIRE(nx >= 0 && ny >= 0, "%s: negative grid size", who);
+    LM_REQUIRE(max_iter >= 1, "%s: max_iter must be >= 1 (got %d)", who, max_iter);
+    LM_REQUIRE(bailout > 0.0 && bailout < 1e150, "%s: bailout out of range", who);
+    return LM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t lm_escape_grid_f64_dev(const double* xs, int64_t nx, const double* ys, int64_t ny,
+                               int32_t max_iter, double bailout, int32_t field_mode,
+                               int32_t* dwell_i32, double* dwell_f64, double* field,
+                               uint64_t* work_units_dev, void* stream) {
+    int32_t rc = lm::require_device();
+    if (rc != LM_OK) return rc;
+    rc = check_grid_args("lm_escape_grid_f64_dev", xs, nx, ys, ny, max_iter, bailout);
+    if (rc != LM_OK) return rc;
+    LM_REQUIRE(field_mode >= LM_FIELD_NONE && field_mode <= LM_FIELD_POW2_FIRST,
+               "lm_escape_grid_f64_dev: unknown field_mode %d", field_mode);
+    LM_REQUIRE(field_mode == LM_FIELD_NONE || field != nullptr,
+               "lm_escape_grid_f64_dev: field_mode %d needs a field buffer", field_mode);
+    if (nx == 0 || ny == 0) return LM_OK;
+    cudaStream_t s = lm::as_stream(stream);
+
+    unsigned long long* counters = nullptr;
+    rc = get_counters(&counters, s);
+    if (rc != LM_OK) return rc;
+    if (work_units_dev) LM_CUDA_TRY(cudaMemsetAsync(work_units_dev, 0, sizeof(uint64_t), s));
+
+    EscapeArgs A{};
+    A.xs = xs; A.ys = ys; A.nx = nx; A.ny = ny;
+    A.chunks_per_row = static_cast<unsigned long long>((nx + TILE - 1) / TILE);
+    A.ntiles = A.chunks_per_row * static_cast<unsigned long long>(ny);
+    A.max_iter = max_iter;
+    A.bailout = bailout;
+    A.dwell = dwell_i32; A.dwell_f64 = dwell_f64;
+    A.field = (field_mode == LM_FIELD_NONE) ? nullptr : field;
+    A.tile_counter = counters;
+    A.work_counter = work_units_dev ? reinterpret_cast<unsigned long long*>(work_units_dev) : nullptr;
+    A.overflow_flag = reinterpret_cast<int*>(counters + 2);
+    A.vec_i32 = (nx % 4 == 0) && (reinterpret_cast<uintptr_t>(dwell_i32) % 16 == 0);
+    A.vec_f64 = (nx % 2 == 0) && (reinterpret_cast<uintptr_t>(dwell_f64) % 16 == 0);
+    A.vec_field = (nx % 2 == 0) && (reinterpret_cast<uintptr_t>(field) % 16 == 0);
+    return launch_escape(false, field_mode, A, s);
+}
+
+int32_t lm_escape_grid_f64(const double* xs, int64_t nx, const double* ys, int64_t ny,
+                           int32_t max_iter, double bailout, int32_t field_mode,
+                           int32_t* dwell_i32, double* dwell_f64, double* field,
+                           lm_stats* stats) {
+    int32_t rc = lm::require_device();
+    if (rc != LM_OK) return rc;
+    rc = check_grid_args("lm_escape_grid_f64", xs, nx, ys, ny, max_iter, bailout);
+    if (rc != LM_OK) return rc;
+    LM_REQUIRE(field_mode == LM_FIELD_NONE || field != nullptr,
+               "lm_escape_grid_f64: field_mode %d needs a field buffer", field_mode);
+    if (stats) *stats = lm_stats{};
+    if (nx == 0 || ny == 0) return LM_OK;
+    const size_t npx = static_cast<size_t>(nx) * static_cast<size_t>(ny);
+    cudaStream_t s = nullptr;
+
+    void *dxs, *dys, *dd = nullptr, *df64 = nullptr, *dfield = nullptr, *dwork;
+    if ((rc = lm::ws_get(lm::WS_XS, nx * sizeof(double), &dxs)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_YS, ny * sizeof(double), &dys)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_SCRATCH, 64, &dwork)) != LM_OK) return rc;
+    if (dwell_i32 && (rc = lm::ws_get(lm::WS_OUT_I32, npx * sizeof(int32_t), &dd)) != LM_OK) return rc;
+    if (dwell_f64 && (rc = lm::ws_get(lm::WS_OUT_F64, npx * sizeof(double), &df64)) != LM_OK) return rc;
+    if (field_mode != LM_FIELD_NONE && (rc = lm::ws_get(lm::WS_FIELD, npx * sizeof(double), &dfield)) != LM_OK) return rc;
+    LM_CUDA_TRY(cudaMemcpyAsync(dxs, xs, nx * sizeof(double), cudaMemcpyHostToDevice, s));
+    LM_CUDA_TRY(cudaMemcpyAsync(dys, ys, ny * sizeof(double), cudaMemcpyHostToDevice, s));
+
+    lm::Timer tm;
+    if ((rc = tm.begin(s)) != LM_OK) return rc;
+    rc = lm_escape_grid_f64_dev(static_cast<double*>(dxs), nx, static_cast<double*>(dys), ny, max_iter,
+                                bailout, field_mode, static_cast<int32_t*>(dd),
+                                static_cast<double*>(df64), static_cast<double*>(dfield),
+                                static_cast<uint64_t*>(dwork), s);
+    if (rc != LM_OK) return rc;
+    float ms = 0.f;
+    if ((rc = tm.end(s, &ms)) != LM_OK) return rc;
+
+    if (dwell_i32) LM_CUDA_TRY(cudaMemcpyAsync(dwell_i32, dd, npx * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (dwell_f64) LM_CUDA_TRY(cudaMemcpyAsync(dwell_f64, df64, npx * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (dfield) LM_CUDA_TRY(cudaMemcpyAsync(field, dfield, npx * sizeof(double), cudaMemcpyDeviceToHost, s));
+    uint64_t work = 0;
+    LM_CUDA_TRY(cudaMemcpyAsync(&work, dwork, sizeof(work), cudaMemcpyDeviceToHost, s));
+    int overflow = 0;
+    void* cnt = nullptr;
+    if ((rc = lm::ws_get(lm::WS_COUNTERS, 64, &cnt)) != LM_OK) return rc;
+    LM_CUDA_TRY(cudaMemcpyAsync(&overflow, static_cast<unsigned long long*>(cnt) + 2, sizeof(int),
+                                cudaMemcpyDeviceToHost, s));
+    LM_CUDA_TRY(cudaStreamSynchronize(s));
+    if (stats) {
+        stats->work_units = work;
+        stats->items = npx;
+        stats->kernel_ms = ms;
+        stats->launches = 1;
+    }
+    if (overflow)
+        return lm::fail(LM_E_OVERFLOW,
+                        "lm_escape_grid_f64: 2**k with k > 1023 (the reference raises OverflowError here)");
+    return LM_OK;
+}
+
+int32_t lm_escape_points_f64(const double* c_re, const double* c_im, int64_t n,
+                             int32_t max_iter, double escape_radius,
+                             double* g, int64_t* it, double* phi_re, double* phi_im,
+                             lm_stats* stats) {
+    int32_t rc = lm::require_device();
+    if (rc != LM_OK) return rc;
+    LM_REQUIRE(n >= 0, "lm_escape_points_f64: negative n");
+    LM_REQUIRE(n == 0 || (c_re && c_im), "lm_escape_points_f64: c_re/c_im is NULL");
+    LM_REQUIRE(max_iter >= 1, "lm_escape_points_f64: max_iter must be >= 1");
+    LM_REQUIRE(escape_radius > 0.0 && escape_radius < 1e150, "lm_escape_points_f64: bad escape_radius");
+    if (stats) *stats = lm_stats{};
+    if (n == 0) return LM_OK;
+    cudaStream_t s = nullptr;
+    const size_t nb = static_cast<size_t>(n) * sizeof(double);
+    void *dre, *dim, *dg, *dit, *dpr, *dpi, *dwork;
+    if ((rc = lm::ws_get(lm::WS_IN_A, nb, &dre)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_IN_B, nb, &dim)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_OUT_A, nb, &dg)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_OUT_B, nb, &dit)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_OUT_C, nb, &dpr)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_OUT_D, nb, &dpi)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_SCRATCH, 64, &dwork)) != LM_OK) return rc;
+    LM_CUDA_TRY(cudaMemcpyAsync(dre, c_re, nb, cudaMemcpyHostToDevice, s));
+    LM_CUDA_TRY(cudaMemcpyAsync(dim, c_im, nb, cudaMemcpyHostToDevice, s));
+    LM_CUDA_TRY(cudaMemsetAsync(dwork, 0, 64, s));
+    unsigned long long* counters = nullptr;
+    if ((rc = get_counters(&counters, s)) != LM_OK) return rc;
+
+    EscapeArgs A{};
+    A.xs = static_cast<const double*>(dre); A.ys = static_cast<const double*>(dim);
+    A.nx = n; A.ny = 1;
+    A.chunks_per_row = static_cast<unsigned long long>((n + TILE - 1) / TILE);
+    A.ntiles = A.chunks_per_row;
+    A.max_iter = max_iter;
+    A.bailout = escape_radius;
+    A.field = static_cast<double*>(dg);
+    A.it64 = static_cast<long long*>(dit);
+    A.phi_re = (phi_re || phi_im) ? static_cast<double*>(dpr) : nullptr;
+    A.phi_im = (phi_re || phi_im) ? static_cast<double*>(dpi) : nullptr;
+    A.tile_counter = counters;
+    A.work_counter = static_cast<unsigned long long*>(dwork);
+    A.overflow_flag = reinterpret_cast<int*>(counters + 2);
+
+    lm::Timer tm;
+    if ((rc = tm.begin(s)) != LM_OK) return rc;
+    if ((rc = launch_escape(true, LM_FIELD_GREEN, A, s)) != LM_OK) return rc;
+    float ms = 0.f;
+    if ((rc = tm.end(s, &ms)) != LM_OK) return rc;
+    if (g) LM_CUDA_TRY(cudaMemcpyAsync(g, dg, nb, cudaMemcpyDeviceToHost, s));
+    if (it) LM_CUDA_TRY(cudaMemcpyAsync(it, dit, nb, cudaMemcpyDeviceToHost, s));
+    if (phi_re) LM_CUDA_TRY(cudaMemcpyAsync(phi_re, dpr, nb, cudaMemcpyDeviceToHost, s));
+    if (phi_im) LM_CUDA_TRY(cudaMemcpyAsync(phi_im, dpi, nb, cudaMemcpyDeviceToHost, s));
+    uint64_t work = 0;
+    LM_CUDA_TRY(cudaMemcpyAsync(&work, dwork, sizeof(work), cudaMemcpyDeviceToHost, s));
+    LM_CUDA_TRY(cudaStreamSynchronize(s));
+    if (stats) {
+        stats->work_units = work;
+        stats->items = static_cast<uint64_t>(n);
+        stats->kernel_ms = ms;
+        stats->launches = 1;
+    }
+    return LM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,235 @@
+"""ctypes front-end of the CPU oracle (oracle/liboracle.so) plus the numpy root oracle.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package never imports this module.
+
+The C side (lm_oracle.c, lm_oracle_contour.c) restates the reference's functions; each
+wrapper below names the reference function it stands for.  The root oracle IS the
+reference's own call, numpy.linalg.eigvals on the companion matrix (LAPACK dgeev via the
+numpy in this image; the reference pins no version: requirements.txt:1).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB_PATH = _HERE / "liboracle.so"
+_lib = None
+
+_f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+
+
+def build(force: bool = False) -> Path:
+    """Compile liboracle.so with gcc (oracle/Makefile)."""
+    srcs = [_HERE / "lm_oracle.c", _HERE / "lm_oracle_contour.c", _HERE / "Makefile"]
+    stale = (not _LIB_PATH.exists()) or any(s.stat().st_mtime > _LIB_PATH.stat().st_mtime for s in srcs)
+    if force or stale:
+        r = subprocess.run(["make", "-C", str(_HERE), "-B", "liboracle.so"], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"oracle build failed:\n{r.stdout}\n{r.stderr}")
+    return _LIB_PATH
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(str(_LIB_PATH))
+        L.oracle_num_threads.restype = C.c_int
+        L.oracle_set_threads.argtypes = [C.c_int]
+        L.oracle_dwell_grid.restype = C.c_uint64
+        L.oracle_dwell_grid.argtypes = [_f64p, C.c_int64, _f64p, C.c_int64, C.c_int32, C.c_double, _i32p]
+        L.oracle_potential_grid.restype = C.c_int
+        L.oracle_potential_grid.argtypes = [_f64p, C.c_int64, _f64p, C.c_int64, C.c_int32, C.c_double,
+                                            C.c_int32, _i32p, _f64p]
+        L.oracle_potential_points.restype = C.c_uint64
+        L.oracle_potential_points.argtypes = [_f64p, _f64p, C.c_int64, C.c_int32, C.c_double,
+                                              _f64p, _i64p, _f64p, _f64p]
+        L.oracle_distance_grid.restype = None
+        L.oracle_distance_grid.argtypes = [_f64p, C.c_int64, _f64p, C.c_int64, C.c_int32, C.c_double,
+                                           C.c_double, C.c_int32, _f64p, _u8p]
+        L.oracle_laplacian5_periodic.restype = None
+        L.oracle_laplacian5_periodic.argtypes = [_f64p, C.c_int64, C.c_int64, C.c_double, _f64p]
+        L.oracle_smooth5_interior.restype = None
+        L.oracle_smooth5_interior.argtypes = [_f64p, C.c_int64, C.c_int64, _f64p]
+        L.oracle_log_potential.restype = None
+        L.oracle_log_potential.argtypes = [_f64p, _f64p, C.c_int64, _f64p, C.c_int64, _f64p, C.c_int64,
+                                           C.c_double, C.c_int32, _f64p]
+        L.oracle_contour_lines.restype = C.c_int
+        L.oracle_contour_lines.argtypes = [_f64p, C.c_int64, _f64p, C.c_int64, _f64p, C.c_double,
+                                           _f64p, C.c_int64, C.POINTER(C.c_int64),
+                                           _i64p, C.c_int64, C.POINTER(C.c_int64)]
+        _lib = L
+    return _lib
+
+
+def num_threads() -> int:
+    return int(lib().oracle_num_threads())
+
+
+def set_threads(n: int) -> None:
+    lib().oracle_set_threads(int(n))
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+# ---- K1 -------------------------------------------------------------------------------
+def dwell_grid(xs, ys, max_iter: int, bail2: float = 4.0):
+    """compute_grid, mandelbrot_boundary_sample.py:32-39 -> (dwell int32[ny,nx], pixel_iters)."""
+    xs = _c(xs, np.float64); ys = _c(ys, np.float64)
+    out = np.empty((ys.size, xs.size), dtype=np.int32)
+    work = lib().oracle_dwell_grid(xs, xs.size, ys, ys.size, int(max_iter), float(bail2), out)
+    return out, int(work)
+
+
+def compute_grid(xlim, ylim, res: int, max_iter: int):
+    """Same signature/return as the reference compute_grid (Z float64)."""
+    xs = np.linspace(xlim[0], xlim[1], res)
+    ys = np.linspace(ylim[0], ylim[1], res)
+    d, _ = dwell_grid(xs, ys, max_iter)
+    return xs, ys, d.astype(np.float64)
+
+
+FIELD_GREEN, FIELD_POW2_ALWAYS, FIELD_INV_K, FIELD_POW2_FIRST = 1, 2, 3, 4
+
+
+def potential_grid(xs, ys, max_iter: int, R: float, mode: int):
+    """Grid potentials (see lm_oracle.c).  Returns (dwell, field); raises OverflowError like the reference."""
+    xs = _c(xs, np.float64); ys = _c(ys, np.float64)
+    d = np.empty((ys.size, xs.size), dtype=np.int32)
+    f = np.empty((ys.size, xs.size), dtype=np.float64)
+    rc = lib().oracle_potential_grid(xs, xs.size, ys, ys.size, int(max_iter), float(R), int(mode), d, f)
+    if rc:
+        raise OverflowError("int too large to convert to float")
+    return d, f
+
+
+def batch_potential(Cpts, max_iter: int = 4000, escape_radius: float = 2.0):
+    """batch_potential, lucas_equipotential_test_v3.py:153-162 -> (g, it, phi)."""
+    Cpts = np.asarray(Cpts, dtype=np.complex128).ravel()
+    cre = _c(Cpts.real, np.float64); cim = _c(Cpts.imag, np.float64)
+    n = Cpts.size
+    g = np.empty(n); it = np.empty(n, dtype=np.int64); pr = np.empty(n); pi = np.empty(n)
+    lib().oracle_potential_points(cre, cim, n, int(max_iter), float(escape_radius), g, it, pr, pi)
+    return g, it, pr + 1j * pi
+
+
+def distance_grid(xs, ys, max_iter: int, bailout: float, eps: float, variant: int):
+    xs = _c(xs, np.float64); ys = _c(ys, np.float64)
+    d = np.empty((ys.size, xs.size), dtype=np.float64)
+    e = np.empty((ys.size, xs.size), dtype=np.uint8)
+    lib().oracle_distance_grid(xs, xs.size, ys, ys.size, int(max_iter), float(bailout), float(eps), int(variant), d, e)
+    return d, e.astype(bool)
+
+
+# ---- K4 / K4a -------------------------------------------------------------------------
+def laplacian(U, h: float):
+    """laplacian, Laplacian_C-M.py:49-59."""
+    U = _c(U, np.float64)
+    out = np.empty_like(U)
+    lib().oracle_laplacian5_periodic(U, U.shape[0], U.shape[1], float(h), out)
+    return out
+
+
+def smooth5(g):
+    """5-point interior average, variograms_construct_mandelbrot.py:169-173."""
+    g = _c(g, np.float64)
+    out = np.empty_like(g)
+    lib().oracle_smooth5_interior(g, g.shape[0], g.shape[1], out)
+    return out
+
+
+def log_potential(points, grid_x, grid_y, eps: float, variant: int):
+    pts = np.asarray(points, dtype=np.float64).reshape(-1, 2)
+    px = _c(pts[:, 0], np.float64); py = _c(pts[:, 1], np.float64)
+    gx = _c(grid_x, np.float64); gy = _c(grid_y, np.float64)
+    U = np.empty((gy.size, gx.size), dtype=np.float64)
+    lib().oracle_log_potential(px, py, px.size, gx, gx.size, gy, gy.size, float(eps), int(variant), U)
+    return U
+
+
+# ---- K2 -------------------------------------------------------------------------------
+def contour_lines(xs, ys, Z, level: float):
+    """plt.contour(xs, ys, Z, levels=[level]).allsegs[0] restated (mpl2014) -> list of (N,2) arrays."""
+    xs = _c(xs, np.float64); ys = _c(ys, np.float64); Z = _c(Z, np.float64)
+    assert Z.shape == (ys.size, xs.size)
+    cap_v, cap_l = 1 << 16, 1 << 12
+    while True:
+        verts = np.empty((cap_v, 2), dtype=np.float64)
+        offs = np.empty(cap_l + 1, dtype=np.int64)
+        nv = C.c_int64(0); nl = C.c_int64(0)
+        rc = lib().oracle_contour_lines(xs, xs.size, ys, ys.size, Z, float(level),
+                                        verts.reshape(-1), cap_v, C.byref(nv), offs, cap_l, C.byref(nl))
+        if rc < 0:
+            raise MemoryError("oracle_contour_lines")
+        if rc == 0:
+            break
+        cap_v = max(cap_v, nv.value + 16); cap_l = max(cap_l, nl.value + 16)
+    return [verts[offs[k]:offs[k + 1]].copy() for k in range(nl.value)]
+
+
+def extract_contour(xs, ys, Z, max_iter: int, level_frac: float = 0.96):
+    """extract_contour, mandelbrot_boundary_sample_spyder.py:35-43 (longest line)."""
+    segs = contour_lines(xs, ys, Z, level_frac * max_iter)
+    if not segs:
+        return None
+    return max(segs, key=lambda a: a.shape[0])
+
+
+# ---- K3 (numpy = the reference's own arithmetic) -----------------------------------------
+def companion_from_toprow(top) -> np.ndarray:
+    """generate_companion_from_toprow, lucas_equipotential_test_v3.py:66-74."""
+    top = np.asarray(top, dtype=float).reshape(-1)
+    n = top.shape[0]
+    Cm = np.zeros((n, n), dtype=float)
+    Cm[0, :] = top
+    for i in range(1, n):
+        Cm[i, i - 1] = 1.0
+    return Cm
+
+
+def family_toprow(name: str, n: int) -> np.ndarray:
+    """family_toprow, lucas_equipotential_test_v3.py:76-91."""
+    if name == "lucas_all_ones":
+        return np.ones(n)
+    if name == "pell_like_all_twos":
+        return 2.0 * np.ones(n)
+    if name == "sparser_gap_1_0_1_then_ones":
+        top = np.ones(n)
+        if n >= 2:
+            top[1] = 0.0
+        return top
+    if name == "padovan_like_0_1_then_ones":
+        top = np.ones(n)
+        top[0] = 0.0
+        return top
+    raise ValueError(f"Unknown family '{name}'")
+
+
+def eigvals_toprow(top) -> np.ndarray:
+    return np.linalg.eigvals(companion_from_toprow(top))
+
+
+def inverse_eigenvalues_toprow(top, tol: float = 1e-12) -> np.ndarray:
+    """One n of compute_inverse_eigenvalues_family, lucas_equipotential_test_v3.py:106-118."""
+    eigs = eigvals_toprow(top)
+    return (1.0 / eigs[np.abs(eigs) > tol]).astype(np.complex128)
+
+
+def compute_inverse_eigenvalues_family(family: str, n_min: int, n_max: int, tol: float = 1e-12) -> np.ndarray:
+    out = [inverse_eigenvalues_toprow(family_toprow(family, n), tol) for n in range(n_min, n_max + 1)]
+    return np.concatenate(out).astype(np.complex128)
+
+
+def roots_batched(toprows: np.ndarray, deg: np.ndarray):
+    """eigvals for a zero-padded batch; returns list of complex arrays (one per polynomial)."""
+    return [eigvals_toprow(toprows[k, : deg[k]]) for k in range(len(deg))]
