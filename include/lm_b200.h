@@ -248,6 +248,13 @@ int32_t lm_log_potential(const double* px, const double* py, int64_t npts,
  * DMUL/DADD-only variant (the unfused mix K1 needs).  Used by bench.py for the
  * roofline denominator because MEASURED_PEAKS.json has no FP64 entry.                */
 int32_t lm_probe_fp64_peak(int32_t iters, double* dfma_tflops, double* dmul_dadd_tinstr);
+/* Cycles per dependent FP64 instruction (one warp, one chain): DFMA, DADD, DMUL. */
+int32_t lm_probe_fp64_latency(double* dfma_cycles, double* dadd_cycles, double* dmul_cycles);
+/* The bare K1 recurrence (6 FP64 instr / iteration, interior points, no escape test) at a
+ * given occupancy: the practical ceiling of the escape kernel's blind path, in
+ * G pixel-iterations/s.  variant 0: recurrence only; 1: + calm tracking and a vote per 16. */
+int32_t lm_probe_k1_loop(int32_t variant, int32_t warps_per_sm, int32_t blocks16,
+                         double* gpixel_iters_per_s);
 /* STREAM-style device copy bandwidth in GB/s (read+write bytes). */
 int32_t lm_probe_hbm_copy(size_t bytes, int32_t reps, double* gbs);
 

@@ -33,7 +33,7 @@ EXPORTS = (
     "lm_roots_batched",
     "lm_laplacian5_periodic", "lm_laplacian5_periodic_dev", "lm_smooth5_interior", "lm_smooth5_interior_dev",
     "lm_log_potential",
-    "lm_probe_fp64_peak", "lm_probe_hbm_copy",
+    "lm_probe_fp64_peak", "lm_probe_fp64_latency", "lm_probe_k1_loop", "lm_probe_hbm_copy",
 )
 
 
@@ -96,6 +96,8 @@ _SIGNATURES = {
     "lm_smooth5_interior_dev": (_i32, [_vp, _i64, _i64, _vp, _vp]),
     "lm_log_potential": (_i32, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _f64, _i32, _vp, _pStats]),
     "lm_probe_fp64_peak": (_i32, [_i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "lm_probe_fp64_latency": (_i32, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "lm_probe_k1_loop": (_i32, [_i32, _i32, _i32, C.POINTER(C.c_double)]),
     "lm_probe_hbm_copy": (_i32, [_sz, _i32, C.POINTER(C.c_double)]),
 }
 

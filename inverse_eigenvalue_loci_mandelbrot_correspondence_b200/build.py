@@ -47,8 +47,14 @@ def _sources() -> list[Path]:
     return sorted(CSRC.glob("*.cu"))
 
 
+def _extra_defs() -> list[str]:
+    """Extra -D flags for tuning sweeps, e.g. LM_NVCC_DEFS="-DLM_K1_FB=32 -DLM_K1_MIN_CTAS=4"."""
+    return os.environ.get("LM_NVCC_DEFS", "").split()
+
+
 def _digest() -> str:
     h = hashlib.sha256()
+    h.update(" ".join(_extra_defs()).encode())
     for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [INCLUDE / "lm_b200.h", Path(__file__)]):
         h.update(p.name.encode())
         h.update(p.read_bytes())
@@ -73,7 +79,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     def compile_one(src: Path) -> Path:
         obj = BUILD_DIR / (src.stem + ".o")
         extra = PER_FILE.get(src.name, DEFAULT_EXTRA)
-        cmd = [nvcc, *ARCH_FLAGS, *COMMON, *extra, "-I", str(INCLUDE), "-I", str(CSRC),
+        cmd = [nvcc, *ARCH_FLAGS, *COMMON, *extra, *_extra_defs(), "-I", str(INCLUDE), "-I", str(CSRC),
                "-c", str(src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas")

@@ -19,10 +19,15 @@
 //     -fmad=false): a=zr*zr, b=zi*zi, p=zr*zi, zr'=(a-b)+cr, zi'=fma(2,p,ci) [== (p+p)+ci
 //     exactly], test fl(a'+b') > bailout^2.  That is 6 FP64-pipe instructions for the
 //     update + 1 DADD for the test;
-//   * "calm" fast path: while every lane has a < T/2 and b < T/2 (checked on the high
-//     words with integer max on the ALU pipe) the sum a+b cannot exceed T, so blocks of
-//     FB iterations run with NO test DADD (6 FP64 instr/iteration) and are rolled back
-//     and re-run carefully if any lane left the calm region;
+//   * blind fast path: for |c| <= cmax (= R^2 - R - 0.05, i.e. 1.95 for R = 2) escape is
+//     absorbing with a margin that dwarfs rounding error: |z_j|^2 = |z_{j+1} - c| <=
+//     |z_{j+1}| + |c|, so if the LAST iterate of a block has fl(a+b) <= R^2 then by backward
+//     induction every earlier iterate of the block had |z_j|^2 <= R + cmax < R^2 - 0.05 and
+//     the reference's test could not have fired.  Blocks of FB iterations therefore run
+//     with NO per-iteration test (6 FP64 instructions per iteration, the issue-port
+//     minimum); one DADD + compare per block decides, and a block in which some lane did
+//     escape is rolled back and re-run with the exact per-iteration test to find the
+//     first-escape index.  Warps holding a pixel with |c| > cmax never go blind;
 //   * results are staged per warp in a shared-memory ring of tiles and leave the SM as
 //     one 128-bit coalesced store per lane per tile; a pixel that is still iterating
 //     when its tile is evicted from the ring patches its own word later.
@@ -36,12 +41,26 @@
 
 namespace {
 
+// tunables (overridable with -D for sweeps; the defaults are the measured best)
+#ifndef LM_K1_WARPS
+#define LM_K1_WARPS 8
+#endif
+#ifndef LM_K1_MIN_CTAS
+#define LM_K1_MIN_CTAS 3
+#endif
+#ifndef LM_K1_FB
+#define LM_K1_FB 32
+#endif
+#ifndef LM_K1_COOL_MIN
+#define LM_K1_COOL_MIN 16
+#endif
+
 constexpr int TILE = 128;          // pixels per tile (one int4 per lane)
-constexpr int WARPS = 8;           // warps per CTA
+constexpr int WARPS = LM_K1_WARPS; // warps per CTA
 constexpr int CTA_THREADS = WARPS * 32;
 constexpr int RING = 4;            // resident tiles per warp
-constexpr int FB = 4;              // iterations per blind (fast) block
-constexpr int CALM_MIN = 8;        // calm careful iterations required before going blind
+constexpr int FB = LM_K1_FB;       // iterations per blind (fast) block
+constexpr int COOL_MIN = LM_K1_COOL_MIN;   // careful iterations after a refill / rollback before going blind
 constexpr unsigned FULL = 0xffffffffu;
 
 struct EscapeArgs {
@@ -52,7 +71,7 @@ struct EscapeArgs {
     int max_iter;
     double thr2;                   // loop threshold on a+b (bailout^2, slightly lowered for hypot tests)
     double bailout;                // R
-    unsigned hi_calm;              // high word of thr2/2: a,b below it => no escape possible
+    double cfar2;                  // lanes with |c|^2 > cfar2 forbid the blind path (<0: never blind)
     int* dwell;                    // [ny*nx] or NULL
     double* dwell_f64;             // [ny*nx] or NULL
     double* field;                 // grid: [ny*nx] or NULL; points: g
@@ -75,10 +94,6 @@ struct EscapeArgs {
         a = __dmul_rn(zr, zr);                       \
         b = __dmul_rn(zi, zi);                       \
     } while (0)
-
-__device__ __forceinline__ unsigned hi_word(double x) {
-    return static_cast<unsigned>(__double2hiint(x));
-}
 
 // field value at the end of an orbit.  iters = iterations performed (1-based escape index
 // when escaped, max_iter otherwise); (zr,zi) = z after `iters` iterations.
@@ -117,7 +132,7 @@ __device__ __forceinline__ double field_value(double zr, double zi, int iters, b
 // HYPOT          : escape test is hypot(zr,zi) > R (the loop test is a slightly lowered
 //                  a+b threshold, confirmed with hypot in the handler)
 template <bool POINTS, int FM, bool HYPOT>
-__global__ void __launch_bounds__(CTA_THREADS, 3) lm_escape_kernel(const EscapeArgs A) {
+__global__ void __launch_bounds__(CTA_THREADS, LM_K1_MIN_CTAS) lm_escape_kernel(const EscapeArgs A) {
     constexpr bool FIELD = (FM != LM_FIELD_NONE);
     constexpr int CB = HYPOT ? 1 : 4;          // iterations per careful block
 
@@ -136,6 +151,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) lm_escape_kernel(const EscapeA
     double zr = 0.0, zi = 0.0, a = 0.0, b = 0.0, cr = 0.0, ci = 0.0;
     int n = 0;                       // iterations performed on the current pixel
     bool idle = true;                // lane holds no pixel
+    bool far = false;                // |c| too large for the absorbing-escape argument
     int my_off = 0;                  // offset of my pixel inside its tile
     unsigned my_seq = 0;             // sequence number (per warp) of my pixel's tile
     long long my_g = 0;              // flat output index of my pixel
@@ -147,7 +163,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) lm_escape_kernel(const EscapeA
     long long base = 0, col0 = 0;    // flat index / first column of the current tile
     double row_ci = 0.0;
     bool exhausted = false;
-    int calm = 0;
+    int cool = 0;                    // careful iterations since the last refill / rollback
     unsigned long long pref = 0;     // prefetched tile id (valid in lane 0)
     if (lane == 0) pref = atomicAdd(A.tile_counter, 1ULL);
 
@@ -232,6 +248,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) lm_escape_kernel(const EscapeA
                 cr = __ldg(A.xs + col0 + my_off);
                 ci = POINTS ? __ldg(A.ys + col0 + my_off) : row_ci;
                 zr = 0.0; zi = 0.0; a = 0.0; b = 0.0; n = 0;
+                far = !(cr * cr + ci * ci <= A.cfar2);
                 idle = false;
                 need = false;
             }
@@ -240,9 +257,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) lm_escape_kernel(const EscapeA
         }
         if (need) {          // nothing left for this lane: spin on the origin, emit nothing
             idle = true;
+            far = false;
             cr = 0.0; ci = 0.0; zr = 0.0; zi = 0.0; a = 0.0; b = 0.0; n = 0;
         }
-        if (assigned_any) calm = 0;
+        if (assigned_any) cool = 0;
     };
 
     refill(true);
@@ -251,23 +269,21 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) lm_escape_kernel(const EscapeA
         if (exhausted && __all_sync(FULL, idle)) break;
 
         int safe = __reduce_min_sync(FULL, A.max_iter - n);   // >= 1: iterations until the first lane hits max_iter
+        const bool blind_ok = !HYPOT && !__any_sync(FULL, far);
         bool done = false;             // this lane escaped inside the current run
         int n_fin = 0;                 // iterations performed when it escaped
         double ze_r = 0.0, ze_i = 0.0; // z at the escape (FIELD modes)
 
         while (true) {
-            if (!HYPOT && safe >= FB && calm >= CALM_MIN) {
-                // ---- blind block: FB iterations without the test DADD
+            if (blind_ok && cool >= COOL_MIN && safe >= FB) {
+                // ---- blind block: FB iterations, 6 FP64 instructions each, one test at the end
                 const double szr = zr, szi = zi, sa = a, sb = b;
-                unsigned acc = 0u;
 #pragma unroll
-                for (int k = 0; k < FB; ++k) {
-                    LM_STEP6();
-                    acc = max(acc, max(hi_word(a), hi_word(b)));
-                }
-                if (__any_sync(FULL, acc >= A.hi_calm)) {
-                    zr = szr; zi = szi; a = sa; b = sb;     // roll back, redo carefully
-                    calm = 0;
+                for (int k = 0; k < FB; ++k) LM_STEP6();
+                const double m = __dadd_rn(a, b);
+                if (__any_sync(FULL, !(m <= A.thr2))) {
+                    zr = szr; zi = szi; a = sa; b = sb;     // some lane escaped in here: redo carefully
+                    cool = 0;
                 } else {
                     n += FB;
                     safe -= FB;
@@ -275,25 +291,34 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) lm_escape_kernel(const EscapeA
                     continue;
                 }
             }
-            // ---- careful block: up to CB iterations with the exact test, sticky per lane
-            const int cnt = safe < CB ? safe : CB;
-            unsigned acc = 0u;
+            // ---- careful block: CB iterations with the exact test (first escape kept per lane)
+            int cnt;
+            if (safe >= CB) {
+                unsigned esc_bits = 0u;
 #pragma unroll
-            for (int k = 0; k < CB; ++k) {
-                if (k < cnt) {
+                for (int k = 0; k < CB; ++k) {
                     LM_STEP6();
                     const double m = __dadd_rn(a, b);
-                    if (m > A.thr2 && !done) {
-                        done = true;
-                        n_fin = n + k + 1;
-                        if (FIELD || HYPOT || POINTS) { ze_r = zr; ze_i = zi; }
+                    if (m > A.thr2) {
+                        if ((FIELD || HYPOT || POINTS) && esc_bits == 0u) { ze_r = zr; ze_i = zi; }
+                        esc_bits |= 1u << k;
                     }
-                    acc = max(acc, max(hi_word(a), hi_word(b)));
                 }
+                if (esc_bits) { done = true; n_fin = n + __ffs(esc_bits); }
+                cnt = CB;
+            } else {
+                // fewer than CB iterations left before some lane reaches max_iter: single step
+                LM_STEP6();
+                const double m = __dadd_rn(a, b);
+                if (m > A.thr2) {
+                    done = true; n_fin = n + 1;
+                    if (FIELD || HYPOT || POINTS) { ze_r = zr; ze_i = zi; }
+                }
+                cnt = 1;
             }
             n += cnt;
             safe -= cnt;
-            if (!HYPOT) calm = __any_sync(FULL, acc >= A.hi_calm) ? 0 : calm + cnt;
+            cool += cnt;
             if (__any_sync(FULL, done) || safe == 0) break;
         }
 
@@ -391,10 +416,9 @@ int32_t launch_escape(bool points, int field_mode, EscapeArgs& A, cudaStream_t s
     if (hypot_test) thr2 = thr2 * (1.0 - 1e-9);   // candidate threshold; hypot decides
     A.thr2 = thr2;
     {
-        const double half = 0.5 * thr2;
-        long long bits;
-        memcpy(&bits, &half, sizeof(bits));
-        A.hi_calm = static_cast<unsigned>(static_cast<unsigned long long>(bits) >> 32);
+        // blind path precondition (see header): |c| <= R^2 - R - 0.05
+        const double cmax = R * R - R - 0.05;
+        A.cfar2 = (!hypot_test && cmax > 0.0 && cmax < 1e100) ? cmax * cmax : -1.0;
     }
     if (points) {
         if (field_mode == LM_FIELD_GREEN) return launch_one<true, LM_FIELD_GREEN, false>(A, stream);
