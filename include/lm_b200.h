@@ -186,16 +186,20 @@ int32_t lm_contour_level_dev(const int32_t* dwell_dev, const double* xs_host, in
                              lm_stats* stats);
 
 /*
- * Multi-GPU building block: classify the quads of rows [0, ny-1) of a dwell block
- * (ny rows incl. one halo row) and return the compacted crossing-quad records to the
- * host; records of several row blocks are concatenated (with row_offset added) and
- * linked by lm_contour_link.  A record is 4 x int64: {quad = j*nx_quads + i (global),
- * corner dwell SW|SE<<32, corner dwell NW|NE<<32, reserved}.
+ * Multi-GPU building block: classify the quads of rows [0, ny-1) of a dwell block on the
+ * device (ny rows including one halo row; ys_host holds the block's ny coordinates) and
+ * return the compacted crossing-quad records, in raster order, to the host.  Records of
+ * consecutive row blocks are concatenated and chained by lm_contour_link.
+ * A record is 8 x int64: {quad = (row_offset + j)*nx + i, SW | SE<<32, NW | NE<<32 (corner
+ * dwell values), meta, exit vertex of segment 0 (x, y as binary64), exit vertex of
+ * segment 1 (saddle quads)}; meta is described in csrc/lm_contour.cu.
  */
-int32_t lm_contour_classify_dev(const int32_t* dwell_dev, int64_t nx, int64_t ny,
-                                int64_t row_offset, double level,
+int32_t lm_contour_classify_dev(const int32_t* dwell_dev, const double* xs_host, int64_t nx,
+                                const double* ys_host, int64_t ny, int64_t row_offset, double level,
                                 int64_t* records, int64_t cap_records, int64_t* n_records,
                                 void* stream);
+/* Host-only: chain raster-ordered records into mpl2014-ordered polylines (xs, ys: the full
+ * grid coordinates).  Does not need a device.                                            */
 int32_t lm_contour_link(const int64_t* records, int64_t n_records,
                         const double* xs, int64_t nx, const double* ys, int64_t ny,
                         double level,

@@ -87,7 +87,7 @@ _SIGNATURES = {
     "lm_distance_grid_f64": (_i32, [_vp, _i64, _vp, _i64, _i32, _f64, _f64, _i32, _vp, _vp, _pStats]),
     "lm_contour_level": (_i32, [_vp, _vp, _i64, _vp, _i64, _f64, _vp, _i64, _pi64, _vp, _i64, _pi64, _pStats]),
     "lm_contour_level_dev": (_i32, [_vp, _vp, _i64, _vp, _i64, _f64, _vp, _i64, _pi64, _vp, _i64, _pi64, _pStats]),
-    "lm_contour_classify_dev": (_i32, [_vp, _i64, _i64, _i64, _f64, _vp, _i64, _pi64, _vp]),
+    "lm_contour_classify_dev": (_i32, [_vp, _vp, _i64, _vp, _i64, _i64, _f64, _vp, _i64, _pi64, _vp]),
     "lm_contour_link": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _f64, _vp, _i64, _pi64, _vp, _i64, _pi64]),
     "lm_roots_batched": (_i32, [_vp, _vp, _i64, _i32, _i32, _f64, _vp, _vp, _vp, _vp, _pStats]),
     "lm_laplacian5_periodic": (_i32, [_vp, _i64, _i64, _f64, _vp, _pStats]),

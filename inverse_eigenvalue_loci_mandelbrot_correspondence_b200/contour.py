@@ -1,0 +1,99 @@
+"""Host side of K2: level set of the dwell field behind the reference's extract_contour.
+
+  extract_contour(xs, ys, Z, max_iter, level_frac)   mandelbrot_boundary_sample.py:41-54,
+                                                     mandelbrot_boundary_sample_spyder.py:35-43
+The reference calls plt.contour(xs, ys, Z, levels=[level_frac*max_iter]) and keeps the line
+with most vertices (cs.allsegs[0] semantics: one (N,2) array per connected line, closed loops
+repeat their first vertex).  Here the quads are classified and the vertices computed on the
+GPU (liblm_b200.so), the ordered chaining follows contourpy's mpl2014 rules.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _shim
+from ._shim import Stats
+
+last_stats: dict = {}
+
+
+def _as_dwell_i32(Z) -> np.ndarray:
+    Z = np.asarray(Z)
+    if Z.dtype == np.int32:
+        return np.ascontiguousarray(Z)
+    Zi = np.ascontiguousarray(Z, dtype=np.int32)
+    if not np.array_equal(Zi, Z):
+        raise ValueError("the contour kernel takes an integer-valued dwell field (as compute_grid returns)")
+    return Zi
+
+
+def _call_with_growing_buffers(fn_name: str, head_args: tuple, level: float, n_pixels: int):
+    cap_v = max(1024, int(0.02 * n_pixels) + 1024)
+    cap_l = 4096
+    st = Stats()
+    while True:
+        verts = np.empty((cap_v, 2), dtype=np.float64)
+        offs = np.empty(cap_l + 1, dtype=np.int64)
+        nv = C.c_int64(0); nl = C.c_int64(0)
+        lib = _shim.load()
+        with _shim._lock:
+            rc = getattr(lib, fn_name)(*head_args, float(level), _shim.ptr(verts), cap_v, C.byref(nv),
+                                       _shim.ptr(offs), cap_l, C.byref(nl), C.byref(st))
+        if rc == _shim.LM_E_CAP:
+            cap_v = max(cap_v, nv.value + 16); cap_l = max(cap_l, nl.value + 16)
+            continue
+        _shim.check(rc)
+        break
+    global last_stats
+    last_stats = st.as_dict()
+    return [verts[offs[k]:offs[k + 1]].copy() for k in range(nl.value)]
+
+
+def contour_lines(xs, ys, Z, level: float):
+    """All level-`level` lines of the dwell field Z[j,i] at (xs[i], ys[j]), in matplotlib's order."""
+    xs = np.ascontiguousarray(xs, dtype=np.float64).ravel()
+    ys = np.ascontiguousarray(ys, dtype=np.float64).ravel()
+    d = _as_dwell_i32(Z)
+    if d.shape != (ys.size, xs.size):
+        raise ValueError("Z must have shape (len(ys), len(xs))")
+    return _call_with_growing_buffers("lm_contour_level", (_shim.ptr(d), _shim.ptr(xs), xs.size, _shim.ptr(ys), ys.size),
+                                      level, d.size)
+
+
+def contour_lines_dev(dwell_dev_ptr: int, xs, ys, level: float):
+    """Same with the int32 dwell grid already resident on the current device."""
+    xs = np.ascontiguousarray(xs, dtype=np.float64).ravel()
+    ys = np.ascontiguousarray(ys, dtype=np.float64).ravel()
+    return _call_with_growing_buffers("lm_contour_level_dev",
+                                      (C.c_void_p(dwell_dev_ptr), _shim.ptr(xs), xs.size, _shim.ptr(ys), ys.size),
+                                      level, xs.size * ys.size)
+
+
+def longest(lines):
+    """max(paths, key=#vertices): the first of the longest lines (mandelbrot_boundary_sample.py:53)."""
+    if not lines:
+        return None
+    return max(lines, key=lambda a: a.shape[0])
+
+
+def extract_contour(xs, ys, Z, max_iter: int, level_frac: float = 0.96):
+    """Drop-in for extract_contour: the longest isocontour of Z at level_frac*max_iter, or None."""
+    target = level_frac * max_iter
+    return longest(contour_lines(xs, ys, Z, target))
+
+
+def link_records(records: np.ndarray, xs, ys, level: float):
+    """Chain raster-ordered crossing records (lm_contour_classify_dev) into polylines (host only)."""
+    xs = np.ascontiguousarray(xs, dtype=np.float64).ravel()
+    ys = np.ascontiguousarray(ys, dtype=np.float64).ravel()
+    records = np.ascontiguousarray(records, dtype=np.int64).reshape(-1, 8)
+    n = records.shape[0]
+    cap_v, cap_l = 4 * n + 16, n + 16
+    verts = np.empty((cap_v, 2), dtype=np.float64)
+    offs = np.empty(cap_l + 1, dtype=np.int64)
+    nv = C.c_int64(0); nl = C.c_int64(0)
+    _shim.call("lm_contour_link", _shim.ptr(records), n, _shim.ptr(xs), xs.size, _shim.ptr(ys), ys.size, float(level),
+               _shim.ptr(verts), cap_v, C.byref(nv), _shim.ptr(offs), cap_l, C.byref(nl))
+    return [verts[offs[k]:offs[k + 1]].copy() for k in range(nl.value)]

@@ -1,0 +1,578 @@
+// lm_contour.cu -- K2: level set of the dwell field (marching squares), HBM bound.
+//
+// Replaces plt.contour(xs, ys, Z, levels=[level]) as used by
+//   extract_contour   mandelbrot_boundary_sample.py:41-54
+//   extract_contour   mandelbrot_boundary_sample_spyder.py:35-43
+// with contourpy's "mpl2014" line semantics: a point is above iff
+// z > level; a vertex on edge p1->p2 is xy1*f + xy2*(1-f) with f = (z2-level)/(z2-z1);
+// higher side on the left; saddles decided by the mean of the four corners; boundary lines
+// first, then interior loops in raster order of their first quad.
+//
+// Pipeline (algorithmic bytes: one 4-byte read of every dwell value):
+//   1. mark kernel   : every warp takes a 128-quad strip of one row pair, loads the two dwell
+//                      rows coalesced, classifies the quads, writes a 1-bit-per-quad crossing
+//                      mask (ballot words, raster order) and adds the strip's count to the
+//                      row counter.  DRAM: 4 B/pixel read (+1/32 written); the second use of
+//                      each row is served by L2.
+//   2. scan kernel   : exclusive scan of the row counters (single CTA).
+//   3. emit kernel   : warp per row walks the mask words, and for every crossing quad gathers
+//                      the four corners, derives the line segment(s) through it and their
+//                      exit vertices in the reference's exact arithmetic, and writes a 64-byte
+//                      record at its raster-order rank (ordered compaction, no sort needed).
+//   4. host link     : the records (~0.1-0.4 % of the quads) are chained into ordered
+//                      polylines following mpl2014's start/direction/saddle rules.
+//
+// Record (8 x int64): [0] quad = j*nx + i (global row j), [1] SW | SE<<32, [2] NW | NE<<32
+// (corner dwell, uint32 each), [3] meta, [4..5] exit vertex of segment 0 (x, y as doubles),
+// [6..7] exit vertex of segment 1 (saddle quads only).
+// meta: bits 0-3 config (NW<<3|NE<<2|SW<<1|SE), bit 4 saddle turns right (mean > level),
+// bits 8-9 entry edge of segment 0, 10-11 its exit edge, 12-13 / 14-15 the same for
+// segment 1, bits 16-17 number of segments.  Edges: E=0, N=1, W=2, S=3.
+#include "lm_common.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int STRIP = 128;                 // quads per warp step (4 ballot words)
+constexpr int MARK_WARPS = 8;
+constexpr int REC_WORDS = 8;               // int64 words per record
+
+enum { EDGE_E = 0, EDGE_N = 1, EDGE_W = 2, EDGE_S = 3, EDGE_NONE = -1 };
+
+__host__ __device__ inline bool above_level(int z, double level) { return static_cast<double>(z) > level; }
+
+// exit edge when entering through `edge` (see lm_oracle_contour.c / mpl2014 follow_interior):
+// dir: +1 left, 0 straight, -1 right
+__host__ __device__ inline int exit_edge_of(int edge, int dir) {
+    // left turn = next edge clockwise seen from inside:  E->S, N->E, W->N, S->W
+    // straight = opposite edge;  right turn: E->N, N->W, W->S, S->E
+    if (dir == 0) return (edge + 2) & 3;
+    if (dir > 0) return (edge + 3) & 3;
+    return (edge + 1) & 3;
+}
+
+// Segments through a quad.  Returns the number of segments (0, 1 or 2) and fills
+// entry[]/exit[]; saddle_right = (mean of corners > level).
+__host__ __device__ inline int quad_segments(bool sw, bool se, bool nw, bool ne, bool saddle_right,
+                                             int entry[2], int exit_[2]) {
+    int n = 0;
+    // an entry edge has its start point above and its end point not above (edges are CCW:
+    // E: SE->NE, N: NE->NW, W: NW->SW, S: SW->SE)
+    const bool ent[4] = {se && !ne, ne && !nw, nw && !sw, sw && !se};
+    for (int e = 3; e >= 0; --e) {           // S first so that segment 0 of a saddle is the S / W entry
+        const int edge = (e == 3) ? EDGE_S : (e == 2) ? EDGE_W : (e == 1) ? EDGE_N : EDGE_E;
+        if (!ent[edge]) continue;
+        // far-left / far-right corners seen from the entry edge
+        bool pl, pr;
+        switch (edge) {
+            case EDGE_E: pl = sw; pr = nw; break;
+            case EDGE_N: pl = se; pr = sw; break;
+            case EDGE_W: pl = ne; pr = se; break;
+            default:     pl = nw; pr = ne; break;
+        }
+        int dir;
+        if (!pl && pr) dir = saddle_right ? -1 : +1;        // saddle
+        else if (!pl && !pr) dir = +1;
+        else if (pl && pr) dir = -1;
+        else dir = 0;
+        if (n < 2) { entry[n] = edge; exit_[n] = exit_edge_of(edge, dir); }
+        ++n;
+    }
+    return n < 2 ? n : 2;
+}
+
+// points of an edge of quad (j, i): returns (j1,i1) start and (j2,i2) end as offsets 0/1
+__host__ __device__ inline void edge_corners(int edge, int& dj1, int& di1, int& dj2, int& di2) {
+    switch (edge) {
+        case EDGE_E: dj1 = 0; di1 = 1; dj2 = 1; di2 = 1; break;   // SE -> NE
+        case EDGE_N: dj1 = 1; di1 = 1; dj2 = 1; di2 = 0; break;   // NE -> NW
+        case EDGE_W: dj1 = 1; di1 = 0; dj2 = 0; di2 = 0; break;   // NW -> SW
+        default:     dj1 = 0; di1 = 0; dj2 = 0; di2 = 1; break;   // SW -> SE
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// 1. mark: crossing mask + row counts
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MARK_WARPS * 32) contour_mark_kernel(
+    const int* __restrict__ dwell, long long nx, long long ny, double level,
+    unsigned* __restrict__ mask, long long words_per_row, unsigned* __restrict__ row_count) {
+    const int lane = threadIdx.x & 31;
+    const long long strips_per_row = words_per_row / 4;
+    const long long total = strips_per_row * (ny - 1);
+    const long long nwarps = static_cast<long long>(gridDim.x) * MARK_WARPS;
+    const long long nq = nx - 1;                                   // quads per row
+    for (long long t = static_cast<long long>(blockIdx.x) * MARK_WARPS + (threadIdx.x >> 5); t < total; t += nwarps) {
+        const long long j = t / strips_per_row;
+        const long long c0 = (t - j * strips_per_row) * STRIP;
+        const int* r0 = dwell + j * nx;
+        const int* r1 = r0 + nx;
+        bool lo[4], hi[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long c = c0 + 32 * k + lane;
+            const bool in = c < nx;
+            lo[k] = in ? above_level(__ldg(r0 + c), level) : false;
+            hi[k] = in ? above_level(__ldg(r1 + c), level) : false;
+        }
+        // the column right of the strip (corner of the last quad)
+        const long long ce = c0 + STRIP;
+        bool lo_e = false, hi_e = false;
+        if (lane == 31 && ce < nx) { lo_e = above_level(__ldg(r0 + ce), level); hi_e = above_level(__ldg(r1 + ce), level); }
+        unsigned words[4];
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            // right neighbours: lane+1 of the same chunk, lane 0 of the next chunk for lane 31
+            const bool nlo = (k < 3) ? lo[k + 1] : lo_e, nhi = (k < 3) ? hi[k + 1] : hi_e;
+            bool rl = __shfl_down_sync(FULL, lo[k], 1), rh = __shfl_down_sync(FULL, hi[k], 1);
+            const bool wl = __shfl_sync(FULL, nlo, (k < 3) ? 0 : 31), wh = __shfl_sync(FULL, nhi, (k < 3) ? 0 : 31);
+            if (lane == 31) { rl = wl; rh = wh; }
+            const long long c = c0 + 32 * k + lane;
+            const int s = static_cast<int>(lo[k]) + static_cast<int>(rl) + static_cast<int>(hi[k]) + static_cast<int>(rh);
+            const bool cross = (c < nq) && s != 0 && s != 4;
+            words[k] = __ballot_sync(FULL, cross);
+            cnt += __popc(words[k]);
+        }
+        if (lane < 4) {
+            const unsigned w = lane == 0 ? words[0] : lane == 1 ? words[1] : lane == 2 ? words[2] : words[3];
+            mask[j * words_per_row + c0 / 32 + lane] = w;
+        }
+        if (lane == 0 && cnt) atomicAdd(row_count + j, static_cast<unsigned>(cnt));
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// 2. exclusive scan of the row counters (one CTA); total -> row_offset[nrows]
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) contour_scan_kernel(const unsigned* __restrict__ row_count, long long nrows,
+                                                            unsigned long long* __restrict__ row_offset) {
+    __shared__ unsigned long long warp_sums[32];
+    __shared__ unsigned long long carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (long long base = 0; base < nrows; base += 1024) {
+        const long long idx = base + threadIdx.x;
+        const unsigned long long v = idx < nrows ? row_count[idx] : 0ULL;
+        unsigned long long x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long y = __shfl_up_sync(FULL, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_sums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long y = __shfl_up_sync(FULL, w, o);
+                if (lane >= o) w += y;
+            }
+            warp_sums[lane] = w;           // inclusive over warps
+        }
+        __syncthreads();
+        const unsigned long long carry = carry_s;
+        const unsigned long long before = (warp ? warp_sums[warp - 1] : 0ULL);
+        if (idx < nrows) row_offset[idx] = carry + before + x - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + before + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) row_offset[nrows] = carry_s;
+}
+
+// vertex on `edge` of quad (j, i): interp(point1 = edge start, point2 = edge end)
+__device__ __forceinline__ void edge_vertex_dev(int edge, const int z[2][2], const double* __restrict__ xs,
+                                                const double* __restrict__ ys, long long j, long long i,
+                                                double level, double& vx, double& vy) {
+    int dj1, di1, dj2, di2;
+    edge_corners(edge, dj1, di1, dj2, di2);
+    const double z1 = static_cast<double>(z[dj1][di1]), z2 = static_cast<double>(z[dj2][di2]);
+    const double f = __ddiv_rn(__dsub_rn(z2, level), __dsub_rn(z2, z1));
+    const double g = __dsub_rn(1.0, f);
+    vx = __dadd_rn(__dmul_rn(__ldg(xs + i + di1), f), __dmul_rn(__ldg(xs + i + di2), g));
+    vy = __dadd_rn(__dmul_rn(__ldg(ys + j + dj1), f), __dmul_rn(__ldg(ys + j + dj2), g));
+}
+
+// ------------------------------------------------------------------------------------
+// 3. emit: ordered records
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MARK_WARPS * 32) contour_emit_kernel(
+    const int* __restrict__ dwell, long long nx, long long ny, long long row_offset_global, double level,
+    const double* __restrict__ xs, const double* __restrict__ ys,   // ys indexed by local row
+    const unsigned* __restrict__ mask, long long words_per_row, const unsigned* __restrict__ row_count,
+    const unsigned long long* __restrict__ row_offset, long long* __restrict__ records) {
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = static_cast<long long>(gridDim.x) * MARK_WARPS;
+    for (long long j = static_cast<long long>(blockIdx.x) * MARK_WARPS + (threadIdx.x >> 5); j < ny - 1; j += nwarps) {
+        if (row_count[j] == 0u) continue;
+        unsigned long long running = row_offset[j];
+        for (long long w0 = 0; w0 < words_per_row; w0 += 32) {
+            const long long w = w0 + lane;
+            unsigned word = (w < words_per_row) ? mask[j * words_per_row + w] : 0u;
+            const int cnt = __popc(word);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += y;
+            }
+            unsigned long long pos = running + static_cast<unsigned long long>(incl - cnt);
+            running += static_cast<unsigned long long>(__shfl_sync(FULL, incl, 31));
+            while (word) {
+                const int bit = __ffs(word) - 1;
+                word &= word - 1;
+                const long long i = w * 32 + bit;
+                int z[2][2];
+                z[0][0] = __ldg(dwell + j * nx + i);
+                z[0][1] = __ldg(dwell + j * nx + i + 1);
+                z[1][0] = __ldg(dwell + (j + 1) * nx + i);
+                z[1][1] = __ldg(dwell + (j + 1) * nx + i + 1);
+                const bool sw = above_level(z[0][0], level), se = above_level(z[0][1], level);
+                const bool nw = above_level(z[1][0], level), ne = above_level(z[1][1], level);
+                // mean of the four corners, summed in the reference's order SW+SE+NW+NE
+                const double zmid = __dmul_rn(0.25, __dadd_rn(__dadd_rn(__dadd_rn(static_cast<double>(z[0][0]),
+                                    static_cast<double>(z[0][1])), static_cast<double>(z[1][0])), static_cast<double>(z[1][1])));
+                const bool saddle_right = zmid > level;
+                int entry[2] = {0, 0}, exit_[2] = {0, 0};
+                const int nseg = quad_segments(sw, se, nw, ne, saddle_right, entry, exit_);
+                double v[4] = {0.0, 0.0, 0.0, 0.0};
+                if (nseg >= 1) edge_vertex_dev(exit_[0], z, xs, ys, j, i, level, v[0], v[1]);
+                if (nseg >= 2) edge_vertex_dev(exit_[1], z, xs, ys, j, i, level, v[2], v[3]);
+                const unsigned config = (nw ? 8u : 0u) | (ne ? 4u : 0u) | (sw ? 2u : 0u) | (se ? 1u : 0u);
+                const long long meta = static_cast<long long>(config | (saddle_right ? 16u : 0u) |
+                                       (static_cast<unsigned>(entry[0]) << 8) | (static_cast<unsigned>(exit_[0]) << 10) |
+                                       (static_cast<unsigned>(entry[1]) << 12) | (static_cast<unsigned>(exit_[1]) << 14) |
+                                       (static_cast<unsigned>(nseg) << 16));
+                long long* r = records + pos * REC_WORDS;
+                longlong2* r2 = reinterpret_cast<longlong2*>(r);
+                r2[0] = make_longlong2((row_offset_global + j) * nx + i,
+                                       static_cast<long long>(static_cast<unsigned>(z[0][0])) |
+                                       (static_cast<long long>(static_cast<unsigned>(z[0][1])) << 32));
+                r2[1] = make_longlong2(static_cast<long long>(static_cast<unsigned>(z[1][0])) |
+                                       (static_cast<long long>(static_cast<unsigned>(z[1][1])) << 32), meta);
+                r2[2] = make_longlong2(__double_as_longlong(v[0]), __double_as_longlong(v[1]));
+                r2[3] = make_longlong2(__double_as_longlong(v[2]), __double_as_longlong(v[3]));
+                ++pos;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// device side driver: dwell block on the device -> ordered records on the host
+// ------------------------------------------------------------------------------------
+int32_t classify_device(const int* dwell_dev, const double* xs_host, long long nx,
+                        const double* ys_host, long long ny, long long row_offset, double level,
+                        std::vector<long long>& records, float* kernel_ms, cudaStream_t s) {
+    records.clear();
+    if (nx < 2 || ny < 2) return LM_OK;
+    const long long nrows = ny - 1;
+    const long long words_per_row = ((nx - 1 + STRIP - 1) / STRIP) * 4;
+    void *dmask, *dcount, *doff, *dxs, *dys;
+    int32_t rc;
+    if ((rc = lm::ws_get(lm::WS_SCRATCH, static_cast<size_t>(nrows) * words_per_row * sizeof(unsigned), &dmask)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_IN_C, static_cast<size_t>(nrows) * sizeof(unsigned), &dcount)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_OUT_D, static_cast<size_t>(nrows + 1) * sizeof(unsigned long long), &doff)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_XS, static_cast<size_t>(nx) * sizeof(double), &dxs)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_YS, static_cast<size_t>(ny) * sizeof(double), &dys)) != LM_OK) return rc;
+    LM_CUDA_TRY(cudaMemcpyAsync(dxs, xs_host, nx * sizeof(double), cudaMemcpyHostToDevice, s));
+    LM_CUDA_TRY(cudaMemcpyAsync(dys, ys_host, ny * sizeof(double), cudaMemcpyHostToDevice, s));
+    LM_CUDA_TRY(cudaMemsetAsync(dcount, 0, static_cast<size_t>(nrows) * sizeof(unsigned), s));
+
+    lm::Timer tm;
+    if ((rc = tm.begin(s)) != LM_OK) return rc;
+    const long long strips = (words_per_row / 4) * nrows;
+    long long blocks = (strips + MARK_WARPS - 1) / MARK_WARPS;
+    const long long cap = static_cast<long long>(lm::sm_count()) * 8;
+    if (blocks > cap) blocks = cap;
+    contour_mark_kernel<<<static_cast<unsigned>(blocks), MARK_WARPS * 32, 0, s>>>(
+        dwell_dev, nx, ny, level, static_cast<unsigned*>(dmask), words_per_row, static_cast<unsigned*>(dcount));
+    LM_CUDA_TRY(cudaGetLastError());
+    contour_scan_kernel<<<1, 1024, 0, s>>>(static_cast<unsigned*>(dcount), nrows, static_cast<unsigned long long*>(doff));
+    LM_CUDA_TRY(cudaGetLastError());
+    unsigned long long total = 0;
+    LM_CUDA_TRY(cudaMemcpyAsync(&total, static_cast<unsigned long long*>(doff) + nrows, sizeof(total),
+                                cudaMemcpyDeviceToHost, s));
+    LM_CUDA_TRY(cudaStreamSynchronize(s));
+    void* drec = nullptr;
+    if (total) {
+        if ((rc = lm::ws_get(lm::WS_RECORDS, static_cast<size_t>(total) * REC_WORDS * sizeof(long long), &drec)) != LM_OK) return rc;
+        long long eblocks = (nrows + MARK_WARPS - 1) / MARK_WARPS;
+        if (eblocks > cap) eblocks = cap;
+        contour_emit_kernel<<<static_cast<unsigned>(eblocks), MARK_WARPS * 32, 0, s>>>(
+            dwell_dev, nx, ny, row_offset, level, static_cast<double*>(dxs), static_cast<double*>(dys),
+            static_cast<unsigned*>(dmask), words_per_row, static_cast<unsigned*>(dcount),
+            static_cast<unsigned long long*>(doff), static_cast<long long*>(drec));
+        LM_CUDA_TRY(cudaGetLastError());
+    }
+    float ms = 0.f;
+    if ((rc = tm.end(s, &ms)) != LM_OK) return rc;
+    if (kernel_ms) *kernel_ms = ms;
+    records.resize(static_cast<size_t>(total) * REC_WORDS);
+    if (total) {
+        LM_CUDA_TRY(cudaMemcpyAsync(records.data(), drec, records.size() * sizeof(long long), cudaMemcpyDeviceToHost, s));
+        LM_CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    return LM_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// 4. host link (mpl2014 order over the sparse records)
+// ------------------------------------------------------------------------------------
+struct Linker {
+    const long long* rec; long long n;
+    const double *xs, *ys; long long nx, ny; double level;
+    std::vector<unsigned char> flags;          // 1 visited, 2 saddle seen, 4 start-SW
+    std::vector<double> verts;                 // x, y interleaved
+    std::vector<long long> offsets;            // line starts (+ end)
+
+    long long quad(long long k) const { return rec[k * REC_WORDS]; }
+    unsigned meta(long long k) const { return static_cast<unsigned>(rec[k * REC_WORDS + 3]); }
+    unsigned config(long long k) const { return meta(k) & 15u; }
+    bool is_saddle(long long k) const { const unsigned c = config(k); return c == 6u || c == 9u; }
+    int corner(long long k, int dj, int di) const {
+        const unsigned long long w = static_cast<unsigned long long>(rec[k * REC_WORDS + 1 + dj]);
+        return static_cast<int>(di ? (w >> 32) : (w & 0xffffffffu));
+    }
+    long long find(long long q) const {
+        long long lo = 0, hi = n;
+        while (lo < hi) {
+            const long long mid = (lo + hi) >> 1;
+            if (quad(mid) < q) lo = mid + 1; else hi = mid;
+        }
+        return (lo < n && quad(lo) == q) ? lo : -1;
+    }
+    bool is_boundary(long long q, int edge) const {
+        const long long i = q % nx, j = q / nx;
+        switch (edge) {
+            case EDGE_E: return i == nx - 2;
+            case EDGE_N: return j == ny - 2;
+            case EDGE_W: return i == 0;
+            default:     return j == 0;
+        }
+    }
+    // vertex on `edge` of record k from that edge's own orientation (host arithmetic, unfused:
+    // this translation unit is compiled with -ffp-contract=off)
+    void push_edge_vertex(long long k, int edge) {
+        int dj1, di1, dj2, di2;
+        edge_corners(edge, dj1, di1, dj2, di2);
+        const long long q = quad(k), i = q % nx, j = q / nx;
+        const double z1 = static_cast<double>(corner(k, dj1, di1)), z2 = static_cast<double>(corner(k, dj2, di2));
+        const double f = (z2 - level) / (z2 - z1);
+        const double g = 1.0 - f;
+        const double ax = xs[i + di1] * f, bx = xs[i + di2] * g;
+        const double ay = ys[j + dj1] * f, by = ys[j + dj2] * g;
+        verts.push_back(ax + bx);
+        verts.push_back(ay + by);
+    }
+    int start_edge(long long k) const {
+        const bool saddle = (flags[k] & 2) != 0, start_sw = (flags[k] & 4) != 0;
+        switch (config(k)) {
+            case 1: return EDGE_E;   case 2: return EDGE_S;   case 3: return EDGE_E;
+            case 4: return EDGE_N;   case 5: return EDGE_N;
+            case 6: return (!saddle || start_sw) ? EDGE_S : EDGE_N;
+            case 7: return EDGE_N;   case 8: return EDGE_W;
+            case 9: return (!saddle || !start_sw) ? EDGE_W : EDGE_E;
+            case 10: return EDGE_S;  case 11: return EDGE_E;  case 12: return EDGE_W;
+            case 13: return EDGE_W;  case 14: return EDGE_S;
+            default: return EDGE_NONE;
+        }
+    }
+    // returns false on an inconsistent record set (missing neighbour)
+    bool follow(long long k, int edge, bool want_initial, bool closed) {
+        const long long k0 = k; const int e0 = edge;
+        if (want_initial) push_edge_vertex(k, edge);
+        for (;;) {
+            const unsigned m = meta(k);
+            if (is_saddle(k)) {
+                if (flags[k] & 2) flags[k] |= 1;
+                else { flags[k] |= 2; if (edge == EDGE_N || edge == EDGE_E) flags[k] |= 4; }
+            } else {
+                flags[k] |= 1;
+            }
+            const int nseg = static_cast<int>((m >> 16) & 3u);
+            int seg = -1;
+            for (int s = 0; s < nseg; ++s)
+                if (static_cast<int>((m >> (8 + 4 * s)) & 3u) == edge) seg = s;
+            if (seg < 0) return false;
+            const int ex = static_cast<int>((m >> (10 + 4 * seg)) & 3u);
+            double vx, vy;
+            memcpy(&vx, &rec[k * REC_WORDS + 4 + 2 * seg], sizeof(double));
+            memcpy(&vy, &rec[k * REC_WORDS + 5 + 2 * seg], sizeof(double));
+            verts.push_back(vx);
+            verts.push_back(vy);
+            const long long q = quad(k);
+            if (is_boundary(q, ex)) return true;
+            long long qn; int en;
+            switch (ex) {
+                case EDGE_E: qn = q + 1;  en = EDGE_W; break;
+                case EDGE_N: qn = q + nx; en = EDGE_S; break;
+                case EDGE_W: qn = q - 1;  en = EDGE_E; break;
+                default:     qn = q - nx; en = EDGE_N; break;
+            }
+            const long long kn = find(qn);
+            if (kn < 0) return false;
+            k = kn; edge = en;
+            if (closed && k == k0 && edge == e0) return true;
+        }
+    }
+    bool run() {
+        flags.assign(static_cast<size_t>(n), 0);
+        verts.clear(); offsets.clear();
+        // lines that start and end on the boundary (edges tested S, W, N, E)
+        for (long long k = 0; k < n; ++k) {
+            if (flags[k] & 1) continue;
+            const long long q = quad(k), i = q % nx, j = q / nx;
+            const unsigned c = config(k);
+            const bool nw = c & 8u, ne = c & 4u, sw = c & 2u, se = c & 1u;
+            const bool cond[4] = {i == nx - 2 && se && !ne, j == ny - 2 && ne && !nw, i == 0 && nw && !sw, j == 0 && sw && !se};
+            const int order[4] = {EDGE_S, EDGE_W, EDGE_N, EDGE_E};
+            for (int t = 0; t < 4; ++t) {
+                const int e = order[t];
+                if (!cond[e]) continue;
+                offsets.push_back(static_cast<long long>(verts.size() / 2));
+                if (!follow(k, e, true, false)) return false;
+                if (flags[k] & 1) break;
+            }
+        }
+        // interior closed loops
+        for (long long k = 0; k < n; ++k) {
+            if (flags[k] & 1) continue;
+            const int se = start_edge(k);
+            if (se == EDGE_NONE) continue;
+            const bool ignore_first = (se == EDGE_N);
+            offsets.push_back(static_cast<long long>(verts.size() / 2));
+            const size_t first = verts.size();
+            if (!follow(k, se, !ignore_first, true)) return false;
+            if (ignore_first && verts.size() > first) {
+                const double fx = verts[first], fy = verts[first + 1];
+                verts.push_back(fx);
+                verts.push_back(fy);
+            }
+            if ((flags[k] & 2) && !(flags[k] & 1)) --k;      // second pass through the saddle
+        }
+        offsets.push_back(static_cast<long long>(verts.size() / 2));
+        return true;
+    }
+};
+
+int32_t link_and_export(const long long* records, long long n_records, const double* xs, long long nx,
+                        const double* ys, long long ny, double level,
+                        double* verts, long long cap_verts, long long* n_verts,
+                        long long* line_offsets, long long cap_lines, long long* n_lines) {
+    Linker L{records, n_records, xs, ys, nx, ny, level, {}, {}, {}};
+    if (!L.run()) return lm::fail(LM_E_INVALID, "lm_contour_link: inconsistent crossing records (missing neighbour quad)");
+    const long long nv = static_cast<long long>(L.verts.size() / 2);
+    const long long nl = static_cast<long long>(L.offsets.size()) - 1;
+    *n_verts = nv;
+    *n_lines = nl;
+    if (nv > cap_verts || nl > cap_lines)
+        return lm::fail(LM_E_CAP, "lm_contour: need room for %lld vertices and %lld lines (got %lld, %lld)",
+                        nv, nl, cap_verts, cap_lines);
+    if (nv) memcpy(verts, L.verts.data(), static_cast<size_t>(nv) * 2 * sizeof(double));
+    memcpy(line_offsets, L.offsets.data(), static_cast<size_t>(nl + 1) * sizeof(long long));
+    return LM_OK;
+}
+
+int32_t check_contour_args(const char* who, const void* dwell, const void* xs, int64_t nx, const void* ys, int64_t ny,
+                           const void* verts, int64_t cap_verts, const void* n_verts, const void* offs,
+                           int64_t cap_lines, const void* n_lines) {
+    LM_REQUIRE(dwell && xs && ys, "%s: NULL input", who);
+    LM_REQUIRE(nx >= 0 && ny >= 0, "%s: negative grid size", who);
+    LM_REQUIRE(n_verts && n_lines, "%s: n_verts / n_lines is NULL", who);
+    LM_REQUIRE(cap_verts >= 0 && cap_lines >= 0, "%s: negative capacity", who);
+    LM_REQUIRE((verts || cap_verts == 0) && offs, "%s: NULL output buffer", who);
+    return LM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t lm_contour_classify_dev(const int32_t* dwell_dev, const double* xs_host, int64_t nx,
+                                const double* ys_host, int64_t ny, int64_t row_offset, double level,
+                                int64_t* records, int64_t cap_records, int64_t* n_records, void* stream) {
+    int32_t rc = lm::require_device();
+    if (rc != LM_OK) return rc;
+    LM_REQUIRE(dwell_dev && xs_host && ys_host && n_records, "lm_contour_classify_dev: NULL argument");
+    LM_REQUIRE(nx >= 0 && ny >= 0 && cap_records >= 0, "lm_contour_classify_dev: negative size");
+    std::vector<long long> recs;
+    rc = classify_device(dwell_dev, xs_host, nx, ys_host, ny, row_offset, level, recs, nullptr, lm::as_stream(stream));
+    if (rc != LM_OK) return rc;
+    const long long n = static_cast<long long>(recs.size() / REC_WORDS);
+    *n_records = n;
+    if (n > cap_records)
+        return lm::fail(LM_E_CAP, "lm_contour_classify_dev: need room for %lld records (got %lld)", n,
+                        static_cast<long long>(cap_records));
+    LM_REQUIRE(records || n == 0, "lm_contour_classify_dev: records is NULL");
+    if (n) memcpy(records, recs.data(), recs.size() * sizeof(long long));
+    return LM_OK;
+}
+
+int32_t lm_contour_link(const int64_t* records, int64_t n_records, const double* xs, int64_t nx,
+                        const double* ys, int64_t ny, double level,
+                        double* verts, int64_t cap_verts, int64_t* n_verts,
+                        int64_t* line_offsets, int64_t cap_lines, int64_t* n_lines) {
+    LM_REQUIRE((records || n_records == 0) && xs && ys && n_verts && n_lines && line_offsets,
+               "lm_contour_link: NULL argument");
+    LM_REQUIRE(n_records >= 0 && nx >= 0 && ny >= 0, "lm_contour_link: negative size");
+    return link_and_export(reinterpret_cast<const long long*>(records), n_records, xs, nx, ys, ny, level, verts, cap_verts,
+                           reinterpret_cast<long long*>(n_verts), reinterpret_cast<long long*>(line_offsets), cap_lines,
+                           reinterpret_cast<long long*>(n_lines));
+}
+
+int32_t lm_contour_level_dev(const int32_t* dwell_dev, const double* xs_host, int64_t nx,
+                             const double* ys_host, int64_t ny, double level,
+                             double* verts, int64_t cap_verts, int64_t* n_verts,
+                             int64_t* line_offsets, int64_t cap_lines, int64_t* n_lines,
+                             lm_stats* stats) {
+    int32_t rc = lm::require_device();
+    if (rc != LM_OK) return rc;
+    rc = check_contour_args("lm_contour_level_dev", dwell_dev, xs_host, nx, ys_host, ny, verts, cap_verts, n_verts,
+                            line_offsets, cap_lines, n_lines);
+    if (rc != LM_OK) return rc;
+    if (stats) *stats = lm_stats{};
+    std::vector<long long> recs;
+    float ms = 0.f;
+    rc = classify_device(dwell_dev, xs_host, nx, ys_host, ny, 0, level, recs, &ms, nullptr);
+    if (rc != LM_OK) return rc;
+    if (stats) {
+        stats->items = static_cast<uint64_t>(nx) * static_cast<uint64_t>(ny);
+        stats->work_units = stats->items * 4;           // algorithmic bytes: one int32 read per pixel
+        stats->kernel_ms = ms;
+        stats->launches = recs.empty() ? 2 : 3;
+    }
+    return link_and_export(recs.data(), static_cast<long long>(recs.size() / REC_WORDS), xs_host, nx, ys_host, ny, level,
+                           verts, cap_verts, reinterpret_cast<long long*>(n_verts),
+                           reinterpret_cast<long long*>(line_offsets), cap_lines, reinterpret_cast<long long*>(n_lines));
+}
+
+int32_t lm_contour_level(const int32_t* dwell, const double* xs, int64_t nx, const double* ys, int64_t ny,
+                         double level, double* verts, int64_t cap_verts, int64_t* n_verts,
+                         int64_t* line_offsets, int64_t cap_lines, int64_t* n_lines, lm_stats* stats) {
+    int32_t rc = lm::require_device();
+    if (rc != LM_OK) return rc;
+    rc = check_contour_args("lm_contour_level", dwell, xs, nx, ys, ny, verts, cap_verts, n_verts, line_offsets,
+                            cap_lines, n_lines);
+    if (rc != LM_OK) return rc;
+    if (nx == 0 || ny == 0) {
+        *n_verts = 0; *n_lines = 0; line_offsets[0] = 0;
+        if (stats) *stats = lm_stats{};
+        return LM_OK;
+    }
+    void* dd = nullptr;
+    const size_t nb = static_cast<size_t>(nx) * ny * sizeof(int32_t);
+    if ((rc = lm::ws_get(lm::WS_OUT_I32, nb, &dd)) != LM_OK) return rc;
+    LM_CUDA_TRY(cudaMemcpyAsync(dd, dwell, nb, cudaMemcpyHostToDevice, nullptr));
+    return lm_contour_level_dev(static_cast<const int32_t*>(dd), xs, nx, ys, ny, level, verts, cap_verts, n_verts,
+                                line_offsets, cap_lines, n_lines, stats);
+}
+
+}  // extern "C"

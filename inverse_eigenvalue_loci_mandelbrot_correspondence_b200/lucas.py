@@ -1,0 +1,137 @@
+"""Host side of K3: the Lucas Loci point cloud behind the reference's function surface.
+
+Mirrors
+  generate_lucas_companion, generate_companion_from_toprow, family_toprow,
+  compute_inverse_eigenvalues, compute_inverse_eigenvalues_family
+                                   lucas_equipotential_test_v3.py:58-118
+  lucas_companion, construct_points   tci_construct_mandelbrot.py:5-19,
+                                      tci_construct_mandelbrot_v002_fixed.py:24-33,
+                                      variograms_construct_mandelbrot.py:40-56
+  construct_points(maxN)              construct_stage1_clean.py:34-48
+
+The eigenvalues are computed on the GPU as the roots of x^n - a_1 x^(n-1) - ... - a_n (batched
+Aberth-Ehrlich, liblm_b200.so:lm_roots_batched).  The reference's order inside one n is
+LAPACK's; here every n is returned sorted lexicographically by (real, imag) of the emitted
+value, so compare as sets / after sorting.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _shim
+from ._shim import Stats
+
+last_stats: dict = {}
+
+FAMILIES = ("lucas_all_ones", "pell_like_all_twos", "sparser_gap_1_0_1_then_ones", "padovan_like_0_1_then_ones")
+
+
+def generate_companion_from_toprow(n: int, top) -> np.ndarray:
+    """n x n companion matrix: first row `top`, ones on the sub-diagonal (host-side helper)."""
+    top = np.asarray(top, dtype=float).reshape(-1)
+    if top.shape[0] != n:
+        raise AssertionError("top row must have n entries")
+    M = np.zeros((n, n), dtype=float)
+    M[0, :] = top
+    idx = np.arange(1, n)
+    M[idx, idx - 1] = 1.0
+    return M
+
+
+def generate_lucas_companion(n: int) -> np.ndarray:
+    return generate_companion_from_toprow(n, np.ones(n))
+
+
+lucas_companion = generate_lucas_companion
+
+
+def family_toprow(name: str, n: int) -> np.ndarray:
+    """First rows of the reference's four families (lucas_equipotential_test_v3.py:76-91)."""
+    top = np.ones(n)
+    if name == "lucas_all_ones":
+        return top
+    if name == "pell_like_all_twos":
+        return 2.0 * top
+    if name == "sparser_gap_1_0_1_then_ones":
+        if n >= 2:
+            top[1] = 0.0
+        return top
+    if name == "padovan_like_0_1_then_ones":
+        top[0] = 0.0
+        return top
+    raise ValueError(f"Unknown family '{name}'")
+
+
+def roots_batched(toprows, deg, invert: bool = False, tol: float = 0.0, sort: bool = True):
+    """Roots of x^d - sum_k a_k x^(d-k) for a zero-padded batch of first rows.
+
+    toprows: float64 [npoly, maxdeg]; deg: int [npoly].
+    Returns (values complex128 [npoly, maxdeg] NaN-padded, n_kept int32 [npoly], iters int32 [npoly]).
+    With invert=True values are 1/lambda for |lambda| > tol (the Lucas Loci points).
+    """
+    toprows = np.ascontiguousarray(toprows, dtype=np.float64)
+    if toprows.ndim != 2:
+        raise ValueError("toprows must be [npoly, maxdeg]")
+    npoly, maxdeg = toprows.shape
+    deg = np.ascontiguousarray(deg, dtype=np.int32).reshape(-1)
+    if deg.shape[0] != npoly:
+        raise ValueError("deg must have one entry per polynomial")
+    ore = np.empty((npoly, maxdeg), dtype=np.float64)
+    oim = np.empty((npoly, maxdeg), dtype=np.float64)
+    kept = np.empty(npoly, dtype=np.int32)
+    iters = np.empty(npoly, dtype=np.int32)
+    st = Stats()
+    _shim.call("lm_roots_batched", _shim.ptr(toprows), _shim.ptr(deg), npoly, maxdeg, int(bool(invert)), float(tol),
+               _shim.ptr(ore), _shim.ptr(oim), _shim.ptr(kept), _shim.ptr(iters), C.byref(st))
+    global last_stats
+    last_stats = st.as_dict()
+    vals = np.empty((npoly, maxdeg), dtype=np.complex128)
+    vals.real = ore
+    vals.imag = oim
+    if sort:
+        vals = np.sort(vals, axis=1)      # lexicographic (real, imag); NaN padding sorts last
+    return vals, kept, iters
+
+
+def eigvals_toprow(top) -> np.ndarray:
+    """Eigenvalues of the companion matrix with first row `top` (np.linalg.eigvals(companion) in the reference)."""
+    top = np.asarray(top, dtype=np.float64).reshape(1, -1)
+    vals, kept, _ = roots_batched(top, [top.shape[1]])
+    return vals[0, : kept[0]]
+
+
+def _inverse_eigs_for_rows(rows: list[np.ndarray], tol: float) -> np.ndarray:
+    if not rows:
+        return np.zeros(0, dtype=np.complex128)
+    maxdeg = max(r.shape[0] for r in rows)
+    tops = np.zeros((len(rows), maxdeg), dtype=np.float64)
+    deg = np.empty(len(rows), dtype=np.int32)
+    for k, r in enumerate(rows):
+        tops[k, : r.shape[0]] = r
+        deg[k] = r.shape[0]
+    vals, kept, _ = roots_batched(tops, deg, invert=True, tol=tol)
+    return np.concatenate([vals[k, : kept[k]] for k in range(len(rows))]).astype(np.complex128)
+
+
+def compute_inverse_eigenvalues(n_min: int, n_max: int, tol: float = 1e-12) -> np.ndarray:
+    """Lucas Loci for n = n_min..n_max (lucas_equipotential_test_v3.py:93-104)."""
+    return _inverse_eigs_for_rows([np.ones(n) for n in range(n_min, n_max + 1)], tol)
+
+
+def compute_inverse_eigenvalues_family(family: str, n_min: int, n_max: int, tol: float = 1e-12) -> np.ndarray:
+    """Same for one of FAMILIES (lucas_equipotential_test_v3.py:106-118)."""
+    return _inverse_eigs_for_rows([family_toprow(family, n) for n in range(n_min, n_max + 1)], tol)
+
+
+def construct_points(ns, tol: float = 1e-10) -> np.ndarray:
+    """construct_points(ns) of tci_construct_mandelbrot.py:11-19 (tol 1e-10 there and in
+    tci_construct_mandelbrot_v002_fixed.py:27-33; variograms_construct_mandelbrot.py:48-56 uses 1e-14)."""
+    return _inverse_eigs_for_rows([np.ones(int(n)) for n in ns], tol)
+
+
+def construct_points_xy(maxN: int = 40) -> np.ndarray:
+    """construct_points(maxN) of construct_stage1_clean.py:34-48: float [N,2] for n = 2..maxN, tol 1e-12."""
+    pts = compute_inverse_eigenvalues(2, maxN, 1e-12)
+    return np.column_stack([pts.real, pts.imag]).astype(float)

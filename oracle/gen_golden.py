@@ -1,0 +1,149 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/reference_vectors.npz by running the REFERENCE's own Python functions.
+
+Run in the build container only (it reads /root/reference, which does not exist on the GPU
+box); the resulting small fixture is committed and is what pins oracle/ and the CUDA path:
+
+    python oracle/gen_golden.py [/root/reference]
+
+Functions are pulled out of the reference scripts with ast (their `def` blocks only, executed
+in a namespace that has numpy/math), because several scripts load CSV files or plot at import
+time and matplotlib is not installed here.  Nothing from the reference is copied into the
+repository: only the numeric outputs are stored.
+"""
+from __future__ import annotations
+
+import ast
+import math
+import sys
+from pathlib import Path
+
+import numpy as np
+
+REF = Path(sys.argv[1] if len(sys.argv) > 1 else "/root/reference")
+OUT = Path(__file__).resolve().parents[1] / "tests" / "golden" / "reference_vectors.npz"
+
+
+def load_defs(fname: str, names: list[str], extra: dict | None = None) -> dict:
+    """exec the named top-level function / class definitions of a reference script."""
+    src = (REF / fname).read_text().replace("\r\n", "\n")
+    tree = ast.parse(src)
+    picked = [n for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name in names]
+    missing = set(names) - {n.name for n in picked}
+    if missing:
+        raise RuntimeError(f"{fname}: missing definitions {missing}")
+    import numpy.linalg as la
+    from dataclasses import dataclass
+    from scipy.linalg import eigvals
+    ns = {"np": np, "numpy": np, "math": math, "la": la, "dataclass": dataclass, "eigvals": eigvals}
+    ns.update(extra or {})
+    mod = ast.Module(body=picked, type_ignores=[])
+    exec(compile(mod, str(REF / fname), "exec"), ns)
+    return ns
+
+
+def main() -> None:
+    g: dict[str, np.ndarray] = {}
+
+    # ---- K1: mandelbrot_dwell / compute_grid (mandelbrot_boundary_sample.py:22-39)
+    mbs = load_defs("mandelbrot_boundary_sample.py", ["mandelbrot_dwell", "compute_grid"])
+    for tag, xlim, ylim, res, mi in [("cfg1", (-2.1, 0.9), (-1.5, 1.5), 72, 500),
+                                     ("seahorse", (-0.755, -0.735), (0.10, 0.12), 40, 300),
+                                     ("tip", (-2.05, -1.7), (-0.05, 0.05), 33, 200)]:
+        xs, ys, Z = mbs["compute_grid"](xlim, ylim, res, mi)
+        g[f"dwell_{tag}_args"] = np.array([xlim[0], xlim[1], ylim[0], ylim[1], res, mi], dtype=np.float64)
+        g[f"dwell_{tag}_xs"] = xs
+        g[f"dwell_{tag}_ys"] = ys
+        g[f"dwell_{tag}_Z"] = Z.astype(np.int32)
+        assert np.array_equal(Z, Z.astype(np.int32))
+    pts = np.array([[0.0, 0.0], [-2.0, 0.0], [0.25, 0.0], [0.26, 0.0], [-0.75, 0.1], [0.3, 0.5], [-1.75, 0.0],
+                    [2.5, 2.5], [-0.1, 0.651], [-1.25, 0.0], [0.0, 1.0], [-0.743643887, 0.131825904]])
+    g["dwell_points_xy"] = pts
+    g["dwell_points_mi"] = np.array([400])
+    g["dwell_points_out"] = np.array([mbs["mandelbrot_dwell"](x, y, 400) for x, y in pts], dtype=np.int32)
+
+    # ---- K3: Lucas Loci (lucas_equipotential_test_v3.py:58-118, tci_construct_mandelbrot.py:5-19)
+    lucas = load_defs("lucas_equipotential_test_v3.py",
+                      ["generate_lucas_companion", "generate_companion_from_toprow", "family_toprow",
+                       "compute_inverse_eigenvalues", "compute_inverse_eigenvalues_family",
+                       "mandelbrot_parameter_potential", "batch_potential"], {"print": lambda *a, **k: None})
+    fam_names = ["lucas_all_ones", "pell_like_all_twos", "sparser_gap_1_0_1_then_ones", "padovan_like_0_1_then_ones"]
+    for fam in fam_names:
+        chunks, counts = [], []
+        for n in range(2, 26):
+            v = lucas["compute_inverse_eigenvalues_family"](fam, n, n, 1e-12)
+            chunks.append(np.sort(v)); counts.append(len(v))
+        g[f"family_{fam}_values"] = np.concatenate(chunks)
+        g[f"family_{fam}_counts"] = np.array(counts, dtype=np.int32)
+    cloud = lucas["compute_inverse_eigenvalues"](2, 40, 1e-12)
+    g["lucas_2_40_sorted_per_n"] = np.concatenate(
+        [np.sort(lucas["compute_inverse_eigenvalues"](n, n, 1e-12)) for n in range(2, 41)])
+    assert len(cloud) == len(g["lucas_2_40_sorted_per_n"])
+    tci = load_defs("tci_construct_mandelbrot.py", ["lucas_companion", "construct_points"])
+    cp = tci["construct_points"](range(20, 301, 20))
+    g["tci_construct_points_count"] = np.array([len(cp)])            # 2400, v3_T25_sigma3_dense.csv:2
+    g["tci_construct_points_n300_sorted"] = np.sort(tci["construct_points"]([300]))
+    g["tci_construct_points_n20_sorted"] = np.sort(tci["construct_points"]([20]))
+
+    # ---- K1d: batch_potential on part of the cloud + some exterior/interior points
+    sample = np.concatenate([cloud[::7], np.array([0.3 + 0.5j, -0.75 + 0.1j, 0.0 + 0.0j, -2.5 + 0.1j, 0.26 + 0.0j])])
+    gg, it, phi = lucas["batch_potential"](sample, max_iter=1500, escape_radius=2.0)
+    g["potential_points_c"] = sample
+    g["potential_points_g"] = gg
+    g["potential_points_it"] = it.astype(np.int64)
+    g["potential_points_phi"] = phi
+
+    # ---- K1c: grid potentials
+    gx = np.linspace(-2, 2, 28); gy = np.linspace(-2, 2, 26)
+    pot = load_defs("Potentials.py", ["log_potential", "escape_potential"])
+    g["potgrid_x"] = gx; g["potgrid_y"] = gy
+    g["potentials_escape_R10_mi60"] = pot["escape_potential"](gx, gy, max_iter=60, R=10)
+    lap = load_defs("Laplacian_C-M.py", ["construct_potential", "mandelbrot_potential", "laplacian"])
+    X, Y = np.meshgrid(gx, gy)
+    g["laplacian_cm_potential_R2_mi80"] = lap["mandelbrot_potential"](X, Y, max_iter=80, R=2.0)
+    itv = load_defs("Iterative_Variogram_Laplacian.py", ["log_potential", "escape_potential", "laplacian_fd"])
+    g["iterative_escape_R10_mi70"] = itv["escape_potential"](gx, gy, max_iter=70, R=10.0)
+    vg = load_defs("variograms_construct_mandelbrot.py",
+                   ["Grid", "make_grid", "log_potential_from_points", "mandelbrot_escape_potential",
+                    "mandelbrot_distance_estimator"])
+    grid = vg["make_grid"](-2.25, 1.25, -1.75, 1.75, 30, 27)
+    g["vario_grid_x"] = grid.x; g["vario_grid_y"] = grid.y
+    g["vario_escape_potential_mi90"] = vg["mandelbrot_escape_potential"](grid, max_iter=90, R=4.0)
+    esc, dist, lastz, lastdz = vg["mandelbrot_distance_estimator"](grid.Z, max_iter=90, R=4.0, eps=1e-14)
+    g["vario_de_escaped"] = esc
+    g["vario_de_dist"] = dist
+
+    # ---- K4a: log-potentials of a small cloud
+    cpts = np.column_stack([cloud.real, cloud.imag])[::11]
+    g["logpot_points"] = cpts
+    g["logpot_potentials"] = pot["log_potential"](cpts, gx, gy)
+    g["logpot_laplacian_cm"] = lap["construct_potential"](X, Y, cpts)
+    g["logpot_iterative"] = itv["log_potential"](cpts, gx, gy)
+    g["logpot_vario_eps1e-6"] = vg["log_potential_from_points"](grid, cloud[::11], eps=1e-6)
+
+    # ---- K4: stencils
+    rng = np.random.default_rng(12345)
+    U = rng.standard_normal((23, 31))
+    g["stencil_U"] = U
+    g["stencil_h"] = np.array([gx[1] - gx[0]])
+    g["stencil_laplacian"] = lap["laplacian"](U, gx[1] - gx[0])
+    g["stencil_laplacian_fd"] = itv["laplacian_fd"](U, gx[1] - gx[0])
+    sm = U.copy()
+    sm[1:-1, 1:-1] = (U[1:-1, 1:-1] + U[:-2, 1:-1] + U[2:, 1:-1] + U[1:-1, :-2] + U[1:-1, 2:]) / 5.0  # variograms_...py:169-173
+    g["stencil_smooth5"] = sm
+
+    # ---- K1b: scalar distance estimator (construct_stage1_clean.py:50-58)
+    cs = load_defs("construct_stage1_clean.py", ["mandelbrot_distance_estimator", "construct_points"])
+    dxs = np.linspace(-2.25, 1.25, 24); dys = np.linspace(-1.25, 1.25, 17)
+    g["de_scalar_x"] = dxs; g["de_scalar_y"] = dys
+    g["de_scalar_dist"] = np.array([[cs["mandelbrot_distance_estimator"](complex(x, y), max_iter=200) for x in dxs]
+                                    for y in dys])
+    g["stage1_construct_points_maxN12"] = cs["construct_points"](12)
+
+    OUT.parent.mkdir(parents=True, exist_ok=True)
+    np.savez_compressed(OUT, **g)
+    print(f"wrote {OUT} ({OUT.stat().st_size / 1024:.1f} KiB, {len(g)} arrays)")
+
+
+if __name__ == "__main__":
+    main()

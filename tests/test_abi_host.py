@@ -1,0 +1,131 @@
+"""CPU: the C-ABI library loads, exports every symbol include/lm_b200.h declares, fails loudly
+without a device, and its host-only logic (contour linker, PNG/CSV writers) is correct."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from helpers import lines_equal, records_from_dwell
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "lm_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported(shim):
+    lib = shim.load()
+    names = declared_symbols()
+    assert len(names) >= 30
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert set(names) == set(shim.EXPORTS), set(names) ^ set(shim.EXPORTS)
+    assert shim.missing_exports() == []
+    assert lib.lm_abi_version() == 1
+
+
+def test_no_cpu_fallback(shim):
+    """Without a GPU every compute entry point must fail with LM_E_NODEV, never compute on the CPU."""
+    if shim.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    xs = np.linspace(-2, 1, 8); ys = np.linspace(-1, 1, 8)
+    out = np.zeros((8, 8), dtype=np.int32)
+    st = shim.Stats()
+    rc = shim.load().lm_escape_grid_f64(shim.ptr(xs), 8, shim.ptr(ys), 8, 50, 2.0, 0, shim.ptr(out), None, None, C.byref(st))
+    assert rc == shim.LM_E_NODEV
+    assert "device" in shim.last_error().lower()
+    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import escape, lucas, stencils
+    with pytest.raises(shim.LmError):
+        escape.compute_grid((-2, 1), (-1, 1), 8, 50)
+    with pytest.raises(shim.LmError):
+        lucas.compute_inverse_eigenvalues(2, 5)
+    with pytest.raises(shim.LmError):
+        stencils.laplacian(np.zeros((4, 4)), 0.1)
+
+
+def test_product_does_not_import_oracle():
+    pkg = ROOT / "inverse_eigenvalue_loci_mandelbrot_correspondence_b200"
+    for f in list(pkg.glob("*.py")) + list((pkg / "csrc").glob("*")):
+        txt = f.read_text()
+        assert "oracle" not in txt.replace("lm_oracle_contour.c / mpl2014", ""), f
+
+
+@pytest.mark.parametrize("case", [(96, 500, (-2.1, 0.9), (-1.5, 1.5), 480.0), (120, 300, (-0.8, -0.7), (0.05, 0.15), 150.0),
+                                  (75, 100, (-1.0, 0.5), (-0.3, 1.2), 3.0), (64, 60, (-0.755, -0.735), (0.10, 0.12), 57.6)])
+def test_contour_linker_matches_oracle(shim, oracle, case):
+    """lm_contour_link (host-only part of K2) against the dense mpl2014 restatement."""
+    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import contour
+    res, mi, xl, yl, lvl = case
+    xs = np.linspace(*xl, res); ys = np.linspace(*yl, res + 7)
+    d, _ = oracle.dwell_grid(xs, ys, mi)
+    ref = oracle.contour_lines(xs, ys, d.astype(float), lvl)
+    got = contour.link_records(records_from_dwell(d, xs, ys, lvl), xs, ys, lvl)
+    assert lines_equal(ref, got)
+
+
+def test_contour_linker_random_fields(shim, oracle):
+    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import contour
+    rng = np.random.default_rng(1)
+    for _ in range(150):
+        ny, nx = rng.integers(2, 14), rng.integers(2, 14)
+        d = rng.integers(0, 6, size=(ny, nx)).astype(np.int32)
+        xs = np.sort(rng.uniform(-1, 1, nx)); ys = np.sort(rng.uniform(-1, 1, ny))
+        lvl = float(rng.choice([1.5, 2.0, 2.5, 3.0]))
+        ref = oracle.contour_lines(xs, ys, d.astype(float), lvl)
+        got = contour.link_records(records_from_dwell(d, xs, ys, lvl), xs, ys, lvl)
+        assert lines_equal(ref, got)
+
+
+def test_contour_linker_split_blocks(shim, oracle):
+    """Records of two row blocks (one halo row each side of the seam) concatenate to the single-block result."""
+    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import contour
+    xs = np.linspace(-2.1, 0.9, 90); ys = np.linspace(-1.5, 1.5, 80)
+    d, _ = oracle.dwell_grid(xs, ys, 200)
+    lvl = 192.0
+    whole = records_from_dwell(d, xs, ys, lvl)
+    cut = 37
+    top = records_from_dwell(d[: cut + 1], xs, ys[: cut + 1], lvl, row_offset=0)
+    bot = records_from_dwell(d[cut:], xs, ys[cut:], lvl, row_offset=cut)
+    both = np.concatenate([top, bot])
+    assert np.array_equal(whole, both)
+    assert lines_equal(contour.link_records(both, xs, ys, lvl), oracle.contour_lines(xs, ys, d.astype(float), lvl))
+
+
+def test_contour_oracle_invariants(oracle):
+    """Internal consistency of the (unpinned) mpl2014 restatement: vertices lie on grid edges that
+    straddle the level, interior lines are closed, the longest line of the README window is closed."""
+    xs = np.linspace(-2.1, 0.9, 150); ys = np.linspace(-1.5, 1.5, 150)
+    d, _ = oracle.dwell_grid(xs, ys, 300)
+    lvl = 0.96 * 300
+    lines = oracle.contour_lines(xs, ys, d.astype(float), lvl)
+    assert lines
+    best = max(lines, key=len)
+    assert np.array_equal(best[0], best[-1]) or np.allclose(best[0], best[-1], rtol=0, atol=1e-12)
+    dx, dy = xs[1] - xs[0], ys[1] - ys[0]
+    for ln in lines:
+        fx = (ln[:, 0] - xs[0]) / dx; fy = (ln[:, 1] - ys[0]) / dy
+        on_v = np.abs(fx - np.rint(fx)) < 1e-9
+        on_h = np.abs(fy - np.rint(fy)) < 1e-9
+        assert (on_v | on_h).all()
+        step = np.hypot(np.diff(ln[:, 0]) / dx, np.diff(ln[:, 1]) / dy)
+        assert (step <= np.sqrt(2) + 1e-9).all()
+
+
+def test_png_and_csv_writers(tmp_path, shim):
+    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import mandelbrot_boundary_sample as mbs
+    t = np.linspace(0, 2 * np.pi, 200)
+    contour = np.column_stack([np.cos(t), np.sin(t)])
+    prefix = str(tmp_path / "out" / "mandel")
+    csv, png, meta = mbs.save_outputs(contour, prefix, [-2.1, 0.9], [-1.5, 1.5], 2000, 500, 0.96)
+    lines = Path(csv).read_text().splitlines()
+    assert lines[0] == "x,y" and len(lines) == 201
+    assert re.fullmatch(r"-?\d\.\d{18}e[+-]\d\d,-?\d\.\d{18}e[+-]\d\d", lines[1])
+    back = np.loadtxt(csv, delimiter=",", skiprows=1)
+    assert np.array_equal(back, contour)                       # %.18e round-trips binary64
+    assert Path(png).read_bytes()[:8] == b"\x89PNG\r\n\x1a\n"
+    assert Path(meta).read_text() == "xlim=[-2.1, 0.9]\nylim=[-1.5, 1.5]\nres=2000\nmax_iter=500\nlevel=0.96\n"

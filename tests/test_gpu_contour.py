@@ -1,0 +1,93 @@
+"""GPU: K2 (level set) through the C ABI against the mpl2014 restatement (bit-exact vertices, same
+line order) and the full drop-in script."""
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from helpers import lines_equal, records_from_dwell
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("res,mi,xlim,ylim,frac", [
+    (400, 500, (-2.1, 0.9), (-1.5, 1.5), 0.96),
+    (513, 300, (-2.1, 0.9), (-1.5, 1.5), 0.5),
+    (300, 400, (-0.755, -0.735), (0.10, 0.12), 0.96),      # lines cut by the window border, many saddles
+    (257, 200, (-1.0, 0.5), (-0.3, 1.2), 0.02),
+    (131, 64, (-2.0, 1.0), (-1.5, 1.5), 0.96),
+])
+def test_contour_vs_oracle(gpu, oracle, res, mi, xlim, ylim, frac):
+    xs = np.linspace(*xlim, res); ys = np.linspace(*ylim, res + 5)
+    d, _ = oracle.dwell_grid(xs, ys, mi)
+    lvl = frac * mi
+    want = oracle.contour_lines(xs, ys, d.astype(float), lvl)
+    got = gpu.contour.contour_lines(xs, ys, d, lvl)
+    assert lines_equal(want, got)
+    best = gpu.contour.extract_contour(xs, ys, d.astype(float), mi, frac)
+    ref_best = oracle.extract_contour(xs, ys, d.astype(float), mi, frac)
+    assert (best is None and ref_best is None) or np.array_equal(best, ref_best)
+
+
+def test_records_match_numpy_restatement(gpu, oracle):
+    import ctypes as C
+    xs = np.linspace(-2.1, 0.9, 300); ys = np.linspace(-1.5, 1.5, 200)
+    d, _ = oracle.dwell_grid(xs, ys, 300)
+    lvl = 288.0
+    want = records_from_dwell(d, xs, ys, lvl)
+    with gpu.device.DeviceGrid(xs, ys) as g:
+        g.escape(300)
+        recs = np.empty((len(want) + 8, 8), dtype=np.int64)
+        n = C.c_int64(0)
+        gpu.shim.call("lm_contour_classify_dev", C.c_void_p(g.d_dwell.ptr), gpu.shim.ptr(xs), xs.size, gpu.shim.ptr(ys), ys.size,
+                      0, lvl, gpu.shim.ptr(recs), recs.shape[0], C.byref(n), None)
+    assert n.value == len(want)
+    assert np.array_equal(recs[: n.value], want)
+
+
+@pytest.mark.parametrize("shape", [(2, 2), (2, 300), (300, 2), (3, 129), (5, 130)])
+def test_contour_small_and_ragged(gpu, oracle, shape):
+    rng = np.random.default_rng(shape[0] * 1000 + shape[1])
+    ny, nx = shape
+    d = rng.integers(0, 5, size=(ny, nx)).astype(np.int32)
+    xs = np.linspace(0, 1, nx); ys = np.linspace(0, 1, ny)
+    for lvl in (0.5, 2.0, 3.5, 10.0):
+        assert lines_equal(oracle.contour_lines(xs, ys, d.astype(float), lvl), gpu.contour.contour_lines(xs, ys, d, lvl))
+
+
+def test_no_contour_returns_none(gpu):
+    xs = np.linspace(2.5, 3.0, 50); ys = np.linspace(2.5, 3.0, 50)     # everything escapes at once
+    _, _, Z = gpu.escape.compute_grid((2.5, 3.0), (2.5, 3.0), 50, 100)
+    assert gpu.contour.extract_contour(xs, ys, Z, 100, 0.96) is None
+    with pytest.raises(ValueError):
+        gpu.contour.contour_lines(xs, ys, Z + 0.5, 1.0)
+
+
+def test_device_resident_pipeline_config1(gpu, oracle):
+    """BASELINE config 1 at full size: K1 -> K2 without the dwell grid leaving the GPU."""
+    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import mandelbrot_boundary_sample as mbs
+    xs, ys, best = mbs.boundary_from_window((-2.1, 0.9), (-1.5, 1.5), 2000, 500, 0.96)
+    d, _ = oracle.dwell_grid(xs, ys, 500)
+    want = oracle.extract_contour(xs, ys, d.astype(float), 500, 0.96)
+    assert np.array_equal(best, want)
+    assert best.shape[0] > 10000 and np.array_equal(best[0], best[-1])
+
+
+def test_script_cli_outputs(gpu, oracle, tmp_path):
+    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import mandelbrot_boundary_sample as mbs
+    prefix = str(tmp_path / "outputs" / "mandel")
+    mbs.main(["--xlim", "-2.1", "0.9", "--ylim", "-1.5", "1.5", "--res", "600", "--max_iter", "300",
+              "--level", "0.96", "--output_prefix", prefix])
+    csv = Path(prefix + "_boundary.csv").read_text().splitlines()
+    assert csv[0] == "x,y"
+    got = np.loadtxt(prefix + "_boundary.csv", delimiter=",", skiprows=1)
+    xs = np.linspace(-2.1, 0.9, 600); ys = np.linspace(-1.5, 1.5, 600)
+    d, _ = oracle.dwell_grid(xs, ys, 300)
+    want = oracle.extract_contour(xs, ys, d.astype(float), 300, 0.96)
+    assert np.array_equal(got, want)
+    assert Path(prefix + "_boundary.png").read_bytes()[:4] == b"\x89PNG"
+    assert Path(prefix + "_meta.txt").read_text() == "xlim=[-2.1, 0.9]\nylim=[-1.5, 1.5]\nres=600\nmax_iter=300\nlevel=0.96\n"
+    with pytest.raises(SystemExit) as e:
+        mbs.main(["--xlim", "2.5", "3.0", "--ylim", "2.5", "3.0", "--res", "64", "--max_iter", "50", "--output_prefix", prefix])
+    assert "Failed to extract a usable contour" in str(e.value)

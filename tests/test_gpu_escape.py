@@ -1,0 +1,142 @@
+"""GPU: K1 (escape-time) through the C ABI against the oracle and the reference's golden vectors.
+Dwell counts and work counts are bit-exact; potentials agree to the stated relative tolerance."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL_POT = 5e-15     # log/hypot of the CUDA math library vs glibc: <= 2 ulp each
+
+
+@pytest.mark.parametrize("tag", ["cfg1", "seahorse", "tip"])
+def test_dwell_golden(gpu, golden, tag):
+    xs, ys, Z = golden[f"dwell_{tag}_xs"], golden[f"dwell_{tag}_ys"], golden[f"dwell_{tag}_Z"]
+    mi = int(golden[f"dwell_{tag}_args"][5])
+    d, _, st = gpu.escape.escape_grid(xs, ys, mi)
+    assert np.array_equal(d, Z)
+    assert st["work_units"] == int(np.minimum(Z.astype(np.int64) + 1, mi).sum())
+    xs2, ys2, Zf = gpu.escape.compute_grid(golden[f"dwell_{tag}_args"][0:2], golden[f"dwell_{tag}_args"][2:4],
+                                           int(golden[f"dwell_{tag}_args"][4]), mi)
+    assert Zf.dtype == np.float64 and np.array_equal(Zf, Z) and np.array_equal(xs2, xs) and np.array_equal(ys2, ys)
+
+
+def test_dwell_points_golden(gpu, golden):
+    mi = int(golden["dwell_points_mi"][0])
+    got = [gpu.escape.mandelbrot_dwell(x, y, mi) for x, y in golden["dwell_points_xy"]]
+    assert got == list(golden["dwell_points_out"])
+
+
+@pytest.mark.parametrize("res,mi,xlim,ylim", [
+    (2000, 500, (-2.1, 0.9), (-1.5, 1.5)),            # BASELINE config 1 (full size)
+    (1024, 2000, (-2.1, 0.9), (-1.5, 1.5)),           # config 2 window, reduced res
+    (384, 10000, (-2.1, 0.9), (-1.5, 1.5)),           # config 3 iteration count
+    (192, 20000, (-0.755, -0.735), (0.10, 0.12)),     # Seahorse valley (config 4 window)
+    (333, 700, (-2.05, -1.6), (-0.2, 0.2)),           # antenna tip: |c| > 1.95 lanes (no blind path), ragged width
+    (129, 64, (-3.0, 3.0), (-3.0, 3.0)),              # mostly |c| > 2
+])
+def test_dwell_vs_oracle(gpu, oracle, res, mi, xlim, ylim):
+    xs = np.linspace(*xlim, res); ys = np.linspace(*ylim, res - 3)
+    want, work = oracle.dwell_grid(xs, ys, mi)
+    got, _, st = gpu.escape.escape_grid(xs, ys, mi)
+    assert np.array_equal(got, want)
+    assert st["work_units"] == work
+    got64, _, _ = gpu.escape.escape_grid(xs, ys, mi, want_dwell="f64")
+    assert np.array_equal(got64, want)
+
+
+@pytest.mark.parametrize("nx,ny", [(1, 1), (1, 77), (130, 1), (127, 3), (128, 2), (129, 5), (4097, 2)])
+def test_dwell_ragged_shapes(gpu, oracle, nx, ny):
+    xs = np.linspace(-2.0, 0.6, nx) if nx > 1 else np.array([-0.3])
+    ys = np.linspace(-1.1, 1.1, ny) if ny > 1 else np.array([0.2])
+    want, work = oracle.dwell_grid(xs, ys, 300)
+    got, _, st = gpu.escape.escape_grid(xs, ys, 300)
+    assert got.shape == (ny, nx) and np.array_equal(got, want) and st["work_units"] == work
+
+
+def test_empty_and_errors(gpu):
+    d, _, st = gpu.escape.escape_grid(np.zeros(0), np.zeros(5), 10)
+    assert d.shape == (5, 0) and st["work_units"] == 0
+    with pytest.raises(ValueError):
+        gpu.escape.escape_grid([0.0], [0.0], 0)
+
+
+def test_max_iter_one_and_edges(gpu, oracle):
+    xs = np.linspace(-2.5, 1.0, 200); ys = np.linspace(-1.5, 1.5, 100)
+    for mi in (1, 2, 3, 31, 32, 33, 47, 48, 49):     # around the blind-block (32) and cool-down (16) sizes
+        want, work = oracle.dwell_grid(xs, ys, mi)
+        got, _, st = gpu.escape.escape_grid(xs, ys, mi)
+        assert np.array_equal(got, want) and st["work_units"] == work
+
+
+@pytest.mark.parametrize("mode,R,mi", [(1, 2.0, 300), (1, 2.0, 1200), (2, 10.0, 300), (3, 2.0, 200), (3, 10.0, 150), (4, 4.0, 500)])
+def test_grid_potentials_vs_oracle(gpu, oracle, mode, R, mi):
+    xs = np.linspace(-2, 2, 200); ys = np.linspace(-2, 2, 190)
+    d_o, f_o = oracle.potential_grid(xs, ys, mi, R, mode)
+    d, f, _ = gpu.escape.escape_grid(xs, ys, mi, R, mode)
+    assert np.array_equal(d, d_o)
+    np.testing.assert_allclose(f, f_o, rtol=RTOL_POT, atol=0)
+
+
+def test_grid_potentials_golden(gpu, golden):
+    gx, gy = golden["potgrid_x"], golden["potgrid_y"]
+    np.testing.assert_allclose(gpu.escape.escape_potential(gx, gy, 60, 10), golden["potentials_escape_R10_mi60"], rtol=RTOL_POT)
+    X, Y = np.meshgrid(gx, gy)
+    np.testing.assert_allclose(gpu.escape.mandelbrot_potential(X, Y, 80, 2.0), golden["laplacian_cm_potential_R2_mi80"], rtol=RTOL_POT)
+    np.testing.assert_allclose(gpu.escape.escape_potential(gx, gy, 70, 10.0, variant="iterative"),
+                               golden["iterative_escape_R10_mi70"], rtol=RTOL_POT)
+
+
+def test_potentials_overflow_like_reference(gpu):
+    """Potentials.py:44 divides by the Python int 2**k: k > 1023 raises OverflowError."""
+    xs = np.linspace(-0.2, 0.2, 8); ys = np.linspace(-0.2, 0.2, 8)     # all bounded: k = max_iter-1
+    with pytest.raises(OverflowError):
+        gpu.escape.escape_potential(xs, ys, 1100, 10)
+    gpu.escape.escape_potential(xs, ys, 1024, 10)
+
+
+def test_batch_potential(gpu, oracle, golden):
+    c = golden["potential_points_c"]
+    g, it, phi = gpu.escape.batch_potential(c, 1500, 2.0)
+    assert np.array_equal(it, golden["potential_points_it"])
+    np.testing.assert_allclose(g, golden["potential_points_g"], rtol=RTOL_POT, atol=0)
+    want = golden["potential_points_phi"]
+    assert np.array_equal(np.isnan(phi.real), np.isnan(want.real))
+    m = ~np.isnan(want.real)
+    np.testing.assert_allclose(phi[m], want[m], rtol=1e-14)
+    # larger random cloud vs the oracle, including the scalar drop-in
+    rng = np.random.default_rng(3)
+    pts = rng.uniform(-2.2, 1.0, 20000) + 1j * rng.uniform(-1.5, 1.5, 20000)
+    g_o, it_o, phi_o = oracle.batch_potential(pts, 4000, 2.0)
+    g, it, phi = gpu.escape.batch_potential(pts, 4000, 2.0)
+    assert np.array_equal(it, it_o)
+    np.testing.assert_allclose(g, g_o, rtol=RTOL_POT, atol=0)
+    gg, kk, pp = gpu.escape.mandelbrot_parameter_potential(complex(pts[5]), 4000, 2.0)
+    assert kk == it_o[5] and gg == pytest.approx(g_o[5], rel=RTOL_POT)
+    assert gpu.escape.batch_potential(np.zeros(0, dtype=complex))[0].shape == (0,)
+
+
+def test_f32_variant_tolerance(gpu, oracle):
+    """fp32 kernel (no reference counterpart): dwell mismatch fraction vs fp64 below 2 % on config 1's window."""
+    import ctypes as C
+    xs = np.linspace(-2.1, 0.9, 800); ys = np.linspace(-1.5, 1.5, 800)
+    want, _ = oracle.dwell_grid(xs, ys, 500)
+    out = np.empty((800, 800), dtype=np.int32)
+    st = gpu.shim.Stats()
+    gpu.shim.call("lm_escape_grid_f32", gpu.shim.ptr(xs), 800, gpu.shim.ptr(ys), 800, 500, 2.0, gpu.shim.ptr(out), C.byref(st))
+    assert (out != want).mean() < 0.02
+    assert ((out == 500) == (want == 500)).mean() > 0.999
+
+
+def test_full_size_properties_config2(gpu):
+    """BASELINE config 2 (8192^2, max_iter 2000) at full size: size-independent checks --
+    mirror symmetry in y (the window is symmetric and conjugation commutes with the recurrence),
+    work-count identity, and agreement of the device-resident path with the host path on a strip."""
+    res, mi = 8192, 2000
+    xs = np.linspace(-2.1, 0.9, res); ys = np.linspace(-1.5, 1.5, res)
+    assert np.array_equal(ys, -ys[::-1])
+    d, _, st = gpu.escape.escape_grid(xs, ys, mi)
+    assert np.array_equal(d, d[::-1, :])
+    assert st["work_units"] == int(np.minimum(d.astype(np.int64) + 1, mi).sum())
+    strip, _, _ = gpu.escape.escape_grid(xs, ys[4000:4016], mi)
+    assert np.array_equal(strip, d[4000:4016])
+    assert 0.16 < (d == mi).mean() < 0.175

@@ -1,0 +1,64 @@
+"""GPU: K4 stencils (bit-exact), K4a log-potentials and K1b distance estimators (tolerance)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("shape", [(1, 4), (4, 1), (2, 2), (3, 5), (23, 31), (200, 200), (301, 257), (400, 400), (1024, 2050), (33, 4096)])
+def test_stencils_bit_exact(gpu, oracle, shape):
+    rng = np.random.default_rng(shape[0] * 7 + shape[1])
+    U = rng.standard_normal(shape) * np.exp(rng.uniform(-20, 20, shape))
+    h = 4.0 / 199
+    assert np.array_equal(gpu.stencils.laplacian(U, h), oracle.laplacian(U, h))
+    assert np.array_equal(gpu.stencils.smooth5(U), oracle.smooth5(U))
+
+
+def test_stencils_golden(gpu, golden):
+    U = golden["stencil_U"]; h = float(golden["stencil_h"][0])
+    assert np.array_equal(gpu.stencils.laplacian(U, h), golden["stencil_laplacian"])
+    assert np.array_equal(gpu.stencils.laplacian_fd(U, h), golden["stencil_laplacian_fd"])
+    assert np.array_equal(gpu.stencils.smooth5(U), golden["stencil_smooth5"])
+
+
+def test_stencil_linearity_full_size(gpu):
+    """8192^2 field: the Laplacian of a constant is exactly 0 and of a linear-in-index ramp is 0 away
+    from the periodic seam; shift-equivariance under np.roll (periodic wrap)."""
+    n = 8192
+    ramp = np.add.outer(np.arange(n, dtype=np.float64) * 3.0, np.arange(n, dtype=np.float64) * 5.0)
+    L = gpu.stencils.laplacian(ramp, 1.0)
+    assert not L[1:-1, 1:-1].any()
+    U = np.random.default_rng(0).standard_normal((512, 768))
+    A = gpu.stencils.laplacian(np.roll(U, (5, -9), axis=(0, 1)), 0.3)
+    B = np.roll(gpu.stencils.laplacian(U, 0.3), (5, -9), axis=(0, 1))
+    assert np.array_equal(A, B)
+
+
+def test_log_potentials(gpu, oracle, golden):
+    P = golden["logpot_points"]; gx, gy = golden["potgrid_x"], golden["potgrid_y"]
+    rt = 1e-12
+    np.testing.assert_allclose(gpu.potentials.log_potential(P, gx, gy), golden["logpot_potentials"], rtol=rt)
+    X, Y = np.meshgrid(gx, gy)
+    np.testing.assert_allclose(gpu.potentials.construct_potential(X, Y, P), golden["logpot_laplacian_cm"], rtol=rt)
+    np.testing.assert_allclose(gpu.potentials.log_potential(P, gx, gy, use_hypot=True), golden["logpot_iterative"], rtol=rt)
+    np.testing.assert_allclose(gpu.potentials.log_potential_from_points(golden["vario_grid_x"], golden["vario_grid_y"],
+                                                                        P[:, 0] + 1j * P[:, 1], 1e-6),
+                               golden["logpot_vario_eps1e-6"], rtol=rt)
+    # bigger: 400^2 grid (Potentials.py:52-53) x 3000 points against the oracle
+    rng = np.random.default_rng(5)
+    pts = rng.uniform(-1.2, 1.2, (3000, 2))
+    g = np.linspace(-2, 2, 400)
+    np.testing.assert_allclose(gpu.potentials.log_potential(pts, g, g), oracle.log_potential(pts, g, g, 1e-12, 0), rtol=rt)
+
+
+def test_distance_estimators(gpu, oracle, golden):
+    d, _ = gpu.potentials.distance_grid(golden["de_scalar_x"], golden["de_scalar_y"], 200, 1e6, 1e-16, 0)
+    np.testing.assert_allclose(d, golden["de_scalar_dist"], rtol=1e-13, atol=0)
+    xs = np.linspace(-2.25, 1.25, 300); ys = np.linspace(-1.75, 1.75, 280)
+    for variant, R, eps in ((0, 1e6, 1e-16), (1, 4.0, 1e-14), (1, 250.0, 1e-12)):
+        want, esc_o = oracle.distance_grid(xs, ys, 250, R, eps, variant)
+        got, esc = gpu.potentials.distance_grid(xs, ys, 250, R, eps, variant)
+        assert np.array_equal(esc, esc_o)
+        np.testing.assert_allclose(got, want, rtol=1e-13, atol=0)
+    assert gpu.potentials.mandelbrot_distance_estimator(0.3 + 0.5j) == pytest.approx(
+        float(oracle.distance_grid([0.3], [0.5], 200, 1e6, 1e-16, 0)[0][0, 0]), rel=1e-13)

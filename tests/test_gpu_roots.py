@@ -1,0 +1,120 @@
+"""GPU: K3 (batched Aberth roots) against numpy.linalg.eigvals (the reference's own call) and the
+golden vectors.  Roots are compared as multisets: relative error <= 1e-10 and a
+backward-error bound."""
+import numpy as np
+import pytest
+
+from conftest import match_sorted_complex
+
+pytestmark = pytest.mark.gpu
+
+RTOL_ROOTS = 1e-10
+FAMILIES = ["lucas_all_ones", "pell_like_all_twos", "sparser_gap_1_0_1_then_ones", "padovan_like_0_1_then_ones"]
+
+
+def backward_error(top, roots):
+    """max |p(r)| / sum |c_k||r|^k over the roots of x^d - sum a_k x^(d-k)."""
+    c = np.concatenate([[1.0], -np.asarray(top, dtype=float)])
+    worst = 0.0
+    for r in roots:
+        if abs(r) <= 1:
+            num = abs(np.polyval(c, r)); den = np.polyval(np.abs(c), abs(r))
+        else:
+            w = 1 / r
+            num = abs(np.polyval(c[::-1], w)); den = np.polyval(np.abs(c[::-1]), abs(w))
+        worst = max(worst, num / den)
+    return worst
+
+
+@pytest.mark.parametrize("fam", FAMILIES)
+def test_families_golden(gpu, golden, fam):
+    vals, counts = golden[f"family_{fam}_values"], golden[f"family_{fam}_counts"]
+    off = 0
+    for n, cnt in zip(range(2, 26), counts):
+        got = gpu.lucas.compute_inverse_eigenvalues_family(fam, n, n, 1e-12)
+        assert len(got) == cnt
+        assert match_sorted_complex(got, vals[off:off + cnt]) < RTOL_ROOTS
+        off += cnt
+
+
+def test_lucas_cloud_golden(gpu, golden):
+    got = gpu.lucas.compute_inverse_eigenvalues(2, 40, 1e-12)
+    want = golden["lucas_2_40_sorted_per_n"]
+    assert got.shape == want.shape
+    off = 0
+    for n in range(2, 41):
+        assert match_sorted_complex(got[off:off + n], want[off:off + n]) < RTOL_ROOTS
+        off += n
+    xy = gpu.lucas.construct_points_xy(12)
+    assert xy.shape == golden["stage1_construct_points_maxN12"].shape
+    assert match_sorted_complex(xy[:, 0] + 1j * xy[:, 1],
+                                golden["stage1_construct_points_maxN12"][:, 0] + 1j * golden["stage1_construct_points_maxN12"][:, 1]) < RTOL_ROOTS
+
+
+def test_tracker_known_answer(gpu, golden):
+    """v3_T25_sigma3_dense.csv:2 -- 2400 points for n = 20..300 step 20; n = 300 values vs the reference."""
+    pts = gpu.lucas.construct_points(range(20, 301, 20))
+    assert len(pts) == 2400 == int(golden["tci_construct_points_count"][0])
+    assert match_sorted_complex(pts[-300:], golden["tci_construct_points_n300_sorted"]) < RTOL_ROOTS
+    assert match_sorted_complex(pts[:20], golden["tci_construct_points_n20_sorted"]) < RTOL_ROOTS
+
+
+def test_analytic(gpu):
+    phi = (1 + 5 ** 0.5) / 2
+    got = np.sort(gpu.lucas.compute_inverse_eigenvalues(2, 2).real)
+    np.testing.assert_allclose(got, [-phi, 1 / phi], rtol=1e-14)
+    lam = gpu.lucas.eigvals_toprow(np.ones(25))
+    assert abs(np.max(np.abs(lam)) - 2.0) < 1e-6            # dominant root -> 2
+    assert np.min(np.abs(lam)) > 0.5
+
+
+def test_random_batch_vs_numpy(gpu, oracle):
+    """Config 5's generator on a 3000-polynomial sample."""
+    rng = np.random.default_rng(0)
+    npoly, maxdeg = 3000, 25
+    deg = rng.integers(2, 26, size=npoly).astype(np.int32)
+    top = np.zeros((npoly, maxdeg))
+    for k in range(npoly):
+        top[k, : deg[k]] = rng.integers(0, 3, size=deg[k])
+        if top[k, deg[k] - 1] == 0:
+            top[k, deg[k] - 1] = 1.0
+    vals, kept, iters = gpu.lucas.roots_batched(top, deg)
+    assert (iters > 0).all() and (kept == deg).all()
+    worst_rel, worst_back = 0.0, 0.0
+    loose = 0
+    for k in range(npoly):
+        mine = vals[k, : deg[k]]
+        ref = oracle.eigvals_toprow(top[k, : deg[k]])
+        be = backward_error(top[k, : deg[k]], mine)
+        worst_back = max(worst_back, be)
+        rel = match_sorted_complex(mine, ref)
+        if rel > RTOL_ROOTS:
+            # ill-conditioned (clustered) roots: LAPACK itself is only sqrt(eps)-accurate there;
+            # require that both are backward stable instead
+            loose += 1
+            assert be < 1e-13 and rel < 1e-5
+        else:
+            worst_rel = max(worst_rel, rel)
+    assert worst_back < 1e-13
+    assert loose < 0.01 * npoly
+
+
+def test_invert_filter_and_zero_roots(gpu):
+    # x^3 - x^2  (top = [1, 0, 0]): roots 1, 0, 0 -> one locus point; x^2 - 4 -> +-2
+    top = np.array([[1.0, 0.0, 0.0], [0.0, 4.0, 0.0]])
+    vals, kept, _ = gpu.lucas.roots_batched(top, [3, 2], invert=True, tol=1e-12)
+    assert list(kept) == [1, 2]
+    np.testing.assert_allclose(vals[0, 0], 1.0, rtol=1e-14)
+    np.testing.assert_allclose(np.sort(vals[1, :2].real), [-0.5, 0.5], rtol=1e-14)
+    assert np.isnan(vals[0, 1:].real).all()
+    vals, kept, _ = gpu.lucas.roots_batched(top, [3, 2], invert=False)
+    assert list(kept) == [3, 2]
+    assert np.sum(np.abs(vals[0, :3]) < 1e-300) == 2
+
+
+def test_high_degree(gpu, oracle):
+    for n in (64, 300, 1220):
+        got = gpu.lucas.construct_points([n])
+        ref = oracle.inverse_eigenvalues_toprow(np.ones(n), 1e-10)
+        assert len(got) == n
+        assert match_sorted_complex(got, ref) < 1e-9

@@ -1,0 +1,116 @@
+"""CPU: the oracle (oracle/) against outputs of the reference's own Python functions.
+
+tests/golden/reference_vectors.npz was produced by oracle/gen_golden.py, which executes the
+function definitions of the scripts under /root/reference.  These tests pin the oracle; the
+GPU tests then compare the CUDA path with the oracle and with the same fixtures.
+"""
+import numpy as np
+import pytest
+
+from conftest import match_sorted_complex
+
+FAMILIES = ["lucas_all_ones", "pell_like_all_twos", "sparser_gap_1_0_1_then_ones", "padovan_like_0_1_then_ones"]
+
+
+@pytest.mark.parametrize("tag", ["cfg1", "seahorse", "tip"])
+def test_dwell_grid_bit_exact(oracle, golden, tag):
+    xlim0, xlim1, ylim0, ylim1, res, mi = golden[f"dwell_{tag}_args"]
+    xs = np.linspace(xlim0, xlim1, int(res)); ys = np.linspace(ylim0, ylim1, int(res))
+    assert np.array_equal(xs, golden[f"dwell_{tag}_xs"]) and np.array_equal(ys, golden[f"dwell_{tag}_ys"])
+    d, work = oracle.dwell_grid(xs, ys, int(mi))
+    Z = golden[f"dwell_{tag}_Z"]
+    assert np.array_equal(d, Z)
+    assert work == int(np.minimum(Z.astype(np.int64) + 1, int(mi)).sum())
+
+
+def test_dwell_points(oracle, golden):
+    mi = int(golden["dwell_points_mi"][0])
+    for (x, y), want in zip(golden["dwell_points_xy"], golden["dwell_points_out"]):
+        d, _ = oracle.dwell_grid([x], [y], mi)
+        assert d[0, 0] == want
+    # analytic facts: dwell(0)=max_iter, |c|>2 escapes at n=0
+    assert oracle.dwell_grid([0.0], [0.0], 123)[0][0, 0] == 123
+    assert oracle.dwell_grid([2.5], [0.0], 123)[0][0, 0] == 0
+
+
+def test_batch_potential(oracle, golden):
+    c = golden["potential_points_c"]
+    g, it, phi = oracle.batch_potential(c, 1500, 2.0)
+    assert np.array_equal(it, golden["potential_points_it"])
+    np.testing.assert_allclose(g, golden["potential_points_g"], rtol=1e-14, atol=0)
+    want = golden["potential_points_phi"]
+    assert np.array_equal(np.isnan(phi.real), np.isnan(want.real))
+    m = ~np.isnan(want.real)
+    np.testing.assert_allclose(phi[m], want[m], rtol=1e-14)
+
+
+def test_grid_potentials(oracle, golden):
+    gx, gy = golden["potgrid_x"], golden["potgrid_y"]
+    _, f = oracle.potential_grid(gx, gy, 60, 10.0, oracle.FIELD_POW2_ALWAYS)      # Potentials.py:32-47
+    np.testing.assert_allclose(f, golden["potentials_escape_R10_mi60"], rtol=1e-14, atol=0)
+    assert (golden["potentials_escape_R10_mi60"] < 0).any()     # bounded orbits with |z|<1 give negative values
+    _, f = oracle.potential_grid(gx, gy, 80, 2.0, oracle.FIELD_INV_K)             # Laplacian_C-M.py:27-43
+    np.testing.assert_allclose(f, golden["laplacian_cm_potential_R2_mi80"], rtol=1e-14, atol=0)
+    _, f = oracle.potential_grid(gx, gy, 70, 10.0, oracle.FIELD_INV_K)            # Iterative_...py:114-130
+    np.testing.assert_allclose(f, golden["iterative_escape_R10_mi70"], rtol=1e-14, atol=0)
+
+
+def test_vario_escape_potential(oracle, golden):
+    """variograms_construct_mandelbrot.py:148-173.  The reference iterates numpy complex ARRAYS, whose
+    multiply is FMA-fused on AVX hosts, so a few pixels may escape one step apart;
+    everything else must agree to rounding."""
+    gx, gy = golden["vario_grid_x"], golden["vario_grid_y"]
+    _, raw = oracle.potential_grid(gx, gy, 90, 4.0, oracle.FIELD_POW2_FIRST)
+    got = oracle.smooth5(raw)
+    want = golden["vario_escape_potential_mi90"]
+    close = np.isclose(got, want, rtol=1e-12, atol=1e-300)
+    assert close.mean() > 0.99
+    assert ((got == 0) == (want == 0)).mean() > 0.99
+
+
+def test_distance_estimators(oracle, golden):
+    d, _ = oracle.distance_grid(golden["de_scalar_x"], golden["de_scalar_y"], 200, 1e6, 1e-16, 0)
+    np.testing.assert_allclose(d, golden["de_scalar_dist"], rtol=1e-13, atol=0)
+    d, esc = oracle.distance_grid(golden["vario_grid_x"], golden["vario_grid_y"], 90, 4.0, 1e-14, 1)
+    want_esc = golden["vario_de_escaped"]
+    assert (esc == want_esc).mean() > 0.99           # numpy array arithmetic is FMA-contaminated, see above
+    both = esc & want_esc
+    close = np.isclose(d[both], golden["vario_de_dist"][both], rtol=1e-9, atol=0)
+    assert close.mean() > 0.98
+
+
+def test_stencils_bit_exact(oracle, golden):
+    U = golden["stencil_U"]; h = float(golden["stencil_h"][0])
+    assert np.array_equal(oracle.laplacian(U, h), golden["stencil_laplacian"])
+    assert np.array_equal(oracle.laplacian(U, h), golden["stencil_laplacian_fd"])
+    assert np.array_equal(oracle.smooth5(U), golden["stencil_smooth5"])
+
+
+def test_log_potentials(oracle, golden):
+    P = golden["logpot_points"]; gx, gy = golden["potgrid_x"], golden["potgrid_y"]
+    np.testing.assert_allclose(oracle.log_potential(P, gx, gy, 1e-12, 0), golden["logpot_potentials"], rtol=1e-12)
+    np.testing.assert_allclose(oracle.log_potential(P, gx, gy, 1e-12, 1), golden["logpot_laplacian_cm"], rtol=1e-12)
+    np.testing.assert_allclose(oracle.log_potential(P, gx, gy, 1e-12, 2), golden["logpot_iterative"], rtol=1e-12)
+    np.testing.assert_allclose(oracle.log_potential(P, golden["vario_grid_x"], golden["vario_grid_y"], 1e-6, 3),
+                               golden["logpot_vario_eps1e-6"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("fam", FAMILIES)
+def test_families(oracle, golden, fam):
+    vals, counts = golden[f"family_{fam}_values"], golden[f"family_{fam}_counts"]
+    off = 0
+    for n, cnt in zip(range(2, 26), counts):
+        got = oracle.inverse_eigenvalues_toprow(oracle.family_toprow(fam, n), 1e-12)
+        assert len(got) == cnt
+        assert match_sorted_complex(got, vals[off:off + cnt]) < 1e-12
+        off += cnt
+
+
+def test_known_answers(oracle, golden):
+    # n = 2 Lucas: roots of x^2 - x - 1 -> loci {1/phi, -phi}   
+    phi = (1 + 5 ** 0.5) / 2
+    got = np.sort(oracle.inverse_eigenvalues_toprow([1.0, 1.0]).real)
+    np.testing.assert_allclose(got, [-phi, 1 / phi], rtol=1e-15)
+    # shipped artefact: 2400 points for n = 20..300 step 20 (v3_T25_sigma3_dense.csv:2)
+    assert int(golden["tci_construct_points_count"][0]) == 2400
+    assert sum(range(20, 301, 20)) == 2400
