@@ -38,6 +38,7 @@
 
 #include <math.h>
 #include <string.h>
+#include <vector>
 
 namespace {
 
@@ -438,6 +439,7 @@ int32_t launch_escape(bool points, int field_mode, EscapeArgs& A, cudaStream_t s
 // A small ring of counter blocks lets several launches be in flight on different streams.
 constexpr int COUNTER_BLOCKS = 64;
 int g_counter_next = 0;
+unsigned long long* g_last_counters = nullptr;   // block handed out by the latest get_counters()
 int32_t get_counters(unsigned long long** out, cudaStream_t stream) {
     void* p = nullptr;
     int32_t rc = lm::ws_get(lm::WS_COUNTERS, 64 * COUNTER_BLOCKS, &p);
@@ -445,6 +447,7 @@ int32_t get_counters(unsigned long long** out, cudaStream_t stream) {
     unsigned char* blk = static_cast<unsigned char*>(p) + 64 * (g_counter_next++ % COUNTER_BLOCKS);
     LM_CUDA_TRY(cudaMemsetAsync(blk, 0, 64, stream));
     *out = reinterpret_cast<unsigned long long*>(blk);
+    g_last_counters = *out;
     return LM_OK;
 }
 
@@ -461,6 +464,31 @@ int32_t check_grid_args(const char* who, const void* xs, int64_t nx, const void*
 
 extern "C" {
 
+// enqueue one K1 launch over rows [0, ny) of a grid whose outputs start at the given pointers
+static int32_t enqueue_grid(const double* xs, int64_t nx, const double* ys, int64_t ny,
+                            int32_t max_iter, double bailout, int32_t field_mode,
+                            int32_t* dwell_i32, double* dwell_f64, double* field,
+                            unsigned long long* work_dev, int* overflow_dev, cudaStream_t s) {
+    unsigned long long* counters = nullptr;
+    int32_t rc = get_counters(&counters, s);
+    if (rc != LM_OK) return rc;
+    EscapeArgs A{};
+    A.xs = xs; A.ys = ys; A.nx = nx; A.ny = ny;
+    A.chunks_per_row = static_cast<unsigned long long>((nx + TILE - 1) / TILE);
+    A.ntiles = A.chunks_per_row * static_cast<unsigned long long>(ny);
+    A.max_iter = max_iter;
+    A.bailout = bailout;
+    A.dwell = dwell_i32; A.dwell_f64 = dwell_f64;
+    A.field = (field_mode == LM_FIELD_NONE) ? nullptr : field;
+    A.tile_counter = counters;
+    A.work_counter = work_dev;
+    A.overflow_flag = overflow_dev ? overflow_dev : reinterpret_cast<int*>(counters + 2);
+    A.vec_i32 = (nx % 4 == 0) && (reinterpret_cast<uintptr_t>(dwell_i32) % 16 == 0);
+    A.vec_f64 = (nx % 2 == 0) && (reinterpret_cast<uintptr_t>(dwell_f64) % 16 == 0);
+    A.vec_field = (nx % 2 == 0) && (reinterpret_cast<uintptr_t>(field) % 16 == 0);
+    return launch_escape(false, field_mode, A, s);
+}
+
 int32_t lm_escape_grid_f64_dev(const double* xs, int64_t nx, const double* ys, int64_t ny,
                                int32_t max_iter, double bailout, int32_t field_mode,
                                int32_t* dwell_i32, double* dwell_f64, double* field,
@@ -473,31 +501,15 @@ int32_t lm_escape_grid_f64_dev(const double* xs, int64_t nx, const double* ys, i
                "lm_escape_grid_f64_dev: unknown field_mode %d", field_mode);
     LM_REQUIRE(field_mode == LM_FIELD_NONE || field != nullptr,
                "lm_escape_grid_f64_dev: field_mode %d needs a field buffer", field_mode);
-    if (nx == 0 || ny == 0) return LM_OK;
     cudaStream_t s = lm::as_stream(stream);
-
-    unsigned long long* counters = nullptr;
-    rc = get_counters(&counters, s);
-    if (rc != LM_OK) return rc;
     if (work_units_dev) LM_CUDA_TRY(cudaMemsetAsync(work_units_dev, 0, sizeof(uint64_t), s));
-
-    EscapeArgs A{};
-    A.xs = xs; A.ys = ys; A.nx = nx; A.ny = ny;
-    A.chunks_per_row = static_cast<unsigned long long>((nx + TILE - 1) / TILE);
-    A.ntiles = A.chunks_per_row * static_cast<unsigned long long>(ny);
-    A.max_iter = max_iter;
-    A.bailout = bailout;
-    A.dwell = dwell_i32; A.dwell_f64 = dwell_f64;
-    A.field = (field_mode == LM_FIELD_NONE) ? nullptr : field;
-    A.tile_counter = counters;
-    A.work_counter = work_units_dev ? reinterpret_cast<unsigned long long*>(work_units_dev) : nullptr;
-    A.overflow_flag = reinterpret_cast<int*>(counters + 2);
-    A.vec_i32 = (nx % 4 == 0) && (reinterpret_cast<uintptr_t>(dwell_i32) % 16 == 0);
-    A.vec_f64 = (nx % 2 == 0) && (reinterpret_cast<uintptr_t>(dwell_f64) % 16 == 0);
-    A.vec_field = (nx % 2 == 0) && (reinterpret_cast<uintptr_t>(field) % 16 == 0);
-    return launch_escape(false, field_mode, A, s);
+    if (nx == 0 || ny == 0) return LM_OK;
+    return enqueue_grid(xs, nx, ys, ny, max_iter, bailout, field_mode, dwell_i32, dwell_f64, field,
+                        reinterpret_cast<unsigned long long*>(work_units_dev), nullptr, s);
 }
 
+// Host entry point.  Large outputs are produced in row chunks on one stream while a second
+// stream copies finished chunks back, so the PCIe transfer hides behind the FP64 work.
 int32_t lm_escape_grid_f64(const double* xs, int64_t nx, const double* ys, int64_t ny,
                            int32_t max_iter, double bailout, int32_t field_mode,
                            int32_t* dwell_i32, double* dwell_f64, double* field,
@@ -506,12 +518,25 @@ int32_t lm_escape_grid_f64(const double* xs, int64_t nx, const double* ys, int64
     if (rc != LM_OK) return rc;
     rc = check_grid_args("lm_escape_grid_f64", xs, nx, ys, ny, max_iter, bailout);
     if (rc != LM_OK) return rc;
+    LM_REQUIRE(field_mode >= LM_FIELD_NONE && field_mode <= LM_FIELD_POW2_FIRST,
+               "lm_escape_grid_f64: unknown field_mode %d", field_mode);
     LM_REQUIRE(field_mode == LM_FIELD_NONE || field != nullptr,
                "lm_escape_grid_f64: field_mode %d needs a field buffer", field_mode);
     if (stats) *stats = lm_stats{};
     if (nx == 0 || ny == 0) return LM_OK;
     const size_t npx = static_cast<size_t>(nx) * static_cast<size_t>(ny);
-    cudaStream_t s = nullptr;
+
+    static cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    static int s_dev = -1;
+    int dev = 0;
+    LM_CUDA_TRY(cudaGetDevice(&dev));
+    if (s_dev != dev) {      // (re)create the two pipeline streams on the current device
+        if (s_compute) { cudaStreamDestroy(s_compute); cudaStreamDestroy(s_copy); }
+        LM_CUDA_TRY(cudaStreamCreateWithFlags(&s_compute, cudaStreamNonBlocking));
+        LM_CUDA_TRY(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
+        s_dev = dev;
+    }
+    LM_CUDA_TRY(cudaDeviceSynchronize());   // earlier default-stream work may still use the workspaces
 
     void *dxs, *dys, *dd = nullptr, *df64 = nullptr, *dfield = nullptr, *dwork;
     if ((rc = lm::ws_get(lm::WS_XS, nx * sizeof(double), &dxs)) != LM_OK) return rc;
@@ -520,37 +545,79 @@ int32_t lm_escape_grid_f64(const double* xs, int64_t nx, const double* ys, int64
     if (dwell_i32 && (rc = lm::ws_get(lm::WS_OUT_I32, npx * sizeof(int32_t), &dd)) != LM_OK) return rc;
     if (dwell_f64 && (rc = lm::ws_get(lm::WS_OUT_F64, npx * sizeof(double), &df64)) != LM_OK) return rc;
     if (field_mode != LM_FIELD_NONE && (rc = lm::ws_get(lm::WS_FIELD, npx * sizeof(double), &dfield)) != LM_OK) return rc;
-    LM_CUDA_TRY(cudaMemcpyAsync(dxs, xs, nx * sizeof(double), cudaMemcpyHostToDevice, s));
-    LM_CUDA_TRY(cudaMemcpyAsync(dys, ys, ny * sizeof(double), cudaMemcpyHostToDevice, s));
+    LM_CUDA_TRY(cudaMemcpyAsync(dxs, xs, nx * sizeof(double), cudaMemcpyHostToDevice, s_compute));
+    LM_CUDA_TRY(cudaMemcpyAsync(dys, ys, ny * sizeof(double), cudaMemcpyHostToDevice, s_compute));
+    LM_CUDA_TRY(cudaMemsetAsync(dwork, 0, 64, s_compute));
+    unsigned long long* work_dev = static_cast<unsigned long long*>(dwork);
+    int* overflow_dev = reinterpret_cast<int*>(work_dev + 1);
 
-    lm::Timer tm;
-    if ((rc = tm.begin(s)) != LM_OK) return rc;
-    rc = lm_escape_grid_f64_dev(static_cast<double*>(dxs), nx, static_cast<double*>(dys), ny, max_iter,
-                                bailout, field_mode, static_cast<int32_t*>(dd),
-                                static_cast<double*>(df64), static_cast<double*>(dfield),
-                                static_cast<uint64_t*>(dwork), s);
-    if (rc != LM_OK) return rc;
+    const size_t bytes_per_row = static_cast<size_t>(nx) * ((dwell_i32 ? 4 : 0) + (dwell_f64 ? 8 : 0) + (dfield ? 8 : 0));
+    const size_t total_bytes = bytes_per_row * static_cast<size_t>(ny);
+    int64_t nchunks = static_cast<int64_t>((total_bytes + (size_t(256) << 20) - 1) / (size_t(256) << 20));
+    if (nchunks < 1) nchunks = 1;
+    if (nchunks > 32) nchunks = 32;
+    if (nchunks > ny) nchunks = ny;
+    const int64_t rows_per_chunk = (ny + nchunks - 1) / nchunks;
+
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    std::vector<cudaEvent_t> ev_chunk(static_cast<size_t>(nchunks), nullptr);
+    auto cleanup = [&]() {
+        if (ev_begin) cudaEventDestroy(ev_begin);
+        if (ev_end) cudaEventDestroy(ev_end);
+        for (cudaEvent_t e : ev_chunk) if (e) cudaEventDestroy(e);
+    };
+#define LM_TRY_CLEAN(expr)                                                                     \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            cleanup();                                                                         \
+            cudaDeviceSynchronize();                                                           \
+            return lm::fail(LM_E_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+        }                                                                                      \
+    } while (0)
+    LM_TRY_CLEAN(cudaEventCreate(&ev_begin));
+    LM_TRY_CLEAN(cudaEventCreate(&ev_end));
+    LM_TRY_CLEAN(cudaEventRecord(ev_begin, s_compute));
+    int launches = 0;
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int64_t r0 = c * rows_per_chunk;
+        const int64_t rows = (r0 + rows_per_chunk <= ny) ? rows_per_chunk : ny - r0;
+        if (rows <= 0) break;
+        const size_t off = static_cast<size_t>(r0) * nx;
+        rc = enqueue_grid(static_cast<double*>(dxs), nx, static_cast<double*>(dys) + r0, rows, max_iter, bailout, field_mode,
+                          dd ? static_cast<int32_t*>(dd) + off : nullptr, df64 ? static_cast<double*>(df64) + off : nullptr,
+                          dfield ? static_cast<double*>(dfield) + off : nullptr, work_dev, overflow_dev, s_compute);
+        if (rc != LM_OK) { cleanup(); cudaDeviceSynchronize(); return rc; }
+        ++launches;
+        LM_TRY_CLEAN(cudaEventCreateWithFlags(&ev_chunk[c], cudaEventDisableTiming));
+        LM_TRY_CLEAN(cudaEventRecord(ev_chunk[c], s_compute));
+    }
+    LM_TRY_CLEAN(cudaEventRecord(ev_end, s_compute));
+    for (int64_t c = 0; c < nchunks; ++c) {
+        if (!ev_chunk[c]) break;
+        const int64_t r0 = c * rows_per_chunk;
+        const int64_t rows = (r0 + rows_per_chunk <= ny) ? rows_per_chunk : ny - r0;
+        const size_t off = static_cast<size_t>(r0) * nx, cnt = static_cast<size_t>(rows) * nx;
+        LM_TRY_CLEAN(cudaStreamWaitEvent(s_copy, ev_chunk[c], 0));
+        if (dwell_i32) LM_TRY_CLEAN(cudaMemcpyAsync(dwell_i32 + off, static_cast<int32_t*>(dd) + off, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, s_copy));
+        if (dwell_f64) LM_TRY_CLEAN(cudaMemcpyAsync(dwell_f64 + off, static_cast<double*>(df64) + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, s_copy));
+        if (dfield) LM_TRY_CLEAN(cudaMemcpyAsync(field + off, static_cast<double*>(dfield) + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, s_copy));
+    }
+    unsigned long long host_counters[2] = {0, 0};
+    LM_TRY_CLEAN(cudaMemcpyAsync(host_counters, dwork, sizeof(host_counters), cudaMemcpyDeviceToHost, s_compute));
+    LM_TRY_CLEAN(cudaStreamSynchronize(s_compute));
+    LM_TRY_CLEAN(cudaStreamSynchronize(s_copy));
     float ms = 0.f;
-    if ((rc = tm.end(s, &ms)) != LM_OK) return rc;
-
-    if (dwell_i32) LM_CUDA_TRY(cudaMemcpyAsync(dwell_i32, dd, npx * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    if (dwell_f64) LM_CUDA_TRY(cudaMemcpyAsync(dwell_f64, df64, npx * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (dfield) LM_CUDA_TRY(cudaMemcpyAsync(field, dfield, npx * sizeof(double), cudaMemcpyDeviceToHost, s));
-    uint64_t work = 0;
-    LM_CUDA_TRY(cudaMemcpyAsync(&work, dwork, sizeof(work), cudaMemcpyDeviceToHost, s));
-    int overflow = 0;
-    void* cnt = nullptr;
-    if ((rc = lm::ws_get(lm::WS_COUNTERS, 64, &cnt)) != LM_OK) return rc;
-    LM_CUDA_TRY(cudaMemcpyAsync(&overflow, static_cast<unsigned long long*>(cnt) + 2, sizeof(int),
-                                cudaMemcpyDeviceToHost, s));
-    LM_CUDA_TRY(cudaStreamSynchronize(s));
+    LM_TRY_CLEAN(cudaEventElapsedTime(&ms, ev_begin, ev_end));
+#undef LM_TRY_CLEAN
+    cleanup();
     if (stats) {
-        stats->work_units = work;
+        stats->work_units = host_counters[0];
         stats->items = npx;
         stats->kernel_ms = ms;
-        stats->launches = 1;
+        stats->launches = launches;
     }
-    if (overflow)
+    if (static_cast<int>(host_counters[1] & 0xffffffffu))
         return lm::fail(LM_E_OVERFLOW,
                         "lm_escape_grid_f64: 2**k with k > 1023 (the reference raises OverflowError here)");
     return LM_OK;

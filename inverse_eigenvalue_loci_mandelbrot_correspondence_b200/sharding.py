@@ -1,0 +1,103 @@
+"""Row sharding of the escape-time grid over the GPUs of one node (one process per GPU).
+
+Rows of the grid are independent for K1; K2 needs one halo row from the next shard.  The
+reference is single-process, so this layer has no reference counterpart:
+it only decides which rows a rank computes and moves the two small things that cross ranks,
+  * the first dwell row of every shard (all-gather, nx*4 bytes per rank) -> halo for K2,
+  * the per-shard crossing records (gather to rank 0) -> one global linking pass.
+Row work varies by three orders of magnitude across the window, so shards are contiguous row
+blocks cut at equal ESTIMATED work (a coarse K1 pre-pass), not equal row counts.
+
+The collective helpers take torch tensors and work with any torch.distributed backend (NCCL on
+the GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def balanced_row_cuts(row_work, nparts: int) -> list[int]:
+    """Cut rows [0, ny) into `nparts` contiguous blocks of (nearly) equal cumulative work.
+
+    Returns nparts+1 increasing cut positions starting at 0 and ending at ny; every block has at
+    least one row when ny >= nparts.
+    """
+    w = np.asarray(row_work, dtype=np.float64).ravel()
+    ny = w.size
+    if nparts < 1:
+        raise ValueError("nparts must be >= 1")
+    if ny < nparts:
+        raise ValueError(f"cannot cut {ny} rows into {nparts} non-empty blocks")
+    w = np.maximum(w, 0.0) + 1e-12 * max(float(w.max(initial=0.0)), 1.0)     # keep the prefix strictly increasing
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+    cuts = [0]
+    for k in range(1, nparts):
+        target = cum[-1] * k / nparts
+        c = int(np.searchsorted(cum, target, side="left"))
+        if c > 0 and abs(cum[c - 1] - target) <= abs(cum[min(c, ny)] - target):
+            c -= 1
+        c = max(c, cuts[-1] + 1)              # non-empty block
+        c = min(c, ny - (nparts - k))         # leave rows for the remaining blocks
+        cuts.append(c)
+    cuts.append(ny)
+    return cuts
+
+
+def parallel_efficiency(row_work, cuts) -> float:
+    """mean block work / max block work for the given cuts (1.0 = perfectly balanced)."""
+    w = np.asarray(row_work, dtype=np.float64).ravel()
+    blocks = [w[a:b].sum() for a, b in zip(cuts[:-1], cuts[1:])]
+    return float(np.mean(blocks) / max(np.max(blocks), 1e-300))
+
+
+def interpolate_row_profile(coarse_rows: np.ndarray, coarse_work: np.ndarray, ny: int) -> np.ndarray:
+    """Per-row work estimate for all ny rows from the work of a subset of rows."""
+    return np.interp(np.arange(ny, dtype=np.float64), np.asarray(coarse_rows, dtype=np.float64),
+                     np.asarray(coarse_work, dtype=np.float64))
+
+
+def coarse_row_profile(xs, ys, max_iter: int, rows: int = 512, cols: int = 1024) -> np.ndarray:
+    """Estimated work of every grid row from a coarse K1 pass on the GPU (subsampled rows/columns)."""
+    from . import escape
+    xs = np.asarray(xs, dtype=np.float64); ys = np.asarray(ys, dtype=np.float64)
+    ri = np.unique(np.linspace(0, ys.size - 1, min(rows, ys.size)).round().astype(np.int64))
+    ci = np.unique(np.linspace(0, xs.size - 1, min(cols, xs.size)).round().astype(np.int64))
+    d, _, _ = escape.escape_grid(xs[ci], ys[ri], max_iter)
+    work = np.minimum(d.astype(np.int64) + 1, max_iter).sum(axis=1).astype(np.float64)
+    return interpolate_row_profile(ri, work, ys.size)
+
+
+# ---- collectives (torch.distributed; backend-agnostic) -------------------------------------
+def exchange_first_rows(first_row, group=None):
+    """All-gather every rank's first dwell row; returns the [world, nx] tensor.
+    Rank r's K2 halo is row r+1 of the result (the last rank has none)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    out = torch.empty((world, first_row.numel()), dtype=first_row.dtype, device=first_row.device)
+    dist.all_gather_into_tensor(out, first_row.contiguous().view(1, -1), group=group)
+    return out
+
+
+def gather_records(records: np.ndarray, device, dst: int = 0, group=None):
+    """Gather the per-rank record arrays ([n, 8] int64, raster order inside a rank) to `dst`,
+    concatenated in rank order (= global raster order for contiguous row blocks)."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    records = np.ascontiguousarray(records, dtype=np.int64).reshape(-1, 8)
+    counts = torch.zeros(world, dtype=torch.int64, device=device)
+    mine = torch.tensor([records.shape[0]], dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(counts, mine, group=group)
+    counts_h = counts.cpu().numpy()
+    cap = int(counts_h.max()) if world else 0
+    padded = torch.zeros((max(cap, 1), 8), dtype=torch.int64, device=device)
+    if records.shape[0]:
+        padded[: records.shape[0]] = torch.from_numpy(records).to(device)
+    if rank == dst:
+        bufs = [torch.empty_like(padded) for _ in range(world)]
+        dist.gather(padded, bufs, dst=dst, group=group)
+        parts = [bufs[r][: int(counts_h[r])].cpu().numpy() for r in range(world)]
+        return np.concatenate(parts) if parts else np.zeros((0, 8), dtype=np.int64)
+    dist.gather(padded, None, dst=dst, group=group)
+    return None

@@ -129,14 +129,15 @@ def test_f32_variant_tolerance(gpu, oracle):
 
 def test_full_size_properties_config2(gpu):
     """BASELINE config 2 (8192^2, max_iter 2000) at full size: size-independent checks --
-    mirror symmetry in y (the window is symmetric and conjugation commutes with the recurrence),
-    work-count identity, and agreement of the device-resident path with the host path on a strip."""
+    work-count identity, conjugation symmetry (dwell(x, -y) == dwell(x, y): negation is exact in
+    binary64 and commutes with every operation of the recurrence), agreement of a strip computed
+    on its own with the same rows of the full grid, and the interior fraction of the window."""
     res, mi = 8192, 2000
     xs = np.linspace(-2.1, 0.9, res); ys = np.linspace(-1.5, 1.5, res)
-    assert np.array_equal(ys, -ys[::-1])
     d, _, st = gpu.escape.escape_grid(xs, ys, mi)
-    assert np.array_equal(d, d[::-1, :])
     assert st["work_units"] == int(np.minimum(d.astype(np.int64) + 1, mi).sum())
     strip, _, _ = gpu.escape.escape_grid(xs, ys[4000:4016], mi)
     assert np.array_equal(strip, d[4000:4016])
+    mirrored, _, _ = gpu.escape.escape_grid(xs, -ys[4000:4016], mi)
+    assert np.array_equal(mirrored, strip)
     assert 0.16 < (d == mi).mean() < 0.175

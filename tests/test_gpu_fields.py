@@ -36,19 +36,19 @@ def test_stencil_linearity_full_size(gpu):
 
 def test_log_potentials(gpu, oracle, golden):
     P = golden["logpot_points"]; gx, gy = golden["potgrid_x"], golden["potgrid_y"]
-    rt = 1e-12
-    np.testing.assert_allclose(gpu.potentials.log_potential(P, gx, gy), golden["logpot_potentials"], rtol=rt)
+    rt = 1e-12           # relative, plus 1e-13 absolute where the sum of logs cancels to ~0
+    np.testing.assert_allclose(gpu.potentials.log_potential(P, gx, gy), golden["logpot_potentials"], rtol=rt, atol=1e-13)
     X, Y = np.meshgrid(gx, gy)
-    np.testing.assert_allclose(gpu.potentials.construct_potential(X, Y, P), golden["logpot_laplacian_cm"], rtol=rt)
-    np.testing.assert_allclose(gpu.potentials.log_potential(P, gx, gy, use_hypot=True), golden["logpot_iterative"], rtol=rt)
+    np.testing.assert_allclose(gpu.potentials.construct_potential(X, Y, P), golden["logpot_laplacian_cm"], rtol=rt, atol=1e-13)
+    np.testing.assert_allclose(gpu.potentials.log_potential(P, gx, gy, use_hypot=True), golden["logpot_iterative"], rtol=rt, atol=1e-13)
     np.testing.assert_allclose(gpu.potentials.log_potential_from_points(golden["vario_grid_x"], golden["vario_grid_y"],
                                                                         P[:, 0] + 1j * P[:, 1], 1e-6),
-                               golden["logpot_vario_eps1e-6"], rtol=rt)
+                               golden["logpot_vario_eps1e-6"], rtol=rt, atol=1e-13)
     # bigger: 400^2 grid (Potentials.py:52-53) x 3000 points against the oracle
     rng = np.random.default_rng(5)
     pts = rng.uniform(-1.2, 1.2, (3000, 2))
     g = np.linspace(-2, 2, 400)
-    np.testing.assert_allclose(gpu.potentials.log_potential(pts, g, g), oracle.log_potential(pts, g, g, 1e-12, 0), rtol=rt)
+    np.testing.assert_allclose(gpu.potentials.log_potential(pts, g, g), oracle.log_potential(pts, g, g, 1e-12, 0), rtol=rt, atol=1e-13)
 
 
 def test_distance_estimators(gpu, oracle, golden):
