@@ -311,18 +311,20 @@ def run_ours(args):
         st = _shim.Stats()
 
         def e2e_step():
-            # K1 through the host-buffer entry point: H2D of xs/ys, chunked compute, overlapped D2H of the dwell block
+            if world == 1:
+                # the fused host-buffer call (compute_grid + extract_contour of the script's main()):
+                # H2D of xs/ys, chunked K1, dwell grid copied back to the pinned host buffer while
+                # K1/K2 still run, K2 records -> ordered polylines on the host
+                lines, stx = contour.boundary_sample(xs_p, ys_p, max_iter, level, dwell_out=out)
+                return stx["work_units"], lines
+            # N > 1: K1 through the host-buffer entry point on this rank's rows, then the shard goes
+            # back up for the halo exchange (NCCL) and K2, records are gathered and linked on rank 0
             _shim.call("lm_escape_grid_f64", _shim.ptr(xs_p), nx, _shim.ptr(ys_p), rows, max_iter, 2.0, 0,
                        _shim.ptr(out), None, None, C.byref(st))
-            if world == 1:
-                # K2 through its host-buffer entry point (uploads the host dwell grid again, as a caller
-                # holding compute_grid's return value would)
-                lines = contour.contour_lines(xs, ys, out, level)
-            else:
-                _shim.call("lm_memcpy_h2d", C.c_void_p(dwell_d.data_ptr()), _shim.ptr(out), out.nbytes, stream)
-                recs_local = k2()                      # NCCL halo all-gather + classify -> records on the host
-                allrec = sharding.gather_records(recs_local, dev, 0)
-                lines = contour.link_records(allrec, xs, ys, level) if rank == 0 else None
+            _shim.call("lm_memcpy_h2d", C.c_void_p(dwell_d.data_ptr()), _shim.ptr(out), out.nbytes, stream)
+            recs_local = k2()
+            allrec = sharding.gather_records(recs_local, dev, 0)
+            lines = contour.link_records(allrec, xs, ys, level) if rank == 0 else None
             return st.work_units, lines
 
         e2e_step()
@@ -342,10 +344,11 @@ def run_ours(args):
             dist.all_reduce(ww, op=dist.ReduceOp.SUM)
         n_vertices = int(max((len(l) for l in lines), default=0)) if lines else 0
         e2e = {"value": int(ww[0]) / float(tt[0]) / 1e9, "unit": "Gpixel-iter/s",
-               "h2d_bytes_per_step": int((nx + rows) * 8 + rows * nx * 4),
+               "h2d_bytes_per_step": int((nx + rows) * 8 + (rows * nx * 4 if world > 1 else 0)),
                "d2h_bytes_per_step": int(rows * nx * 4 + n_rec.value * 64), "ms_per_step": 1e3 * float(tt[0]) / args.steps,
                "boundary_vertices": n_vertices,
-               "api": "lm_escape_grid_f64 (pinned numpy buffers) + lm_contour_level / lm_contour_link"}
+               "api": ("lm_boundary_sample (pinned numpy buffers in, dwell grid + ordered boundary polylines out)" if world == 1 else
+                       "lm_escape_grid_f64 (pinned numpy buffers) + lm_contour_classify_dev + lm_contour_link")}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only)
     cpu = None

@@ -186,6 +186,21 @@ int32_t lm_contour_level_dev(const int32_t* dwell_dev, const double* xs_host, in
                              lm_stats* stats);
 
 /*
+ * The fused boundary stage of the reference script's main()
+ * (xs, ys, Z = compute_grid(...); contour = extract_contour(xs, ys, Z, max_iter, level),
+ * mandelbrot_boundary_sample.py:66-67) as one host-buffer call: the dwell grid stays in HBM
+ * between K1 and K2 and is returned to dwell_i32 / dwell_f64 (either may be NULL) by a copy
+ * stream that overlaps the compute.  `level` is the absolute level (level_frac * max_iter).
+ * Lines come back as in lm_contour_level; LM_E_CAP reports the required capacities.
+ */
+int32_t lm_boundary_sample(const double* xs, int64_t nx, const double* ys, int64_t ny,
+                           int32_t max_iter, double level,
+                           int32_t* dwell_i32, double* dwell_f64,
+                           double* verts, int64_t cap_verts, int64_t* n_verts,
+                           int64_t* line_offsets, int64_t cap_lines, int64_t* n_lines,
+                           lm_stats* stats);
+
+/*
  * Multi-GPU building block: classify the quads of rows [0, ny-1) of a dwell block on the
  * device (ny rows including one halo row; ys_host holds the block's ny coordinates) and
  * return the compacted crossing-quad records, in raster order, to the host.  Records of

@@ -29,7 +29,15 @@ def _as_dwell_i32(Z) -> np.ndarray:
     return Zi
 
 
-def _call_with_growing_buffers(fn_name: str, head_args: tuple, level: float, n_pixels: int):
+def _split(verts: np.ndarray, offs: np.ndarray, nv: int, nl: int):
+    """(N,2) array per line; one compact copy of the used vertices, the lines are views into it."""
+    if nl == 0:
+        return []
+    used = verts[:nv].copy()
+    return np.split(used, offs[1:nl])
+
+
+def _call_with_growing_buffers(fn_name: str, head_args: tuple, level: float, n_pixels: int, tail_args: tuple = ()):
     cap_v = max(1024, int(0.02 * n_pixels) + 1024)
     cap_l = 4096
     st = Stats()
@@ -39,7 +47,7 @@ def _call_with_growing_buffers(fn_name: str, head_args: tuple, level: float, n_p
         nv = C.c_int64(0); nl = C.c_int64(0)
         lib = _shim.load()
         with _shim._lock:
-            rc = getattr(lib, fn_name)(*head_args, float(level), _shim.ptr(verts), cap_v, C.byref(nv),
+            rc = getattr(lib, fn_name)(*head_args, float(level), *tail_args, _shim.ptr(verts), cap_v, C.byref(nv),
                                        _shim.ptr(offs), cap_l, C.byref(nl), C.byref(st))
         if rc == _shim.LM_E_CAP:
             cap_v = max(cap_v, nv.value + 16); cap_l = max(cap_l, nl.value + 16)
@@ -48,7 +56,7 @@ def _call_with_growing_buffers(fn_name: str, head_args: tuple, level: float, n_p
         break
     global last_stats
     last_stats = st.as_dict()
-    return [verts[offs[k]:offs[k + 1]].copy() for k in range(nl.value)]
+    return _split(verts, offs, nv.value, nl.value)
 
 
 def contour_lines(xs, ys, Z, level: float):
@@ -69,6 +77,29 @@ def contour_lines_dev(dwell_dev_ptr: int, xs, ys, level: float):
     return _call_with_growing_buffers("lm_contour_level_dev",
                                       (C.c_void_p(dwell_dev_ptr), _shim.ptr(xs), xs.size, _shim.ptr(ys), ys.size),
                                       level, xs.size * ys.size)
+
+
+def boundary_sample(xs, ys, max_iter: int, level: float, dwell_out: np.ndarray | None = None):
+    """compute_grid + plt.contour in one host-buffer call (lm_boundary_sample): the dwell grid never
+    leaves the GPU between K1 and K2.  dwell_out: optional int32 or float64 [ny, nx] array that
+    receives the dwell grid (copied back while the GPU is still computing).
+    Returns (lines, stats) with lines as in contour_lines."""
+    xs = np.ascontiguousarray(xs, dtype=np.float64).ravel()
+    ys = np.ascontiguousarray(ys, dtype=np.float64).ravel()
+    d32 = d64 = None
+    if dwell_out is not None:
+        if dwell_out.shape != (ys.size, xs.size) or not dwell_out.flags["C_CONTIGUOUS"]:
+            raise ValueError("dwell_out must be a C-contiguous [len(ys), len(xs)] array")
+        if dwell_out.dtype == np.int32:
+            d32 = dwell_out
+        elif dwell_out.dtype == np.float64:
+            d64 = dwell_out
+        else:
+            raise ValueError("dwell_out must be int32 or float64")
+    lines = _call_with_growing_buffers("lm_boundary_sample",
+                                       (_shim.ptr(xs), xs.size, _shim.ptr(ys), ys.size, int(max_iter)),
+                                       level, xs.size * ys.size, tail_args=(_shim.ptr(d32), _shim.ptr(d64)))
+    return lines, last_stats
 
 
 def longest(lines):
@@ -96,4 +127,4 @@ def link_records(records: np.ndarray, xs, ys, level: float):
     nv = C.c_int64(0); nl = C.c_int64(0)
     _shim.call("lm_contour_link", _shim.ptr(records), n, _shim.ptr(xs), xs.size, _shim.ptr(ys), ys.size, float(level),
                _shim.ptr(verts), cap_v, C.byref(nv), _shim.ptr(offs), cap_l, C.byref(nl))
-    return [verts[offs[k]:offs[k + 1]].copy() for k in range(nl.value)]
+    return _split(verts, offs, nv.value, nl.value)

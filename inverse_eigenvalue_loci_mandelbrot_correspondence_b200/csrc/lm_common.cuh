@@ -7,6 +7,8 @@
 #include <stdio.h>
 #include <stdarg.h>
 
+#include <vector>
+
 #include "lm_b200.h"
 
 namespace lm {
@@ -39,7 +41,8 @@ int     sm_count();
 // per purpose; a slot grows monotonically and is freed by lm_release_workspace().
 enum WsSlot {
     WS_XS = 0, WS_YS, WS_OUT_I32, WS_OUT_F64, WS_FIELD, WS_COUNTERS, WS_IN_A, WS_IN_B,
-    WS_IN_C, WS_OUT_A, WS_OUT_B, WS_OUT_C, WS_OUT_D, WS_RECORDS, WS_SCRATCH, WS_NSLOTS
+    WS_IN_C, WS_OUT_A, WS_OUT_B, WS_OUT_C, WS_OUT_D, WS_RECORDS, WS_SCRATCH,
+    WS_K1_WORK, WS_K2_MASK, WS_K2_COUNT, WS_K2_OFFSET, WS_K2_XS, WS_K2_YS, WS_NSLOTS
 };
 int32_t ws_get(WsSlot slot, size_t bytes, void** out);
 void    ws_release_all();
@@ -53,5 +56,29 @@ struct Timer {
 };
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- cross-file internals ---------------------------------------------------------------
+// An in-flight host-buffer K1 job (lm_escape.cu): row chunks are computed on s_compute while
+// s_copy returns finished chunks to the caller's host buffers.
+struct GridHostJob {
+    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    std::vector<cudaEvent_t> ev_chunk;
+    void* dwork = nullptr;            // device: [0] work counter, [1] overflow flag
+    int32_t* dwell_dev = nullptr;     // device int32 dwell grid (when produced)
+    int launches = 0;
+    size_t npx = 0;
+    void release_events();
+};
+int32_t grid_host_begin(const double* xs, int64_t nx, const double* ys, int64_t ny, int32_t max_iter, double bailout,
+                        int32_t field_mode, int32_t* dwell_i32, double* dwell_f64, double* field,
+                        bool need_dev_dwell, GridHostJob* job);
+int32_t grid_host_finish(GridHostJob* job, lm_stats* stats);
+// K2 on a device-resident dwell grid -> polylines in host buffers (lm_contour.cu); enqueues on s
+// and synchronises s while fetching the records.
+int32_t contour_device_to_host(const int32_t* dwell_dev, const double* xs_host, int64_t nx, const double* ys_host,
+                               int64_t ny, double level, double* verts, int64_t cap_verts, int64_t* n_verts,
+                               int64_t* line_offsets, int64_t cap_lines, int64_t* n_lines,
+                               float* kernel_ms, int* launches, cudaStream_t s);
 
 }  // namespace lm

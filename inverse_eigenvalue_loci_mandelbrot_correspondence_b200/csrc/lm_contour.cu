@@ -31,6 +31,8 @@
 #include "lm_common.cuh"
 
 #include <algorithm>
+#include <climits>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -96,53 +98,102 @@ __host__ __device__ inline void edge_corners(int edge, int& dj1, int& di1, int& 
 }
 
 // ------------------------------------------------------------------------------------
-// 1. mark: crossing mask + row counts
+// 1. mark: crossing mask + row counts.  One CTA per quad row j; its warps stride over the
+// 128-column strips of that row.  "z > level" for an integer z is "z > floor(level)", so
+// the classification is pure integer work.
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(MARK_WARPS * 32) contour_mark_kernel(
-    const int* __restrict__ dwell, long long nx, long long ny, double level,
+// vector path (nx % 4 == 0, 16-byte aligned grid): lane l loads columns c0+4l .. c0+4l+3 of both
+// rows with one 128-bit load each; the crossing nibble comes from bit-parallel XORs and the
+// four ballot-order mask words from a partitioned warp OR-reduction.
+__global__ void __launch_bounds__(MARK_WARPS * 32) contour_mark_vec_kernel(
+    const int* __restrict__ dwell, long long nx, long long ny, int ilevel,
     unsigned* __restrict__ mask, long long words_per_row, unsigned* __restrict__ row_count) {
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long strips_per_row = words_per_row / 4;
-    const long long total = strips_per_row * (ny - 1);
-    const long long nwarps = static_cast<long long>(gridDim.x) * MARK_WARPS;
-    const long long nq = nx - 1;                                   // quads per row
-    for (long long t = static_cast<long long>(blockIdx.x) * MARK_WARPS + (threadIdx.x >> 5); t < total; t += nwarps) {
-        const long long j = t / strips_per_row;
-        const long long c0 = (t - j * strips_per_row) * STRIP;
+    const long long nq = nx - 1;
+    for (long long j = blockIdx.x; j < ny - 1; j += gridDim.x) {
         const int* r0 = dwell + j * nx;
         const int* r1 = r0 + nx;
-        bool lo[4], hi[4];
+        unsigned cnt = 0;
+        for (long long sidx = warp; sidx < strips_per_row; sidx += MARK_WARPS) {
+            const long long c0 = sidx * STRIP;
+            const long long c = c0 + 4 * lane;
+            int4 a = make_int4(0, 0, 0, 0), b = make_int4(0, 0, 0, 0);
+            const bool in = c < nx;                         // nx % 4 == 0: all four columns are in range together
+            if (in) {
+                a = __ldg(reinterpret_cast<const int4*>(r0 + c));
+                b = __ldg(reinterpret_cast<const int4*>(r1 + c));
+            }
+            unsigned L = (a.x > ilevel ? 1u : 0u) | (a.y > ilevel ? 2u : 0u) | (a.z > ilevel ? 4u : 0u) | (a.w > ilevel ? 8u : 0u);
+            unsigned H = (b.x > ilevel ? 1u : 0u) | (b.y > ilevel ? 2u : 0u) | (b.z > ilevel ? 4u : 0u) | (b.w > ilevel ? 8u : 0u);
+            if (!in) { L = 0u; H = 0u; }
+            // corner right of my fourth column: first column of lane+1, or the strip's edge column
+            unsigned nxt = __shfl_down_sync(FULL, (L & 1u) | ((H & 1u) << 1), 1);
+            if (lane == 31) {
+                nxt = 0u;
+                const long long ce = c0 + STRIP;
+                if (ce < nx) nxt = (__ldg(r0 + ce) > ilevel ? 1u : 0u) | (__ldg(r1 + ce) > ilevel ? 2u : 0u);
+            }
+            const unsigned L5 = L | ((nxt & 1u) << 4), H5 = H | ((nxt >> 1) << 4);
+            unsigned cross = ((L5 ^ (L5 >> 1)) | (H5 ^ (H5 >> 1)) | (L5 ^ H5)) & 0xFu;
+            // only quads c .. c+3 with column < nx-1 exist
+            const long long left = nq - c;
+            if (left < 4) cross &= (left <= 0) ? 0u : ((1u << left) - 1u);
+            const unsigned word = __reduce_or_sync(0xFFu << (lane & 24), cross << (4 * (lane & 7)));
+            if ((lane & 7) == 0) {
+                mask[j * words_per_row + c0 / 32 + (lane >> 3)] = word;
+                cnt += __popc(word);
+            }
+        }
+        if (cnt) atomicAdd(row_count + j, cnt);
+    }
+}
+
+// scalar path: any nx / alignment
+__global__ void __launch_bounds__(MARK_WARPS * 32) contour_mark_kernel(
+    const int* __restrict__ dwell, long long nx, long long ny, int ilevel,
+    unsigned* __restrict__ mask, long long words_per_row, unsigned* __restrict__ row_count) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long strips_per_row = words_per_row / 4;
+    const long long nq = nx - 1;                                   // quads per row
+    for (long long j = blockIdx.x; j < ny - 1; j += gridDim.x) {
+        const int* r0 = dwell + j * nx;
+        const int* r1 = r0 + nx;
+        for (long long sidx = warp; sidx < strips_per_row; sidx += MARK_WARPS) {
+            const long long c0 = sidx * STRIP;
+            bool lo[4], hi[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const long long c = c0 + 32 * k + lane;
-            const bool in = c < nx;
-            lo[k] = in ? above_level(__ldg(r0 + c), level) : false;
-            hi[k] = in ? above_level(__ldg(r1 + c), level) : false;
-        }
-        // the column right of the strip (corner of the last quad)
-        const long long ce = c0 + STRIP;
-        bool lo_e = false, hi_e = false;
-        if (lane == 31 && ce < nx) { lo_e = above_level(__ldg(r0 + ce), level); hi_e = above_level(__ldg(r1 + ce), level); }
-        unsigned words[4];
-        int cnt = 0;
+            for (int k = 0; k < 4; ++k) {
+                const long long c = c0 + 32 * k + lane;
+                const bool in = c < nx;
+                lo[k] = in ? (__ldg(r0 + c) > ilevel) : false;
+                hi[k] = in ? (__ldg(r1 + c) > ilevel) : false;
+            }
+            // the column right of the strip (corner of the last quad)
+            const long long ce = c0 + STRIP;
+            bool lo_e = false, hi_e = false;
+            if (lane == 31 && ce < nx) { lo_e = __ldg(r0 + ce) > ilevel; hi_e = __ldg(r1 + ce) > ilevel; }
+            unsigned words[4];
+            int cnt = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            // right neighbours: lane+1 of the same chunk, lane 0 of the next chunk for lane 31
-            const bool nlo = (k < 3) ? lo[k + 1] : lo_e, nhi = (k < 3) ? hi[k + 1] : hi_e;
-            bool rl = __shfl_down_sync(FULL, lo[k], 1), rh = __shfl_down_sync(FULL, hi[k], 1);
-            const bool wl = __shfl_sync(FULL, nlo, (k < 3) ? 0 : 31), wh = __shfl_sync(FULL, nhi, (k < 3) ? 0 : 31);
-            if (lane == 31) { rl = wl; rh = wh; }
-            const long long c = c0 + 32 * k + lane;
-            const int s = static_cast<int>(lo[k]) + static_cast<int>(rl) + static_cast<int>(hi[k]) + static_cast<int>(rh);
-            const bool cross = (c < nq) && s != 0 && s != 4;
-            words[k] = __ballot_sync(FULL, cross);
-            cnt += __popc(words[k]);
+            for (int k = 0; k < 4; ++k) {
+                // right neighbours: lane+1 of the same chunk, lane 0 of the next chunk for lane 31
+                const bool nlo = (k < 3) ? lo[k < 3 ? k + 1 : 3] : lo_e, nhi = (k < 3) ? hi[k < 3 ? k + 1 : 3] : hi_e;
+                bool rl = __shfl_down_sync(FULL, lo[k], 1), rh = __shfl_down_sync(FULL, hi[k], 1);
+                const bool wl = __shfl_sync(FULL, nlo, (k < 3) ? 0 : 31), wh = __shfl_sync(FULL, nhi, (k < 3) ? 0 : 31);
+                if (lane == 31) { rl = wl; rh = wh; }
+                const long long c = c0 + 32 * k + lane;
+                const int sum = static_cast<int>(lo[k]) + static_cast<int>(rl) + static_cast<int>(hi[k]) + static_cast<int>(rh);
+                const bool cross = (c < nq) && sum != 0 && sum != 4;
+                words[k] = __ballot_sync(FULL, cross);
+                cnt += __popc(words[k]);
+            }
+            if (lane < 4) {
+                const unsigned w = lane == 0 ? words[0] : lane == 1 ? words[1] : lane == 2 ? words[2] : words[3];
+                mask[j * words_per_row + c0 / 32 + lane] = w;
+            }
+            if (lane == 0 && cnt) atomicAdd(row_count + j, static_cast<unsigned>(cnt));
         }
-        if (lane < 4) {
-            const unsigned w = lane == 0 ? words[0] : lane == 1 ? words[1] : lane == 2 ? words[2] : words[3];
-            mask[j * words_per_row + c0 / 32 + lane] = w;
-        }
-        if (lane == 0 && cnt) atomicAdd(row_count + j, static_cast<unsigned>(cnt));
     }
 }
 
@@ -270,30 +321,40 @@ __global__ void __launch_bounds__(MARK_WARPS * 32) contour_emit_kernel(
 // ------------------------------------------------------------------------------------
 int32_t classify_device(const int* dwell_dev, const double* xs_host, long long nx,
                         const double* ys_host, long long ny, long long row_offset, double level,
-                        std::vector<long long>& records, float* kernel_ms, cudaStream_t s) {
-    records.clear();
+                        const long long** records_out, long long* n_out, float* kernel_ms, cudaStream_t s) {
+    *records_out = nullptr; *n_out = 0;
     if (nx < 2 || ny < 2) return LM_OK;
     const long long nrows = ny - 1;
     const long long words_per_row = ((nx - 1 + STRIP - 1) / STRIP) * 4;
     void *dmask, *dcount, *doff, *dxs, *dys;
     int32_t rc;
-    if ((rc = lm::ws_get(lm::WS_SCRATCH, static_cast<size_t>(nrows) * words_per_row * sizeof(unsigned), &dmask)) != LM_OK) return rc;
-    if ((rc = lm::ws_get(lm::WS_IN_C, static_cast<size_t>(nrows) * sizeof(unsigned), &dcount)) != LM_OK) return rc;
-    if ((rc = lm::ws_get(lm::WS_OUT_D, static_cast<size_t>(nrows + 1) * sizeof(unsigned long long), &doff)) != LM_OK) return rc;
-    if ((rc = lm::ws_get(lm::WS_XS, static_cast<size_t>(nx) * sizeof(double), &dxs)) != LM_OK) return rc;
-    if ((rc = lm::ws_get(lm::WS_YS, static_cast<size_t>(ny) * sizeof(double), &dys)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_K2_MASK, static_cast<size_t>(nrows) * words_per_row * sizeof(unsigned), &dmask)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_K2_COUNT, static_cast<size_t>(nrows) * sizeof(unsigned), &dcount)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_K2_OFFSET, static_cast<size_t>(nrows + 1) * sizeof(unsigned long long), &doff)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_K2_XS, static_cast<size_t>(nx) * sizeof(double), &dxs)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_K2_YS, static_cast<size_t>(ny) * sizeof(double), &dys)) != LM_OK) return rc;
     LM_CUDA_TRY(cudaMemcpyAsync(dxs, xs_host, nx * sizeof(double), cudaMemcpyHostToDevice, s));
     LM_CUDA_TRY(cudaMemcpyAsync(dys, ys_host, ny * sizeof(double), cudaMemcpyHostToDevice, s));
     LM_CUDA_TRY(cudaMemsetAsync(dcount, 0, static_cast<size_t>(nrows) * sizeof(unsigned), s));
 
     lm::Timer tm;
     if ((rc = tm.begin(s)) != LM_OK) return rc;
-    const long long strips = (words_per_row / 4) * nrows;
-    long long blocks = (strips + MARK_WARPS - 1) / MARK_WARPS;
-    const long long cap = static_cast<long long>(lm::sm_count()) * 8;
+    // z > level  <=>  z > floor(level) for integer z (clamped to the int32 range)
+    int ilevel;
+    if (!(level >= -2147483648.0)) ilevel = INT_MIN;            // also NaN: nothing is above a NaN level
+    else if (level >= 2147483647.0) ilevel = INT_MAX;
+    else ilevel = static_cast<int>(floor(level));
+    if (level != level) ilevel = INT_MAX;
+    long long blocks = nrows;
+    const long long cap = static_cast<long long>(lm::sm_count()) * 64;
     if (blocks > cap) blocks = cap;
-    contour_mark_kernel<<<static_cast<unsigned>(blocks), MARK_WARPS * 32, 0, s>>>(
-        dwell_dev, nx, ny, level, static_cast<unsigned*>(dmask), words_per_row, static_cast<unsigned*>(dcount));
+    const bool vec = (nx % 4 == 0) && (reinterpret_cast<uintptr_t>(dwell_dev) % 16 == 0);
+    if (vec)
+        contour_mark_vec_kernel<<<static_cast<unsigned>(blocks), MARK_WARPS * 32, 0, s>>>(
+            dwell_dev, nx, ny, ilevel, static_cast<unsigned*>(dmask), words_per_row, static_cast<unsigned*>(dcount));
+    else
+        contour_mark_kernel<<<static_cast<unsigned>(blocks), MARK_WARPS * 32, 0, s>>>(
+            dwell_dev, nx, ny, ilevel, static_cast<unsigned*>(dmask), words_per_row, static_cast<unsigned*>(dcount));
     LM_CUDA_TRY(cudaGetLastError());
     contour_scan_kernel<<<1, 1024, 0, s>>>(static_cast<unsigned*>(dcount), nrows, static_cast<unsigned long long*>(doff));
     LM_CUDA_TRY(cudaGetLastError());
@@ -315,10 +376,25 @@ int32_t classify_device(const int* dwell_dev, const double* xs_host, long long n
     float ms = 0.f;
     if ((rc = tm.end(s, &ms)) != LM_OK) return rc;
     if (kernel_ms) *kernel_ms = ms;
-    records.resize(static_cast<size_t>(total) * REC_WORDS);
     if (total) {
-        LM_CUDA_TRY(cudaMemcpyAsync(records.data(), drec, records.size() * sizeof(long long), cudaMemcpyDeviceToHost, s));
+        // page-locked staging buffer, cached across calls (records are read by the host linker)
+        static long long* h_stage = nullptr;
+        static size_t h_cap = 0;
+        const size_t need = static_cast<size_t>(total) * REC_WORDS * sizeof(long long);
+        if (need > h_cap) {
+            if (h_stage) cudaFreeHost(h_stage);
+            h_stage = nullptr; h_cap = 0;
+            const size_t want = need + need / 4;
+            if (cudaHostAlloc(reinterpret_cast<void**>(&h_stage), want, cudaHostAllocDefault) != cudaSuccess) {
+                cudaGetLastError();
+                return lm::fail(LM_E_NOMEM, "lm_contour: cudaHostAlloc(%zu) failed", want);
+            }
+            h_cap = want;
+        }
+        LM_CUDA_TRY(cudaMemcpyAsync(h_stage, drec, need, cudaMemcpyDeviceToHost, s));
         LM_CUDA_TRY(cudaStreamSynchronize(s));
+        *records_out = h_stage;
+        *n_out = static_cast<long long>(total);
     }
     return LM_OK;
 }
@@ -341,8 +417,22 @@ struct Linker {
         const unsigned long long w = static_cast<unsigned long long>(rec[k * REC_WORDS + 1 + dj]);
         return static_cast<int>(di ? (w >> 32) : (w & 0xffffffffu));
     }
-    long long find(long long q) const {
-        long long lo = 0, hi = n;
+    std::vector<long long> row_start;          // row_start[j] = first record of row >= j (size ny + 1)
+    void build_row_index() {
+        row_start.assign(static_cast<size_t>(ny) + 1, n);
+        long long k = 0;
+        for (long long j = 0; j <= ny; ++j) {
+            while (k < n && quad(k) / nx < j) ++k;
+            row_start[static_cast<size_t>(j)] = k;
+        }
+    }
+    // record index of quad q, searching only inside its row; `hint` is the record we come from
+    long long find(long long q, long long hint) const {
+        if (hint + 1 < n && quad(hint + 1) == q) return hint + 1;     // east neighbour
+        if (hint > 0 && quad(hint - 1) == q) return hint - 1;         // west neighbour
+        const long long j = q / nx;
+        if (j < 0 || j >= ny) return -1;
+        long long lo = row_start[static_cast<size_t>(j)], hi = row_start[static_cast<size_t>(j) + 1];
         while (lo < hi) {
             const long long mid = (lo + hi) >> 1;
             if (quad(mid) < q) lo = mid + 1; else hi = mid;
@@ -385,13 +475,28 @@ struct Linker {
             default: return EDGE_NONE;
         }
     }
+    // record index of quad q in row j, coming from record `hint`
+    long long find_in_row(long long q, long long j, long long hint) const {
+        if (hint + 1 < n && quad(hint + 1) == q) return hint + 1;     // east neighbour
+        if (hint > 0 && quad(hint - 1) == q) return hint - 1;         // west neighbour
+        if (j < 0 || j >= ny) return -1;
+        long long lo = row_start[static_cast<size_t>(j)], hi = row_start[static_cast<size_t>(j) + 1];
+        while (lo < hi) {
+            const long long mid = (lo + hi) >> 1;
+            if (quad(mid) < q) lo = mid + 1; else hi = mid;
+        }
+        return (lo < n && quad(lo) == q) ? lo : -1;
+    }
     // returns false on an inconsistent record set (missing neighbour)
     bool follow(long long k, int edge, bool want_initial, bool closed) {
         const long long k0 = k; const int e0 = edge;
         if (want_initial) push_edge_vertex(k, edge);
+        long long q = quad(k);
+        long long j = q / nx, i = q - j * nx;           // tracked incrementally along the line
         for (;;) {
             const unsigned m = meta(k);
-            if (is_saddle(k)) {
+            const unsigned cfg = m & 15u;
+            if (cfg == 6u || cfg == 9u) {
                 if (flags[k] & 2) flags[k] |= 1;
                 else { flags[k] |= 2; if (edge == EDGE_N || edge == EDGE_E) flags[k] |= 4; }
             } else {
@@ -403,27 +508,27 @@ struct Linker {
                 if (static_cast<int>((m >> (8 + 4 * s)) & 3u) == edge) seg = s;
             if (seg < 0) return false;
             const int ex = static_cast<int>((m >> (10 + 4 * seg)) & 3u);
-            double vx, vy;
-            memcpy(&vx, &rec[k * REC_WORDS + 4 + 2 * seg], sizeof(double));
-            memcpy(&vy, &rec[k * REC_WORDS + 5 + 2 * seg], sizeof(double));
-            verts.push_back(vx);
-            verts.push_back(vy);
-            const long long q = quad(k);
-            if (is_boundary(q, ex)) return true;
-            long long qn; int en;
+            double v[2];
+            memcpy(v, &rec[k * REC_WORDS + 4 + 2 * seg], sizeof(v));
+            verts.push_back(v[0]);
+            verts.push_back(v[1]);
+            int en;
             switch (ex) {
-                case EDGE_E: qn = q + 1;  en = EDGE_W; break;
-                case EDGE_N: qn = q + nx; en = EDGE_S; break;
-                case EDGE_W: qn = q - 1;  en = EDGE_E; break;
-                default:     qn = q - nx; en = EDGE_N; break;
+                case EDGE_E: if (i == nx - 2) return true; q += 1;  ++i; en = EDGE_W; break;
+                case EDGE_N: if (j == ny - 2) return true; q += nx; ++j; en = EDGE_S; break;
+                case EDGE_W: if (i == 0) return true;      q -= 1;  --i; en = EDGE_E; break;
+                default:     if (j == 0) return true;      q -= nx; --j; en = EDGE_N; break;
             }
-            const long long kn = find(qn);
+            const long long kn = find_in_row(q, j, k);
             if (kn < 0) return false;
             k = kn; edge = en;
             if (closed && k == k0 && edge == e0) return true;
         }
     }
     bool run() {
+        for (long long k = 1; k < n; ++k)
+            if (quad(k) <= quad(k - 1)) return false;       // records must be in raster order
+        build_row_index();
         flags.assign(static_cast<size_t>(n), 0);
         verts.clear(); offsets.clear();
         // lines that start and end on the boundary (edges tested S, W, N, E)
@@ -467,8 +572,8 @@ int32_t link_and_export(const long long* records, long long n_records, const dou
                         const double* ys, long long ny, double level,
                         double* verts, long long cap_verts, long long* n_verts,
                         long long* line_offsets, long long cap_lines, long long* n_lines) {
-    Linker L{records, n_records, xs, ys, nx, ny, level, {}, {}, {}};
-    if (!L.run()) return lm::fail(LM_E_INVALID, "lm_contour_link: inconsistent crossing records (missing neighbour quad)");
+    Linker L{records, n_records, xs, ys, nx, ny, level, {}, {}, {}, {}};
+    if (!L.run()) return lm::fail(LM_E_INVALID, "lm_contour_link: inconsistent crossing records (not in raster order, or a neighbour quad is missing)");
     const long long nv = static_cast<long long>(L.verts.size() / 2);
     const long long nl = static_cast<long long>(L.offsets.size()) - 1;
     *n_verts = nv;
@@ -494,6 +599,22 @@ int32_t check_contour_args(const char* who, const void* dwell, const void* xs, i
 
 }  // namespace
 
+namespace lm {
+int32_t contour_device_to_host(const int32_t* dwell_dev, const double* xs_host, int64_t nx, const double* ys_host,
+                               int64_t ny, double level, double* verts, int64_t cap_verts, int64_t* n_verts,
+                               int64_t* line_offsets, int64_t cap_lines, int64_t* n_lines,
+                               float* kernel_ms, int* launches, cudaStream_t s) {
+    const long long* recs = nullptr;
+    long long nrec = 0;
+    int32_t rc = classify_device(dwell_dev, xs_host, nx, ys_host, ny, 0, level, &recs, &nrec, kernel_ms, s);
+    if (rc != LM_OK) return rc;
+    if (launches) *launches = nrec ? 3 : 2;
+    return link_and_export(recs, nrec, xs_host, nx, ys_host, ny, level, verts, cap_verts,
+                           reinterpret_cast<long long*>(n_verts), reinterpret_cast<long long*>(line_offsets), cap_lines,
+                           reinterpret_cast<long long*>(n_lines));
+}
+}  // namespace lm
+
 extern "C" {
 
 int32_t lm_contour_classify_dev(const int32_t* dwell_dev, const double* xs_host, int64_t nx,
@@ -503,16 +624,16 @@ int32_t lm_contour_classify_dev(const int32_t* dwell_dev, const double* xs_host,
     if (rc != LM_OK) return rc;
     LM_REQUIRE(dwell_dev && xs_host && ys_host && n_records, "lm_contour_classify_dev: NULL argument");
     LM_REQUIRE(nx >= 0 && ny >= 0 && cap_records >= 0, "lm_contour_classify_dev: negative size");
-    std::vector<long long> recs;
-    rc = classify_device(dwell_dev, xs_host, nx, ys_host, ny, row_offset, level, recs, nullptr, lm::as_stream(stream));
+    const long long* recs = nullptr;
+    long long n = 0;
+    rc = classify_device(dwell_dev, xs_host, nx, ys_host, ny, row_offset, level, &recs, &n, nullptr, lm::as_stream(stream));
     if (rc != LM_OK) return rc;
-    const long long n = static_cast<long long>(recs.size() / REC_WORDS);
     *n_records = n;
     if (n > cap_records)
         return lm::fail(LM_E_CAP, "lm_contour_classify_dev: need room for %lld records (got %lld)", n,
                         static_cast<long long>(cap_records));
     LM_REQUIRE(records || n == 0, "lm_contour_classify_dev: records is NULL");
-    if (n) memcpy(records, recs.data(), recs.size() * sizeof(long long));
+    if (n) memcpy(records, recs, static_cast<size_t>(n) * REC_WORDS * sizeof(long long));
     return LM_OK;
 }
 
@@ -539,19 +660,17 @@ int32_t lm_contour_level_dev(const int32_t* dwell_dev, const double* xs_host, in
                             line_offsets, cap_lines, n_lines);
     if (rc != LM_OK) return rc;
     if (stats) *stats = lm_stats{};
-    std::vector<long long> recs;
     float ms = 0.f;
-    rc = classify_device(dwell_dev, xs_host, nx, ys_host, ny, 0, level, recs, &ms, nullptr);
-    if (rc != LM_OK) return rc;
+    int launches = 0;
+    rc = lm::contour_device_to_host(dwell_dev, xs_host, nx, ys_host, ny, level, verts, cap_verts, n_verts, line_offsets,
+                                    cap_lines, n_lines, &ms, &launches, nullptr);
     if (stats) {
         stats->items = static_cast<uint64_t>(nx) * static_cast<uint64_t>(ny);
         stats->work_units = stats->items * 4;           // algorithmic bytes: one int32 read per pixel
         stats->kernel_ms = ms;
-        stats->launches = recs.empty() ? 2 : 3;
+        stats->launches = launches;
     }
-    return link_and_export(recs.data(), static_cast<long long>(recs.size() / REC_WORDS), xs_host, nx, ys_host, ny, level,
-                           verts, cap_verts, reinterpret_cast<long long*>(n_verts),
-                           reinterpret_cast<long long*>(line_offsets), cap_lines, reinterpret_cast<long long*>(n_lines));
+    return rc;
 }
 
 int32_t lm_contour_level(const int32_t* dwell, const double* xs, int64_t nx, const double* ys, int64_t ny,

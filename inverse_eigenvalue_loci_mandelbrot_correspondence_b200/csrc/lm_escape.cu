@@ -460,12 +460,8 @@ int32_t check_grid_args(const char* who, const void* xs, int64_t nx, const void*
     return LM_OK;
 }
 
-}  // namespace
-
-extern "C" {
-
 // enqueue one K1 launch over rows [0, ny) of a grid whose outputs start at the given pointers
-static int32_t enqueue_grid(const double* xs, int64_t nx, const double* ys, int64_t ny,
+int32_t enqueue_grid(const double* xs, int64_t nx, const double* ys, int64_t ny,
                             int32_t max_iter, double bailout, int32_t field_mode,
                             int32_t* dwell_i32, double* dwell_f64, double* field,
                             unsigned long long* work_dev, int* overflow_dev, cudaStream_t s) {
@@ -489,6 +485,130 @@ static int32_t enqueue_grid(const double* xs, int64_t nx, const double* ys, int6
     return launch_escape(false, field_mode, A, s);
 }
 
+}  // namespace
+
+namespace lm {
+
+void GridHostJob::release_events() {
+    if (ev_begin) cudaEventDestroy(ev_begin);
+    if (ev_end) cudaEventDestroy(ev_end);
+    for (cudaEvent_t e : ev_chunk) if (e) cudaEventDestroy(e);
+    ev_begin = ev_end = nullptr;
+    ev_chunk.clear();
+}
+
+#define LM_JOB_TRY(expr)                                                                       \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            job->release_events();                                                             \
+            cudaDeviceSynchronize();                                                           \
+            return lm::fail(LM_E_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+        }                                                                                      \
+    } while (0)
+
+// Host-buffer K1.  Large outputs are produced in row chunks on one stream while a second
+// stream copies finished chunks back, so the PCIe transfer hides behind the FP64 work.
+int32_t grid_host_begin(const double* xs, int64_t nx, const double* ys, int64_t ny, int32_t max_iter, double bailout,
+                        int32_t field_mode, int32_t* dwell_i32, double* dwell_f64, double* field,
+                        bool need_dev_dwell, GridHostJob* job) {
+    int32_t rc;
+    const size_t npx = static_cast<size_t>(nx) * static_cast<size_t>(ny);
+    job->npx = npx;
+    static cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    static int s_dev = -1;
+    int dev = 0;
+    LM_CUDA_TRY(cudaGetDevice(&dev));
+    if (s_dev != dev) {      // (re)create the two pipeline streams on the current device
+        if (s_compute) { cudaStreamDestroy(s_compute); cudaStreamDestroy(s_copy); }
+        LM_CUDA_TRY(cudaStreamCreateWithFlags(&s_compute, cudaStreamNonBlocking));
+        LM_CUDA_TRY(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
+        s_dev = dev;
+    }
+    job->s_compute = s_compute;
+    job->s_copy = s_copy;
+    LM_CUDA_TRY(cudaDeviceSynchronize());   // earlier default-stream work may still use the workspaces
+
+    const bool want_i32 = dwell_i32 != nullptr || need_dev_dwell;
+    void *dxs, *dys, *dd = nullptr, *df64 = nullptr, *dfield = nullptr, *dwork;
+    if ((rc = ws_get(WS_XS, nx * sizeof(double), &dxs)) != LM_OK) return rc;
+    if ((rc = ws_get(WS_YS, ny * sizeof(double), &dys)) != LM_OK) return rc;
+    if ((rc = ws_get(WS_K1_WORK, 64, &dwork)) != LM_OK) return rc;
+    if (want_i32 && (rc = ws_get(WS_OUT_I32, npx * sizeof(int32_t), &dd)) != LM_OK) return rc;
+    if (dwell_f64 && (rc = ws_get(WS_OUT_F64, npx * sizeof(double), &df64)) != LM_OK) return rc;
+    if (field_mode != LM_FIELD_NONE && (rc = ws_get(WS_FIELD, npx * sizeof(double), &dfield)) != LM_OK) return rc;
+    job->dwork = dwork;
+    job->dwell_dev = static_cast<int32_t*>(dd);
+    LM_CUDA_TRY(cudaMemcpyAsync(dxs, xs, nx * sizeof(double), cudaMemcpyHostToDevice, s_compute));
+    LM_CUDA_TRY(cudaMemcpyAsync(dys, ys, ny * sizeof(double), cudaMemcpyHostToDevice, s_compute));
+    LM_CUDA_TRY(cudaMemsetAsync(dwork, 0, 64, s_compute));
+    unsigned long long* work_dev = static_cast<unsigned long long*>(dwork);
+    int* overflow_dev = reinterpret_cast<int*>(work_dev + 1);
+
+    const size_t bytes_per_row = static_cast<size_t>(nx) * ((dwell_i32 ? 4 : 0) + (dwell_f64 ? 8 : 0) + (dfield ? 8 : 0));
+    const size_t total_bytes = bytes_per_row * static_cast<size_t>(ny);
+    int64_t nchunks = static_cast<int64_t>((total_bytes + (size_t(256) << 20) - 1) / (size_t(256) << 20));
+    if (nchunks < 1) nchunks = 1;
+    if (nchunks > 32) nchunks = 32;
+    if (nchunks > ny) nchunks = ny;
+    const int64_t rows_per_chunk = (ny + nchunks - 1) / nchunks;
+    job->ev_chunk.assign(static_cast<size_t>(nchunks), nullptr);
+
+    LM_JOB_TRY(cudaEventCreate(&job->ev_begin));
+    LM_JOB_TRY(cudaEventCreate(&job->ev_end));
+    LM_JOB_TRY(cudaEventRecord(job->ev_begin, s_compute));
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int64_t r0 = c * rows_per_chunk;
+        const int64_t rows = (r0 + rows_per_chunk <= ny) ? rows_per_chunk : ny - r0;
+        if (rows <= 0) break;
+        const size_t off = static_cast<size_t>(r0) * nx;
+        rc = enqueue_grid(static_cast<double*>(dxs), nx, static_cast<double*>(dys) + r0, rows, max_iter, bailout, field_mode,
+                          dd ? static_cast<int32_t*>(dd) + off : nullptr, df64 ? static_cast<double*>(df64) + off : nullptr,
+                          dfield ? static_cast<double*>(dfield) + off : nullptr, work_dev, overflow_dev, s_compute);
+        if (rc != LM_OK) { job->release_events(); cudaDeviceSynchronize(); return rc; }
+        ++job->launches;
+        LM_JOB_TRY(cudaEventCreateWithFlags(&job->ev_chunk[c], cudaEventDisableTiming));
+        LM_JOB_TRY(cudaEventRecord(job->ev_chunk[c], s_compute));
+    }
+    LM_JOB_TRY(cudaEventRecord(job->ev_end, s_compute));
+    for (int64_t c = 0; c < nchunks; ++c) {
+        if (!job->ev_chunk[c]) break;
+        const int64_t r0 = c * rows_per_chunk;
+        const int64_t rows = (r0 + rows_per_chunk <= ny) ? rows_per_chunk : ny - r0;
+        const size_t off = static_cast<size_t>(r0) * nx, cnt = static_cast<size_t>(rows) * nx;
+        LM_JOB_TRY(cudaStreamWaitEvent(s_copy, job->ev_chunk[c], 0));
+        if (dwell_i32) LM_JOB_TRY(cudaMemcpyAsync(dwell_i32 + off, static_cast<int32_t*>(dd) + off, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, s_copy));
+        if (dwell_f64) LM_JOB_TRY(cudaMemcpyAsync(dwell_f64 + off, static_cast<double*>(df64) + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, s_copy));
+        if (dfield) LM_JOB_TRY(cudaMemcpyAsync(field + off, static_cast<double*>(dfield) + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, s_copy));
+    }
+    return LM_OK;
+}
+
+int32_t grid_host_finish(GridHostJob* job, lm_stats* stats) {
+    unsigned long long host_counters[2] = {0, 0};
+    LM_JOB_TRY(cudaMemcpyAsync(host_counters, job->dwork, sizeof(host_counters), cudaMemcpyDeviceToHost, job->s_compute));
+    LM_JOB_TRY(cudaStreamSynchronize(job->s_compute));
+    LM_JOB_TRY(cudaStreamSynchronize(job->s_copy));
+    float ms = 0.f;
+    LM_JOB_TRY(cudaEventElapsedTime(&ms, job->ev_begin, job->ev_end));
+    job->release_events();
+    if (stats) {
+        stats->work_units = host_counters[0];
+        stats->items = job->npx;
+        stats->kernel_ms = ms;
+        stats->launches = job->launches;
+    }
+    if (static_cast<int>(host_counters[1] & 0xffffffffu))
+        return lm::fail(LM_E_OVERFLOW,
+                        "lm_escape_grid_f64: 2**k with k > 1023 (the reference raises OverflowError here)");
+    return LM_OK;
+}
+#undef LM_JOB_TRY
+
+}  // namespace lm
+
+extern "C" {
+
 int32_t lm_escape_grid_f64_dev(const double* xs, int64_t nx, const double* ys, int64_t ny,
                                int32_t max_iter, double bailout, int32_t field_mode,
                                int32_t* dwell_i32, double* dwell_f64, double* field,
@@ -508,8 +628,6 @@ int32_t lm_escape_grid_f64_dev(const double* xs, int64_t nx, const double* ys, i
                         reinterpret_cast<unsigned long long*>(work_units_dev), nullptr, s);
 }
 
-// Host entry point.  Large outputs are produced in row chunks on one stream while a second
-// stream copies finished chunks back, so the PCIe transfer hides behind the FP64 work.
 int32_t lm_escape_grid_f64(const double* xs, int64_t nx, const double* ys, int64_t ny,
                            int32_t max_iter, double bailout, int32_t field_mode,
                            int32_t* dwell_i32, double* dwell_f64, double* field,
@@ -524,103 +642,10 @@ int32_t lm_escape_grid_f64(const double* xs, int64_t nx, const double* ys, int64
                "lm_escape_grid_f64: field_mode %d needs a field buffer", field_mode);
     if (stats) *stats = lm_stats{};
     if (nx == 0 || ny == 0) return LM_OK;
-    const size_t npx = static_cast<size_t>(nx) * static_cast<size_t>(ny);
-
-    static cudaStream_t s_compute = nullptr, s_copy = nullptr;
-    static int s_dev = -1;
-    int dev = 0;
-    LM_CUDA_TRY(cudaGetDevice(&dev));
-    if (s_dev != dev) {      // (re)create the two pipeline streams on the current device
-        if (s_compute) { cudaStreamDestroy(s_compute); cudaStreamDestroy(s_copy); }
-        LM_CUDA_TRY(cudaStreamCreateWithFlags(&s_compute, cudaStreamNonBlocking));
-        LM_CUDA_TRY(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
-        s_dev = dev;
-    }
-    LM_CUDA_TRY(cudaDeviceSynchronize());   // earlier default-stream work may still use the workspaces
-
-    void *dxs, *dys, *dd = nullptr, *df64 = nullptr, *dfield = nullptr, *dwork;
-    if ((rc = lm::ws_get(lm::WS_XS, nx * sizeof(double), &dxs)) != LM_OK) return rc;
-    if ((rc = lm::ws_get(lm::WS_YS, ny * sizeof(double), &dys)) != LM_OK) return rc;
-    if ((rc = lm::ws_get(lm::WS_SCRATCH, 64, &dwork)) != LM_OK) return rc;
-    if (dwell_i32 && (rc = lm::ws_get(lm::WS_OUT_I32, npx * sizeof(int32_t), &dd)) != LM_OK) return rc;
-    if (dwell_f64 && (rc = lm::ws_get(lm::WS_OUT_F64, npx * sizeof(double), &df64)) != LM_OK) return rc;
-    if (field_mode != LM_FIELD_NONE && (rc = lm::ws_get(lm::WS_FIELD, npx * sizeof(double), &dfield)) != LM_OK) return rc;
-    LM_CUDA_TRY(cudaMemcpyAsync(dxs, xs, nx * sizeof(double), cudaMemcpyHostToDevice, s_compute));
-    LM_CUDA_TRY(cudaMemcpyAsync(dys, ys, ny * sizeof(double), cudaMemcpyHostToDevice, s_compute));
-    LM_CUDA_TRY(cudaMemsetAsync(dwork, 0, 64, s_compute));
-    unsigned long long* work_dev = static_cast<unsigned long long*>(dwork);
-    int* overflow_dev = reinterpret_cast<int*>(work_dev + 1);
-
-    const size_t bytes_per_row = static_cast<size_t>(nx) * ((dwell_i32 ? 4 : 0) + (dwell_f64 ? 8 : 0) + (dfield ? 8 : 0));
-    const size_t total_bytes = bytes_per_row * static_cast<size_t>(ny);
-    int64_t nchunks = static_cast<int64_t>((total_bytes + (size_t(256) << 20) - 1) / (size_t(256) << 20));
-    if (nchunks < 1) nchunks = 1;
-    if (nchunks > 32) nchunks = 32;
-    if (nchunks > ny) nchunks = ny;
-    const int64_t rows_per_chunk = (ny + nchunks - 1) / nchunks;
-
-    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-    std::vector<cudaEvent_t> ev_chunk(static_cast<size_t>(nchunks), nullptr);
-    auto cleanup = [&]() {
-        if (ev_begin) cudaEventDestroy(ev_begin);
-        if (ev_end) cudaEventDestroy(ev_end);
-        for (cudaEvent_t e : ev_chunk) if (e) cudaEventDestroy(e);
-    };
-#define LM_TRY_CLEAN(expr)                                                                     \
-    do {                                                                                       \
-        cudaError_t e__ = (expr);                                                              \
-        if (e__ != cudaSuccess) {                                                              \
-            cleanup();                                                                         \
-            cudaDeviceSynchronize();                                                           \
-            return lm::fail(LM_E_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
-        }                                                                                      \
-    } while (0)
-    LM_TRY_CLEAN(cudaEventCreate(&ev_begin));
-    LM_TRY_CLEAN(cudaEventCreate(&ev_end));
-    LM_TRY_CLEAN(cudaEventRecord(ev_begin, s_compute));
-    int launches = 0;
-    for (int64_t c = 0; c < nchunks; ++c) {
-        const int64_t r0 = c * rows_per_chunk;
-        const int64_t rows = (r0 + rows_per_chunk <= ny) ? rows_per_chunk : ny - r0;
-        if (rows <= 0) break;
-        const size_t off = static_cast<size_t>(r0) * nx;
-        rc = enqueue_grid(static_cast<double*>(dxs), nx, static_cast<double*>(dys) + r0, rows, max_iter, bailout, field_mode,
-                          dd ? static_cast<int32_t*>(dd) + off : nullptr, df64 ? static_cast<double*>(df64) + off : nullptr,
-                          dfield ? static_cast<double*>(dfield) + off : nullptr, work_dev, overflow_dev, s_compute);
-        if (rc != LM_OK) { cleanup(); cudaDeviceSynchronize(); return rc; }
-        ++launches;
-        LM_TRY_CLEAN(cudaEventCreateWithFlags(&ev_chunk[c], cudaEventDisableTiming));
-        LM_TRY_CLEAN(cudaEventRecord(ev_chunk[c], s_compute));
-    }
-    LM_TRY_CLEAN(cudaEventRecord(ev_end, s_compute));
-    for (int64_t c = 0; c < nchunks; ++c) {
-        if (!ev_chunk[c]) break;
-        const int64_t r0 = c * rows_per_chunk;
-        const int64_t rows = (r0 + rows_per_chunk <= ny) ? rows_per_chunk : ny - r0;
-        const size_t off = static_cast<size_t>(r0) * nx, cnt = static_cast<size_t>(rows) * nx;
-        LM_TRY_CLEAN(cudaStreamWaitEvent(s_copy, ev_chunk[c], 0));
-        if (dwell_i32) LM_TRY_CLEAN(cudaMemcpyAsync(dwell_i32 + off, static_cast<int32_t*>(dd) + off, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, s_copy));
-        if (dwell_f64) LM_TRY_CLEAN(cudaMemcpyAsync(dwell_f64 + off, static_cast<double*>(df64) + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, s_copy));
-        if (dfield) LM_TRY_CLEAN(cudaMemcpyAsync(field + off, static_cast<double*>(dfield) + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, s_copy));
-    }
-    unsigned long long host_counters[2] = {0, 0};
-    LM_TRY_CLEAN(cudaMemcpyAsync(host_counters, dwork, sizeof(host_counters), cudaMemcpyDeviceToHost, s_compute));
-    LM_TRY_CLEAN(cudaStreamSynchronize(s_compute));
-    LM_TRY_CLEAN(cudaStreamSynchronize(s_copy));
-    float ms = 0.f;
-    LM_TRY_CLEAN(cudaEventElapsedTime(&ms, ev_begin, ev_end));
-#undef LM_TRY_CLEAN
-    cleanup();
-    if (stats) {
-        stats->work_units = host_counters[0];
-        stats->items = npx;
-        stats->kernel_ms = ms;
-        stats->launches = launches;
-    }
-    if (static_cast<int>(host_counters[1] & 0xffffffffu))
-        return lm::fail(LM_E_OVERFLOW,
-                        "lm_escape_grid_f64: 2**k with k > 1023 (the reference raises OverflowError here)");
-    return LM_OK;
+    lm::GridHostJob job;
+    rc = lm::grid_host_begin(xs, nx, ys, ny, max_iter, bailout, field_mode, dwell_i32, dwell_f64, field, false, &job);
+    if (rc != LM_OK) return rc;
+    return lm::grid_host_finish(&job, stats);
 }
 
 int32_t lm_escape_points_f64(const double* c_re, const double* c_im, int64_t n,

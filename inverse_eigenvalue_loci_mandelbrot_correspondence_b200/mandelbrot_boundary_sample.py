@@ -20,7 +20,6 @@ import os
 import numpy as np
 
 from . import contour as _contour
-from . import device as _device
 from .contour import extract_contour  # noqa: F401  (reference-compatible name)
 from .escape import compute_grid, mandelbrot_dwell  # noqa: F401
 
@@ -31,9 +30,7 @@ def boundary_from_window(xlim, ylim, res: int, max_iter: int, level_frac: float)
     """compute_grid + extract_contour with the dwell grid kept resident on the device."""
     xs = np.linspace(xlim[0], xlim[1], res)
     ys = np.linspace(ylim[0], ylim[1], res)
-    with _device.DeviceGrid(xs, ys) as grid:
-        grid.escape(max_iter)
-        lines = grid.contour(level_frac * max_iter)
+    lines, _ = _contour.boundary_sample(xs, ys, max_iter, level_frac * max_iter)
     return xs, ys, _contour.longest(lines)
 
 

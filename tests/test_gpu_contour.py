@@ -91,3 +91,26 @@ def test_script_cli_outputs(gpu, oracle, tmp_path):
     with pytest.raises(SystemExit) as e:
         mbs.main(["--xlim", "2.5", "3.0", "--ylim", "2.5", "3.0", "--res", "64", "--max_iter", "50", "--output_prefix", prefix])
     assert "Failed to extract a usable contour" in str(e.value)
+
+
+def test_fused_boundary_sample(gpu, oracle):
+    """lm_boundary_sample == compute_grid followed by extract_contour, dwell optionally returned."""
+    xs = np.linspace(-2.1, 0.9, 700); ys = np.linspace(-1.5, 1.5, 500)
+    d_ref, work = oracle.dwell_grid(xs, ys, 400)
+    want = oracle.contour_lines(xs, ys, d_ref.astype(float), 384.0)
+    lines, st = gpu.contour.boundary_sample(xs, ys, 400, 384.0)
+    assert lines_equal(want, lines) and st["work_units"] == work
+    for dt in (np.int32, np.float64):
+        out = np.full((500, 700), -7, dtype=dt)
+        lines, _ = gpu.contour.boundary_sample(xs, ys, 400, 384.0, dwell_out=out)
+        assert lines_equal(want, lines) and np.array_equal(out, d_ref)
+    # large enough for several row chunks (> 256 MB of output): pinned int32 output, checked by symmetry + strip
+    res = 9000
+    xs = np.linspace(-2.1, 0.9, res); ys = np.linspace(-1.5, 1.5, res)
+    out = gpu.shim.pinned_empty((res, res), np.int32)
+    lines, st = gpu.contour.boundary_sample(xs, ys, 200, 192.0, dwell_out=out)
+    strip, _, _ = gpu.escape.escape_grid(xs, ys[4500:4508], 200)
+    assert np.array_equal(out[4500:4508], strip)
+    assert st["work_units"] == int(np.minimum(out.astype(np.int64) + 1, 200).sum())
+    best = gpu.contour.longest(lines)
+    assert np.array_equal(best[0], best[-1]) and len(best) > 20000
