@@ -185,6 +185,11 @@ int32_t lm_contour_level_dev(const int32_t* dwell_dev, const double* xs_host, in
                              int64_t* line_offsets, int64_t cap_lines, int64_t* n_lines,
                              lm_stats* stats);
 
+/* After lm_contour_level[_dev] / lm_boundary_sample / lm_contour_link returned LM_E_CAP the
+ * linked polylines are kept by the library; this copies them out (nothing is recomputed).   */
+int32_t lm_contour_fetch_last(double* verts, int64_t cap_verts, int64_t* n_verts,
+                              int64_t* line_offsets, int64_t cap_lines, int64_t* n_lines);
+
 /*
  * The fused boundary stage of the reference script's main()
  * (xs, ys, Z = compute_grid(...); contour = extract_contour(xs, ys, Z, max_iter, level),

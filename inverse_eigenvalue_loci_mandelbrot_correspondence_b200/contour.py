@@ -38,22 +38,23 @@ def _split(verts: np.ndarray, offs: np.ndarray, nv: int, nl: int):
 
 
 def _call_with_growing_buffers(fn_name: str, head_args: tuple, level: float, n_pixels: int, tail_args: tuple = ()):
-    cap_v = max(1024, int(0.02 * n_pixels) + 1024)
-    cap_l = 4096
+    cap_v = max(4096, min(int(0.002 * n_pixels), 1 << 22))
+    cap_l = max(1024, cap_v // 16)
     st = Stats()
-    while True:
-        verts = np.empty((cap_v, 2), dtype=np.float64)
-        offs = np.empty(cap_l + 1, dtype=np.int64)
-        nv = C.c_int64(0); nl = C.c_int64(0)
-        lib = _shim.load()
-        with _shim._lock:
-            rc = getattr(lib, fn_name)(*head_args, float(level), *tail_args, _shim.ptr(verts), cap_v, C.byref(nv),
-                                       _shim.ptr(offs), cap_l, C.byref(nl), C.byref(st))
+    verts = np.empty((cap_v, 2), dtype=np.float64)
+    offs = np.empty(cap_l + 1, dtype=np.int64)
+    nv = C.c_int64(0); nl = C.c_int64(0)
+    lib = _shim.load()
+    with _shim._lock:
+        rc = getattr(lib, fn_name)(*head_args, float(level), *tail_args, _shim.ptr(verts), cap_v, C.byref(nv),
+                                   _shim.ptr(offs), cap_l, C.byref(nl), C.byref(st))
         if rc == _shim.LM_E_CAP:
-            cap_v = max(cap_v, nv.value + 16); cap_l = max(cap_l, nl.value + 16)
-            continue
-        _shim.check(rc)
-        break
+            # the library kept the linked result: fetch it into buffers of the reported size
+            cap_v, cap_l = nv.value + 1, nl.value + 1
+            verts = np.empty((cap_v, 2), dtype=np.float64)
+            offs = np.empty(cap_l + 1, dtype=np.int64)
+            rc = lib.lm_contour_fetch_last(_shim.ptr(verts), cap_v, C.byref(nv), _shim.ptr(offs), cap_l, C.byref(nl))
+    _shim.check(rc)
     global last_stats
     last_stats = st.as_dict()
     return _split(verts, offs, nv.value, nl.value)

@@ -568,19 +568,27 @@ struct Linker {
     }
 };
 
+// result of the most recent linking pass that did not fit the caller's buffers (lm_contour_fetch_last)
+std::vector<double> g_pending_verts;
+std::vector<long long> g_pending_offsets;
+
 int32_t link_and_export(const long long* records, long long n_records, const double* xs, long long nx,
                         const double* ys, long long ny, double level,
                         double* verts, long long cap_verts, long long* n_verts,
                         long long* line_offsets, long long cap_lines, long long* n_lines) {
     Linker L{records, n_records, xs, ys, nx, ny, level, {}, {}, {}, {}};
-    if (!L.run()) return lm::fail(LM_E_INVALID, "lm_contour_link: inconsistent crossing records (not in raster order, or a neighbour quad is missing)");
+    if (!L.run())
+        return lm::fail(LM_E_INVALID, "lm_contour_link: inconsistent crossing records (not in raster order, or a neighbour quad is missing)");
     const long long nv = static_cast<long long>(L.verts.size() / 2);
     const long long nl = static_cast<long long>(L.offsets.size()) - 1;
     *n_verts = nv;
     *n_lines = nl;
-    if (nv > cap_verts || nl > cap_lines)
-        return lm::fail(LM_E_CAP, "lm_contour: need room for %lld vertices and %lld lines (got %lld, %lld)",
-                        nv, nl, cap_verts, cap_lines);
+    if (nv > cap_verts || nl > cap_lines) {
+        g_pending_verts.swap(L.verts);          // keep the result: the caller re-fetches it, nothing is recomputed
+        g_pending_offsets.swap(L.offsets);
+        return lm::fail(LM_E_CAP, "lm_contour: need room for %lld vertices and %lld lines (got %lld, %lld); "
+                        "call lm_contour_fetch_last with larger buffers", nv, nl, cap_verts, cap_lines);
+    }
     if (nv) memcpy(verts, L.verts.data(), static_cast<size_t>(nv) * 2 * sizeof(double));
     memcpy(line_offsets, L.offsets.data(), static_cast<size_t>(nl + 1) * sizeof(long long));
     return LM_OK;
@@ -616,6 +624,23 @@ int32_t contour_device_to_host(const int32_t* dwell_dev, const double* xs_host, 
 }  // namespace lm
 
 extern "C" {
+
+int32_t lm_contour_fetch_last(double* verts, int64_t cap_verts, int64_t* n_verts,
+                              int64_t* line_offsets, int64_t cap_lines, int64_t* n_lines) {
+    LM_REQUIRE(n_verts && n_lines && line_offsets, "lm_contour_fetch_last: NULL argument");
+    LM_REQUIRE(!g_pending_offsets.empty(), "lm_contour_fetch_last: no pending result (the last call did not return LM_E_CAP)");
+    const long long nv = static_cast<long long>(g_pending_verts.size() / 2);
+    const long long nl = static_cast<long long>(g_pending_offsets.size()) - 1;
+    *n_verts = nv; *n_lines = nl;
+    if (nv > cap_verts || nl > cap_lines)
+        return lm::fail(LM_E_CAP, "lm_contour_fetch_last: need room for %lld vertices and %lld lines", nv, nl);
+    LM_REQUIRE(verts || nv == 0, "lm_contour_fetch_last: verts is NULL");
+    if (nv) memcpy(verts, g_pending_verts.data(), static_cast<size_t>(nv) * 2 * sizeof(double));
+    memcpy(line_offsets, g_pending_offsets.data(), static_cast<size_t>(nl + 1) * sizeof(long long));
+    std::vector<double>().swap(g_pending_verts);
+    std::vector<long long>().swap(g_pending_offsets);
+    return LM_OK;
+}
 
 int32_t lm_contour_classify_dev(const int32_t* dwell_dev, const double* xs_host, int64_t nx,
                                 const double* ys_host, int64_t ny, int64_t row_offset, double level,

@@ -1,0 +1,105 @@
+"""CPU: the N > 1 host logic with torch.distributed (gloo, world_size 2): work-balanced row cuts,
+first-row all-gather for the K2 halo, record gather + global linking.  The per-rank compute is
+stood in by the oracle (dwell) and the numpy record restatement; the collectives and the linker
+are the product's."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_balanced_row_cuts_properties():
+    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import sharding
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        ny = int(rng.integers(8, 400)); parts = int(rng.integers(1, 9))
+        w = rng.random(ny) ** 8 * 1000 + (rng.random(ny) < 0.3) * 5000
+        cuts = sharding.balanced_row_cuts(w, parts)
+        assert cuts[0] == 0 and cuts[-1] == ny and len(cuts) == parts + 1
+        assert all(b > a for a, b in zip(cuts[:-1], cuts[1:]))
+    with pytest.raises(ValueError):
+        sharding.balanced_row_cuts(np.ones(3), 4)
+    assert sharding.balanced_row_cuts(np.ones(8), 4) == [0, 2, 4, 6, 8]
+
+
+def test_work_balanced_beats_equal_rows(oracle):
+    """equal-rows sharding is ~50 % / ~37 % efficient at 4 / 8 shards, work-balanced >= 95 %."""
+    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import sharding
+    xs = np.linspace(-2.1, 0.9, 256); ys = np.linspace(-1.5, 1.5, 512)
+    d, _ = oracle.dwell_grid(xs, ys, 2000)
+    w = np.minimum(d.astype(np.int64) + 1, 2000).sum(axis=1)
+    for parts, eq_max in ((4, 0.60), (8, 0.45)):
+        equal = [round(k * 512 / parts) for k in range(parts + 1)]
+        cuts = sharding.balanced_row_cuts(w, parts)
+        assert sharding.parallel_efficiency(w, equal) < eq_max
+        assert sharding.parallel_efficiency(w, cuts) > 0.95
+    # a coarse profile (every 8th row) interpolated to all rows still balances well
+    prof = sharding.interpolate_row_profile(np.arange(0, 512, 8), w[::8], 512)
+    assert sharding.parallel_efficiency(w, sharding.balanced_row_cuts(prof, 8)) > 0.9
+
+
+def _free_port() -> int:
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank: int, world: int, port: int, q):
+    try:
+        sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+        import torch
+        import torch.distributed as dist
+        from helpers import lines_equal, records_from_dwell
+        from oracle import oracle
+        from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import contour, sharding
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        xs = np.linspace(-2.1, 0.9, 140); ys = np.linspace(-1.5, 1.5, 120)
+        mi, lvl = 200, 192.0
+        # every rank derives the same cuts from the same (deterministic) coarse profile
+        coarse_rows = np.arange(0, ys.size, 4)
+        dc, _ = oracle.dwell_grid(xs[::2], ys[coarse_rows], mi)
+        prof = sharding.interpolate_row_profile(coarse_rows, np.minimum(dc.astype(np.int64) + 1, mi).sum(axis=1), ys.size)
+        cuts = sharding.balanced_row_cuts(prof, world)
+        r0, r1 = cuts[rank], cuts[rank + 1]
+        mine, _ = oracle.dwell_grid(xs, ys[r0:r1], mi)                       # this rank's K1 rows
+        firsts = sharding.exchange_first_rows(torch.from_numpy(mine[0].copy()))
+        assert firsts.shape == (world, xs.size)
+        has_halo = rank < world - 1
+        block = np.vstack([mine, firsts[rank + 1].numpy()[None, :]]) if has_halo else mine
+        recs = records_from_dwell(block, xs, ys[r0:r1 + (1 if has_halo else 0)], lvl, row_offset=r0, nx_global=xs.size)
+        allrec = sharding.gather_records(recs, torch.device("cpu"), 0)
+        ok = True
+        if rank == 0:
+            full, _ = oracle.dwell_grid(xs, ys, mi)
+            ok = np.array_equal(allrec, records_from_dwell(full, xs, ys, lvl))
+            lines = contour.link_records(allrec, xs, ys, lvl)
+            ok = ok and lines_equal(lines, oracle.contour_lines(xs, ys, full.astype(float), lvl))
+        else:
+            ok = allrec is None
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, bool(ok), ""))
+    except Exception as e:          # pragma: no cover
+        import traceback
+        q.put((rank, False, traceback.format_exc()))
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_boundary_gloo(shim, oracle, world):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok, err in results:
+        assert ok, f"rank {rank}: {err}"
