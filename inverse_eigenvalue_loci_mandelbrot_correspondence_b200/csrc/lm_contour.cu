@@ -105,47 +105,68 @@ __host__ __device__ inline void edge_corners(int edge, int& dj1, int& di1, int& 
 // vector path (nx % 4 == 0, 16-byte aligned grid): lane l loads columns c0+4l .. c0+4l+3 of both
 // rows with one 128-bit load each; the crossing nibble comes from bit-parallel XORs and the
 // four ballot-order mask words from a partitioned warp OR-reduction.
-__global__ void __launch_bounds__(MARK_WARPS * 32) contour_mark_vec_kernel(
+constexpr int MARK_ROWS = 4;               // quad rows per CTA pass in the vector kernel (5 dwell rows in flight)
+
+__global__ void __launch_bounds__(MARK_WARPS * 32, 4) contour_mark_vec_kernel(
     const int* __restrict__ dwell, long long nx, long long ny, int ilevel,
     unsigned* __restrict__ mask, long long words_per_row, unsigned* __restrict__ row_count) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long strips_per_row = words_per_row / 4;
     const long long nq = nx - 1;
-    for (long long j = blockIdx.x; j < ny - 1; j += gridDim.x) {
-        const int* r0 = dwell + j * nx;
-        const int* r1 = r0 + nx;
-        unsigned cnt = 0;
+    const long long ngroups = (ny - 1 + MARK_ROWS - 1) / MARK_ROWS;
+    for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const long long j0 = grp * MARK_ROWS;
+        unsigned cnt[MARK_ROWS];
+#pragma unroll
+        for (int r = 0; r < MARK_ROWS; ++r) cnt[r] = 0u;
         for (long long sidx = warp; sidx < strips_per_row; sidx += MARK_WARPS) {
             const long long c0 = sidx * STRIP;
             const long long c = c0 + 4 * lane;
-            int4 a = make_int4(0, 0, 0, 0), b = make_int4(0, 0, 0, 0);
             const bool in = c < nx;                         // nx % 4 == 0: all four columns are in range together
-            if (in) {
-                a = __ldg(reinterpret_cast<const int4*>(r0 + c));
-                b = __ldg(reinterpret_cast<const int4*>(r1 + c));
+            // above-nibbles of the MARK_ROWS+1 dwell rows this pass needs, all loads issued up front
+            int4 v[MARK_ROWS + 1];
+#pragma unroll
+            for (int r = 0; r <= MARK_ROWS; ++r) {
+                v[r] = make_int4(INT_MIN, INT_MIN, INT_MIN, INT_MIN);
+                if (in && j0 + r < ny) v[r] = __ldg(reinterpret_cast<const int4*>(dwell + (j0 + r) * nx + c));
             }
-            unsigned L = (a.x > ilevel ? 1u : 0u) | (a.y > ilevel ? 2u : 0u) | (a.z > ilevel ? 4u : 0u) | (a.w > ilevel ? 8u : 0u);
-            unsigned H = (b.x > ilevel ? 1u : 0u) | (b.y > ilevel ? 2u : 0u) | (b.z > ilevel ? 4u : 0u) | (b.w > ilevel ? 8u : 0u);
-            if (!in) { L = 0u; H = 0u; }
-            // corner right of my fourth column: first column of lane+1, or the strip's edge column
-            unsigned nxt = __shfl_down_sync(FULL, (L & 1u) | ((H & 1u) << 1), 1);
+            unsigned edge = 0u;                             // bit r: corner right of the strip in row j0+r
             if (lane == 31) {
-                nxt = 0u;
                 const long long ce = c0 + STRIP;
-                if (ce < nx) nxt = (__ldg(r0 + ce) > ilevel ? 1u : 0u) | (__ldg(r1 + ce) > ilevel ? 2u : 0u);
+                if (ce < nx) {
+#pragma unroll
+                    for (int r = 0; r <= MARK_ROWS; ++r)
+                        if (j0 + r < ny && __ldg(dwell + (j0 + r) * nx + ce) > ilevel) edge |= 1u << r;
+                }
             }
-            const unsigned L5 = L | ((nxt & 1u) << 4), H5 = H | ((nxt >> 1) << 4);
-            unsigned cross = ((L5 ^ (L5 >> 1)) | (H5 ^ (H5 >> 1)) | (L5 ^ H5)) & 0xFu;
-            // only quads c .. c+3 with column < nx-1 exist
+            unsigned A[MARK_ROWS + 1];                      // 5 bits: my four columns + the one to their right
+            unsigned first = 0u;
+#pragma unroll
+            for (int r = 0; r <= MARK_ROWS; ++r) {
+                A[r] = (v[r].x > ilevel ? 1u : 0u) | (v[r].y > ilevel ? 2u : 0u) | (v[r].z > ilevel ? 4u : 0u) | (v[r].w > ilevel ? 8u : 0u);
+                first |= (A[r] & 1u) << r;
+            }
+            unsigned nxt = __shfl_down_sync(FULL, first, 1);
+            if (lane == 31) nxt = edge;
+#pragma unroll
+            for (int r = 0; r <= MARK_ROWS; ++r) A[r] |= ((nxt >> r) & 1u) << 4;
             const long long left = nq - c;
-            if (left < 4) cross &= (left <= 0) ? 0u : ((1u << left) - 1u);
-            const unsigned word = __reduce_or_sync(0xFFu << (lane & 24), cross << (4 * (lane & 7)));
-            if ((lane & 7) == 0) {
-                mask[j * words_per_row + c0 / 32 + (lane >> 3)] = word;
-                cnt += __popc(word);
+            const unsigned valid = (left >= 4) ? 0xFu : ((left <= 0) ? 0u : ((1u << left) - 1u));
+#pragma unroll
+            for (int r = 0; r < MARK_ROWS; ++r) {
+                const unsigned L5 = A[r], H5 = A[r + 1];
+                unsigned cross = ((L5 ^ (L5 >> 1)) | (H5 ^ (H5 >> 1)) | (L5 ^ H5)) & valid;
+                if (j0 + r >= ny - 1) cross = 0u;
+                const unsigned word = __reduce_or_sync(0xFFu << (lane & 24), cross << (4 * (lane & 7)));
+                if ((lane & 7) == 0 && j0 + r < ny - 1) {
+                    mask[(j0 + r) * words_per_row + c0 / 32 + (lane >> 3)] = word;
+                    cnt[r] += __popc(word);
+                }
             }
         }
-        if (cnt) atomicAdd(row_count + j, cnt);
+#pragma unroll
+        for (int r = 0; r < MARK_ROWS; ++r)
+            if (cnt[r]) atomicAdd(row_count + j0 + r, cnt[r]);
     }
 }
 
@@ -349,8 +370,10 @@ int32_t classify_device(const int* dwell_dev, const double* xs_host, long long n
     const long long cap = static_cast<long long>(lm::sm_count()) * 64;
     if (blocks > cap) blocks = cap;
     const bool vec = (nx % 4 == 0) && (reinterpret_cast<uintptr_t>(dwell_dev) % 16 == 0);
+    long long vblocks = (nrows + MARK_ROWS - 1) / MARK_ROWS;
+    if (vblocks > cap) vblocks = cap;
     if (vec)
-        contour_mark_vec_kernel<<<static_cast<unsigned>(blocks), MARK_WARPS * 32, 0, s>>>(
+        contour_mark_vec_kernel<<<static_cast<unsigned>(vblocks), MARK_WARPS * 32, 0, s>>>(
             dwell_dev, nx, ny, ilevel, static_cast<unsigned*>(dmask), words_per_row, static_cast<unsigned*>(dcount));
     else
         contour_mark_kernel<<<static_cast<unsigned>(blocks), MARK_WARPS * 32, 0, s>>>(
