@@ -98,122 +98,116 @@ __host__ __device__ inline void edge_corners(int edge, int& dj1, int& di1, int& 
 }
 
 // ------------------------------------------------------------------------------------
-// 1. mark: crossing mask + row counts.  One CTA per quad row j; its warps stride over the
-// 128-column strips of that row.  "z > level" for an integer z is "z > floor(level)", so
-// the classification is pure integer work.
+// 1. mark: crossing mask + row counts.  A CTA takes MARK_ROWS quad rows at a time
+// (MARK_ROWS+1 dwell rows), its warps stride over 128-column strips.  "z > level" for an
+// integer z is "z > floor(level)"; every 32-column chunk of a dwell row becomes one ballot
+// word (coalesced 128-byte loads), and the crossing words follow from warp-uniform bit
+// operations on those words:  quad (r, b) is crossed iff its four corner bits are not equal,
+//   X = (L ^ L') | (H ^ H') | (L ^ H),  L' / H' = the row words shifted by one column
+// (the funnel shift pulls in the first bit of the next chunk / the strip's edge column).
 // ------------------------------------------------------------------------------------
-// vector path (nx % 4 == 0, 16-byte aligned grid): lane l loads columns c0+4l .. c0+4l+3 of both
-// rows with one 128-bit load each; the crossing nibble comes from bit-parallel XORs and the
-// four ballot-order mask words from a partitioned warp OR-reduction.
-constexpr int MARK_ROWS = 4;               // quad rows per CTA pass in the vector kernel (5 dwell rows in flight)
+constexpr int MARK_ROWS = 4;
 
-__global__ void __launch_bounds__(MARK_WARPS * 32, 4) contour_mark_vec_kernel(
-    const int* __restrict__ dwell, long long nx, long long ny, int ilevel,
-    unsigned* __restrict__ mask, long long words_per_row, unsigned* __restrict__ row_count) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long strips_per_row = words_per_row / 4;
-    const long long nq = nx - 1;
-    const long long ngroups = (ny - 1 + MARK_ROWS - 1) / MARK_ROWS;
-    for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
-        const long long j0 = grp * MARK_ROWS;
-        unsigned cnt[MARK_ROWS];
+template <bool SAFE>
+__device__ __forceinline__ void mark_strip(const int* __restrict__ row0, const long long nx, const long long ny,
+                                           const long long j0, const long long c0, const int ilevel, const int lane,
+                                           unsigned* __restrict__ mrow0, const long long words_per_row,
+                                           unsigned (&cnt)[MARK_ROWS]) {
+    unsigned M[MARK_ROWS + 1][4];
+    unsigned E;                                       // bit r: corner right of the strip in dwell row j0 + r
+    const int* p = row0 + c0 + lane;
+    if (SAFE) {
+        int z[MARK_ROWS + 1][4];
 #pragma unroll
-        for (int r = 0; r < MARK_ROWS; ++r) cnt[r] = 0u;
-        for (long long sidx = warp; sidx < strips_per_row; sidx += MARK_WARPS) {
-            const long long c0 = sidx * STRIP;
-            const long long c = c0 + 4 * lane;
-            const bool in = c < nx;                         // nx % 4 == 0: all four columns are in range together
-            // above-nibbles of the MARK_ROWS+1 dwell rows this pass needs, all loads issued up front
-            int4 v[MARK_ROWS + 1];
+        for (int r = 0; r <= MARK_ROWS; ++r)
 #pragma unroll
-            for (int r = 0; r <= MARK_ROWS; ++r) {
-                v[r] = make_int4(INT_MIN, INT_MIN, INT_MIN, INT_MIN);
-                if (in && j0 + r < ny) v[r] = __ldg(reinterpret_cast<const int4*>(dwell + (j0 + r) * nx + c));
+            for (int k = 0; k < 4; ++k) z[r][k] = __ldg(p + r * nx + 32 * k);
+        const int ze = (lane <= MARK_ROWS) ? __ldg(row0 + lane * nx + c0 + STRIP) : INT_MIN;
+#pragma unroll
+        for (int r = 0; r <= MARK_ROWS; ++r)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) M[r][k] = __ballot_sync(FULL, z[r][k] > ilevel);
+        E = __ballot_sync(FULL, ze > ilevel);
+    } else {
+#pragma unroll
+        for (int r = 0; r <= MARK_ROWS; ++r)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool in = (j0 + r < ny) && (c0 + 32 * k + lane < nx);
+                const int z = in ? __ldg(p + r * nx + 32 * k) : INT_MIN;
+                M[r][k] = __ballot_sync(FULL, z > ilevel);
             }
-            unsigned edge = 0u;                             // bit r: corner right of the strip in row j0+r
-            if (lane == 31) {
-                const long long ce = c0 + STRIP;
-                if (ce < nx) {
+        const bool ein = (lane <= MARK_ROWS) && (j0 + lane < ny) && (c0 + STRIP < nx);
+        const int ze = ein ? __ldg(row0 + lane * nx + c0 + STRIP) : INT_MIN;
+        E = __ballot_sync(FULL, ze > ilevel);
+    }
+    // row words shifted by one column
+    unsigned S[MARK_ROWS + 1][4];
 #pragma unroll
-                    for (int r = 0; r <= MARK_ROWS; ++r)
-                        if (j0 + r < ny && __ldg(dwell + (j0 + r) * nx + ce) > ilevel) edge |= 1u << r;
-                }
+    for (int r = 0; r <= MARK_ROWS; ++r) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) S[r][k] = __funnelshift_r(M[r][k], M[r][k + 1], 1);
+        S[r][3] = __funnelshift_r(M[r][3], (E >> r) & 1u, 1);
+    }
+    unsigned* mp = mrow0 + (c0 >> 5);
+#pragma unroll
+    for (int r = 0; r < MARK_ROWS; ++r) {
+        if (!SAFE && j0 + r >= ny - 1) break;
+        uint4 w;
+        unsigned* wp = &w.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            unsigned x = (M[r][k] ^ S[r][k]) | (M[r + 1][k] ^ S[r + 1][k]) | (M[r][k] ^ M[r + 1][k]);
+            if (!SAFE) {
+                // quads exist for columns < nx - 1
+                const long long left = (nx - 1) - (c0 + 32 * k);
+                x &= (left >= 32) ? 0xffffffffu : ((left <= 0) ? 0u : ((1u << left) - 1u));
             }
-            unsigned A[MARK_ROWS + 1];                      // 5 bits: my four columns + the one to their right
-            unsigned first = 0u;
-#pragma unroll
-            for (int r = 0; r <= MARK_ROWS; ++r) {
-                A[r] = (v[r].x > ilevel ? 1u : 0u) | (v[r].y > ilevel ? 2u : 0u) | (v[r].z > ilevel ? 4u : 0u) | (v[r].w > ilevel ? 8u : 0u);
-                first |= (A[r] & 1u) << r;
-            }
-            unsigned nxt = __shfl_down_sync(FULL, first, 1);
-            if (lane == 31) nxt = edge;
-#pragma unroll
-            for (int r = 0; r <= MARK_ROWS; ++r) A[r] |= ((nxt >> r) & 1u) << 4;
-            const long long left = nq - c;
-            const unsigned valid = (left >= 4) ? 0xFu : ((left <= 0) ? 0u : ((1u << left) - 1u));
-#pragma unroll
-            for (int r = 0; r < MARK_ROWS; ++r) {
-                const unsigned L5 = A[r], H5 = A[r + 1];
-                unsigned cross = ((L5 ^ (L5 >> 1)) | (H5 ^ (H5 >> 1)) | (L5 ^ H5)) & valid;
-                if (j0 + r >= ny - 1) cross = 0u;
-                const unsigned word = __reduce_or_sync(0xFFu << (lane & 24), cross << (4 * (lane & 7)));
-                if ((lane & 7) == 0 && j0 + r < ny - 1) {
-                    mask[(j0 + r) * words_per_row + c0 / 32 + (lane >> 3)] = word;
-                    cnt[r] += __popc(word);
-                }
-            }
+            wp[k] = x;
         }
-#pragma unroll
-        for (int r = 0; r < MARK_ROWS; ++r)
-            if (cnt[r]) atomicAdd(row_count + j0 + r, cnt[r]);
+        if (lane == 0) *reinterpret_cast<uint4*>(mp + r * words_per_row) = w;
+        cnt[r] += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
     }
 }
 
-// scalar path: any nx / alignment
+// Work order: consecutive CTAs take consecutive 8-strip chunks of the SAME row group, so at any
+// moment the whole chip streams through a few neighbouring dwell rows (long contiguous DRAM
+// runs) instead of thousands of separate rows.
 __global__ void __launch_bounds__(MARK_WARPS * 32) contour_mark_kernel(
     const int* __restrict__ dwell, long long nx, long long ny, int ilevel,
     unsigned* __restrict__ mask, long long words_per_row, unsigned* __restrict__ row_count) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long strips_per_row = words_per_row / 4;
-    const long long nq = nx - 1;                                   // quads per row
-    for (long long j = blockIdx.x; j < ny - 1; j += gridDim.x) {
-        const int* r0 = dwell + j * nx;
-        const int* r1 = r0 + nx;
-        for (long long sidx = warp; sidx < strips_per_row; sidx += MARK_WARPS) {
-            const long long c0 = sidx * STRIP;
-            bool lo[4], hi[4];
+    const long long ngroups = (ny - 1 + MARK_ROWS - 1) / MARK_ROWS;
+    const long long chunks_per_group = (strips_per_row + MARK_WARPS - 1) / MARK_WARPS;
+    const long long nitems = ngroups * chunks_per_group;
+    const long long safe_strips = (nx - 1) / STRIP;          // strips with c0 + STRIP <= nx - 1
+    for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+        long long grp, chunk;
+        if ((nitems >> 31) == 0) {
+            const unsigned g32 = static_cast<unsigned>(item) / static_cast<unsigned>(chunks_per_group);
+            grp = g32;
+            chunk = static_cast<unsigned>(item) - g32 * static_cast<unsigned>(chunks_per_group);
+        } else {
+            grp = item / chunks_per_group;
+            chunk = item - grp * chunks_per_group;
+        }
+        const long long sidx = chunk * MARK_WARPS + warp;
+        if (sidx >= strips_per_row) continue;
+        const long long j0 = grp * MARK_ROWS;
+        const int* row0 = dwell + j0 * nx;
+        unsigned* mrow0 = mask + j0 * words_per_row;
+        unsigned cnt[MARK_ROWS];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const long long c = c0 + 32 * k + lane;
-                const bool in = c < nx;
-                lo[k] = in ? (__ldg(r0 + c) > ilevel) : false;
-                hi[k] = in ? (__ldg(r1 + c) > ilevel) : false;
-            }
-            // the column right of the strip (corner of the last quad)
-            const long long ce = c0 + STRIP;
-            bool lo_e = false, hi_e = false;
-            if (lane == 31 && ce < nx) { lo_e = __ldg(r0 + ce) > ilevel; hi_e = __ldg(r1 + ce) > ilevel; }
-            unsigned words[4];
-            int cnt = 0;
+        for (int r = 0; r < MARK_ROWS; ++r) cnt[r] = 0u;
+        if (j0 + MARK_ROWS < ny && sidx < safe_strips)
+            mark_strip<true>(row0, nx, ny, j0, sidx * STRIP, ilevel, lane, mrow0, words_per_row, cnt);
+        else
+            mark_strip<false>(row0, nx, ny, j0, sidx * STRIP, ilevel, lane, mrow0, words_per_row, cnt);
+        if (lane == 0) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                // right neighbours: lane+1 of the same chunk, lane 0 of the next chunk for lane 31
-                const bool nlo = (k < 3) ? lo[k < 3 ? k + 1 : 3] : lo_e, nhi = (k < 3) ? hi[k < 3 ? k + 1 : 3] : hi_e;
-                bool rl = __shfl_down_sync(FULL, lo[k], 1), rh = __shfl_down_sync(FULL, hi[k], 1);
-                const bool wl = __shfl_sync(FULL, nlo, (k < 3) ? 0 : 31), wh = __shfl_sync(FULL, nhi, (k < 3) ? 0 : 31);
-                if (lane == 31) { rl = wl; rh = wh; }
-                const long long c = c0 + 32 * k + lane;
-                const int sum = static_cast<int>(lo[k]) + static_cast<int>(rl) + static_cast<int>(hi[k]) + static_cast<int>(rh);
-                const bool cross = (c < nq) && sum != 0 && sum != 4;
-                words[k] = __ballot_sync(FULL, cross);
-                cnt += __popc(words[k]);
-            }
-            if (lane < 4) {
-                const unsigned w = lane == 0 ? words[0] : lane == 1 ? words[1] : lane == 2 ? words[2] : words[3];
-                mask[j * words_per_row + c0 / 32 + lane] = w;
-            }
-            if (lane == 0 && cnt) atomicAdd(row_count + j, static_cast<unsigned>(cnt));
+            for (int r = 0; r < MARK_ROWS; ++r)
+                if (cnt[r]) atomicAdd(row_count + j0 + r, cnt[r]);
         }
     }
 }
@@ -366,18 +360,12 @@ int32_t classify_device(const int* dwell_dev, const double* xs_host, long long n
     else if (level >= 2147483647.0) ilevel = INT_MAX;
     else ilevel = static_cast<int>(floor(level));
     if (level != level) ilevel = INT_MAX;
-    long long blocks = nrows;
     const long long cap = static_cast<long long>(lm::sm_count()) * 64;
+    const long long strips_per_row = words_per_row / 4;
+    long long blocks = ((nrows + MARK_ROWS - 1) / MARK_ROWS) * ((strips_per_row + MARK_WARPS - 1) / MARK_WARPS);
     if (blocks > cap) blocks = cap;
-    const bool vec = (nx % 4 == 0) && (reinterpret_cast<uintptr_t>(dwell_dev) % 16 == 0);
-    long long vblocks = (nrows + MARK_ROWS - 1) / MARK_ROWS;
-    if (vblocks > cap) vblocks = cap;
-    if (vec)
-        contour_mark_vec_kernel<<<static_cast<unsigned>(vblocks), MARK_WARPS * 32, 0, s>>>(
-            dwell_dev, nx, ny, ilevel, static_cast<unsigned*>(dmask), words_per_row, static_cast<unsigned*>(dcount));
-    else
-        contour_mark_kernel<<<static_cast<unsigned>(blocks), MARK_WARPS * 32, 0, s>>>(
-            dwell_dev, nx, ny, ilevel, static_cast<unsigned*>(dmask), words_per_row, static_cast<unsigned*>(dcount));
+    contour_mark_kernel<<<static_cast<unsigned>(blocks), MARK_WARPS * 32, 0, s>>>(
+        dwell_dev, nx, ny, ilevel, static_cast<unsigned*>(dmask), words_per_row, static_cast<unsigned*>(dcount));
     LM_CUDA_TRY(cudaGetLastError());
     contour_scan_kernel<<<1, 1024, 0, s>>>(static_cast<unsigned*>(dcount), nrows, static_cast<unsigned long long*>(doff));
     LM_CUDA_TRY(cudaGetLastError());

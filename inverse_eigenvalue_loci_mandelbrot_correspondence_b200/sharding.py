@@ -56,7 +56,7 @@ def interpolate_row_profile(coarse_rows: np.ndarray, coarse_work: np.ndarray, ny
                      np.asarray(coarse_work, dtype=np.float64))
 
 
-def coarse_row_profile(xs, ys, max_iter: int, rows: int = 512, cols: int = 1024) -> np.ndarray:
+def coarse_row_profile(xs, ys, max_iter: int, rows: int = 2048, cols: int = 2048) -> np.ndarray:
     """Estimated work of every grid row from a coarse K1 pass on the GPU (subsampled rows/columns)."""
     from . import escape
     xs = np.asarray(xs, dtype=np.float64); ys = np.asarray(ys, dtype=np.float64)
