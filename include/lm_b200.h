@@ -70,6 +70,12 @@ extern "C" {
  * d = log(max(|z|,1)) |z| / max(|2 z dz|, eps), non-finite -> 0.
  * variograms_construct_mandelbrot.py:61-88.                                          */
 #define LM_DE_FIRST_ESCAPE     1
+/* dz0 = 1, z captured at the first escape abs(z) > R but dz taken AFTER all max_iter
+ * iterations (it keeps iterating and usually overflows, which makes d = 0);
+ * d = log|z| |z| / max(|2 z dz_final|, eps), non-finite -> 0.  This is what
+ * tci_construct_mandelbrot.py:21-39 and tci_construct_mandelbrot_v002_fixed.py:35-47 compute
+ * (the module gi_assumption_tracker_v3.py loads).                                       */
+#define LM_DE_FINAL_DZ         2
 
 /* ---- log-potential variants (K4a) ---------------------------------------------- */
 /* U = (1/N) sum_p log(sqrt(dx^2+dy^2) + eps)         Potentials.py:19-27             */

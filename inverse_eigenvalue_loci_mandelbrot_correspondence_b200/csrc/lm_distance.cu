@@ -2,7 +2,9 @@
 //
 //   mandelbrot_distance_estimator   construct_stage1_clean.py:50-58           (LM_DE_SCALAR)
 //   mandelbrot_distance_estimator   variograms_construct_mandelbrot.py:61-88  (LM_DE_FIRST_ESCAPE)
-//     (the same first-escape form is used by tci_construct_mandelbrot.py:21-39)
+//   mandelbrot_distance_estimator   tci_construct_mandelbrot.py:21-39,
+//                                   tci_construct_mandelbrot_v002_fixed.py:35-47 (LM_DE_FINAL_DZ: z from the
+//                                   first escape, dz from the END of the loop)
 //
 // The reference runs these on small grids (120x80 ... 912^2, max_iter <= 500), so a plain
 // one-thread-per-pixel kernel is used; the recurrences are unfused (__dmul_rn/__dadd_rn) in
@@ -43,7 +45,7 @@ __global__ void __launch_bounds__(256) distance_kernel(const double* __restrict_
                 if (VARIANT == LM_DE_SCALAR) {
                     const double adz = hypot(dr, di);
                     d = __ddiv_rn(__dmul_rn(az, log(az)), adz > 1e-16 ? adz : 1e-16);
-                } else {
+                } else if (VARIANT == LM_DE_FIRST_ESCAPE) {
                     const double qr = __dsub_rn(__dmul_rn(__dmul_rn(2.0, zr), dr), __dmul_rn(__dmul_rn(2.0, zi), di));
                     const double qi = __dadd_rn(__dmul_rn(__dmul_rn(2.0, zr), di), __dmul_rn(__dmul_rn(2.0, zi), dr));
                     const double den0 = hypot(qr, qi);
@@ -51,6 +53,30 @@ __global__ void __launch_bounds__(256) distance_kernel(const double* __restrict_
                     const double num = __dmul_rn(log(az > 1.0 ? az : 1.0), az);
                     d = isnan(den0) ? nan("") : __ddiv_rn(num, den);
                     if (!isfinite(d)) d = 0.0;
+                } else {
+                    // LM_DE_FINAL_DZ: keep z of this first escape, run dz (and z) on to the end of the loop
+                    const double ezr = zr, ezi = zi;
+                    for (int m2 = n + 1; m2 < max_iter; ++m2) {
+                        const double tr2 = __dmul_rn(2.0, zr), ti2 = __dmul_rn(2.0, zi);
+                        const double ndr2 = __dadd_rn(__dsub_rn(__dmul_rn(tr2, dr), __dmul_rn(ti2, di)), 1.0);
+                        const double ndi2 = __dadd_rn(__dmul_rn(tr2, di), __dmul_rn(ti2, dr));
+                        dr = ndr2; di = ndi2;
+                        const double re2 = __dsub_rn(__dmul_rn(zr, zr), __dmul_rn(zi, zi));
+                        const double pp2 = __dmul_rn(zr, zi);
+                        zr = __dadd_rn(re2, cr);
+                        zi = __dadd_rn(__dadd_rn(pp2, pp2), ci);
+                        if (!(isfinite(dr) && isfinite(di))) break;     // stays non-finite: d = 0
+                    }
+                    d = 0.0;
+                    if (isfinite(dr) && isfinite(di)) {
+                        const double qr = __dsub_rn(__dmul_rn(__dmul_rn(2.0, ezr), dr), __dmul_rn(__dmul_rn(2.0, ezi), di));
+                        const double qi = __dadd_rn(__dmul_rn(__dmul_rn(2.0, ezr), di), __dmul_rn(__dmul_rn(2.0, ezi), dr));
+                        const double den0 = hypot(qr, qi);
+                        if (isfinite(den0)) {
+                            d = __ddiv_rn(__dmul_rn(log(az), az), den0 > eps ? den0 : eps);
+                            if (!isfinite(d)) d = 0.0;
+                        }
+                    }
                 }
                 break;
             }
@@ -97,7 +123,7 @@ int32_t lm_distance_grid_f64(const double* xs, int64_t nx, const double* ys, int
     LM_REQUIRE(xs && ys && dist, "lm_distance_grid_f64: NULL buffer");
     LM_REQUIRE(nx >= 0 && ny >= 0 && max_iter >= 0, "lm_distance_grid_f64: negative size");
     LM_REQUIRE(bailout > 0.0 && bailout < 1e150, "lm_distance_grid_f64: bailout out of range");
-    LM_REQUIRE(variant == LM_DE_SCALAR || variant == LM_DE_FIRST_ESCAPE, "lm_distance_grid_f64: unknown variant %d", variant);
+    LM_REQUIRE(variant >= LM_DE_SCALAR && variant <= LM_DE_FINAL_DZ, "lm_distance_grid_f64: unknown variant %d", variant);
     if (stats) *stats = lm_stats{};
     if (nx * ny == 0) return LM_OK;
     cudaStream_t s = nullptr;
@@ -116,10 +142,14 @@ int32_t lm_distance_grid_f64(const double* xs, int64_t nx, const double* ys, int
         distance_kernel<LM_DE_SCALAR><<<blocks, 256, 0, s>>>(static_cast<double*>(dxs), nx, static_cast<double*>(dys), ny,
                                                              max_iter, bailout, eps, static_cast<double*>(dd),
                                                              static_cast<unsigned char*>(de));
-    else
+    else if (variant == LM_DE_FIRST_ESCAPE)
         distance_kernel<LM_DE_FIRST_ESCAPE><<<blocks, 256, 0, s>>>(static_cast<double*>(dxs), nx, static_cast<double*>(dys), ny,
                                                                    max_iter, bailout, eps, static_cast<double*>(dd),
                                                                    static_cast<unsigned char*>(de));
+    else
+        distance_kernel<LM_DE_FINAL_DZ><<<blocks, 256, 0, s>>>(static_cast<double*>(dxs), nx, static_cast<double*>(dys), ny,
+                                                               max_iter, bailout, eps, static_cast<double*>(dd),
+                                                               static_cast<unsigned char*>(de));
     LM_CUDA_TRY(cudaGetLastError());
     float ms = 0.f;
     if ((rc = tm.end(s, &ms)) != LM_OK) return rc;

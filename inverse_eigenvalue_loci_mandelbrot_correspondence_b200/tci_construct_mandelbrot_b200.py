@@ -1,0 +1,149 @@
+#!/usr/bin/env python3
+"""GPU-backed module for `gi_assumption_tracker_v3.py --module <this file>`.
+
+The tracker loads a script by path (gi_assumption_tracker_v3.py:84-90, 193), overwrites the
+attributes `domain`, `mandelbrot_grid`, `mandelbrot_samples` per level (:194, 208-209) and calls
+`construct_points(ns)`, `sample_mandelbrot_boundary()`, `entropic_ot_alignment(C, M)`,
+`procrustes_align_no_scale(X, Y)`, `KL(P, X)` and reads `eps` (:212-228, 109-120).  The stock module is
+tci_construct_mandelbrot_v002_fixed.py; this one keeps its attribute names, defaults and call
+signatures and moves the two generators onto the B200:
+
+  construct_points(ns)            -> K3  lm_roots_batched            (…_v002_fixed.py:27-33)
+  mandelbrot_distance_estimator   -> K1b lm_distance_grid_f64, LM_DE_FINAL_DZ (…_v002_fixed.py:35-47)
+  sample_mandelbrot_boundary()    -> K1b + the same quantile mask / np.random.choice on the host
+                                     (…_v002_fixed.py:49-59), so a seeded run draws the same sample
+
+The matching / Procrustes / histogram helpers are host numpy on <= 4*10^4 points, as in the stock
+module.  Differences a user can see: inside one n the cloud is sorted by (re, im) instead of in
+LAPACK's order, and `mandelbrot_distance_estimator` wants a meshgrid (`X + 1j*Y`) and returns
+`last = None` (z of the first escape stays on the device).
+"""
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import numpy as np
+
+_ROOT = Path(__file__).resolve().parents[1]
+if str(_ROOT) not in sys.path:           # loaded by file path, not as a package member
+    sys.path.insert(0, str(_ROOT))
+
+from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import lucas as _lucas  # noqa: E402
+from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import potentials as _potentials  # noqa: E402
+
+# ---------- CONFIG (names and defaults of tci_construct_mandelbrot_v002_fixed.py:12-22) ----------
+np.random.seed(7)
+construct_ns = list(range(20, 301, 20))
+mandelbrot_grid = 600
+mandelbrot_samples = 25000
+escape_R, max_iter = 250, 250
+grid_bins = 128
+domain = (-2.25, 1.25, -1.75, 1.75)
+alpha, T, eps = 0.2, 60, 1e-12
+sinkhorn_eps, sinkhorn_iter = 0.8, 600
+# ---------------------------------------------------------------------------------------------------
+
+lucas_companion = _lucas.lucas_companion
+
+
+def construct_points(ns):
+    """Lucas Loci for the given orders, |lambda| > 1e-10 kept (K3 on the GPU)."""
+    return _lucas.construct_points(ns, tol=1e-10)
+
+
+def _axes_of_meshgrid(c: np.ndarray):
+    c = np.asarray(c, dtype=np.complex128)
+    if c.ndim != 2:
+        raise ValueError("mandelbrot_distance_estimator expects a 2-D meshgrid X + 1j*Y")
+    xs = np.ascontiguousarray(c[0, :].real)
+    ys = np.ascontiguousarray(c[:, 0].imag)
+    if not (np.array_equal(c.real, np.broadcast_to(xs[None, :], c.shape)) and
+            np.array_equal(c.imag, np.broadcast_to(ys[:, None], c.shape))):
+        raise ValueError("mandelbrot_distance_estimator expects a 2-D meshgrid X + 1j*Y")
+    return xs, ys
+
+
+def mandelbrot_distance_estimator(c):
+    """(escaped mask, distance estimate, None) on the meshgrid c; module-level max_iter/escape_R/eps apply."""
+    xs, ys = _axes_of_meshgrid(c)
+    d, esc = _potentials.distance_grid(xs, ys, int(max_iter), float(escape_R), float(eps), _potentials.DE_FINAL_DZ)
+    return esc, d, None
+
+
+def sample_mandelbrot_boundary():
+    xs = np.linspace(domain[0], domain[1], mandelbrot_grid)
+    ys = np.linspace(domain[2], domain[3], mandelbrot_grid)
+    d, esc = _potentials.distance_grid(xs, ys, int(max_iter), float(escape_R), float(eps), _potentials.DE_FINAL_DZ)
+    if not esc.any():
+        raise RuntimeError("No escape points")
+    q = np.quantile(d[esc], 0.25)
+    jj, ii = np.nonzero(esc & (d <= q))                   # row-major, the order C[mask].ravel() has
+    pts = xs[ii] + 1j * ys[jj]
+    if pts.size > mandelbrot_samples:
+        pts = np.random.choice(pts, mandelbrot_samples, replace=False)
+    return pts
+
+
+def entropic_ot_alignment(X, Y):
+    """The stock module's 'simplified Sinkhorn': equalise the sizes by random subsampling, then match every
+    X to the Y with the largest exp(-dist/(mean dist * sinkhorn_eps)), i.e. its nearest Y (first index on
+    ties).  Done in row blocks so the n x m distance matrix is never materialised."""
+    X = np.asarray(X); Y = np.asarray(Y)
+    n, m = len(X), len(Y)
+    if n > m:
+        X = np.random.choice(X, m, replace=False)
+    if m > n:
+        Y = np.random.choice(Y, n, replace=False)
+    yr, yi = Y.real[None, :], Y.imag[None, :]
+    match = np.empty(len(X), dtype=np.int64)
+    step = max(1, (1 << 24) // max(len(Y), 1))
+    for s in range(0, len(X), step):
+        xr = X.real[s:s + step, None]; xi = X.imag[s:s + step, None]
+        match[s:s + step] = np.argmin(np.sqrt((xr - yr) ** 2 + (xi - yi) ** 2), axis=1)
+    return Y[match], X
+
+
+def procrustes_align_no_scale(Xc, Yc):
+    """Rotation (no scaling) of the centred X onto the centred Y, translated to Y's centroid."""
+    A = np.column_stack([Xc.real, Xc.imag]); B = np.column_stack([Yc.real, Yc.imag])
+    muA, muB = A.mean(axis=0), B.mean(axis=0)
+    U, _, Vt = np.linalg.svd((B - muB).T @ (A - muA), full_matrices=False)
+    out = (A - muA) @ (U @ Vt) + muB
+    return out[:, 0] + 1j * out[:, 1]
+
+
+def to_prob(cloud, bins=grid_bins):
+    H, _, _ = np.histogram2d(cloud.real, cloud.imag, bins=(bins, bins),
+                             range=[[domain[0], domain[1]], [domain[2], domain[3]]])
+    H = np.maximum(H, eps)
+    return H / H.sum()
+
+
+def KL(P, X):
+    p = np.clip(P, eps, None); x = np.clip(X, eps, None)
+    return float(np.sum(p * (np.log(p) - np.log(x))))
+
+
+def tci_flow(P, X0):
+    X = X0.copy()
+    kls, traj = [KL(P, X)], [X]
+    for _ in range(T):
+        X = (1 - alpha) * X + alpha * P
+        kls.append(KL(P, X)); traj.append(X.copy())
+    return np.array(kls), traj
+
+
+if __name__ == "__main__":
+    import json
+    import time
+    t0 = time.time()
+    Cpts = construct_points(construct_ns)
+    Mpts = sample_mandelbrot_boundary()
+    Mmatch, Ctrim = entropic_ot_alignment(Cpts, Mpts)
+    Caligned = procrustes_align_no_scale(Ctrim, Mmatch)
+    kls, _ = tci_flow(to_prob(Mpts), to_prob(Caligned))
+    out = {"n_construct_pts": int(Cpts.size), "n_mandel_pts": int(Mpts.size), "KL_initial": float(kls[0]),
+           "KL_final": float(kls[-1]), "runtime_sec": time.time() - t0}
+    json.dump(out, open("tci_results.json", "w"), indent=2)
+    print("Done. Results:", out)

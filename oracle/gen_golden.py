@@ -140,6 +140,29 @@ def main() -> None:
                                     for y in dys])
     g["stage1_construct_points_maxN12"] = cs["construct_points"](12)
 
+    # ---- the tracker module's DE (tci_construct_mandelbrot_v002_fixed.py:35-47): dz read after the loop
+    fx = load_defs("tci_construct_mandelbrot_v002_fixed.py", ["mandelbrot_distance_estimator"],
+                   {"max_iter": 250, "escape_R": 250, "eps": 1e-12})
+    fxs = np.linspace(-2.25, 1.25, 61); fys = np.linspace(-1.75, 1.75, 53)
+    FX, FY = np.meshgrid(fxs, fys)
+    esc, dd, last = fx["mandelbrot_distance_estimator"](FX + 1j * FY)
+    g["tci_fixed_x"] = fxs; g["tci_fixed_y"] = fys
+    g["tci_fixed_escaped"] = esc
+    g["tci_fixed_dist"] = dd
+    # a zoom on the boundary, where some points escape in the last iterations and dz stays finite
+    zxs = np.linspace(-0.7600, -0.7400, 96); zys = np.linspace(0.0900, 0.1100, 90)
+    ZX, ZY = np.meshgrid(zxs, zys)
+    esc, dd, last = fx["mandelbrot_distance_estimator"](ZX + 1j * ZY)
+    g["tci_fixed_zoom_x"] = zxs; g["tci_fixed_zoom_y"] = zys
+    g["tci_fixed_zoom_escaped"] = esc
+    g["tci_fixed_zoom_dist"] = dd
+
+    # sample_mandelbrot_boundary() of the same module at a tracker-like level (grid 150, no subsampling)
+    fxm = load_defs("tci_construct_mandelbrot_v002_fixed.py", ["mandelbrot_distance_estimator", "sample_mandelbrot_boundary"],
+                    {"max_iter": 250, "escape_R": 250, "eps": 1e-12, "domain": (-2.25, 1.25, -1.75, 1.75),
+                     "mandelbrot_grid": 150, "mandelbrot_samples": 10 ** 9})
+    g["tci_fixed_boundary_sample_grid150"] = fxm["sample_mandelbrot_boundary"]()
+
     OUT.parent.mkdir(parents=True, exist_ok=True)
     np.savez_compressed(OUT, **g)
     print(f"wrote {OUT} ({OUT.stat().st_size / 1024:.1f} KiB, {len(g)} arrays)")

@@ -55,10 +55,25 @@ def test_distance_estimators(gpu, oracle, golden):
     d, _ = gpu.potentials.distance_grid(golden["de_scalar_x"], golden["de_scalar_y"], 200, 1e6, 1e-16, 0)
     np.testing.assert_allclose(d, golden["de_scalar_dist"], rtol=1e-13, atol=0)
     xs = np.linspace(-2.25, 1.25, 300); ys = np.linspace(-1.75, 1.75, 280)
-    for variant, R, eps in ((0, 1e6, 1e-16), (1, 4.0, 1e-14), (1, 250.0, 1e-12)):
+    for variant, R, eps in ((0, 1e6, 1e-16), (1, 4.0, 1e-14), (1, 250.0, 1e-12), (2, 250.0, 1e-12), (2, 4.0, 1e-12)):
         want, esc_o = oracle.distance_grid(xs, ys, 250, R, eps, variant)
         got, esc = gpu.potentials.distance_grid(xs, ys, 250, R, eps, variant)
         assert np.array_equal(esc, esc_o)
         np.testing.assert_allclose(got, want, rtol=1e-13, atol=0)
     assert gpu.potentials.mandelbrot_distance_estimator(0.3 + 0.5j) == pytest.approx(
         float(oracle.distance_grid([0.3], [0.5], 200, 1e6, 1e-16, 0)[0][0, 0]), rel=1e-13)
+
+
+def test_distance_estimator_tracker_module(gpu, oracle, golden):
+    """LM_DE_FINAL_DZ against the reference's own output (tci_construct_mandelbrot_v002_fixed.py:35-47) and,
+    on the zoom where dz stays finite, against the oracle to rounding."""
+    for tag in ("tci_fixed", "tci_fixed_zoom"):
+        got, esc = gpu.potentials.distance_grid(golden[tag + "_x"], golden[tag + "_y"], 250, 250.0, 1e-12, 2)
+        want, want_esc = golden[tag + "_dist"], golden[tag + "_escaped"]
+        assert (esc == want_esc).mean() > 0.999
+        assert np.array_equal(got != 0, want != 0)
+        m = want != 0
+        np.testing.assert_allclose(got[m], want[m], rtol=1e-4)       # FMA-contaminated numpy arrays, see CPU test
+        o, oesc = oracle.distance_grid(golden[tag + "_x"], golden[tag + "_y"], 250, 250.0, 1e-12, 2)
+        assert np.array_equal(esc, oesc)
+        np.testing.assert_allclose(got, o, rtol=1e-13, atol=0)

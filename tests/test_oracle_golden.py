@@ -79,6 +79,21 @@ def test_distance_estimators(oracle, golden):
     assert close.mean() > 0.98
 
 
+def test_distance_estimator_tracker_module(oracle, golden):
+    """tci_construct_mandelbrot_v002_fixed.py:35-47 (the module gi_assumption_tracker_v3.py loads): z of the
+    first escape, dz read after the loop.  dz normally overflows (d = 0); it stays finite only for points
+    that escape in the last iterations, and there the FMA-fused numpy array recurrence has
+    been amplified by ~240 chaotic steps, hence the loose tolerance on those few values."""
+    for tag in ("tci_fixed", "tci_fixed_zoom"):
+        d, esc = oracle.distance_grid(golden[tag + "_x"], golden[tag + "_y"], 250, 250.0, 1e-12, 2)
+        want, want_esc = golden[tag + "_dist"], golden[tag + "_escaped"]
+        assert (esc == want_esc).mean() > 0.999
+        assert np.array_equal(d != 0, want != 0)
+        m = want != 0
+        np.testing.assert_allclose(d[m], want[m], rtol=1e-4)
+    assert (golden["tci_fixed_zoom_dist"] != 0).sum() >= 10
+
+
 def test_stencils_bit_exact(oracle, golden):
     U = golden["stencil_U"]; h = float(golden["stencil_h"][0])
     assert np.array_equal(oracle.laplacian(U, h), golden["stencil_laplacian"])

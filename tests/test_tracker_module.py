@@ -1,0 +1,79 @@
+"""The GPU-backed module for `gi_assumption_tracker_v3.py --module`: loaded by file path
+exactly as the tracker does (gi_assumption_tracker_v3.py:84-90), attributes overwritten per level (:194,
+208-209), generators compared with the stock module's outputs (tests/golden, from
+tci_construct_mandelbrot_v002_fixed.py) and with the shipped artefact counts (v3_T25_sigma3_dense.csv:2-5)."""
+import importlib.util
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+MODULE = (Path(__file__).resolve().parents[1] / "inverse_eigenvalue_loci_mandelbrot_correspondence_b200"
+          / "tci_construct_mandelbrot_b200.py")
+
+
+def load_module(path, name="tci_fixed_import"):
+    spec = importlib.util.spec_from_file_location(name, str(path))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_module_contract_cpu(shim):
+    mod = load_module(MODULE)
+    for attr in ("domain", "eps", "mandelbrot_grid", "mandelbrot_samples", "max_iter", "escape_R", "grid_bins"):
+        assert hasattr(mod, attr)
+    for fn in ("construct_points", "sample_mandelbrot_boundary", "entropic_ot_alignment", "procrustes_align_no_scale",
+               "KL", "to_prob", "tci_flow", "mandelbrot_distance_estimator", "lucas_companion"):
+        assert callable(getattr(mod, fn))
+    assert mod.domain == (-2.25, 1.25, -1.75, 1.75) and mod.eps == 1e-12 and mod.mandelbrot_grid == 600
+    # host helpers: nearest-neighbour matching, rigid alignment, histogram probabilities, KL
+    rng = np.random.default_rng(3)
+    Y = rng.standard_normal(50) + 1j * rng.standard_normal(50)
+    X = Y[rng.permutation(50)] + 1e-3
+    Ym, Xs = mod.entropic_ot_alignment(X, Y)
+    assert np.allclose(Ym, Xs - 1e-3)
+    back = mod.procrustes_align_no_scale(Y + (2 - 1j), Y)                # pure translation is undone
+    assert np.allclose(back, Y, atol=1e-12)
+    moved = mod.procrustes_align_no_scale(Y * np.exp(0.3j) + (2 - 1j), Y)  # always a rigid motion onto Y's centroid
+    assert abs(moved.mean() - Y.mean()) < 1e-12
+    assert np.allclose(np.abs(moved[:, None] - moved[None, :]), np.abs(Y[:, None] - Y[None, :]), atol=1e-12)
+    P = mod.to_prob(Y, 16); Q = mod.to_prob(X, 16)
+    assert P.shape == (16, 16) and abs(P.sum() - 1) < 1e-12
+    assert mod.KL(P, P) == 0.0 and mod.KL(P, Q) > 0
+    kls, traj = mod.tci_flow(P, Q)
+    assert len(kls) == mod.T + 1 and kls[-1] < kls[0] * 1e-4 and np.all(np.diff(kls) < 0)
+    if shim.device_count() < 1:          # no CPU fallback behind the module either
+        with pytest.raises(RuntimeError):
+            mod.construct_points([3])
+
+
+@pytest.mark.gpu
+def test_tracker_levels(gpu, golden):
+    mod = load_module(MODULE)
+    mod.domain = (-2.25, 1.25, -1.75, 1.75)
+    # n_construct_pts of the shipped tracker runs: 2400 / 6000 / 14820 / 37820 for construct_max_n 300/480/760/1220
+    for nmax, want in ((300, 2400), (480, 6000), (760, 14820), (1220, 37820)):
+        pts = mod.construct_points(list(range(20, nmax + 1, 20)))
+        assert pts.size == want and np.isfinite(pts).all()
+    # sample_mandelbrot_boundary at a level the stock module was run at for the fixture
+    mod.mandelbrot_grid = 150; mod.mandelbrot_samples = 10 ** 9
+    got = mod.sample_mandelbrot_boundary()
+    want = golden["tci_fixed_boundary_sample_grid150"]
+    common = np.intersect1d(got, want).size
+    assert common >= 0.999 * max(got.size, want.size)
+    if got.size == want.size:
+        assert (got == want).mean() > 0.99             # same row-major order
+    # seeded subsampling draws through numpy's global stream like the stock module
+    mod.mandelbrot_samples = 500
+    np.random.seed(7); a = mod.sample_mandelbrot_boundary()
+    np.random.seed(7); b = mod.sample_mandelbrot_boundary()
+    assert a.size == 500 and np.array_equal(a, b)
+    # one tracker level end to end
+    mod.mandelbrot_grid = 600; mod.mandelbrot_samples = 25000
+    np.random.seed(7)
+    Cp = mod.construct_points(list(range(20, 301, 20))); M = mod.sample_mandelbrot_boundary()
+    Mmatch, Csub = mod.entropic_ot_alignment(Cp, M)
+    Cal = mod.procrustes_align_no_scale(Csub, Mmatch)
+    assert Cal.size == 2400 and Mmatch.size == 2400
+    assert np.isfinite(mod.KL(mod.to_prob(Mmatch, 64), mod.to_prob(Cal, 64)))
