@@ -106,6 +106,16 @@ typedef struct lm_stats {
     int32_t  launches;          /* kernels launched by this call                      */
 } lm_stats;
 
+/* per-stage report of lm_lucas_cloud_fields */
+typedef struct lm_cloud_stats {
+    uint64_t n_roots;           /* sum of the degrees                                   */
+    uint64_t n_points;          /* cloud size (roots with |lambda| > tol)               */
+    uint64_t potential_work;    /* K1d iterations performed                             */
+    uint64_t pairs;             /* K4a (cell, point) pairs                              */
+    float    roots_ms, compact_ms, potential_ms, logpot_ms, stencil_ms;   /* device time */
+    int32_t  launches;
+} lm_cloud_stats;
+
 /* ---- context, memory ----------------------------------------------------------- */
 int32_t     lm_abi_version(void);
 const char* lm_last_error(void);
@@ -161,6 +171,13 @@ int32_t lm_escape_points_f64(const double* c_re, const double* c_im, int64_t n,
                              int32_t max_iter, double escape_radius,
                              double* g, int64_t* it, double* phi_re, double* phi_im,
                              lm_stats* stats);
+
+/* device-resident variant: all pointers are device pointers (outputs may be NULL), work_units_dev
+ * (1 counter, may be NULL) receives the iteration count; enqueues on `stream`, never syncs.  */
+int32_t lm_escape_points_f64_dev(const double* c_re_dev, const double* c_im_dev, int64_t n,
+                                 int32_t max_iter, double escape_radius,
+                                 double* g_dev, int64_t* it_dev, double* phi_re_dev, double* phi_im_dev,
+                                 uint64_t* work_units_dev, void* stream);
 
 /* ---- K1b: distance-estimator grid ---------------------------------------------- */
 /* construct_stage1_clean.py:50-58 (LM_DE_SCALAR), variograms_construct_mandelbrot.py:61-88
@@ -251,6 +268,39 @@ int32_t lm_roots_batched(const double* toprows, const int32_t* deg, int64_t npol
                          double* out_re, double* out_im, int32_t* n_kept, int32_t* iters,
                          lm_stats* stats);
 
+/* Device-resident variant: every pointer is a device pointer; the batch is sorted by degree on
+ * the device and the solver launches read their ranges from device memory, so the call only
+ * enqueues on `stream`.  status_dev (2 x int32, may be NULL): [0] != 0 when some polynomial did
+ * not converge, [1] != 0 when some deg[k] is outside [1, maxdeg] (those are skipped).          */
+int32_t lm_roots_batched_dev(const double* toprows_dev, const int32_t* deg_dev, int64_t npoly,
+                             int32_t maxdeg, int32_t invert, double tol,
+                             double* out_re_dev, double* out_im_dev, int32_t* n_kept_dev,
+                             int32_t* iters_dev, int32_t* status_dev, void* stream);
+/* The cloud of the reference (pts.extend(1/vals) per n, lucas_equipotential_test_v3.py:98-99):
+ * the first n_kept[k] slots of every polynomial, concatenated in polynomial order, written to
+ * px_dev / py_dev (capacity cap_points; excess is dropped); *n_points_dev = full count.       */
+int32_t lm_cloud_compact_dev(const double* re_dev, const double* im_dev, const int32_t* n_kept_dev,
+                             int64_t npoly, int32_t maxdeg, double* px_dev, double* py_dev,
+                             int64_t cap_points, int64_t* n_points_dev, void* stream);
+
+/*
+ * The Lucas-Loci field stage (BASELINE.json config 5) as one host-buffer call:
+ *   K3 roots -> cloud of 1/lambda (|lambda| > tol, polynomial order)
+ *   -> K1d batch_potential at every cloud point (lucas_equipotential_test_v3.py:153-162; skipped
+ *      when g and it are NULL) -> K4a log-potential of the cloud on the grid (variant/eps as
+ *      lm_log_potential) -> K4 periodic Laplacian of that field (Laplacian_C-M.py:49-59).
+ * cloud_re/cloud_im/g/it have capacity cap_points (any may be NULL); U / lapU are [ny*nx]
+ * (either may be NULL).  *n_points receives the cloud size; LM_E_CAP if it exceeds
+ * cap_points while a per-point output was requested.
+ */
+int32_t lm_lucas_cloud_fields(const double* toprows, const int32_t* deg, int64_t npoly, int32_t maxdeg,
+                              double tol, double* cloud_re, double* cloud_im, int64_t cap_points,
+                              int64_t* n_points, int32_t pot_max_iter, double pot_radius,
+                              double* g, int64_t* it,
+                              const double* gx, int64_t nx, const double* gy, int64_t ny,
+                              double eps, int32_t variant, double h, double* U, double* lapU,
+                              lm_cloud_stats* stats);
+
 /* ---- K4: 5-point stencils ------------------------------------------------------ */
 /* lap = (((((-4 U) + U[j-1]) + U[j+1]) + U[:,i-1]) + U[:,i+1]) / (h*h), periodic wrap.
  * Laplacian_C-M.py:49-59, Iterative_Variogram_Laplacian.py:132-136.  Bit-exact.      */
@@ -268,10 +318,19 @@ int32_t lm_smooth5_interior_dev(const double* g, int64_t ny, int64_t nx, double*
 /* ---- K4a: log-potential of a point cloud on a grid ------------------------------ */
 /* Potentials.py:19-27, Laplacian_C-M.py:16-25, Iterative_Variogram_Laplacian.py:102-112,
  * variograms_construct_mandelbrot.py:128-146 (variant = LM_LOGPOT_*).
- * Points are accumulated sequentially in input order per grid cell.                  */
+ * All four are +-(1/N) sum_p log(|z - p| + eps); the reference's variants differ from each
+ * other in the last ulp, parity is 1e-12 (the sum is re-associated, see csrc/lm_logpot.cu).   */
 int32_t lm_log_potential(const double* px, const double* py, int64_t npts,
                          const double* gx, int64_t nx, const double* gy, int64_t ny,
                          double eps, int32_t variant, double* U, lm_stats* stats);
+/* Multi-GPU building blocks (device pointers, enqueue only): raw per-cell sums
+ * sums[cell] = sum_p log(|z_cell - p| + eps) over THIS rank's slice of the cloud; after an
+ * all-reduce(sum) of `sums` across ranks, `finish` applies the variant's +-1/N_total.        */
+int32_t lm_log_potential_sums_dev(const double* px_dev, const double* py_dev, int64_t npts,
+                                  const double* gx_dev, int64_t nx, const double* gy_dev, int64_t ny,
+                                  double eps, int32_t variant, double* sums_dev, void* stream);
+int32_t lm_log_potential_finish_dev(const double* sums_dev, int64_t ncells, int64_t n_total_points,
+                                    int32_t variant, double* U_dev, void* stream);
 
 /* ---- measurement probes -------------------------------------------------------- */
 /* Dependent-free DFMA loop on every SM: FP64 peak (TFLOP/s, 2 flops per DFMA) and a

@@ -30,9 +30,9 @@ EXPORTS = (
     "lm_escape_grid_f64", "lm_escape_grid_f64_dev", "lm_escape_grid_f32", "lm_escape_points_f64",
     "lm_distance_grid_f64",
     "lm_contour_level", "lm_contour_level_dev", "lm_contour_classify_dev", "lm_contour_link", "lm_contour_fetch_last", "lm_boundary_sample",
-    "lm_roots_batched",
+    "lm_roots_batched", "lm_roots_batched_dev", "lm_cloud_compact_dev", "lm_lucas_cloud_fields", "lm_escape_points_f64_dev",
     "lm_laplacian5_periodic", "lm_laplacian5_periodic_dev", "lm_smooth5_interior", "lm_smooth5_interior_dev",
-    "lm_log_potential",
+    "lm_log_potential", "lm_log_potential_sums_dev", "lm_log_potential_finish_dev",
     "lm_probe_fp64_peak", "lm_probe_fp64_latency", "lm_probe_k1_loop", "lm_probe_hbm_copy",
 )
 
@@ -56,6 +56,15 @@ class Stats(C.Structure):
     def as_dict(self) -> dict:
         return {"work_units": int(self.work_units), "items": int(self.items),
                 "kernel_ms": float(self.kernel_ms), "launches": int(self.launches)}
+
+
+class CloudStats(C.Structure):
+    _fields_ = [("n_roots", C.c_uint64), ("n_points", C.c_uint64), ("potential_work", C.c_uint64), ("pairs", C.c_uint64),
+                ("roots_ms", C.c_float), ("compact_ms", C.c_float), ("potential_ms", C.c_float), ("logpot_ms", C.c_float),
+                ("stencil_ms", C.c_float), ("launches", C.c_int32)]
+
+    def as_dict(self) -> dict:
+        return {k: (int(getattr(self, k)) if "ms" not in k else float(getattr(self, k))) for k, _ in self._fields_}
 
 
 _lock = threading.RLock()
@@ -92,6 +101,13 @@ _SIGNATURES = {
     "lm_contour_classify_dev": (_i32, [_vp, _vp, _i64, _vp, _i64, _i64, _f64, _vp, _i64, _pi64, _vp]),
     "lm_contour_link": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _f64, _vp, _i64, _pi64, _vp, _i64, _pi64]),
     "lm_roots_batched": (_i32, [_vp, _vp, _i64, _i32, _i32, _f64, _vp, _vp, _vp, _vp, _pStats]),
+    "lm_roots_batched_dev": (_i32, [_vp, _vp, _i64, _i32, _i32, _f64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lm_cloud_compact_dev": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp]),
+    "lm_lucas_cloud_fields": (_i32, [_vp, _vp, _i64, _i32, _f64, _vp, _vp, _i64, _pi64, _i32, _f64, _vp, _vp,
+                                     _vp, _i64, _vp, _i64, _f64, _i32, _f64, _vp, _vp, C.POINTER(CloudStats)]),
+    "lm_escape_points_f64_dev": (_i32, [_vp, _vp, _i64, _i32, _f64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lm_log_potential_sums_dev": (_i32, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _f64, _i32, _vp, _vp]),
+    "lm_log_potential_finish_dev": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp]),
     "lm_laplacian5_periodic": (_i32, [_vp, _i64, _i64, _f64, _vp, _pStats]),
     "lm_laplacian5_periodic_dev": (_i32, [_vp, _i64, _i64, _f64, _vp, _vp]),
     "lm_smooth5_interior": (_i32, [_vp, _i64, _i64, _vp, _pStats]),

@@ -712,4 +712,36 @@ int32_t lm_escape_points_f64(const double* c_re, const double* c_im, int64_t n,
     return LM_OK;
 }
 
+int32_t lm_escape_points_f64_dev(const double* c_re_dev, const double* c_im_dev, int64_t n,
+                                 int32_t max_iter, double escape_radius,
+                                 double* g_dev, int64_t* it_dev, double* phi_re_dev, double* phi_im_dev,
+                                 uint64_t* work_units_dev, void* stream) {
+    int32_t rc = lm::require_device();
+    if (rc != LM_OK) return rc;
+    LM_REQUIRE(n >= 0, "lm_escape_points_f64_dev: negative n");
+    LM_REQUIRE(n == 0 || (c_re_dev && c_im_dev), "lm_escape_points_f64_dev: c_re/c_im is NULL");
+    LM_REQUIRE(max_iter >= 1, "lm_escape_points_f64_dev: max_iter must be >= 1");
+    LM_REQUIRE(escape_radius > 0.0 && escape_radius < 1e150, "lm_escape_points_f64_dev: bad escape_radius");
+    cudaStream_t s = lm::as_stream(stream);
+    if (work_units_dev) LM_CUDA_TRY(cudaMemsetAsync(work_units_dev, 0, sizeof(uint64_t), s));
+    if (n == 0) return LM_OK;
+    unsigned long long* counters = nullptr;
+    if ((rc = get_counters(&counters, s)) != LM_OK) return rc;
+    EscapeArgs A{};
+    A.xs = c_re_dev; A.ys = c_im_dev;
+    A.nx = n; A.ny = 1;
+    A.chunks_per_row = static_cast<unsigned long long>((n + TILE - 1) / TILE);
+    A.ntiles = A.chunks_per_row;
+    A.max_iter = max_iter;
+    A.bailout = escape_radius;
+    A.field = g_dev;
+    A.it64 = reinterpret_cast<long long*>(it_dev);
+    A.phi_re = phi_re_dev;
+    A.phi_im = phi_im_dev;
+    A.tile_counter = counters;
+    A.work_counter = work_units_dev ? reinterpret_cast<unsigned long long*>(work_units_dev) : counters + 1;
+    A.overflow_flag = reinterpret_cast<int*>(counters + 2);
+    return launch_escape(true, LM_FIELD_GREEN, A, s);
+}
+
 }  // extern "C"

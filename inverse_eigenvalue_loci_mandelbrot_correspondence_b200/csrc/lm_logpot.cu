@@ -1,14 +1,27 @@
-// lm_logpot.cu -- K4a: log-potential of a point cloud on a grid (FP64 pipe: sqrt + log per pair).
+// lm_logpot.cu -- K4a: log-potential of a point cloud on a grid (FP64 pipe).
 //
 //   log_potential               Potentials.py:19-27                       (LM_LOGPOT_SUM_SQRT)
 //   construct_potential         Laplacian_C-M.py:16-25                    (LM_LOGPOT_NEG_PERTERM)
 //   log_potential               Iterative_Variogram_Laplacian.py:102-112  (LM_LOGPOT_SUM_HYPOT)
 //   log_potential_from_points   variograms_construct_mandelbrot.py:128-146 (LM_LOGPOT_LOG_INV)
 //
-// One thread per grid cell accumulates the points sequentially in input order (the order the
-// reference's loop over points uses), points are staged through shared memory in chunks so
-// the whole CTA reads each coordinate once.  Parity is tolerance based (1e-12 relative): the
-// reference's log/sqrt come from numpy's SIMD loops, ours from the CUDA math library.
+// All four are  U = +-(1/N) sum_p log(|z - p| + eps)  up to the association of the sum, and the
+// reference's own variants agree with each other only to rounding, so parity is
+// tolerance based (1e-12) and the kernel is free to reorder.  What it exploits:
+//
+//  * sum of logs = log of product.  A thread multiplies the 8 terms of a point group and takes ONE
+//    log per group (the product of 8 terms in [eps, ~10] cannot leave the double range; a group
+//    whose product is not a normal number is redone term by term with the library functions).
+//  * eps <= 1e-10 (three of the four variants use 1e-12):  log(s + eps) = log(s) + log1p(eps/s),
+//    and for eps/s <= 1e-8 the second term is eps/s to 5e-17.  So the group accumulates the
+//    product of r^2 = dx^2 + dy^2 (no square root at all) and the sum of MUFU.RSQ64H(r^2)
+//    (a 22-bit 1/s is plenty for a term of relative size <= 1e-8); a group containing a pair
+//    with s < eps*1e8 takes the exact path.  6 FP64 instructions per (cell, point) pair become
+//    ~4.5 with four cells of one grid row per thread (dy^2 shared).
+//  * 2-D decomposition: (tiles of 4 x 256 cells) x (point splits), partial sums reduced in a fixed
+//    order by a second kernel, so the grid fills the chip for a 400^2 grid and results are
+//    deterministic.  The same partial-sum entry point serves the multi-GPU path, where every rank
+//    holds a slice of the cloud and the per-cell sums are all-reduced (NCCL) before `finish`.
 #include "lm_common.cuh"
 
 #include <math.h>
@@ -16,45 +29,218 @@
 namespace {
 
 constexpr int LP_THREADS = 256;
-constexpr int LP_CHUNK = 512;
+constexpr int LP_CPT = 4;            // cells per thread, consecutive in x
+constexpr int LP_CHUNK = 1024;       // points staged in shared memory per round
+constexpr int LP_GROUP = 8;          // terms per product
 
+__device__ __forceinline__ double rsqrt_approx(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+
+// exact term, as the reference writes it
 template <int V>
-__global__ void __launch_bounds__(LP_THREADS) logpot_kernel(const double* __restrict__ px, const double* __restrict__ py,
-                                                            long long npts, const double* __restrict__ gx, long long nx,
-                                                            const double* __restrict__ gy, long long ny, double eps,
-                                                            double* __restrict__ U) {
-    __shared__ double spx[LP_CHUNK], spy[LP_CHUNK];
-    const long long idx = static_cast<long long>(blockIdx.x) * LP_THREADS + threadIdx.x;
-    const bool live = idx < nx * ny;
-    const long long j = live ? idx / nx : 0, i = live ? idx - j * nx : 0;
-    const double x = gx[i], y = gy[j];
-    const double N = static_cast<double>(npts);
-    double acc = 0.0;
-    for (long long base = 0; base < npts; base += LP_CHUNK) {
-        const int m = static_cast<int>(npts - base < LP_CHUNK ? npts - base : LP_CHUNK);
-        for (int k = threadIdx.x; k < m; k += LP_THREADS) { spx[k] = px[base + k]; spy[k] = py[base + k]; }
+__device__ __forceinline__ double exact_term(double dx, double dy, double eps) {
+    if (V == LM_LOGPOT_SUM_SQRT || V == LM_LOGPOT_NEG_PERTERM) return log(sqrt(dx * dx + dy * dy) + eps);
+    return log(hypot(dx, dy) + eps);
+}
+
+// sqrt by Goldschmidt iteration from the 22-bit reciprocal square root (<= 2 ulp); x > 0 normal
+__device__ __forceinline__ double sqrt_fast(double x) {
+    const double y0 = rsqrt_approx(x);
+    double g = x * y0, h = 0.5 * y0;
+    double r = fma(-g, h, 0.5);
+    g = fma(g, r, g); h = fma(h, r, h);
+    r = fma(-g, h, 0.5);
+    return fma(g, r, g);
+}
+
+// Raw per-cell sums  S[cell] = sum over this split's points of log(|z - p| + eps).
+//   partial[split * ncells + cell]
+template <int V, bool FAST>
+__global__ void __launch_bounds__(LP_THREADS) logpot_partial_kernel(
+    const double* __restrict__ px, const double* __restrict__ py, long long npts, long long pts_per_split,
+    const double* __restrict__ gx, long long nx, const double* __restrict__ gy, long long ny, double eps,
+    double* __restrict__ partial) {
+    __shared__ double2 spt[LP_CHUNK];
+    const long long tiles_x = (nx + LP_CPT - 1) / LP_CPT;                 // threads per grid row
+    const long long tid = static_cast<long long>(blockIdx.x) * LP_THREADS + threadIdx.x;
+    const bool live = tid < tiles_x * ny;
+    const long long j = live ? tid / tiles_x : 0;
+    const long long i0 = live ? (tid - j * tiles_x) * LP_CPT : 0;
+    double x[LP_CPT];
+#pragma unroll
+    for (int c = 0; c < LP_CPT; ++c) x[c] = gx[(i0 + c < nx) ? i0 + c : nx - 1];
+    const double y = gy[j];
+    const long long p_begin = static_cast<long long>(blockIdx.y) * pts_per_split;
+    const long long p_end = (p_begin + pts_per_split < npts) ? p_begin + pts_per_split : npts;
+    // a pair is "near" when s < eps * 1e8, i.e. rsqrt(r^2) > 1e-8 / eps (compared on the high words)
+    const int near_hi = FAST ? __double2hiint(1e-8 / eps) : 0;
+
+    double acc[LP_CPT], esum[LP_CPT];
+#pragma unroll
+    for (int c = 0; c < LP_CPT; ++c) { acc[c] = 0.0; esum[c] = 0.0; }
+
+    for (long long base = p_begin; base < p_end; base += LP_CHUNK) {
+        const int m = static_cast<int>(p_end - base < LP_CHUNK ? p_end - base : LP_CHUNK);
         __syncthreads();
-        if (live) {
-#pragma unroll 4
-            for (int k = 0; k < m; ++k) {
-                const double dx = x - spx[k], dy = y - spy[k];
-                if (V == LM_LOGPOT_SUM_SQRT) acc = acc + log(sqrt(dx * dx + dy * dy) + eps);
-                else if (V == LM_LOGPOT_NEG_PERTERM) acc = acc - log(sqrt(dx * dx + dy * dy) + eps) / N;
-                else if (V == LM_LOGPOT_SUM_HYPOT) acc = acc + log(hypot(dx, dy) + eps);
-                else acc = acc + log(1.0 / (hypot(dx, dy) + eps));
+        for (int k = threadIdx.x; k < m; k += LP_THREADS) spt[k] = make_double2(px[base + k], py[base + k]);
+        __syncthreads();
+        if (!live) continue;
+        int k0 = 0;
+        for (; k0 + LP_GROUP <= m; k0 += LP_GROUP) {
+            double P[LP_CPT], E[LP_CPT];
+            int mx[LP_CPT];
+#pragma unroll
+            for (int c = 0; c < LP_CPT; ++c) { P[c] = 1.0; E[c] = 0.0; mx[c] = 0; }
+#pragma unroll
+            for (int k = 0; k < LP_GROUP; ++k) {
+                const double2 p = spt[k0 + k];
+                const double dy = y - p.y;
+                const double dy2 = dy * dy;
+#pragma unroll
+                for (int c = 0; c < LP_CPT; ++c) {
+                    const double dx = x[c] - p.x;
+                    const double r2 = fma(dx, dx, dy2);
+                    if (FAST) {
+                        const double y0 = rsqrt_approx(r2);
+                        P[c] *= r2;
+                        E[c] += y0;
+                        mx[c] = max(mx[c], __double2hiint(y0));
+                    } else {
+                        P[c] *= sqrt_fast(r2) + eps;
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < LP_CPT; ++c) {
+                // the product must be a comfortably normal number and (FAST) no pair may be near
+                const bool ok = (P[c] > 1e-280) && (P[c] < 1e280) && (!FAST || mx[c] < near_hi);
+                if (ok) {
+                    if (FAST) { acc[c] = fma(0.5, log(P[c]), acc[c]); esum[c] += E[c]; }
+                    else acc[c] += log(P[c]);
+                } else {
+                    for (int k = 0; k < LP_GROUP; ++k) {
+                        const double2 p = spt[k0 + k];
+                        acc[c] += exact_term<V>(x[c] - p.x, y - p.y, eps);
+                    }
+                }
             }
         }
-        __syncthreads();
+        for (; k0 < m; ++k0) {
+            const double2 p = spt[k0];
+#pragma unroll
+            for (int c = 0; c < LP_CPT; ++c) acc[c] += exact_term<V>(x[c] - p.x, y - p.y, eps);
+        }
     }
     if (live) {
-        if (V != LM_LOGPOT_NEG_PERTERM && npts > 0) acc = acc / N;
-        U[idx] = acc;
+        double* out = partial + static_cast<long long>(blockIdx.y) * nx * ny + j * nx + i0;
+#pragma unroll
+        for (int c = 0; c < LP_CPT; ++c)
+            if (i0 + c < nx) out[c] = FAST ? fma(eps, esum[c], acc[c]) : acc[c];
     }
+}
+
+// U[cell] = scale * sum_s partial[s][cell]   (fixed order over the splits: deterministic)
+__global__ void __launch_bounds__(256) logpot_reduce_kernel(const double* __restrict__ partial, int nsplit, long long ncells,
+                                                            double scale, double* __restrict__ U) {
+    const long long c = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+    if (c >= ncells) return;
+    double s = 0.0;
+    for (int k = 0; k < nsplit; ++k) s += partial[static_cast<long long>(k) * ncells + c];
+    U[c] = s * scale;
+}
+
+int split_count(long long npts, long long nx, long long ny) {
+    const long long tiles = ((nx + LP_CPT - 1) / LP_CPT) * ny;
+    const long long cell_blocks = (tiles + LP_THREADS - 1) / LP_THREADS;
+    const long long want_blocks = static_cast<long long>(lm::sm_count()) * 8 * 2;        // two waves of 8 CTAs/SM
+    long long s = (want_blocks + cell_blocks - 1) / cell_blocks;
+    const long long max_by_pts = (npts + LP_CHUNK - 1) / LP_CHUNK;                       // at least one chunk per split
+    if (s > max_by_pts) s = max_by_pts;
+    if (s > 1024) s = 1024;
+    if (s < 1) s = 1;
+    return static_cast<int>(s);
+}
+
+// sum_dev[cell] = sum_p log(|z_cell - p| + eps) over the npts device-resident points
+int32_t logpot_sums_dev(const double* px, const double* py, long long npts, const double* gx, long long nx,
+                        const double* gy, long long ny, double eps, int32_t variant, double scale,
+                        double* out_dev, int* launches, cudaStream_t s) {
+    const long long ncells = nx * ny;
+    const int nsplit = split_count(npts, nx, ny);
+    void* dpart = nullptr;
+    int32_t rc;
+    if ((rc = lm::ws_get(lm::WS_LOGPOT_PART, static_cast<size_t>(nsplit) * ncells * sizeof(double), &dpart)) != LM_OK) return rc;
+    const long long pts_per_split = ((npts + nsplit - 1) / nsplit + LP_GROUP - 1) / LP_GROUP * LP_GROUP;
+    const long long tiles = ((nx + LP_CPT - 1) / LP_CPT) * ny;
+    const dim3 grid(static_cast<unsigned>((tiles + LP_THREADS - 1) / LP_THREADS), static_cast<unsigned>(nsplit));
+    const bool fast = eps > 0.0 && eps <= 1e-10;
+#define LM_LP_LAUNCH(V)                                                                                             \
+    do {                                                                                                            \
+        if (fast) logpot_partial_kernel<V, true><<<grid, LP_THREADS, 0, s>>>(px, py, npts, pts_per_split, gx, nx, gy, ny, eps, \
+                                                                             static_cast<double*>(dpart));            \
+        else logpot_partial_kernel<V, false><<<grid, LP_THREADS, 0, s>>>(px, py, npts, pts_per_split, gx, nx, gy, ny, eps,     \
+                                                                         static_cast<double*>(dpart));                \
+    } while (0)
+    switch (variant) {
+        case LM_LOGPOT_SUM_SQRT:    LM_LP_LAUNCH(LM_LOGPOT_SUM_SQRT); break;
+        case LM_LOGPOT_NEG_PERTERM: LM_LP_LAUNCH(LM_LOGPOT_NEG_PERTERM); break;
+        case LM_LOGPOT_SUM_HYPOT:   LM_LP_LAUNCH(LM_LOGPOT_SUM_HYPOT); break;
+        default:                    LM_LP_LAUNCH(LM_LOGPOT_LOG_INV); break;
+    }
+#undef LM_LP_LAUNCH
+    LM_CUDA_TRY(cudaGetLastError());
+    logpot_reduce_kernel<<<static_cast<unsigned>((ncells + 255) / 256), 256, 0, s>>>(static_cast<double*>(dpart), nsplit, ncells,
+                                                                                      scale, out_dev);
+    LM_CUDA_TRY(cudaGetLastError());
+    if (launches) *launches += 2;
+    return LM_OK;
+}
+
+// the variant's normalisation of the raw sum: +1/N, or -1/N for the two "negative log" forms
+double variant_scale(int32_t variant, long long n_total) {
+    if (n_total <= 0) return 0.0;
+    const double inv = 1.0 / static_cast<double>(n_total);
+    return (variant == LM_LOGPOT_NEG_PERTERM || variant == LM_LOGPOT_LOG_INV) ? -inv : inv;
 }
 
 }  // namespace
 
 extern "C" {
+
+int32_t lm_log_potential_sums_dev(const double* px_dev, const double* py_dev, int64_t npts,
+                                  const double* gx_dev, int64_t nx, const double* gy_dev, int64_t ny,
+                                  double eps, int32_t variant, double* sums_dev, void* stream) {
+    int32_t rc = lm::require_device();
+    if (rc != LM_OK) return rc;
+    LM_REQUIRE(npts >= 0 && nx >= 0 && ny >= 0, "lm_log_potential_sums_dev: negative size");
+    LM_REQUIRE(variant >= LM_LOGPOT_SUM_SQRT && variant <= LM_LOGPOT_LOG_INV, "lm_log_potential_sums_dev: unknown variant %d", variant);
+    LM_REQUIRE((npts == 0 || (px_dev && py_dev)) && (nx * ny == 0 || (gx_dev && gy_dev && sums_dev)),
+               "lm_log_potential_sums_dev: NULL buffer");
+    if (nx * ny == 0) return LM_OK;
+    cudaStream_t s = lm::as_stream(stream);
+    if (npts == 0) {
+        LM_CUDA_TRY(cudaMemsetAsync(sums_dev, 0, static_cast<size_t>(nx) * ny * sizeof(double), s));
+        return LM_OK;
+    }
+    return logpot_sums_dev(px_dev, py_dev, npts, gx_dev, nx, gy_dev, ny, eps, variant, 1.0, sums_dev, nullptr, s);
+}
+
+int32_t lm_log_potential_finish_dev(const double* sums_dev, int64_t ncells, int64_t n_total_points, int32_t variant,
+                                    double* U_dev, void* stream) {
+    int32_t rc = lm::require_device();
+    if (rc != LM_OK) return rc;
+    LM_REQUIRE(ncells >= 0 && n_total_points >= 0, "lm_log_potential_finish_dev: negative size");
+    LM_REQUIRE(variant >= LM_LOGPOT_SUM_SQRT && variant <= LM_LOGPOT_LOG_INV, "lm_log_potential_finish_dev: unknown variant %d", variant);
+    LM_REQUIRE(ncells == 0 || (sums_dev && U_dev), "lm_log_potential_finish_dev: NULL buffer");
+    if (ncells == 0) return LM_OK;
+    logpot_reduce_kernel<<<static_cast<unsigned>((ncells + 255) / 256), 256, 0, lm::as_stream(stream)>>>(
+        sums_dev, 1, ncells, variant_scale(variant, n_total_points), U_dev);
+    LM_CUDA_TRY(cudaGetLastError());
+    return LM_OK;
+}
 
 int32_t lm_log_potential(const double* px, const double* py, int64_t npts,
                          const double* gx, int64_t nx, const double* gy, int64_t ny,
@@ -80,29 +266,26 @@ int32_t lm_log_potential(const double* px, const double* py, int64_t npts,
     }
     LM_CUDA_TRY(cudaMemcpyAsync(dgx, gx, nx * sizeof(double), cudaMemcpyHostToDevice, s));
     LM_CUDA_TRY(cudaMemcpyAsync(dgy, gy, ny * sizeof(double), cudaMemcpyHostToDevice, s));
-    const long long cells = static_cast<long long>(nx) * ny;
-    const unsigned blocks = static_cast<unsigned>((cells + LP_THREADS - 1) / LP_THREADS);
     lm::Timer tm;
     if ((rc = tm.begin(s)) != LM_OK) return rc;
-#define LM_LP_LAUNCH(V) logpot_kernel<V><<<blocks, LP_THREADS, 0, s>>>(static_cast<double*>(dpx), static_cast<double*>(dpy), npts, \
-        static_cast<double*>(dgx), nx, static_cast<double*>(dgy), ny, eps, static_cast<double*>(dU))
-    switch (variant) {
-        case LM_LOGPOT_SUM_SQRT: LM_LP_LAUNCH(LM_LOGPOT_SUM_SQRT); break;
-        case LM_LOGPOT_NEG_PERTERM: LM_LP_LAUNCH(LM_LOGPOT_NEG_PERTERM); break;
-        case LM_LOGPOT_SUM_HYPOT: LM_LP_LAUNCH(LM_LOGPOT_SUM_HYPOT); break;
-        default: LM_LP_LAUNCH(LM_LOGPOT_LOG_INV); break;
+    int launches = 0;
+    if (npts == 0) {
+        LM_CUDA_TRY(cudaMemsetAsync(dU, 0, ub, s));
+    } else {
+        rc = logpot_sums_dev(static_cast<double*>(dpx), static_cast<double*>(dpy), npts, static_cast<double*>(dgx), nx,
+                             static_cast<double*>(dgy), ny, eps, variant, variant_scale(variant, npts),
+                             static_cast<double*>(dU), &launches, s);
+        if (rc != LM_OK) return rc;
     }
-#undef LM_LP_LAUNCH
-    LM_CUDA_TRY(cudaGetLastError());
     float ms = 0.f;
     if ((rc = tm.end(s, &ms)) != LM_OK) return rc;
     LM_CUDA_TRY(cudaMemcpyAsync(U, dU, ub, cudaMemcpyDeviceToHost, s));
     LM_CUDA_TRY(cudaStreamSynchronize(s));
     if (stats) {
-        stats->items = static_cast<uint64_t>(cells);
-        stats->work_units = static_cast<uint64_t>(cells) * static_cast<uint64_t>(npts);   // (cell, point) pairs
+        stats->items = static_cast<uint64_t>(nx) * static_cast<uint64_t>(ny);
+        stats->work_units = stats->items * static_cast<uint64_t>(npts);   // (cell, point) pairs
         stats->kernel_ms = ms;
-        stats->launches = 1;
+        stats->launches = launches;
     }
     return LM_OK;
 }

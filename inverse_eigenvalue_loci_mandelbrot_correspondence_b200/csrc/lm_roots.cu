@@ -12,20 +12,25 @@
 // Aberth-Ehrlich simultaneous iteration, which is embarrassingly parallel over roots:
 //   z_i <- z_i - N_i / (1 - N_i * sum_{j != i} 1/(z_i - z_j)),   N_i = p(z_i)/p'(z_i).
 //
-// Mapping: a group of G lanes (G = 8, 16 or 32, chosen per polynomial from its degree by
-// host-side binning) owns one polynomial; coefficients and the current root estimates are
-// staged in shared memory; lane l updates roots l, l+G, ... (Gauss-Seidel between rounds);
-// group-wide decisions use tile shuffles/ballots.  Initial guesses follow Bini's Newton-
-// polygon rule (radii from the upper convex hull of (k, log|c_k|)), which puts the Lucas
-// family straight onto the unit circle.  For |z| > 1 the reversed polynomial is evaluated
-// at 1/z so degrees in the thousands neither overflow nor underflow.  A root is frozen when
-// |p(z)| falls below the rounding-error bound of its own Horner evaluation.
-// Parity with LAPACK is tolerance based (sorted roots, 1e-10 relative; see tests).
+// Mapping: a group of G lanes owns one polynomial (G = 4 for degree <= 32, 8 up to 128, 32
+// above); coefficients and the current root estimates are staged in shared memory; lane l
+// updates roots l, l+G, ... (Gauss-Seidel between rounds); group-wide decisions use tile
+// shuffles/ballots.  The batch is counting-sorted by degree ON THE DEVICE first (histogram,
+// scan, scatter), so the groups that share a warp hold polynomials of the same degree and run
+// the same trip counts; the solver launches read their index ranges from device memory, so
+// the whole pipeline is asynchronous on one stream (lm_roots_batched_dev).
+// The O(d^2) inner loops avoid IEEE division: 1/|z_i - z_j|^2 comes from MUFU.RCP64H plus one
+// Newton step (2^-44 relative; the Aberth sum only steers the iteration, its fixed points are
+// the zeros of p whatever the sum's accuracy), the Newton ratio p/p' uses two steps.
+// Initial guesses follow Bini's Newton-polygon rule (radii from the upper convex hull of
+// (k, log|c_k|)), which puts the Lucas family straight onto the unit circle.  For |z| > 1 the
+// reversed polynomial is evaluated at 1/z so degrees in the thousands neither overflow nor
+// underflow.  A root is frozen when |p(z)| falls below the rounding-error bound of its own
+// Horner evaluation.  Parity with LAPACK is tolerance based (sorted roots, 1e-10 relative).
 #include "lm_common.cuh"
 
 #include <cooperative_groups.h>
 #include <math.h>
-#include <vector>
 
 namespace cg = cooperative_groups;
 
@@ -36,33 +41,147 @@ constexpr int MAX_SWEEPS = 160;
 constexpr double TWO_PI = 6.283185307179586476925286766559;
 constexpr double EPS = 2.220446049250313e-16;
 
+constexpr int CLASS_SMALL_MAX = 32;      // degree <= 32  -> 4 lanes per polynomial
+constexpr int CLASS_MID_MAX = 128;       // degree <= 128 -> 8 lanes, above: a full warp
+constexpr int HIST_BINS = 4096;          // degrees >= HIST_BINS-1 share the last bin
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_ITEMS = 16;           // polynomials per thread in the sort kernels
+
+// device-side bookkeeping of one batch (lives in the workspace)
+struct RootsPlan {
+    long long bounds[4];                 // index ranges of the three classes: [bounds[c], bounds[c+1])
+    int fail_flag;                       // some polynomial did not converge
+    int bad_degree;                      // some deg[k] outside [1, maxdeg]
+    unsigned long long hist[HIST_BINS];  // per-degree counts, then running cursors
+};
+
 struct RootsArgs {
     const double* toprows;     // [npoly * maxdeg]
     const int* deg;            // [npoly]
-    const long long* index;    // polynomial ids handled by this launch [count]
-    long long count;
+    const long long* index;    // degree-sorted polynomial ids
+    RootsPlan* plan;
+    int cls;                   // which class this launch handles
     int maxdeg;
     int invert;
     double tol;
     double* out_re; double* out_im;   // [npoly * maxdeg]
     int* n_kept; int* iters;          // may be NULL
-    int* fail_flag;
     int smem_deg;              // degree capacity of the shared-memory slices
 };
 
 struct cplx { double r, i; };
 __device__ __forceinline__ cplx cmul(cplx a, cplx b) { return {a.r * b.r - a.i * b.i, a.r * b.i + a.i * b.r}; }
+
+// 1/x from MUFU.RCP64H and NR steps (x normal, positive here); STEPS = 1: 2^-44, 2: ~1 ulp
+template <int STEPS>
+__device__ __forceinline__ double rcp_fast(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#pragma unroll
+    for (int k = 0; k < STEPS; ++k) r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+}
+__device__ __forceinline__ cplx cinv_fast(cplx a) {
+    const double s = rcp_fast<2>(a.r * a.r + a.i * a.i);
+    return {a.r * s, -a.i * s};
+}
 __device__ __forceinline__ cplx cinv(cplx a) {
     const double s = 1.0 / (a.r * a.r + a.i * a.i);
     return {a.r * s, -a.i * s};
 }
 
-// per-group shared-memory slice layout (doubles): coef[D+1] | zr[D] | zi[D] | logc[D+1], then ints hull[D+1], then bytes frozen[D]
+__host__ __device__ inline int degree_bin(int d) { return d < HIST_BINS - 1 ? d : HIST_BINS - 1; }
+
+// ---------------------------------------------------------------------------------------
+// counting sort of the polynomial ids by degree
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SORT_THREADS) roots_hist_kernel(const int* __restrict__ deg, long long npoly, int maxdeg,
+                                                                  RootsPlan* __restrict__ plan) {
+    __shared__ unsigned sh[HIST_BINS];
+    for (int k = threadIdx.x; k < HIST_BINS; k += SORT_THREADS) sh[k] = 0u;
+    __syncthreads();
+    const long long base = static_cast<long long>(blockIdx.x) * (SORT_THREADS * SORT_ITEMS);
+    bool bad = false;
+    for (int t = 0; t < SORT_ITEMS; ++t) {
+        const long long k = base + t * SORT_THREADS + threadIdx.x;
+        if (k < npoly) {
+            const int d = deg[k];
+            if (d < 1 || d > maxdeg) bad = true;
+            else atomicAdd(&sh[degree_bin(d)], 1u);
+        }
+    }
+    if (bad) plan->bad_degree = 1;
+    __syncthreads();
+    for (int k = threadIdx.x; k < HIST_BINS; k += SORT_THREADS)
+        if (sh[k]) atomicAdd(&plan->hist[k], static_cast<unsigned long long>(sh[k]));
+}
+
+// exclusive scan of the histogram (in place: hist becomes the cursors) + class boundaries
+__global__ void __launch_bounds__(1024) roots_plan_kernel(RootsPlan* __restrict__ plan) {
+    __shared__ unsigned long long part[1024];
+    constexpr int PER = HIST_BINS / 1024;
+    unsigned long long v[PER], sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { v[k] = plan->hist[threadIdx.x * PER + k]; sum += v[k]; }
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const unsigned long long y = (threadIdx.x >= o) ? part[threadIdx.x - o] : 0ULL;
+        __syncthreads();
+        part[threadIdx.x] += y;
+        __syncthreads();
+    }
+    unsigned long long run = part[threadIdx.x] - sum;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int bin = threadIdx.x * PER + k;
+        plan->hist[bin] = run;
+        if (bin == 0) plan->bounds[0] = 0;
+        if (bin == CLASS_SMALL_MAX + 1) plan->bounds[1] = static_cast<long long>(run);
+        if (bin == CLASS_MID_MAX + 1) plan->bounds[2] = static_cast<long long>(run);
+        run += v[k];
+    }
+    if (threadIdx.x == 1023) plan->bounds[3] = static_cast<long long>(run);
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) roots_scatter_kernel(const int* __restrict__ deg, long long npoly, int maxdeg,
+                                                                     RootsPlan* __restrict__ plan, long long* __restrict__ index) {
+    __shared__ unsigned cnt[HIST_BINS];
+    __shared__ unsigned long long start[HIST_BINS];
+    for (int k = threadIdx.x; k < HIST_BINS; k += SORT_THREADS) cnt[k] = 0u;
+    __syncthreads();
+    const long long base = static_cast<long long>(blockIdx.x) * (SORT_THREADS * SORT_ITEMS);
+    int bins[SORT_ITEMS];
+    unsigned rank[SORT_ITEMS];
+#pragma unroll
+    for (int t = 0; t < SORT_ITEMS; ++t) {
+        const long long k = base + t * SORT_THREADS + threadIdx.x;
+        bins[t] = -1;
+        if (k < npoly) {
+            const int d = deg[k];
+            if (d >= 1 && d <= maxdeg) { bins[t] = degree_bin(d); rank[t] = atomicAdd(&cnt[bins[t]], 1u); }
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < HIST_BINS; k += SORT_THREADS)
+        if (cnt[k]) start[k] = atomicAdd(&plan->hist[k], static_cast<unsigned long long>(cnt[k]));
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < SORT_ITEMS; ++t)
+        if (bins[t] >= 0) index[start[bins[t]] + rank[t]] = base + t * SORT_THREADS + threadIdx.x;
+}
+
+// ---------------------------------------------------------------------------------------
+// the solver
+// ---------------------------------------------------------------------------------------
+// per-group shared-memory slice: coef[D+1] | z[D] (re, im interleaved) | logc[D+1] | int hull[D+1] | bytes frozen[D]
 __host__ __device__ inline size_t group_smem_bytes(int D) {
-    size_t b = sizeof(double) * (static_cast<size_t>(D + 1) + D + D + (D + 1));
+    size_t b = sizeof(double) * (static_cast<size_t>(D + 2) + 2 * static_cast<size_t>(D) + (D + 1));
     b += sizeof(int) * static_cast<size_t>(D + 1);
     b += static_cast<size_t>(D);
-    return (b + 15) & ~static_cast<size_t>(15);
+    b = (b + 15) & ~static_cast<size_t>(15);
+    if (((b >> 4) & 1) == 0) b += 16;        // stride = 16 * odd: the groups of a warp never share a bank row
+    return b;
 }
 
 template <int G>
@@ -76,15 +195,15 @@ __global__ void __launch_bounds__(ROOTS_THREADS) roots_kernel(const RootsArgs A)
     const int D = A.smem_deg;
     unsigned char* base = smem + static_cast<size_t>(gid) * group_smem_bytes(D);
     double* coef = reinterpret_cast<double*>(base);            // coef[k] multiplies x^(d-k); coef[0] = 1
-    double* zr = coef + (D + 1);
-    double* zi = zr + D;
-    double* logc = zi + D;
+    double2* zz = reinterpret_cast<double2*>(coef + ((D + 2) & ~1));
+    double* logc = reinterpret_cast<double*>(zz + D);
     int* hull = reinterpret_cast<int*>(logc + (D + 1));
     unsigned char* frozen = reinterpret_cast<unsigned char*>(hull + (D + 1));
+    const long long first = A.plan->bounds[A.cls], last = A.plan->bounds[A.cls + 1];
 
-    for (long long item = static_cast<long long>(blockIdx.x) * groups_per_cta + gid; item < A.count;
+    for (long long item = first + static_cast<long long>(blockIdx.x) * groups_per_cta + gid; item < last;
          item += static_cast<long long>(gridDim.x) * groups_per_cta) {
-        const long long pid = A.index ? A.index[item] : item;
+        const long long pid = A.index[item];
         const int d_full = A.deg[pid];
         const double* top = A.toprows + pid * A.maxdeg;
         // trailing zero coefficients are roots at 0: deflate
@@ -132,8 +251,7 @@ __global__ void __launch_bounds__(ROOTS_THREADS) roots_kernel(const RootsArgs A)
             const double ang = TWO_PI * (k - i1) / m + TWO_PI * e / d + 0.7;
             double sn, cs;
             sincos(ang, &sn, &cs);
-            zr[k] = radius * cs;
-            zi[k] = radius * sn;
+            zz[k] = make_double2(radius * cs, radius * sn);
             frozen[k] = 0;
         }
         tile.sync();
@@ -147,78 +265,90 @@ __global__ void __launch_bounds__(ROOTS_THREADS) roots_kernel(const RootsArgs A)
             for (int r0 = 0; r0 < d; r0 += G) {
                 const int i = r0 + l;
                 cplx znew = {0.0, 0.0};
-                bool active = (i < d) && !frozen[i];
+                const bool active = (i < d) && !frozen[i];
                 bool freeze = false, stagnant = false;
                 if (active) {
-                    const cplx z = {zr[i], zi[i]};
-                    const double az = sqrt(z.r * z.r + z.i * z.i);
+                    const double2 zi2 = zz[i];
+                    const cplx z = {zi2.x, zi2.y};
+                    const double az2 = z.r * z.r + z.i * z.i;
+                    const double az = sqrt(az2);
                     cplx newton;           // p/p'
                     if (az <= 1.0) {
                         cplx b = {coef[0], 0.0}, bp = {0.0, 0.0};
                         double s = fabs(coef[0]);
                         for (int k = 1; k <= d; ++k) {
-                            bp = cmul(bp, z); bp.r += b.r; bp.i += b.i;
-                            b = cmul(b, z); b.r += coef[k];
-                            s = s * az + fabs(coef[k]);
+                            const double ck = coef[k];
+                            bp = {fma(bp.r, z.r, fma(-bp.i, z.i, b.r)), fma(bp.r, z.i, fma(bp.i, z.r, b.i))};
+                            b = {fma(b.r, z.r, fma(-b.i, z.i, ck)), fma(b.r, z.i, b.i * z.r)};
+                            s = fma(s, az, fabs(ck));
                         }
-                        const double ab = sqrt(b.r * b.r + b.i * b.i);
-                        freeze = ab <= EPS * s * (d + 1) || ab == 0.0;
+                        const double ab2 = b.r * b.r + b.i * b.i;
+                        const double bound = EPS * s * (d + 1);
+                        freeze = ab2 <= bound * bound;
                         const double dp = bp.r * bp.r + bp.i * bp.i;
-                        newton = (dp > 0.0) ? cmul(b, cinv(bp)) : cplx{1e-3 * (az + 1e-3), 1e-3 * (az + 1e-3)};
+                        newton = (dp > 1e-290 && dp < 1e290) ? cmul(b, cinv_fast(bp))
+                               : (dp > 0.0 ? cmul(b, cinv(bp)) : cplx{1e-3 * (az + 1e-3), 1e-3 * (az + 1e-3)});
                     } else {
                         // p(z) = z^d q(w), w = 1/z, q(w) = sum_k coef[k] w^k; Horner from coef[d] down
-                        const cplx w = cinv(z);
-                        const double aw = 1.0 / az;
+                        const double iz2 = rcp_fast<2>(az2);
+                        const cplx w = {z.r * iz2, -z.i * iz2};
+                        const double aw = az * iz2;
                         cplx b = {coef[d], 0.0}, bp = {0.0, 0.0};
                         double s = fabs(coef[d]);
                         for (int k = d - 1; k >= 0; --k) {
-                            bp = cmul(bp, w); bp.r += b.r; bp.i += b.i;
-                            b = cmul(b, w); b.r += coef[k];
-                            s = s * aw + fabs(coef[k]);
+                            const double ck = coef[k];
+                            bp = {fma(bp.r, w.r, fma(-bp.i, w.i, b.r)), fma(bp.r, w.i, fma(bp.i, w.r, b.i))};
+                            b = {fma(b.r, w.r, fma(-b.i, w.i, ck)), fma(b.r, w.i, b.i * w.r)};
+                            s = fma(s, aw, fabs(ck));
                         }
-                        const double ab = sqrt(b.r * b.r + b.i * b.i);
-                        freeze = ab <= EPS * s * (d + 1) || ab == 0.0;
+                        const double ab2 = b.r * b.r + b.i * b.i;
+                        const double bound = EPS * s * (d + 1);
+                        freeze = ab2 <= bound * bound;
                         // p/p' = z / (d - w q'(w)/q(w))
                         cplx den = {static_cast<double>(d), 0.0};
-                        if (ab > 0.0) {
-                            const cplx t = cmul(cmul(w, bp), cinv(b));
+                        if (ab2 > 0.0) {
+                            const cplx t = cmul(cmul(w, bp), (ab2 > 1e-290 && ab2 < 1e290) ? cinv_fast(b) : cinv(b));
                             den.r -= t.r; den.i -= t.i;
                         }
                         const double dd = den.r * den.r + den.i * den.i;
-                        newton = (dd > 0.0) ? cmul(z, cinv(den)) : cplx{1e-3 * az, 1e-3 * az};
+                        newton = (dd > 1e-290 && dd < 1e290) ? cmul(z, cinv_fast(den))
+                               : (dd > 0.0 ? cmul(z, cinv(den)) : cplx{1e-3 * az, 1e-3 * az});
                     }
                     if (!freeze) {
-                        cplx S = {0.0, 0.0};
+                        double Sr = 0.0, Si = 0.0;
+#pragma unroll 4
                         for (int j = 0; j < d; ++j) {
-                            if (j == i) continue;
-                            const double dr = z.r - zr[j], di = z.i - zi[j];
-                            const double q = dr * dr + di * di;
-                            if (q > 0.0) {
-                                const double inv = 1.0 / q;
-                                S.r += dr * inv; S.i -= di * inv;
-                            }
+                            const double2 zj = zz[j];
+                            const double dr = z.r - zj.x, di = z.i - zj.y;
+                            const double q = fma(dr, dr, di * di);
+                            // j == i (q == 0) and coinciding estimates contribute nothing; the
+                            // reciprocal's NaN/Inf for q == 0 is discarded by the select
+                            const double inv = (q > 1e-300) ? rcp_fast<1>(q) : 0.0;
+                            Sr = fma(dr, inv, Sr);
+                            Si = fma(-di, inv, Si);
                         }
-                        const cplx ns = cmul(newton, S);
-                        cplx den = {1.0 - ns.r, -ns.i};
+                        const cplx ns = cmul(newton, cplx{Sr, Si});
+                        const cplx den = {1.0 - ns.r, -ns.i};
                         const double dd = den.r * den.r + den.i * den.i;
-                        const cplx corr = (dd > 0.0) ? cmul(newton, cinv(den)) : newton;
+                        const cplx corr = (dd > 1e-290 && dd < 1e290) ? cmul(newton, cinv_fast(den))
+                                        : (dd > 0.0 ? cmul(newton, cinv(den)) : newton);
                         znew = {z.r - corr.r, z.i - corr.i};
                         if (!(isfinite(znew.r) && isfinite(znew.i))) znew = {z.r * 0.5 + 1e-3, z.i * 0.5 - 1e-3};
                         // stagnation: the correction is below the resolution of z -> next sweep freezes it
-                        if (corr.r * corr.r + corr.i * corr.i <= (4.0 * EPS * EPS) * (az * az)) stagnant = true;
+                        if (corr.r * corr.r + corr.i * corr.i <= (4.0 * EPS * EPS) * az2) stagnant = true;
                         mine_done = false;
                     }
                 }
                 tile.sync();               // everybody has read the old estimates of this round
                 if (active) {
                     if (freeze) frozen[i] = 1;
-                    else { zr[i] = znew.r; zi[i] = znew.i; if (stagnant) frozen[i] = 1; }
+                    else { zz[i] = make_double2(znew.r, znew.i); if (stagnant) frozen[i] = 1; }
                 }
                 tile.sync();
             }
             all_done = tile.all(mine_done);
         }
-        if (!all_done && A.fail_flag) { if (l == 0) atomicExch(A.fail_flag, 1); }
+        if (!all_done && l == 0) atomicExch(&A.plan->fail_flag, 1);
 
         // ---- output: [zero roots] + computed roots, optionally inverted / filtered / compacted
         double* ore = A.out_re + pid * A.maxdeg;
@@ -230,7 +360,8 @@ __global__ void __launch_bounds__(ROOTS_THREADS) roots_kernel(const RootsArgs A)
             bool keep = false;
             cplx v = {0.0, 0.0};
             if (i < total) {
-                const cplx z = (i < d) ? cplx{zr[i], zi[i]} : cplx{0.0, 0.0};
+                cplx z = {0.0, 0.0};
+                if (i < d) { const double2 t = zz[i]; z = {t.x, t.y}; }
                 if (A.invert) {
                     const double az = sqrt(z.r * z.r + z.i * z.i);
                     keep = az > A.tol;
@@ -258,8 +389,7 @@ __global__ void __launch_bounds__(ROOTS_THREADS) roots_kernel(const RootsArgs A)
 }
 
 template <int G>
-int32_t launch_roots(RootsArgs A, cudaStream_t s) {
-    if (A.count == 0) return LM_OK;
+int32_t launch_roots(RootsArgs A, long long npoly, cudaStream_t s) {
     auto kern = roots_kernel<G>;
     int groups = ROOTS_THREADS / G;
     const size_t per_group = group_smem_bytes(A.smem_deg);
@@ -270,7 +400,7 @@ int32_t launch_roots(RootsArgs A, cudaStream_t s) {
                         A.smem_deg, per_group);
     const size_t smem = per_group * groups;
     LM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    long long blocks = (A.count + groups - 1) / groups;
+    long long blocks = (npoly + groups - 1) / groups;          // the class size is only known on the device
     const long long cap = static_cast<long long>(lm::sm_count()) * 16;
     if (blocks > cap) blocks = cap;
     kern<<<static_cast<unsigned>(blocks), groups * G, smem, s>>>(A);
@@ -278,9 +408,177 @@ int32_t launch_roots(RootsArgs A, cudaStream_t s) {
     return LM_OK;
 }
 
+// the whole K3 pipeline on one stream, device buffers in and out; plan_out = device bookkeeping
+int32_t roots_enqueue(const double* toprows, const int* deg, long long npoly, int maxdeg, int invert, double tol,
+                      double* out_re, double* out_im, int* n_kept, int* iters, RootsPlan** plan_out, int* launches,
+                      cudaStream_t s) {
+    int32_t rc;
+    void *dplan, *dindex;
+    if ((rc = lm::ws_get(lm::WS_ROOTS_PLAN, sizeof(RootsPlan), &dplan)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_ROOTS_INDEX, static_cast<size_t>(npoly) * sizeof(long long), &dindex)) != LM_OK) return rc;
+    RootsPlan* plan = static_cast<RootsPlan*>(dplan);
+    LM_CUDA_TRY(cudaMemsetAsync(plan, 0, sizeof(RootsPlan), s));
+    const unsigned sort_blocks = static_cast<unsigned>((npoly + SORT_THREADS * SORT_ITEMS - 1) / (SORT_THREADS * SORT_ITEMS));
+    roots_hist_kernel<<<sort_blocks, SORT_THREADS, 0, s>>>(deg, npoly, maxdeg, plan);
+    roots_plan_kernel<<<1, 1024, 0, s>>>(plan);
+    roots_scatter_kernel<<<sort_blocks, SORT_THREADS, 0, s>>>(deg, npoly, maxdeg, plan, static_cast<long long*>(dindex));
+    LM_CUDA_TRY(cudaGetLastError());
+    RootsArgs A{};
+    A.toprows = toprows; A.deg = deg; A.index = static_cast<const long long*>(dindex); A.plan = plan;
+    A.maxdeg = maxdeg; A.invert = invert; A.tol = tol;
+    A.out_re = out_re; A.out_im = out_im; A.n_kept = n_kept; A.iters = iters;
+    int n = 3;
+    A.cls = 0; A.smem_deg = maxdeg < CLASS_SMALL_MAX ? maxdeg : CLASS_SMALL_MAX;
+    if ((rc = launch_roots<4>(A, npoly, s)) != LM_OK) return rc;
+    ++n;
+    if (maxdeg > CLASS_SMALL_MAX) {
+        A.cls = 1; A.smem_deg = maxdeg < CLASS_MID_MAX ? maxdeg : CLASS_MID_MAX;
+        if ((rc = launch_roots<8>(A, npoly, s)) != LM_OK) return rc;
+        ++n;
+    }
+    if (maxdeg > CLASS_MID_MAX) {
+        A.cls = 2; A.smem_deg = maxdeg;
+        if ((rc = launch_roots<32>(A, npoly, s)) != LM_OK) return rc;
+        ++n;
+    }
+    if (plan_out) *plan_out = plan;
+    if (launches) *launches = n;
+    return LM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// cloud compaction: the valid slots of every polynomial, concatenated in polynomial order
+// ---------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;             // elements per thread -> 2048 per block
+
+__global__ void __launch_bounds__(SCAN_THREADS) kept_block_sums_kernel(const int* __restrict__ n_kept, long long npoly,
+                                                                       unsigned long long* __restrict__ block_sums) {
+    __shared__ unsigned long long wsum[SCAN_THREADS / 32];
+    const long long base = static_cast<long long>(blockIdx.x) * (SCAN_THREADS * SCAN_ITEMS) + threadIdx.x * SCAN_ITEMS;
+    unsigned long long s = 0;
+#pragma unroll
+    for (int t = 0; t < SCAN_ITEMS; ++t) if (base + t < npoly) s += static_cast<unsigned long long>(n_kept[base + t]);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int k = 0; k < SCAN_THREADS / 32; ++k) t += wsum[k];
+        block_sums[blockIdx.x] = t;
+    }
+}
+
+// exclusive scan of the block sums in place (single CTA), total -> *total_out
+__global__ void __launch_bounds__(1024) kept_scan_sums_kernel(unsigned long long* __restrict__ block_sums, long long nblocks,
+                                                              long long* __restrict__ total_out) {
+    __shared__ unsigned long long part[1024];
+    __shared__ unsigned long long carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (long long base = 0; base < nblocks; base += 1024) {
+        const long long idx = base + threadIdx.x;
+        const unsigned long long v = idx < nblocks ? block_sums[idx] : 0ULL;
+        part[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const unsigned long long y = (threadIdx.x >= o) ? part[threadIdx.x - o] : 0ULL;
+            __syncthreads();
+            part[threadIdx.x] += y;
+            __syncthreads();
+        }
+        const unsigned long long carry = carry_s;
+        if (idx < nblocks) block_sums[idx] = carry + part[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + part[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = static_cast<long long>(carry_s);
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) cloud_gather_kernel(const double* __restrict__ re, const double* __restrict__ im,
+                                                                    const int* __restrict__ n_kept, long long npoly, int maxdeg,
+                                                                    const unsigned long long* __restrict__ block_offsets,
+                                                                    double* __restrict__ px, double* __restrict__ py,
+                                                                    long long cap) {
+    __shared__ unsigned long long wsum[SCAN_THREADS / 32];
+    const long long base = static_cast<long long>(blockIdx.x) * (SCAN_THREADS * SCAN_ITEMS) + threadIdx.x * SCAN_ITEMS;
+    int cnt[SCAN_ITEMS];
+    unsigned long long mine = 0;
+#pragma unroll
+    for (int t = 0; t < SCAN_ITEMS; ++t) { cnt[t] = (base + t < npoly) ? n_kept[base + t] : 0; mine += cnt[t]; }
+    unsigned long long incl = mine;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    unsigned long long before = block_offsets[blockIdx.x];
+    for (int k = 0; k < warp; ++k) before += wsum[k];
+    unsigned long long pos = before + incl - mine;
+#pragma unroll
+    for (int t = 0; t < SCAN_ITEMS; ++t) {
+        const long long pid = base + t;
+        for (int r = 0; r < cnt[t]; ++r) {
+            if (static_cast<long long>(pos) < cap) { px[pos] = re[pid * maxdeg + r]; py[pos] = im[pid * maxdeg + r]; }
+            ++pos;
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+int32_t lm_roots_batched_dev(const double* toprows_dev, const int32_t* deg_dev, int64_t npoly, int32_t maxdeg,
+                             int32_t invert, double tol, double* out_re_dev, double* out_im_dev,
+                             int32_t* n_kept_dev, int32_t* iters_dev, int32_t* status_dev, void* stream) {
+    int32_t rc = lm::require_device();
+    if (rc != LM_OK) return rc;
+    LM_REQUIRE(npoly >= 0 && maxdeg >= 1, "lm_roots_batched_dev: bad sizes");
+    LM_REQUIRE(npoly == 0 || (toprows_dev && deg_dev && out_re_dev && out_im_dev), "lm_roots_batched_dev: NULL buffer");
+    cudaStream_t s = lm::as_stream(stream);
+    if (npoly == 0) {
+        if (status_dev) LM_CUDA_TRY(cudaMemsetAsync(status_dev, 0, 2 * sizeof(int32_t), s));
+        return LM_OK;
+    }
+    RootsPlan* plan = nullptr;
+    rc = roots_enqueue(toprows_dev, deg_dev, npoly, maxdeg, invert, tol, out_re_dev, out_im_dev, n_kept_dev, iters_dev,
+                       &plan, nullptr, s);
+    if (rc != LM_OK) return rc;
+    if (status_dev)
+        LM_CUDA_TRY(cudaMemcpyAsync(status_dev, &plan->fail_flag, 2 * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+    return LM_OK;
+}
+
+int32_t lm_cloud_compact_dev(const double* re_dev, const double* im_dev, const int32_t* n_kept_dev, int64_t npoly,
+                             int32_t maxdeg, double* px_dev, double* py_dev, int64_t cap_points,
+                             int64_t* n_points_dev, void* stream) {
+    int32_t rc = lm::require_device();
+    if (rc != LM_OK) return rc;
+    LM_REQUIRE(npoly >= 0 && maxdeg >= 1 && cap_points >= 0, "lm_cloud_compact_dev: bad sizes");
+    LM_REQUIRE(n_points_dev != nullptr, "lm_cloud_compact_dev: n_points_dev is NULL");
+    LM_REQUIRE(npoly == 0 || (re_dev && im_dev && n_kept_dev && (cap_points == 0 || (px_dev && py_dev))),
+               "lm_cloud_compact_dev: NULL buffer");
+    cudaStream_t s = lm::as_stream(stream);
+    if (npoly == 0) {
+        LM_CUDA_TRY(cudaMemsetAsync(n_points_dev, 0, sizeof(int64_t), s));
+        return LM_OK;
+    }
+    const long long per_block = SCAN_THREADS * SCAN_ITEMS;
+    const long long nblocks = (npoly + per_block - 1) / per_block;
+    void* dsums;
+    if ((rc = lm::ws_get(lm::WS_CLOUD_SCAN, static_cast<size_t>(nblocks) * sizeof(unsigned long long), &dsums)) != LM_OK) return rc;
+    unsigned long long* sums = static_cast<unsigned long long*>(dsums);
+    kept_block_sums_kernel<<<static_cast<unsigned>(nblocks), SCAN_THREADS, 0, s>>>(n_kept_dev, npoly, sums);
+    kept_scan_sums_kernel<<<1, 1024, 0, s>>>(sums, nblocks, reinterpret_cast<long long*>(n_points_dev));
+    cloud_gather_kernel<<<static_cast<unsigned>(nblocks), SCAN_THREADS, 0, s>>>(re_dev, im_dev, n_kept_dev, npoly, maxdeg, sums,
+                                                                                px_dev, py_dev, cap_points);
+    LM_CUDA_TRY(cudaGetLastError());
+    return LM_OK;
+}
 
 int32_t lm_roots_batched(const double* toprows, const int32_t* deg, int64_t npoly, int32_t maxdeg,
                          int32_t invert, double tol, double* out_re, double* out_im,
@@ -291,82 +589,51 @@ int32_t lm_roots_batched(const double* toprows, const int32_t* deg, int64_t npol
     LM_REQUIRE(npoly == 0 || (toprows && deg && out_re && out_im), "lm_roots_batched: NULL buffer");
     if (stats) *stats = lm_stats{};
     if (npoly == 0) return LM_OK;
-    // bin the polynomials by degree: 8, 16 or 32 lanes per polynomial
-    std::vector<long long> bins[3];
-    uint64_t nroots = 0;
-    int deg_max_seen = 1;
-    for (int64_t k = 0; k < npoly; ++k) {
-        const int d = deg[k];
-        LM_REQUIRE(d >= 1 && d <= maxdeg, "lm_roots_batched: deg[%lld] = %d outside [1, %d]", static_cast<long long>(k), d, maxdeg);
-        nroots += static_cast<uint64_t>(d);
-        if (d > deg_max_seen) deg_max_seen = d;
-        bins[d <= 8 ? 0 : (d <= 16 ? 1 : 2)].push_back(k);
-    }
     cudaStream_t s = nullptr;
     const size_t ncoef = static_cast<size_t>(npoly) * maxdeg;
-    void *dtop, *ddeg, *dre, *dim, *dkept, *diters, *dindex, *dflag;
+    void *dtop, *ddeg, *dre, *dim, *dkept, *diters;
     if ((rc = lm::ws_get(lm::WS_IN_A, ncoef * sizeof(double), &dtop)) != LM_OK) return rc;
     if ((rc = lm::ws_get(lm::WS_IN_B, static_cast<size_t>(npoly) * sizeof(int), &ddeg)) != LM_OK) return rc;
     if ((rc = lm::ws_get(lm::WS_OUT_A, ncoef * sizeof(double), &dre)) != LM_OK) return rc;
     if ((rc = lm::ws_get(lm::WS_OUT_B, ncoef * sizeof(double), &dim)) != LM_OK) return rc;
     if ((rc = lm::ws_get(lm::WS_OUT_C, static_cast<size_t>(npoly) * sizeof(int), &dkept)) != LM_OK) return rc;
     if ((rc = lm::ws_get(lm::WS_OUT_D, static_cast<size_t>(npoly) * sizeof(int), &diters)) != LM_OK) return rc;
-    if ((rc = lm::ws_get(lm::WS_IN_C, static_cast<size_t>(npoly) * sizeof(long long), &dindex)) != LM_OK) return rc;
-    if ((rc = lm::ws_get(lm::WS_SCRATCH, 64, &dflag)) != LM_OK) return rc;
     LM_CUDA_TRY(cudaMemcpyAsync(dtop, toprows, ncoef * sizeof(double), cudaMemcpyHostToDevice, s));
     LM_CUDA_TRY(cudaMemcpyAsync(ddeg, deg, static_cast<size_t>(npoly) * sizeof(int), cudaMemcpyHostToDevice, s));
-    LM_CUDA_TRY(cudaMemsetAsync(dflag, 0, 64, s));
-    size_t off = 0;
-    long long* dindex_ll = static_cast<long long*>(dindex);
-    for (int b = 0; b < 3; ++b) {
-        if (bins[b].empty()) continue;
-        LM_CUDA_TRY(cudaMemcpyAsync(dindex_ll + off, bins[b].data(), bins[b].size() * sizeof(long long),
-                                    cudaMemcpyHostToDevice, s));
-        off += bins[b].size();
-    }
-    RootsArgs A{};
-    A.toprows = static_cast<const double*>(dtop);
-    A.deg = static_cast<const int*>(ddeg);
-    A.maxdeg = maxdeg;
-    A.invert = invert;
-    A.tol = tol;
-    A.out_re = static_cast<double*>(dre);
-    A.out_im = static_cast<double*>(dim);
-    A.n_kept = static_cast<int*>(dkept);
-    A.iters = static_cast<int*>(diters);
-    A.fail_flag = static_cast<int*>(dflag);
     lm::Timer tm;
     if ((rc = tm.begin(s)) != LM_OK) return rc;
-    off = 0;
+    RootsPlan* plan = nullptr;
     int launches = 0;
-    for (int b = 0; b < 3; ++b) {
-        if (bins[b].empty()) continue;
-        A.index = dindex_ll + off;
-        A.count = static_cast<long long>(bins[b].size());
-        A.smem_deg = (b == 0) ? 8 : (b == 1) ? 16 : deg_max_seen;
-        if (b == 0) rc = launch_roots<8>(A, s);
-        else if (b == 1) rc = launch_roots<16>(A, s);
-        else rc = launch_roots<32>(A, s);
-        if (rc != LM_OK) return rc;
-        off += bins[b].size();
-        ++launches;
-    }
+    rc = roots_enqueue(static_cast<double*>(dtop), static_cast<int*>(ddeg), npoly, maxdeg, invert, tol,
+                       static_cast<double*>(dre), static_cast<double*>(dim), static_cast<int*>(dkept),
+                       static_cast<int*>(diters), &plan, &launches, s);
+    if (rc != LM_OK) return rc;
     float ms = 0.f;
     if ((rc = tm.end(s, &ms)) != LM_OK) return rc;
+    int flags[2] = {0, 0};
+    LM_CUDA_TRY(cudaMemcpyAsync(flags, &plan->fail_flag, sizeof(flags), cudaMemcpyDeviceToHost, s));
+    LM_CUDA_TRY(cudaStreamSynchronize(s));
+    if (flags[1]) {
+        for (int64_t k = 0; k < npoly; ++k)
+            if (deg[k] < 1 || deg[k] > maxdeg)
+                return lm::fail(LM_E_INVALID, "lm_roots_batched: deg[%lld] = %d outside [1, %d]", static_cast<long long>(k),
+                                deg[k], maxdeg);
+        return lm::fail(LM_E_INVALID, "lm_roots_batched: a degree outside [1, %d]", maxdeg);
+    }
     LM_CUDA_TRY(cudaMemcpyAsync(out_re, dre, ncoef * sizeof(double), cudaMemcpyDeviceToHost, s));
     LM_CUDA_TRY(cudaMemcpyAsync(out_im, dim, ncoef * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (n_kept) LM_CUDA_TRY(cudaMemcpyAsync(n_kept, dkept, static_cast<size_t>(npoly) * sizeof(int), cudaMemcpyDeviceToHost, s));
     if (iters) LM_CUDA_TRY(cudaMemcpyAsync(iters, diters, static_cast<size_t>(npoly) * sizeof(int), cudaMemcpyDeviceToHost, s));
-    int failed = 0;
-    LM_CUDA_TRY(cudaMemcpyAsync(&failed, dflag, sizeof(int), cudaMemcpyDeviceToHost, s));
     LM_CUDA_TRY(cudaStreamSynchronize(s));
     if (stats) {
+        uint64_t nroots = 0;
+        for (int64_t k = 0; k < npoly; ++k) nroots += static_cast<uint64_t>(deg[k]);
         stats->items = static_cast<uint64_t>(npoly);
         stats->work_units = nroots;
         stats->kernel_ms = ms;
         stats->launches = launches;
     }
-    if (failed)
+    if (flags[0])
         return lm::fail(LM_E_NOCONV, "lm_roots_batched: Aberth iteration did not converge within %d sweeps for some polynomial "
                         "(iters < 0 marks them; outputs hold the last estimates)", MAX_SWEEPS);
     return LM_OK;

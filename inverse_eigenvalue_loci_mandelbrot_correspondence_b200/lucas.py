@@ -21,7 +21,7 @@ import ctypes as C
 import numpy as np
 
 from . import _shim
-from ._shim import Stats
+from ._shim import CloudStats, LOGPOT_SUM_SQRT, Stats
 
 last_stats: dict = {}
 
@@ -135,3 +135,54 @@ def construct_points_xy(maxN: int = 40) -> np.ndarray:
     """construct_points(maxN) of construct_stage1_clean.py:34-48: float [N,2] for n = 2..maxN, tol 1e-12."""
     pts = compute_inverse_eigenvalues(2, maxN, 1e-12)
     return np.column_stack([pts.real, pts.imag]).astype(float)
+
+
+def cloud_fields(toprows, deg, grid_x=None, grid_y=None, tol: float = 1e-12, eps: float = 1e-12,
+                 variant: int = LOGPOT_SUM_SQRT, h: float | None = None, potential: tuple[int, float] | None = None,
+                 return_cloud: bool = True, laplacian: bool = True) -> dict:
+    """The Lucas-Loci field stage in one call (BASELINE.json config 5), everything resident in HBM between
+    the stages: roots of every polynomial (K3) -> cloud of 1/lambda in polynomial order
+    (lucas_equipotential_test_v3.py:93-118) -> batch_potential at the cloud (K1d, :153-162, when
+    `potential=(max_iter, R)`) -> log-potential on the grid (K4a, Potentials.py:19-27 by default) -> periodic
+    5-point Laplacian (K4, Laplacian_C-M.py:49-59; h defaults to the x spacing as there).
+
+    Returns {"cloud", "g", "it", "U", "lapU", "stats"}; entries not asked for are None.
+    """
+    toprows = np.ascontiguousarray(toprows, dtype=np.float64)
+    if toprows.ndim != 2:
+        raise ValueError("toprows must be [npoly, maxdeg]")
+    npoly, maxdeg = toprows.shape
+    deg = np.ascontiguousarray(deg, dtype=np.int32).reshape(-1)
+    if deg.shape[0] != npoly:
+        raise ValueError("deg must have one entry per polynomial")
+    cap = int(np.clip(deg, 0, None).sum())
+    want_pts = return_cloud or potential is not None
+    cre = np.empty(cap, dtype=np.float64) if return_cloud else None
+    cim = np.empty(cap, dtype=np.float64) if return_cloud else None
+    g = np.empty(cap, dtype=np.float64) if potential is not None else None
+    it = np.empty(cap, dtype=np.int64) if potential is not None else None
+    U = lap = gx = gy = None
+    nx = ny = 0
+    if grid_x is not None and grid_y is not None:
+        gx = np.ascontiguousarray(grid_x, dtype=np.float64).ravel()
+        gy = np.ascontiguousarray(grid_y, dtype=np.float64).ravel()
+        nx, ny = gx.size, gy.size
+        U = np.empty((ny, nx), dtype=np.float64)
+        if laplacian:
+            lap = np.empty((ny, nx), dtype=np.float64)
+            if h is None:
+                h = float(gx[1] - gx[0])
+    st = CloudStats()
+    n = C.c_int64(0)
+    pmi, pR = (int(potential[0]), float(potential[1])) if potential is not None else (1, 2.0)
+    _shim.call("lm_lucas_cloud_fields", _shim.ptr(toprows), _shim.ptr(deg), npoly, maxdeg, float(tol),
+               _shim.ptr(cre), _shim.ptr(cim), cap if want_pts else 0, C.byref(n), pmi, pR, _shim.ptr(g), _shim.ptr(it),
+               _shim.ptr(gx), nx, _shim.ptr(gy), ny, float(eps), int(variant), float(h if h is not None else 1.0),
+               _shim.ptr(U), _shim.ptr(lap), C.byref(st))
+    k = int(n.value)
+    cloud = None
+    if return_cloud:
+        cloud = np.empty(k, dtype=np.complex128)
+        cloud.real = cre[:k]; cloud.imag = cim[:k]
+    return {"cloud": cloud, "g": None if g is None else g[:k], "it": None if it is None else it[:k],
+            "U": U, "lapU": lap, "n_points": k, "stats": st.as_dict()}

@@ -101,3 +101,25 @@ def gather_records(records: np.ndarray, device, dst: int = 0, group=None):
         return np.concatenate(parts) if parts else np.zeros((0, 8), dtype=np.int64)
     dist.gather(padded, None, dst=dst, group=group)
     return None
+
+
+# ---- Lucas-Loci cloud (config 5): polynomials are independent -> contiguous slices, one all-reduce ----
+def item_slices(n_items: int, nparts: int) -> list[int]:
+    """nparts+1 cut positions of [0, n_items) into contiguous, nearly equal slices (K3 is embarrassingly
+    parallel over polynomials; random degrees balance themselves)."""
+    if nparts < 1:
+        raise ValueError("nparts must be >= 1")
+    return [(n_items * k) // nparts for k in range(nparts + 1)]
+
+
+def allreduce_field_sums(sums, n_points_local: int, group=None):
+    """Sum the per-cell raw log sums (a torch tensor, on the GPU for NCCL) and the cloud sizes over the
+    ranks: the one data-path collective of the cloud stage (K4a with the points sharded).
+    Returns (sums, n_points_total); `sums` is reduced in place."""
+    import torch
+    import torch.distributed as dist
+    cnt = torch.tensor([int(n_points_local)], dtype=torch.int64, device=sums.device)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
+    return sums, int(cnt.item())

@@ -61,3 +61,20 @@ c = lucas.compute_inverse_eigenvalues(2, 200)
 t0 = time.perf_counter(); gg, it, phi = escape.batch_potential(c, 20000, 2.0); dt = time.perf_counter() - t0
 st = escape.last_stats
 print(f"batch_potential {c.size} pts max_iter 20000: kernel {st['kernel_ms']:.2f} ms = {st['work_units']/st['kernel_ms']/1e6:.1f} Gpi/s, host {dt*1e3:.1f} ms")
+# log potential at larger point counts, all variants
+for npts, variant, eps in ((2_000_000, 0, 1e-12), (2_000_000, 2, 1e-12), (2_000_000, 3, 1e-6)):
+    pts = np.random.default_rng(1).uniform(-1.8, 1.8, (npts, 2))
+    potentials._logpot(pts[:, 0], pts[:, 1], g, g, eps, variant); st = potentials.last_stats
+    print(f"log_potential 400^2 x {npts} pts variant {variant} eps {eps:g}: kernel {st['kernel_ms']:.1f} ms = "
+          f"{st['work_units']/st['kernel_ms']/1e6:.1f} G pairs/s")
+# the fused cloud stage (config 5) on the same batch
+for rep in range(2):
+    t0 = time.perf_counter()
+    out = lucas.cloud_fields(top, deg, g, g, potential=(20000, 2.0))
+    dt = time.perf_counter() - t0
+    st = out["stats"]
+    print(f"cloud_fields {npoly} polys: {st['n_points']} pts, host {dt*1e3:.0f} ms; roots {st['roots_ms']:.1f} ms "
+          f"({st['n_roots']/st['roots_ms']/1e3:.0f} M roots/s), compact {st['compact_ms']:.2f} ms, "
+          f"potential {st['potential_ms']:.1f} ms ({st['potential_work']/max(st['potential_ms'],1e-9)/1e6:.0f} Gpi/s, "
+          f"inside {(out['it']==20000).mean():.3f}), logpot {st['logpot_ms']:.1f} ms ({st['pairs']/st['logpot_ms']/1e6:.0f} G pairs/s), "
+          f"stencil {st['stencil_ms']:.3f} ms", flush=True)

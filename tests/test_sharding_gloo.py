@@ -103,3 +103,63 @@ def test_sharded_boundary_gloo(shim, oracle, world):
         p.join(timeout=60)
     for rank, ok, err in results:
         assert ok, f"rank {rank}: {err}"
+
+
+def _cloud_worker(rank: int, world: int, port: int, q):
+    try:
+        sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+        import torch
+        import torch.distributed as dist
+        from oracle import oracle
+        from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import sharding
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        # config-5 shaped batch; every rank owns a contiguous slice of the polynomials
+        rng = np.random.default_rng(0)
+        npoly = 41
+        deg = rng.integers(2, 9, size=npoly)
+        tops = [np.where(np.arange(d) == d - 1, 1.0, rng.integers(0, 3, size=d).astype(float)) for d in deg]
+        cuts = sharding.item_slices(npoly, world)
+        mine = [oracle.inverse_eigenvalues_toprow(tops[k], 1e-12) for k in range(cuts[rank], cuts[rank + 1])]
+        cloud = np.concatenate(mine) if mine else np.zeros(0, complex)
+        gx = np.linspace(-2, 2, 17); gy = np.linspace(-2, 2, 13)
+        # raw per-cell sums of this rank's slice (what lm_log_potential_sums_dev produces on the GPU)
+        pts = np.column_stack([cloud.real, cloud.imag])
+        sums = oracle.log_potential(pts, gx, gy, 1e-12, 0) * max(len(cloud), 1) if len(cloud) else np.zeros((13, 17))
+        t, n_total = sharding.allreduce_field_sums(torch.from_numpy(sums.copy()), len(cloud))
+        U = t.numpy() / n_total
+        full = np.concatenate([oracle.inverse_eigenvalues_toprow(tp, 1e-12) for tp in tops])
+        want = oracle.log_potential(np.column_stack([full.real, full.imag]), gx, gy, 1e-12, 0)
+        ok = n_total == full.size and np.allclose(U, want, rtol=1e-12, atol=1e-13)
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, bool(ok), ""))
+    except Exception:          # pragma: no cover
+        import traceback
+        q.put((rank, False, traceback.format_exc()))
+
+
+def test_item_slices():
+    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import sharding
+    assert sharding.item_slices(10, 3) == [0, 3, 6, 10]
+    assert sharding.item_slices(2, 4) == [0, 0, 1, 1, 2]
+    c = sharding.item_slices(10 ** 7, 8)
+    assert c[0] == 0 and c[-1] == 10 ** 7 and max(np.diff(c)) - min(np.diff(c)) <= 1
+
+
+@pytest.mark.parametrize("world", [2])
+def test_sharded_cloud_field_gloo(oracle, world):
+    """K4a with the cloud sharded over the ranks: all-reduce(sum) of the raw per-cell sums and of the cloud
+    sizes, then the 1/N normalisation -- equals the single-process field."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_cloud_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok, err in results:
+        assert ok, f"rank {rank}: {err}"
