@@ -43,7 +43,7 @@ enum WsSlot {
     WS_XS = 0, WS_YS, WS_OUT_I32, WS_OUT_F64, WS_FIELD, WS_COUNTERS, WS_IN_A, WS_IN_B,
     WS_IN_C, WS_OUT_A, WS_OUT_B, WS_OUT_C, WS_OUT_D, WS_RECORDS, WS_SCRATCH,
     WS_K1_WORK, WS_K2_MASK, WS_K2_COUNT, WS_K2_OFFSET, WS_K2_XS, WS_K2_YS,
-    WS_LOGPOT_PART, WS_ROOTS_PLAN, WS_ROOTS_INDEX, WS_CLOUD_SCAN, WS_CLOUD_A, WS_CLOUD_B, WS_CLOUD_C, WS_CLOUD_D, WS_NSLOTS
+    WS_K1_SURVIVORS, WS_LOGPOT_PART, WS_ROOTS_PLAN, WS_ROOTS_INDEX, WS_CLOUD_SCAN, WS_CLOUD_A, WS_CLOUD_B, WS_CLOUD_C, WS_CLOUD_D, WS_NSLOTS
 };
 int32_t ws_get(WsSlot slot, size_t bytes, void** out);
 void    ws_release_all();

@@ -37,6 +37,7 @@
 #include "lm_common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -83,6 +84,11 @@ struct EscapeArgs {
     unsigned long long* work_counter;   // may be NULL
     int* overflow_flag;            // set when the reference would raise OverflowError
     int vec_i32, vec_f64, vec_field;
+    // points only: two-pass schedule (see lm_escape_points_f64_dev)
+    const long long* index;        // pass 2: point ids to process (NULL: 0..nx-1)
+    const unsigned long long* count_dev;   // pass 2: number of ids, read on the device (NULL: nx)
+    long long* survivors;          // pass 1: ids of points still bounded after max_iter (NULL: none kept)
+    unsigned long long* survivor_count;
 };
 
 // one unfused iteration z <- z*z + c given the squares a, b of the current z
@@ -143,6 +149,15 @@ __global__ void __launch_bounds__(CTA_THREADS, LM_K1_MIN_CTAS) lm_escape_kernel(
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+
+    // item count: the launch arguments, or (points, pass 2) a device-side counter
+    long long NX = A.nx;
+    unsigned long long NTILES = A.ntiles, CHUNKS = A.chunks_per_row;
+    if (POINTS && A.count_dev) {
+        NX = static_cast<long long>(*A.count_dev);
+        NTILES = static_cast<unsigned long long>((NX + TILE - 1) / TILE);
+        CHUNKS = NTILES;
+    }
 
     int* s_dwell = reinterpret_cast<int*>(smem_raw) + warp * (RING * TILE);
     double* s_field = reinterpret_cast<double*>(smem_raw + WARPS * RING * TILE * sizeof(int)) +
@@ -214,21 +229,21 @@ __global__ void __launch_bounds__(CTA_THREADS, LM_K1_MIN_CTAS) lm_escape_kernel(
             if (cursor == width) {
                 if (exhausted) break;
                 const unsigned long long t = __shfl_sync(FULL, pref, 0);
-                if (t >= A.ntiles) { exhausted = true; break; }
+                if (t >= NTILES) { exhausted = true; break; }
                 if (lane == 0) pref = atomicAdd(A.tile_counter, 1ULL);
                 unsigned long long row, chunk;
-                if ((A.ntiles >> 32) == 0ULL) {
-                    const unsigned r32 = static_cast<unsigned>(t) / static_cast<unsigned>(A.chunks_per_row);
+                if ((NTILES >> 32) == 0ULL) {
+                    const unsigned r32 = static_cast<unsigned>(t) / static_cast<unsigned>(CHUNKS);
                     row = r32;
-                    chunk = static_cast<unsigned>(t) - r32 * static_cast<unsigned>(A.chunks_per_row);
+                    chunk = static_cast<unsigned>(t) - r32 * static_cast<unsigned>(CHUNKS);
                 } else {
-                    row = t / A.chunks_per_row;
-                    chunk = t - row * A.chunks_per_row;
+                    row = t / CHUNKS;
+                    chunk = t - row * CHUNKS;
                 }
                 col0 = static_cast<long long>(chunk) * TILE;
-                const long long left = A.nx - col0;
+                const long long left = NX - col0;
                 width = left < TILE ? static_cast<int>(left) : TILE;
-                base = static_cast<long long>(row) * A.nx + col0;
+                base = static_cast<long long>(row) * NX + col0;
                 if (!POINTS) {
                     const int slot = seq % RING;
                     if (seq >= RING) flush_slot(slot);
@@ -246,8 +261,14 @@ __global__ void __launch_bounds__(CTA_THREADS, LM_K1_MIN_CTAS) lm_escape_kernel(
                 my_off = cursor + rank;
                 my_seq = seq - 1;
                 my_g = base + my_off;
-                cr = __ldg(A.xs + col0 + my_off);
-                ci = POINTS ? __ldg(A.ys + col0 + my_off) : row_ci;
+                if (POINTS) {
+                    if (A.index) my_g = __ldg(A.index + my_g);
+                    cr = __ldg(A.xs + my_g);
+                    ci = __ldg(A.ys + my_g);
+                } else {
+                    cr = __ldg(A.xs + col0 + my_off);
+                    ci = row_ci;
+                }
                 zr = 0.0; zi = 0.0; a = 0.0; b = 0.0; n = 0;
                 far = !(cr * cr + ci * ci <= A.cfar2);
                 idle = false;
@@ -331,6 +352,10 @@ __global__ void __launch_bounds__(CTA_THREADS, LM_K1_MIN_CTAS) lm_escape_kernel(
         bool need = false;
         if (idle) {
             if (done || n >= A.max_iter) n = 0;
+        } else if (POINTS && !done && n >= A.max_iter && A.survivors) {
+            // pass 1 of the two-pass point schedule: still bounded after the short budget -> queue for pass 2
+            A.survivors[atomicAdd(A.survivor_count, 1ULL)] = my_g;
+            need = true;
         } else if (done || n >= A.max_iter) {
             const int iters = done ? n_fin : A.max_iter;
             const int dw = done ? n_fin - 1 : A.max_iter;
@@ -648,6 +673,83 @@ int32_t lm_escape_grid_f64(const double* xs, int64_t nx, const double* ys, int64
     return lm::grid_host_finish(&job, stats);
 }
 
+}  // extern "C"
+
+namespace {
+
+// Point lists mix short-lived and never-escaping orbits at random (a Lucas-Loci cloud: ~90 % of the
+// points leave within a few iterations, the rest run to max_iter), which would keep every warp in
+// the careful path: each refill resets the blind-mode cool-down.  Two passes restore coherence:
+// pass 1 runs every point for PASS1_ITERS iterations and queues the ones still bounded; pass 2 runs
+// only those (from z = 0 again, so the recurrence and the counts are unchanged) with the blind path.
+constexpr int PASS1_ITERS = 128;
+constexpr long long TWO_PASS_MIN_POINTS = 1 << 14;
+
+int32_t enqueue_points(const double* c_re, const double* c_im, int64_t n, int32_t max_iter, double escape_radius,
+                       double* g, long long* it, double* phi_re, double* phi_im,
+                       unsigned long long* work_dev, int* launches, cudaStream_t s) {
+    int32_t rc;
+    EscapeArgs A{};
+    A.xs = c_re; A.ys = c_im;
+    A.nx = n; A.ny = 1;
+    A.chunks_per_row = static_cast<unsigned long long>((n + TILE - 1) / TILE);
+    A.ntiles = A.chunks_per_row;
+    A.bailout = escape_radius;
+    A.field = g;
+    A.it64 = it;
+    A.phi_re = phi_re;
+    A.phi_im = phi_im;
+    A.work_counter = work_dev;
+    unsigned long long* counters = nullptr;
+    if ((rc = get_counters(&counters, s)) != LM_OK) return rc;
+    A.tile_counter = counters;
+    A.overflow_flag = reinterpret_cast<int*>(counters + 2);
+    bool two_pass = max_iter > 4 * PASS1_ITERS && n >= TWO_PASS_MIN_POINTS;
+    if (const char* e = getenv("LM_K1D_TWO_PASS")) two_pass = (e[0] == '1');     // tuning override
+    if (!two_pass) {
+        A.max_iter = max_iter;
+        if (launches) *launches += 1;
+        return launch_escape(true, LM_FIELD_GREEN, A, s);
+    }
+    void* dsurv = nullptr;
+    if ((rc = lm::ws_get(lm::WS_K1_SURVIVORS, static_cast<size_t>(n) * sizeof(long long), &dsurv)) != LM_OK) return rc;
+    A.max_iter = PASS1_ITERS;
+    A.survivors = static_cast<long long*>(dsurv);
+    A.survivor_count = counters + 3;
+    if ((rc = launch_escape(true, LM_FIELD_GREEN, A, s)) != LM_OK) return rc;
+    unsigned long long* counters2 = nullptr;
+    if ((rc = get_counters(&counters2, s)) != LM_OK) return rc;
+    A.tile_counter = counters2;
+    A.overflow_flag = reinterpret_cast<int*>(counters2 + 2);
+    A.max_iter = max_iter;
+    A.survivors = nullptr; A.survivor_count = nullptr;
+    A.index = static_cast<const long long*>(dsurv);
+    A.count_dev = counters + 3;
+    if (launches) *launches += 2;
+    return launch_escape(true, LM_FIELD_GREEN, A, s);      // grid sized for n; the kernel reads the real count
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t lm_escape_points_f64_dev(const double* c_re_dev, const double* c_im_dev, int64_t n,
+                                 int32_t max_iter, double escape_radius,
+                                 double* g_dev, int64_t* it_dev, double* phi_re_dev, double* phi_im_dev,
+                                 uint64_t* work_units_dev, void* stream) {
+    int32_t rc = lm::require_device();
+    if (rc != LM_OK) return rc;
+    LM_REQUIRE(n >= 0, "lm_escape_points_f64_dev: negative n");
+    LM_REQUIRE(n == 0 || (c_re_dev && c_im_dev), "lm_escape_points_f64_dev: c_re/c_im is NULL");
+    LM_REQUIRE(max_iter >= 1, "lm_escape_points_f64_dev: max_iter must be >= 1");
+    LM_REQUIRE(escape_radius > 0.0 && escape_radius < 1e150, "lm_escape_points_f64_dev: bad escape_radius");
+    cudaStream_t s = lm::as_stream(stream);
+    if (work_units_dev) LM_CUDA_TRY(cudaMemsetAsync(work_units_dev, 0, sizeof(uint64_t), s));
+    if (n == 0) return LM_OK;
+    return enqueue_points(c_re_dev, c_im_dev, n, max_iter, escape_radius, g_dev, reinterpret_cast<long long*>(it_dev),
+                          phi_re_dev, phi_im_dev, reinterpret_cast<unsigned long long*>(work_units_dev), nullptr, s);
+}
+
 int32_t lm_escape_points_f64(const double* c_re, const double* c_im, int64_t n,
                              int32_t max_iter, double escape_radius,
                              double* g, int64_t* it, double* phi_re, double* phi_im,
@@ -673,27 +775,15 @@ int32_t lm_escape_points_f64(const double* c_re, const double* c_im, int64_t n,
     LM_CUDA_TRY(cudaMemcpyAsync(dre, c_re, nb, cudaMemcpyHostToDevice, s));
     LM_CUDA_TRY(cudaMemcpyAsync(dim, c_im, nb, cudaMemcpyHostToDevice, s));
     LM_CUDA_TRY(cudaMemsetAsync(dwork, 0, 64, s));
-    unsigned long long* counters = nullptr;
-    if ((rc = get_counters(&counters, s)) != LM_OK) return rc;
-
-    EscapeArgs A{};
-    A.xs = static_cast<const double*>(dre); A.ys = static_cast<const double*>(dim);
-    A.nx = n; A.ny = 1;
-    A.chunks_per_row = static_cast<unsigned long long>((n + TILE - 1) / TILE);
-    A.ntiles = A.chunks_per_row;
-    A.max_iter = max_iter;
-    A.bailout = escape_radius;
-    A.field = static_cast<double*>(dg);
-    A.it64 = static_cast<long long*>(dit);
-    A.phi_re = (phi_re || phi_im) ? static_cast<double*>(dpr) : nullptr;
-    A.phi_im = (phi_re || phi_im) ? static_cast<double*>(dpi) : nullptr;
-    A.tile_counter = counters;
-    A.work_counter = static_cast<unsigned long long*>(dwork);
-    A.overflow_flag = reinterpret_cast<int*>(counters + 2);
-
     lm::Timer tm;
     if ((rc = tm.begin(s)) != LM_OK) return rc;
-    if ((rc = launch_escape(true, LM_FIELD_GREEN, A, s)) != LM_OK) return rc;
+    int launches = 0;
+    const bool want_phi = phi_re || phi_im;
+    rc = enqueue_points(static_cast<double*>(dre), static_cast<double*>(dim), n, max_iter, escape_radius,
+                        static_cast<double*>(dg), static_cast<long long*>(dit),
+                        want_phi ? static_cast<double*>(dpr) : nullptr, want_phi ? static_cast<double*>(dpi) : nullptr,
+                        static_cast<unsigned long long*>(dwork), &launches, s);
+    if (rc != LM_OK) return rc;
     float ms = 0.f;
     if ((rc = tm.end(s, &ms)) != LM_OK) return rc;
     if (g) LM_CUDA_TRY(cudaMemcpyAsync(g, dg, nb, cudaMemcpyDeviceToHost, s));
@@ -707,41 +797,9 @@ int32_t lm_escape_points_f64(const double* c_re, const double* c_im, int64_t n,
         stats->work_units = work;
         stats->items = static_cast<uint64_t>(n);
         stats->kernel_ms = ms;
-        stats->launches = 1;
+        stats->launches = launches;
     }
     return LM_OK;
-}
-
-int32_t lm_escape_points_f64_dev(const double* c_re_dev, const double* c_im_dev, int64_t n,
-                                 int32_t max_iter, double escape_radius,
-                                 double* g_dev, int64_t* it_dev, double* phi_re_dev, double* phi_im_dev,
-                                 uint64_t* work_units_dev, void* stream) {
-    int32_t rc = lm::require_device();
-    if (rc != LM_OK) return rc;
-    LM_REQUIRE(n >= 0, "lm_escape_points_f64_dev: negative n");
-    LM_REQUIRE(n == 0 || (c_re_dev && c_im_dev), "lm_escape_points_f64_dev: c_re/c_im is NULL");
-    LM_REQUIRE(max_iter >= 1, "lm_escape_points_f64_dev: max_iter must be >= 1");
-    LM_REQUIRE(escape_radius > 0.0 && escape_radius < 1e150, "lm_escape_points_f64_dev: bad escape_radius");
-    cudaStream_t s = lm::as_stream(stream);
-    if (work_units_dev) LM_CUDA_TRY(cudaMemsetAsync(work_units_dev, 0, sizeof(uint64_t), s));
-    if (n == 0) return LM_OK;
-    unsigned long long* counters = nullptr;
-    if ((rc = get_counters(&counters, s)) != LM_OK) return rc;
-    EscapeArgs A{};
-    A.xs = c_re_dev; A.ys = c_im_dev;
-    A.nx = n; A.ny = 1;
-    A.chunks_per_row = static_cast<unsigned long long>((n + TILE - 1) / TILE);
-    A.ntiles = A.chunks_per_row;
-    A.max_iter = max_iter;
-    A.bailout = escape_radius;
-    A.field = g_dev;
-    A.it64 = reinterpret_cast<long long*>(it_dev);
-    A.phi_re = phi_re_dev;
-    A.phi_im = phi_im_dev;
-    A.tile_counter = counters;
-    A.work_counter = work_units_dev ? reinterpret_cast<unsigned long long*>(work_units_dev) : counters + 1;
-    A.overflow_flag = reinterpret_cast<int*>(counters + 2);
-    return launch_escape(true, LM_FIELD_GREEN, A, s);
 }
 
 }  // extern "C"

@@ -9,9 +9,10 @@
 // reference's own variants agree with each other only to rounding, so parity is
 // tolerance based (1e-12) and the kernel is free to reorder.  What it exploits:
 //
-//  * sum of logs = log of product.  A thread multiplies the 8 terms of a point group and takes ONE
-//    log per group (the product of 8 terms in [eps, ~10] cannot leave the double range; a group
-//    whose product is not a normal number is redone term by term with the library functions).
+//  * sum of logs = log of product.  A thread multiplies the 16 terms of a point group (the product of
+//    16 terms in [eps, ~10] cannot leave the double range; a group whose product is not a normal
+//    number is redone term by term with the library functions), folds the group into a running
+//    (mantissa, integer exponent) product and takes ONE log at the very end.
 //  * eps <= 1e-10 (three of the four variants use 1e-12):  log(s + eps) = log(s) + log1p(eps/s),
 //    and for eps/s <= 1e-8 the second term is eps/s to 5e-17.  So the group accumulates the
 //    product of r^2 = dx^2 + dy^2 (no square root at all) and the sum of MUFU.RSQ64H(r^2)
@@ -31,7 +32,7 @@ namespace {
 constexpr int LP_THREADS = 256;
 constexpr int LP_CPT = 4;            // cells per thread, consecutive in x
 constexpr int LP_CHUNK = 1024;       // points staged in shared memory per round
-constexpr int LP_GROUP = 8;          // terms per product
+constexpr int LP_GROUP = 16;         // terms per group product (range check / exponent extraction once per group)
 
 __device__ __forceinline__ double rsqrt_approx(double x) {
     double y;
@@ -58,6 +59,9 @@ __device__ __forceinline__ double sqrt_fast(double x) {
 
 // Raw per-cell sums  S[cell] = sum over this split's points of log(|z - p| + eps).
 //   partial[split * ncells + cell]
+// The running product of a cell is kept as (mantissa in [1,2), integer exponent): after every group
+// the exponent field is moved into an integer accumulator, so ONE log per thread is taken at the very
+// end (rounding of the mantissa product: <= 1 ulp per factor, far inside the 1e-12 parity bound).
 template <int V, bool FAST>
 __global__ void __launch_bounds__(LP_THREADS) logpot_partial_kernel(
     const double* __restrict__ px, const double* __restrict__ py, long long npts, long long pts_per_split,
@@ -75,12 +79,14 @@ __global__ void __launch_bounds__(LP_THREADS) logpot_partial_kernel(
     const double y = gy[j];
     const long long p_begin = static_cast<long long>(blockIdx.y) * pts_per_split;
     const long long p_end = (p_begin + pts_per_split < npts) ? p_begin + pts_per_split : npts;
-    // a pair is "near" when s < eps * 1e8, i.e. rsqrt(r^2) > 1e-8 / eps (compared on the high words)
-    const int near_hi = FAST ? __double2hiint(1e-8 / eps) : 0;
+    // a pair is "near" when s < eps * 1e8, i.e. rsqrt(r^2) > 1e-8 / eps; a group whose rsqrt sum stays
+    // below that bound cannot contain one
+    const double near_sum = FAST ? 1e-8 / eps : 0.0;
 
-    double acc[LP_CPT], esum[LP_CPT];
+    double P[LP_CPT], E[LP_CPT], slow[LP_CPT], eacc[LP_CPT];
+    int esum[LP_CPT];
 #pragma unroll
-    for (int c = 0; c < LP_CPT; ++c) { acc[c] = 0.0; esum[c] = 0.0; }
+    for (int c = 0; c < LP_CPT; ++c) { P[c] = 1.0; E[c] = 0.0; slow[c] = 0.0; eacc[c] = 0.0; esum[c] = 0; }
 
     for (long long base = p_begin; base < p_end; base += LP_CHUNK) {
         const int m = static_cast<int>(p_end - base < LP_CHUNK ? p_end - base : LP_CHUNK);
@@ -90,10 +96,9 @@ __global__ void __launch_bounds__(LP_THREADS) logpot_partial_kernel(
         if (!live) continue;
         int k0 = 0;
         for (; k0 + LP_GROUP <= m; k0 += LP_GROUP) {
-            double P[LP_CPT], E[LP_CPT];
-            int mx[LP_CPT];
+            double Pg[LP_CPT], Eg[LP_CPT];
 #pragma unroll
-            for (int c = 0; c < LP_CPT; ++c) { P[c] = 1.0; E[c] = 0.0; mx[c] = 0; }
+            for (int c = 0; c < LP_CPT; ++c) { Pg[c] = 1.0; Eg[c] = 0.0; }
 #pragma unroll
             for (int k = 0; k < LP_GROUP; ++k) {
                 const double2 p = spt[k0 + k];
@@ -104,26 +109,30 @@ __global__ void __launch_bounds__(LP_THREADS) logpot_partial_kernel(
                     const double dx = x[c] - p.x;
                     const double r2 = fma(dx, dx, dy2);
                     if (FAST) {
-                        const double y0 = rsqrt_approx(r2);
-                        P[c] *= r2;
-                        E[c] += y0;
-                        mx[c] = max(mx[c], __double2hiint(y0));
+                        Pg[c] *= r2;
+                        Eg[c] += rsqrt_approx(r2);
                     } else {
-                        P[c] *= sqrt_fast(r2) + eps;
+                        Pg[c] *= sqrt_fast(r2) + eps;
                     }
                 }
             }
 #pragma unroll
             for (int c = 0; c < LP_CPT; ++c) {
-                // the product must be a comfortably normal number and (FAST) no pair may be near
-                const bool ok = (P[c] > 1e-280) && (P[c] < 1e280) && (!FAST || mx[c] < near_hi);
+                // the group product must be a comfortably normal number (biased exponent in [100, 1946]; this
+                // also rejects 0, Inf and NaN) and (FAST) no pair of the group may be near
+                const unsigned ex = (static_cast<unsigned>(__double2hiint(Pg[c])) >> 20) & 0x7ffu;
+                const bool ok = (ex - 100u <= 1846u) && (!FAST || Eg[c] < near_sum);
                 if (ok) {
-                    if (FAST) { acc[c] = fma(0.5, log(P[c]), acc[c]); esum[c] += E[c]; }
-                    else acc[c] += log(P[c]);
+                    const double t = P[c] * Pg[c];                  // P in [1,2): cannot leave the range either
+                    const int hi = __double2hiint(t);
+                    const int e = (hi >> 20) - 1023;
+                    esum[c] += e;
+                    P[c] = __hiloint2double(hi - (e << 20), __double2loint(t));
+                    if (FAST) E[c] += Eg[c];
                 } else {
                     for (int k = 0; k < LP_GROUP; ++k) {
                         const double2 p = spt[k0 + k];
-                        acc[c] += exact_term<V>(x[c] - p.x, y - p.y, eps);
+                        slow[c] += exact_term<V>(x[c] - p.x, y - p.y, eps);
                     }
                 }
             }
@@ -131,14 +140,19 @@ __global__ void __launch_bounds__(LP_THREADS) logpot_partial_kernel(
         for (; k0 < m; ++k0) {
             const double2 p = spt[k0];
 #pragma unroll
-            for (int c = 0; c < LP_CPT; ++c) acc[c] += exact_term<V>(x[c] - p.x, y - p.y, eps);
+            for (int c = 0; c < LP_CPT; ++c) slow[c] += exact_term<V>(x[c] - p.x, y - p.y, eps);
         }
+#pragma unroll
+        for (int c = 0; c < LP_CPT; ++c) { eacc[c] += static_cast<double>(esum[c]); esum[c] = 0; }
     }
     if (live) {
         double* out = partial + static_cast<long long>(blockIdx.y) * nx * ny + j * nx + i0;
 #pragma unroll
-        for (int c = 0; c < LP_CPT; ++c)
-            if (i0 + c < nx) out[c] = FAST ? fma(eps, esum[c], acc[c]) : acc[c];
+        for (int c = 0; c < LP_CPT; ++c) {
+            if (i0 + c >= nx) continue;
+            const double lp = fma(eacc[c], 0.693147180559945309417232, log(P[c]));    // log of the whole product
+            out[c] = FAST ? fma(eps, E[c], fma(0.5, lp, slow[c])) : lp + slow[c];
+        }
     }
 }
 

@@ -115,6 +115,29 @@ def test_batch_potential(gpu, oracle, golden):
     assert gpu.escape.batch_potential(np.zeros(0, dtype=complex))[0].shape == (0,)
 
 
+def test_batch_potential_two_pass(gpu, oracle):
+    """>= 2^14 points with max_iter > 512 take the two-pass schedule (short pass, then the survivors alone):
+    same it / g / phi as the oracle, identical work count, and identical to the single-pass result."""
+    rng = np.random.default_rng(8)
+    n = 50_000
+    pts = rng.uniform(-2.3, 1.2, n) + 1j * rng.uniform(-1.6, 1.6, n)
+    pts[:7] = [0.0, -1.0, 0.25, -2.0, 2.0 + 2.0j, -0.75 + 0.1j, 0.3 + 0.5j]
+    g_o, it_o, phi_o = oracle.batch_potential(pts, 3000, 2.0)
+    g, it, phi = gpu.escape.batch_potential(pts, 3000, 2.0)
+    st = gpu.escape.last_stats
+    assert st["launches"] == 2 and st["work_units"] == int(it_o.sum())
+    assert np.array_equal(it, it_o)
+    np.testing.assert_allclose(g, g_o, rtol=RTOL_POT, atol=0)
+    assert np.array_equal(np.isnan(phi.real), np.isnan(phi_o.real))
+    m = ~np.isnan(phi_o.real)
+    np.testing.assert_allclose(phi[m], phi_o[m], rtol=1e-13)
+    # the same points in two halves below the two-pass threshold (single pass): bit-identical outputs
+    parts = [gpu.escape.batch_potential(pts[k:k + 12_500], 3000, 2.0) for k in range(0, n, 12_500)]
+    assert gpu.escape.last_stats["launches"] == 1
+    assert np.array_equal(np.concatenate([p[1] for p in parts]), it)
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), g)
+
+
 def test_f32_variant_tolerance(gpu, oracle):
     """fp32 kernel (no reference counterpart): dwell mismatch fraction vs fp64 below 2 % on config 1's window."""
     import ctypes as C
