@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py -- headline benchmark of the B200 hot path (contract: see the repo brief).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2|cfg1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2|cfg1|cfg4|cfg5]
 
 Metric (BASELINE.json): G pixel-iterations/s in fp64, work unit = sum over pixels of
 min(dwell+1, max_iter) counted exactly by the kernel.  A step is one pass of the boundary stage
@@ -45,6 +45,23 @@ WORKLOADS = {
 }
 FLOPS_PER_PIXEL_ITER = 8          # 3 mul + 5 add under the reference's unfused semantics
 
+# BASELINE.json configs[4]: 10^7 generalized-Lucas polynomials of degree <= 25, generated in
+# 16 independently seeded chunks so that every rank can build just its slice
+CFG5 = dict(npoly=10_000_000, maxdeg=25, chunks=16, grid=400, pot_max_iter=20000, pot_radius=2.0, eps=1e-12)
+
+
+def cfg5_chunk(k: int, npoly_total: int = CFG5["npoly"], chunks: int = CFG5["chunks"], maxdeg: int = CFG5["maxdeg"]):
+    """Chunk k of the config-5 batch: degrees uniform in [2, maxdeg], first-row entries in {0,1,2}, a_d >= 1."""
+    lo, hi = (npoly_total * k) // chunks, (npoly_total * (k + 1)) // chunks
+    n = hi - lo
+    rng = np.random.default_rng([0, k])
+    deg = rng.integers(2, maxdeg + 1, size=n).astype(np.int32)
+    top = rng.integers(0, 3, size=(n, maxdeg)).astype(np.float64)
+    top[np.arange(maxdeg)[None, :] >= deg[:, None]] = 0.0
+    last = top[np.arange(n), deg - 1]
+    top[np.arange(n), deg - 1] = np.where(last == 0, 1.0, last)
+    return top, deg
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -52,7 +69,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg3")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["cfg5"], default="cfg3")
+    ap.add_argument("--no-roots", action="store_true", help="skip the Lucas-roots leg of the default run")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -350,6 +368,20 @@ def run_ours(args):
                "api": ("lm_boundary_sample (pinned numpy buffers in, dwell grid + ordered boundary polylines out)" if world == 1 else
                        "lm_escape_grid_f64 (pinned numpy buffers) + lm_contour_classify_dev + lm_contour_link")}
 
+    # ---- the other half of BASELINE.json's metric: Lucas roots/s (K3) on the config-5 batch, sharded by polynomial
+    lucas_roots = None
+    if not args.no_roots:
+        try:
+            r = measure_roots(args, rank, world, dev, stream, full_fields=False)
+            lucas_roots = {k: r[k] for k in ("value", "unit", "ms_per_step", "roots", "mean_sweeps", "not_converged") if k in r}
+            lucas_roots["workload"] = r["config"]["workload"]
+            if "e2e" in r:
+                lucas_roots["e2e"] = r["e2e"]
+            if rank == 0 and world == 1 and not args.no_cpu_baseline:
+                lucas_roots["cpu_numpy"] = cpu_roots_baseline(8.0)
+        except Exception as e:          # the headline line must survive a failure of the secondary leg
+            lucas_roots = {"error": f"{type(e).__name__}: {e}"}
+
     # ---- CPU baseline beside it (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -368,8 +400,208 @@ def run_ours(args):
                        "sharding": f"contiguous row blocks at equal estimated work, cuts={cuts}, balance={balance:.3f}",
                        "l2": "FP64-bound; per step every rank writes its dwell block (>= L2 for cfg2/cfg3) and reads 2*res coordinates"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
-            "k1_ms_per_step_max_rank": k1_ms_max / args.steps,
+            "k1_ms_per_step_max_rank": k1_ms_max / args.steps, "lucas_roots": lucas_roots,
         }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
+# Lucas-Loci cloud (BASELINE.json configs[4]; the "Lucas roots/s vs CPU numpy" half of the metric)
+# ---------------------------------------------------------------------------------------------
+def _eigvals_stack(args):
+    """np.linalg.eigvals on the stacked companions of one degree (the reference's own call, batched)."""
+    top, d = args
+    M = np.zeros((top.shape[0], d, d))
+    M[:, 0, :] = top[:, :d]
+    idx = np.arange(1, d)
+    M[:, idx, idx - 1] = 1.0
+    return int(np.linalg.eigvals(M).size)
+
+
+def cpu_roots_pass(npoly_sample: int, procs: int):
+    """numpy (LAPACK dgeev) on the first npoly_sample polynomials of chunk 0, `procs` worker processes.
+    -> (roots, seconds)"""
+    import multiprocessing as mp
+    top, deg = cfg5_chunk(0)
+    top, deg = top[:npoly_sample], deg[:npoly_sample]
+    jobs = []
+    for d in range(2, CFG5["maxdeg"] + 1):
+        sel = np.where(deg == d)[0]
+        for part in np.array_split(sel, max(1, procs // 2)):
+            if part.size:
+                jobs.append((top[part], d))
+    jobs.sort(key=lambda j: -j[0].shape[0] * j[1] ** 3)
+    with mp.get_context("fork").Pool(procs) as pool:
+        pool.map(_eigvals_stack, jobs[:procs])                       # spin the workers up
+        t0 = time.perf_counter()
+        roots = sum(pool.map(_eigvals_stack, jobs, chunksize=1))
+        dt = time.perf_counter() - t0
+    return roots, dt
+
+
+def cpu_roots_baseline(target_s: float = 10.0) -> dict:
+    procs = os.cpu_count() or 1
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    roots, dt = cpu_roots_pass(4000 * procs, procs)
+    n = int(min(max(4000 * procs * target_s / max(dt, 1e-3), 4000 * procs), CFG5["npoly"] // CFG5["chunks"]))
+    roots, dt = cpu_roots_pass(n, procs)
+    return {"value": roots / dt / 1e6, "unit": "Mroots/s", "cores": procs, "kind": "reference",
+            "sample": f"np.linalg.eigvals on the stacked companion matrices of the first {n} polynomials of the "
+                      f"config-5 batch ({roots} roots), {procs} worker processes, {dt:.1f} s"}
+
+
+def measure_roots(args, rank, world, dev, stream, full_fields: bool):
+    """K3 (+ cloud compaction) over this rank's slice of the 10^7-polynomial batch, device resident; optionally the
+    field stage (K1d, K4a with an NCCL all-reduce of the per-cell sums, K4).  -> dict for the JSON line."""
+    import torch
+    import torch.distributed as dist
+    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import _shim, lucas, sharding
+    P = lambda t: C.c_void_p(t.data_ptr())
+    cuts = sharding.item_slices(CFG5["chunks"], world)
+    mine = range(cuts[rank], cuts[rank + 1])
+    parts = [cfg5_chunk(k) for k in mine]
+    maxdeg = CFG5["maxdeg"]
+    top_h = np.concatenate([p[0] for p in parts]) if parts else np.zeros((0, maxdeg))
+    deg_h = np.concatenate([p[1] for p in parts]) if parts else np.zeros(0, np.int32)
+    npoly = int(deg_h.size)
+    nroots = int(deg_h.sum())
+    top = torch.from_numpy(top_h).to(dev); deg = torch.from_numpy(deg_h).to(dev)
+    re = torch.empty((max(npoly, 1), maxdeg), dtype=torch.float64, device=dev); im = torch.empty_like(re)
+    kept = torch.empty(max(npoly, 1), dtype=torch.int32, device=dev)
+    iters = torch.empty(max(npoly, 1), dtype=torch.int32, device=dev)
+    status = torch.zeros(2, dtype=torch.int32, device=dev)
+    px = torch.empty(max(nroots, 1), dtype=torch.float64, device=dev); py = torch.empty_like(px)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def step():
+        _shim.call("lm_roots_batched_dev", P(top), P(deg), npoly, maxdeg, 1, 1e-12, P(re), P(im), P(kept), P(iters), P(status), stream)
+        _shim.call("lm_cloud_compact_dev", P(re), P(im), P(kept), npoly, maxdeg, P(px), P(py), nroots, P(cnt), stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    tot = torch.tensor([nroots, npoly, int(cnt.item()), int(status[0].item()), int(iters[:npoly].sum().item())], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms = float(t[0]) / args.steps
+    roots_total, npoly_total, pts_total, failed, sweeps = (int(v) for v in tot)
+    out = {"metric": "lucas_roots_per_s", "value": roots_total / ms / 1e3, "unit": "Mroots/s", "ms_per_step": ms,
+           "config": {"workload": f"{npoly_total} generalized-Lucas characteristic polynomials, degree 2..{maxdeg}, first-row entries in "
+                                  "{0,1,2} (BASELINE.json configs[4]), K3 roots + cloud compaction, device resident",
+                      "sharding": f"{CFG5['chunks']} independently seeded chunks dealt contiguously to the ranks, no collective"},
+           "roots": roots_total, "cloud_points": pts_total, "mean_sweeps": sweeps / max(npoly_total, 1), "not_converged": failed,
+           "gpu_launches": 9 * args.steps}
+
+    # e2e: host numpy arrays in, cloud on the host out, through the fused host-buffer call
+    if not args.no_e2e:
+        lucas.cloud_fields(top_h[:1000], deg_h[:1000])
+        barrier()
+        t0 = time.perf_counter()
+        res = lucas.cloud_fields(top_h, deg_h)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        out["e2e"] = {"value": roots_total / float(dt[0]) / 1e6, "unit": "Mroots/s", "h2d_bytes_per_step": int(top_h.nbytes + deg_h.nbytes),
+                      "d2h_bytes_per_step": int(res["n_points"] * 16), "ms_per_step": 1e3 * float(dt[0]),
+                      "api": "lm_lucas_cloud_fields (numpy first rows in, cloud of 1/lambda out)"}
+
+    if full_fields:
+        g = torch.linspace(-2.0, 2.0, CFG5["grid"], dtype=torch.float64, device=dev)
+        ncell = CFG5["grid"] ** 2
+        sums = torch.empty(ncell, dtype=torch.float64, device=dev); U = torch.empty_like(sums); lap = torch.empty_like(sums)
+        gpot = torch.empty_like(px); it = torch.empty(px.numel(), dtype=torch.int64, device=dev)
+        work = torch.zeros(1, dtype=torch.int64, device=dev)
+        n_local = int(cnt.item())
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        barrier()
+        ev[0].record()
+        _shim.call("lm_escape_points_f64_dev", P(px), P(py), n_local, CFG5["pot_max_iter"], CFG5["pot_radius"], P(gpot), P(it),
+                   None, None, P(work), stream)
+        ev[1].record()
+        _shim.call("lm_log_potential_sums_dev", P(px), P(py), n_local, P(g), CFG5["grid"], P(g), CFG5["grid"], CFG5["eps"], 0,
+                   P(sums), stream)
+        ev[2].record()
+        _, n_total = sharding.allreduce_field_sums(sums, n_local)
+        _shim.call("lm_log_potential_finish_dev", P(sums), ncell, n_total, 0, P(U), stream)
+        _shim.call("lm_laplacian5_periodic_dev", P(U), CFG5["grid"], CFG5["grid"], 4.0 / (CFG5["grid"] - 1), P(lap), stream)
+        ev[3].record()
+        barrier()
+        tt = torch.tensor([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])], dtype=torch.float64, device=dev)
+        ww = torch.tensor([int(work.item()), n_local * ncell], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ww, op=dist.ReduceOp.SUM)
+        peak_tflops = C.c_double(0.0); mix = C.c_double(0.0)
+        _shim.call("lm_probe_fp64_peak", 2000, C.byref(peak_tflops), C.byref(mix))
+        pairs_per_s = n_local * ncell / (ev[1].elapsed_time(ev[2]) * 1e-3)
+        out["field_stage"] = {
+            "k1d_batch_potential": {"ms": float(tt[0]), "gpixel_iter_per_s": int(ww[0]) / float(tt[0]) / 1e6, "max_iter": CFG5["pot_max_iter"]},
+            "k4a_log_potential": {"ms": float(tt[1]), "tpairs_per_s": int(ww[1]) / float(tt[1]) / 1e9, "grid": f"{CFG5['grid']}^2 over [-2,2]^2",
+                                  "roofline": {"bound": "fp64", "kernel": "logpot_partial_kernel<SUM_SQRT, fast>", "unit": "T FP64 instr/s",
+                                               "achieved": pairs_per_s * 4.5 / 1e12, "peak": peak_tflops.value / 2,
+                                               "frac": pairs_per_s * 4.5 / 1e12 / (peak_tflops.value / 2),
+                                               "algorithmic_fp64_instr_per_pair": 4.5}},
+            "allreduce_finish_laplacian_ms": float(tt[2]), "field_checksum": float(U.sum().item()), "laplacian_abs_max": float(lap.abs().max().item()),
+            "collective": "NCCL all-reduce(sum) of the 400^2 per-cell sums + cloud sizes" if world > 1 else "none (N=1)"}
+    return out
+
+
+def run_cfg5(args):
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank == 0:
+            cpu = cpu_roots_baseline(10.0 * max(args.steps, 1) / 2)
+            line = {"impl": "reference", "metric": "lucas_roots_per_s", "value": cpu["value"], "unit": "Mroots/s", "n_gpus": args.gpus,
+                    "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "strong",
+                    "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                    "config": {"workload": "generalized-Lucas characteristic polynomials, degree 2..25 (BASELINE.json configs[4])",
+                               "sample": cpu["sample"]},
+                    "cpu_baseline": cpu, "e2e": {"value": cpu["value"], "unit": "Mroots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                    "gpu_launches": 0}
+            print(json.dumps(line), flush=True)
+        return
+    import torch
+    import torch.distributed as dist
+    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import _shim, build
+    build.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank); _shim.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    out = measure_roots(args, rank, world, dev, stream, full_fields=True)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        cpu = None if (args.no_cpu_baseline or world > 1) else cpu_roots_baseline()
+        line = {"metric": out["metric"], "value": out["value"], "unit": out["unit"], "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": out["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": out["config"],
+                "roofline": out["field_stage"]["k4a_log_potential"]["roofline"], "cpu_baseline": cpu, "e2e": out.get("e2e"),
+                "gpu_launches": out["gpu_launches"], "clocks": clocks,
+                "lucas": {k: out[k] for k in ("roots", "cloud_points", "mean_sweeps", "not_converged")},
+                "field_stage": out["field_stage"]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -377,7 +609,9 @@ def run_ours(args):
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
+    if args.workload == "cfg5":
+        run_cfg5(args)
+    elif args.impl == "reference":
         run_reference_arm(args)
     else:
         run_ours(args)

@@ -81,8 +81,6 @@ int32_t lm_lucas_cloud_fields(const double* toprows, const int32_t* deg, int64_t
         return lm::fail(LM_E_CAP, "lm_lucas_cloud_fields: the cloud has %lld points, capacity %lld",
                         static_cast<long long>(count), static_cast<long long>(cap_points));
     const size_t cb = static_cast<size_t>(count) * sizeof(double);
-    if (cloud_re && count) LM_CUDA_TRY(cudaMemcpyAsync(cloud_re, dpx, cb, cudaMemcpyDeviceToHost, s));
-    if (cloud_im && count) LM_CUDA_TRY(cudaMemcpyAsync(cloud_im, dpy, cb, cudaMemcpyDeviceToHost, s));
 
     int launches = 0;
     void *dg = nullptr, *dit = nullptr;
@@ -119,6 +117,17 @@ int32_t lm_lucas_cloud_fields(const double* toprows, const int32_t* deg, int64_t
         ++launches;
     }
     LM_CUDA_TRY(cudaEventRecord(ev[5], s));
+    // the cloud goes back on a second stream while the field kernels (already enqueued) run
+    cudaStream_t s_copy = nullptr;
+    if ((cloud_re || cloud_im) && count) {
+        LM_CUDA_TRY(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
+        cudaError_t ce = cudaSuccess;
+        if (cloud_re) ce = cudaMemcpyAsync(cloud_re, dpx, cb, cudaMemcpyDeviceToHost, s_copy);
+        if (ce == cudaSuccess && cloud_im) ce = cudaMemcpyAsync(cloud_im, dpy, cb, cudaMemcpyDeviceToHost, s_copy);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(s_copy);
+        cudaStreamDestroy(s_copy);
+        LM_CUDA_TRY(ce);
+    }
     if (want_pot && count) {
         if (g) LM_CUDA_TRY(cudaMemcpyAsync(g, dg, cb, cudaMemcpyDeviceToHost, s));
         if (it) LM_CUDA_TRY(cudaMemcpyAsync(it, dit, cb, cudaMemcpyDeviceToHost, s));

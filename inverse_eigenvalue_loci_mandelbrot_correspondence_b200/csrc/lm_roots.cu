@@ -273,47 +273,36 @@ __global__ void __launch_bounds__(ROOTS_THREADS) roots_kernel(const RootsArgs A)
                     const double az2 = z.r * z.r + z.i * z.i;
                     const double az = sqrt(az2);
                     cplx newton;           // p/p'
-                    if (az <= 1.0) {
-                        cplx b = {coef[0], 0.0}, bp = {0.0, 0.0};
-                        double s = fabs(coef[0]);
-                        for (int k = 1; k <= d; ++k) {
-                            const double ck = coef[k];
-                            bp = {fma(bp.r, z.r, fma(-bp.i, z.i, b.r)), fma(bp.r, z.i, fma(bp.i, z.r, b.i))};
-                            b = {fma(b.r, z.r, fma(-b.i, z.i, ck)), fma(b.r, z.i, b.i * z.r)};
-                            s = fma(s, az, fabs(ck));
-                        }
-                        const double ab2 = b.r * b.r + b.i * b.i;
-                        const double bound = EPS * s * (d + 1);
-                        freeze = ab2 <= bound * bound;
-                        const double dp = bp.r * bp.r + bp.i * bp.i;
-                        newton = (dp > 1e-290 && dp < 1e290) ? cmul(b, cinv_fast(bp))
-                               : (dp > 0.0 ? cmul(b, cinv(bp)) : cplx{1e-3 * (az + 1e-3), 1e-3 * (az + 1e-3)});
-                    } else {
-                        // p(z) = z^d q(w), w = 1/z, q(w) = sum_k coef[k] w^k; Horner from coef[d] down
-                        const double iz2 = rcp_fast<2>(az2);
-                        const cplx w = {z.r * iz2, -z.i * iz2};
-                        const double aw = az * iz2;
-                        cplx b = {coef[d], 0.0}, bp = {0.0, 0.0};
-                        double s = fabs(coef[d]);
-                        for (int k = d - 1; k >= 0; --k) {
-                            const double ck = coef[k];
-                            bp = {fma(bp.r, w.r, fma(-bp.i, w.i, b.r)), fma(bp.r, w.i, fma(bp.i, w.r, b.i))};
-                            b = {fma(b.r, w.r, fma(-b.i, w.i, ck)), fma(b.r, w.i, b.i * w.r)};
-                            s = fma(s, aw, fabs(ck));
-                        }
-                        const double ab2 = b.r * b.r + b.i * b.i;
-                        const double bound = EPS * s * (d + 1);
-                        freeze = ab2 <= bound * bound;
-                        // p/p' = z / (d - w q'(w)/q(w))
-                        cplx den = {static_cast<double>(d), 0.0};
-                        if (ab2 > 0.0) {
-                            const cplx t = cmul(cmul(w, bp), (ab2 > 1e-290 && ab2 < 1e290) ? cinv_fast(b) : cinv(b));
-                            den.r -= t.r; den.i -= t.i;
-                        }
-                        const double dd = den.r * den.r + den.i * den.i;
-                        newton = (dd > 1e-290 && dd < 1e290) ? cmul(z, cinv_fast(den))
-                               : (dd > 0.0 ? cmul(z, cinv(den)) : cplx{1e-3 * az, 1e-3 * az});
+                    // One Horner loop for both regimes, so lanes inside and outside the unit circle do not
+                    // diverge:  |z| <= 1 evaluates p at w = z from coef[0] up;  |z| > 1 evaluates the reversed
+                    // polynomial q(w) = sum_k coef[k] w^k at w = 1/z from coef[d] down (p(z) = z^d q(1/z)).
+                    const bool inside = az <= 1.0;
+                    const double iz2 = rcp_fast<2>(inside ? 1.0 : az2);
+                    const cplx w = inside ? z : cplx{z.r * iz2, -z.i * iz2};
+                    const double aw = inside ? az : az * iz2;
+                    const int k_first = inside ? 0 : d, k_step = inside ? 1 : -1;
+                    cplx b = {coef[k_first], 0.0}, bp = {0.0, 0.0};
+                    double s = fabs(b.r);
+                    for (int k = 1, idx = k_first + k_step; k <= d; ++k, idx += k_step) {
+                        const double ck = coef[idx];
+                        bp = {fma(bp.r, w.r, fma(-bp.i, w.i, b.r)), fma(bp.r, w.i, fma(bp.i, w.r, b.i))};
+                        b = {fma(b.r, w.r, fma(-b.i, w.i, ck)), fma(b.r, w.i, b.i * w.r)};
+                        s = fma(s, aw, fabs(ck));
                     }
+                    const double ab2 = b.r * b.r + b.i * b.i;
+                    const double bound = EPS * s * (d + 1);
+                    freeze = ab2 <= bound * bound;
+                    // inside:  p/p' = b / bp;   outside:  p/p' = z / (d - w q'(w)/q(w)) = z b / (d b - w bp)
+                    cplx num, den;
+                    if (inside) { num = b; den = bp; }
+                    else {
+                        const cplx wbp = cmul(w, bp);
+                        num = cmul(z, b);
+                        den = {fma(static_cast<double>(d), b.r, -wbp.r), fma(static_cast<double>(d), b.i, -wbp.i)};
+                    }
+                    const double dd = den.r * den.r + den.i * den.i;
+                    newton = (dd > 1e-290 && dd < 1e290) ? cmul(num, cinv_fast(den))
+                           : (dd > 0.0 ? cmul(num, cinv(den)) : cplx{1e-3 * (az + 1e-3), 1e-3 * (az + 1e-3)});
                     if (!freeze) {
                         double Sr = 0.0, Si = 0.0;
 #pragma unroll 4
