@@ -248,15 +248,10 @@ def run_ours(args):
                    max_iter, 2.0, 0, C.c_void_p(dwell_d.data_ptr()), None, None, C.c_void_p(work_d.data_ptr()), stream)
         launches["n"] += 1
 
-    def k2():
+    def classify(block_ptr, nrows_k2):
         nonlocal records
-        if world > 1:
-            firsts = sharding.exchange_first_rows(dwell_d[0])
-            if has_halo:
-                dwell_d[rows].copy_(firsts[rank + 1])
-        nrows_k2 = rows + (1 if has_halo else 0)
         while True:
-            rc = lib.lm_contour_classify_dev(C.c_void_p(dwell_d.data_ptr()), _shim.ptr(xs), nx, _shim.ptr(ys_block), nrows_k2,
+            rc = lib.lm_contour_classify_dev(block_ptr, _shim.ptr(xs), nx, _shim.ptr(ys_block), nrows_k2,
                                              r0, float(level), _shim.ptr(records), records.shape[0], C.byref(n_rec), stream)
             if rc == _shim.LM_E_CAP:
                 records = np.empty((n_rec.value + 1024, 8), dtype=np.int64)
@@ -265,6 +260,13 @@ def run_ours(args):
             break
         launches["n"] += 3 if n_rec.value else 2
         return records[: n_rec.value]
+
+    def k2():
+        if world > 1:
+            firsts = sharding.exchange_first_rows(dwell_d[0])
+            if has_halo:
+                dwell_d[rows].copy_(firsts[rank + 1])
+        return classify(C.c_void_p(dwell_d.data_ptr()), rows + (1 if has_halo else 0))
 
     def barrier():
         if world > 1:
@@ -327,6 +329,7 @@ def run_ours(args):
         xs_p = _shim.pinned_empty(nx, np.float64); xs_p[:] = xs
         ys_p = _shim.pinned_empty(rows, np.float64); ys_p[:] = ys[r0:r1]
         st = _shim.Stats()
+        edge_d = torch.empty(nx, dtype=torch.int32, device=dev)
 
         def e2e_step():
             if world == 1:
@@ -335,12 +338,18 @@ def run_ours(args):
                 # K1/K2 still run, K2 records -> ordered polylines on the host
                 lines, stx = contour.boundary_sample(xs_p, ys_p, max_iter, level, dwell_out=out)
                 return stx["work_units"], lines
-            # N > 1: K1 through the host-buffer entry point on this rank's rows, then the shard goes
-            # back up for the halo exchange (NCCL) and K2, records are gathered and linked on rank 0
-            _shim.call("lm_escape_grid_f64", _shim.ptr(xs_p), nx, _shim.ptr(ys_p), rows, max_iter, 2.0, 0,
-                       _shim.ptr(out), None, None, C.byref(st))
-            _shim.call("lm_memcpy_h2d", C.c_void_p(dwell_d.data_ptr()), _shim.ptr(out), out.nbytes, stream)
-            recs_local = k2()
+            # N > 1: K1 on this rank's rows through the host-buffer shard call (dwell block returned to the pinned
+            # host buffer by the copy stream AND kept in HBM), shard-edge rows all-gathered over NCCL straight
+            # from / into that block, K2 on it, records gathered and linked on rank 0
+            dev_block = C.c_void_p()
+            _shim.call("lm_shard_escape", _shim.ptr(xs_p), nx, _shim.ptr(ys_p), rows, max_iter, _shim.ptr(out), 1,
+                       C.byref(dev_block), C.byref(st))
+            _shim.call("lm_memcpy_d2d", C.c_void_p(edge_d.data_ptr()), dev_block, nx * 4, stream)
+            firsts = sharding.exchange_first_rows(edge_d)
+            if has_halo:
+                _shim.call("lm_memcpy_d2d", C.c_void_p(dev_block.value + rows * nx * 4), C.c_void_p(firsts[rank + 1].data_ptr()),
+                           nx * 4, stream)
+            recs_local = classify(dev_block, rows + (1 if has_halo else 0))
             allrec = sharding.gather_records(recs_local, dev, 0)
             lines = contour.link_records(allrec, xs, ys, level) if rank == 0 else None
             return st.work_units, lines
@@ -362,11 +371,11 @@ def run_ours(args):
             dist.all_reduce(ww, op=dist.ReduceOp.SUM)
         n_vertices = int(max((len(l) for l in lines), default=0)) if lines else 0
         e2e = {"value": int(ww[0]) / float(tt[0]) / 1e9, "unit": "Gpixel-iter/s",
-               "h2d_bytes_per_step": int((nx + rows) * 8 + (rows * nx * 4 if world > 1 else 0)),
+               "h2d_bytes_per_step": int((nx + rows) * 8),
                "d2h_bytes_per_step": int(rows * nx * 4 + n_rec.value * 64), "ms_per_step": 1e3 * float(tt[0]) / args.steps,
                "boundary_vertices": n_vertices,
                "api": ("lm_boundary_sample (pinned numpy buffers in, dwell grid + ordered boundary polylines out)" if world == 1 else
-                       "lm_escape_grid_f64 (pinned numpy buffers) + lm_contour_classify_dev + lm_contour_link")}
+                       "lm_shard_escape (pinned numpy buffers; block kept in HBM) + NCCL edge rows + lm_contour_classify_dev + lm_contour_link")}
 
     # ---- the other half of BASELINE.json's metric: Lucas roots/s (K3) on the config-5 batch, sharded by polynomial
     lucas_roots = None

@@ -131,6 +131,7 @@ void*   lm_dev_alloc(size_t bytes);                /* NULL on failure */
 int32_t lm_dev_free(void* p);
 int32_t lm_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes, void* stream);
 int32_t lm_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes, void* stream);
+int32_t lm_memcpy_d2d(void* dst_dev, const void* src_dev, size_t bytes, void* stream);
 int32_t lm_stream_synchronize(void* stream);
 
 /* ---- K1: escape-time grid ------------------------------------------------------ */
@@ -154,6 +155,18 @@ int32_t lm_escape_grid_f64_dev(const double* xs, int64_t nx, const double* ys, i
                                int32_t* dwell_i32, double* dwell_f64, double* field,
                                uint64_t* work_units_dev /* 1 counter, may be NULL */,
                                void* stream);
+
+/*
+ * Multi-GPU building block (one process per GPU, each owning a contiguous block of rows): K1 over the
+ * ny rows of this shard exactly like lm_escape_grid_f64 (chunked, the dwell block returned to
+ * dwell_i32 -- may be NULL -- by a copy stream that overlaps the compute), but the int32 block ALSO
+ * stays in HBM with room for `halo_rows` more rows behind it.  *dwell_dev_out is that device block
+ * ([ny + halo_rows] x nx, library owned, valid until the next grid call on this device): the caller
+ * exchanges shard-edge rows over NCCL straight from / into it (lm_memcpy_d2d) and then runs
+ * lm_contour_classify_dev on it, so nothing is uploaded twice.
+ */
+int32_t lm_shard_escape(const double* xs, int64_t nx, const double* ys, int64_t ny, int32_t max_iter,
+                        int32_t* dwell_i32, int64_t halo_rows, int32_t** dwell_dev_out, lm_stats* stats);
 
 /* fp32 variant of the dwell grid (no reference counterpart; validated against the
  * fp64 kernel by mismatch fraction).                                                 */

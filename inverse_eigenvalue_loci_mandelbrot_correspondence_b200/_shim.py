@@ -26,8 +26,8 @@ LOGPOT_SUM_SQRT, LOGPOT_NEG_PERTERM, LOGPOT_SUM_HYPOT, LOGPOT_LOG_INV = 0, 1, 2,
 EXPORTS = (
     "lm_abi_version", "lm_last_error", "lm_device_count", "lm_set_device", "lm_get_device_info",
     "lm_device_synchronize", "lm_release_workspace", "lm_host_alloc", "lm_host_free", "lm_dev_alloc",
-    "lm_dev_free", "lm_memcpy_h2d", "lm_memcpy_d2h", "lm_stream_synchronize",
-    "lm_escape_grid_f64", "lm_escape_grid_f64_dev", "lm_escape_grid_f32", "lm_escape_points_f64",
+    "lm_dev_free", "lm_memcpy_h2d", "lm_memcpy_d2h", "lm_memcpy_d2d", "lm_stream_synchronize",
+    "lm_escape_grid_f64", "lm_escape_grid_f64_dev", "lm_shard_escape", "lm_escape_grid_f32", "lm_escape_points_f64",
     "lm_distance_grid_f64",
     "lm_contour_level", "lm_contour_level_dev", "lm_contour_classify_dev", "lm_contour_link", "lm_contour_fetch_last", "lm_boundary_sample",
     "lm_roots_batched", "lm_roots_batched_dev", "lm_cloud_compact_dev", "lm_lucas_cloud_fields", "lm_escape_points_f64_dev",
@@ -88,7 +88,9 @@ _SIGNATURES = {
     "lm_dev_free": (_i32, [_vp]),
     "lm_memcpy_h2d": (_i32, [_vp, _vp, _sz, _vp]),
     "lm_memcpy_d2h": (_i32, [_vp, _vp, _sz, _vp]),
+    "lm_memcpy_d2d": (_i32, [_vp, _vp, _sz, _vp]),
     "lm_stream_synchronize": (_i32, [_vp]),
+    "lm_shard_escape": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, C.POINTER(C.c_void_p), _pStats]),
     "lm_escape_grid_f64": (_i32, [_vp, _i64, _vp, _i64, _i32, _f64, _i32, _vp, _vp, _vp, _pStats]),
     "lm_escape_grid_f64_dev": (_i32, [_vp, _i64, _vp, _i64, _i32, _f64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "lm_escape_grid_f32": (_i32, [_vp, _i64, _vp, _i64, _i32, _f64, _vp, _pStats]),

@@ -200,6 +200,10 @@ int32_t lm_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes, void* s
     LM_CUDA_TRY(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, as_stream(stream)));
     return LM_OK;
 }
+int32_t lm_memcpy_d2d(void* dst_dev, const void* src_dev, size_t bytes, void* stream) {
+    LM_CUDA_TRY(cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice, as_stream(stream)));
+    return LM_OK;
+}
 int32_t lm_stream_synchronize(void* stream) {
     LM_CUDA_TRY(cudaStreamSynchronize(as_stream(stream)));
     return LM_OK;

@@ -25,7 +25,7 @@ int32_t lm_boundary_sample(const double* xs, int64_t nx, const double* ys, int64
     *n_verts = 0; *n_lines = 0; line_offsets[0] = 0;
     if (nx == 0 || ny == 0) return LM_OK;
     lm::GridHostJob job;
-    rc = lm::grid_host_begin(xs, nx, ys, ny, max_iter, 2.0, LM_FIELD_NONE, dwell_i32, dwell_f64, nullptr, true, &job);
+    rc = lm::grid_host_begin(xs, nx, ys, ny, max_iter, 2.0, LM_FIELD_NONE, dwell_i32, dwell_f64, nullptr, true, 0, &job);
     if (rc != LM_OK) return rc;
     float k2_ms = 0.f;
     int k2_launches = 0;

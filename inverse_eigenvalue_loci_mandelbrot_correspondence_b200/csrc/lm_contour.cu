@@ -274,14 +274,32 @@ __global__ void __launch_bounds__(MARK_WARPS * 32) contour_emit_kernel(
     const double* __restrict__ xs, const double* __restrict__ ys,   // ys indexed by local row
     const unsigned* __restrict__ mask, long long words_per_row, const unsigned* __restrict__ row_count,
     const unsigned long long* __restrict__ row_offset, long long* __restrict__ records) {
+    __shared__ unsigned s_words[MARK_WARPS][32 * 32];
     const int lane = threadIdx.x & 31;
     const long long nwarps = static_cast<long long>(gridDim.x) * MARK_WARPS;
     for (long long j = static_cast<long long>(blockIdx.x) * MARK_WARPS + (threadIdx.x >> 5); j < ny - 1; j += nwarps) {
         if (row_count[j] == 0u) continue;
         unsigned long long running = row_offset[j];
-        for (long long w0 = 0; w0 < words_per_row; w0 += 32) {
-            const long long w = w0 + lane;
-            unsigned word = (w < words_per_row) ? mask[j * words_per_row + w] : 0u;
+        // the row's mask words are fetched 32 x 32 at a time (32 independent coalesced loads in flight per
+        // warp) so the walk below does not pay one DRAM round trip per 32 words
+        for (long long s0 = 0; s0 < words_per_row; s0 += 32 * 32) {
+          {
+              unsigned wv[32];
+#pragma unroll
+              for (int t = 0; t < 32; ++t) {
+                  const long long w = s0 + t * 32 + lane;
+                  wv[t] = (w < words_per_row) ? __ldg(mask + j * words_per_row + w) : 0u;
+              }
+              __syncwarp();
+#pragma unroll
+              for (int t = 0; t < 32; ++t) s_words[threadIdx.x >> 5][t * 32 + lane] = wv[t];
+              __syncwarp();
+          }
+          for (int t = 0; t < 32; ++t) {
+            const long long w = s0 + t * 32 + lane;
+            if (s0 + t * 32 >= words_per_row) break;
+            unsigned word = s_words[threadIdx.x >> 5][t * 32 + lane];
+            if (__ballot_sync(FULL, word != 0u) == 0u) continue;
             const int cnt = __popc(word);
             int incl = cnt;
 #pragma unroll
@@ -327,6 +345,7 @@ __global__ void __launch_bounds__(MARK_WARPS * 32) contour_emit_kernel(
                 r2[3] = make_longlong2(__double_as_longlong(v[2]), __double_as_longlong(v[3]));
                 ++pos;
             }
+          }
         }
     }
 }
@@ -433,7 +452,8 @@ struct Linker {
         row_start.assign(static_cast<size_t>(ny) + 1, n);
         long long k = 0;
         for (long long j = 0; j <= ny; ++j) {
-            while (k < n && quad(k) / nx < j) ++k;
+            const long long first_quad = j * nx;            // quad(k) / nx < j  <=>  quad(k) < j * nx
+            while (k < n && quad(k) < first_quad) ++k;
             row_start[static_cast<size_t>(j)] = k;
         }
     }
@@ -542,10 +562,12 @@ struct Linker {
         build_row_index();
         flags.assign(static_cast<size_t>(n), 0);
         verts.clear(); offsets.clear();
-        // lines that start and end on the boundary (edges tested S, W, N, E)
-        for (long long k = 0; k < n; ++k) {
-            if (flags[k] & 1) continue;
-            const long long q = quad(k), i = q % nx, j = q / nx;
+        // lines that start and end on the boundary (edges tested S, W, N, E).  Only quads on the grid border can
+        // start one: every record of the first and last quad row, and the first / last record of the rows between
+        // (visited in raster order, like a scan over all records would).
+        verts.reserve(static_cast<size_t>(n) * 2 + 64);
+        auto try_boundary_start = [&](long long k, long long i, long long j) -> bool {
+            if (flags[k] & 1) return true;
             const unsigned c = config(k);
             const bool nw = c & 8u, ne = c & 4u, sw = c & 2u, se = c & 1u;
             const bool cond[4] = {i == nx - 2 && se && !ne, j == ny - 2 && ne && !nw, i == 0 && nw && !sw, j == 0 && sw && !se};
@@ -556,6 +578,19 @@ struct Linker {
                 offsets.push_back(static_cast<long long>(verts.size() / 2));
                 if (!follow(k, e, true, false)) return false;
                 if (flags[k] & 1) break;
+            }
+            return true;
+        };
+        for (long long j = 0; j + 1 < ny; ++j) {
+            const long long a = row_start[static_cast<size_t>(j)], b = row_start[static_cast<size_t>(j) + 1];
+            if (a >= b) continue;
+            if (j == 0 || j == ny - 2) {
+                for (long long k = a; k < b; ++k)
+                    if (!try_boundary_start(k, quad(k) - j * nx, j)) return false;
+            } else {
+                const long long ia = quad(a) - j * nx, ib = quad(b - 1) - j * nx;
+                if (ia == 0 || ia == nx - 2) { if (!try_boundary_start(a, ia, j)) return false; }
+                if (b - 1 > a && (ib == 0 || ib == nx - 2)) { if (!try_boundary_start(b - 1, ib, j)) return false; }
             }
         }
         // interior closed loops

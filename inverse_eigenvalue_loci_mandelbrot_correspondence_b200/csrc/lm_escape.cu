@@ -536,7 +536,7 @@ void GridHostJob::release_events() {
 // stream copies finished chunks back, so the PCIe transfer hides behind the FP64 work.
 int32_t grid_host_begin(const double* xs, int64_t nx, const double* ys, int64_t ny, int32_t max_iter, double bailout,
                         int32_t field_mode, int32_t* dwell_i32, double* dwell_f64, double* field,
-                        bool need_dev_dwell, GridHostJob* job) {
+                        bool need_dev_dwell, int64_t extra_rows, GridHostJob* job) {
     int32_t rc;
     const size_t npx = static_cast<size_t>(nx) * static_cast<size_t>(ny);
     job->npx = npx;
@@ -559,7 +559,7 @@ int32_t grid_host_begin(const double* xs, int64_t nx, const double* ys, int64_t 
     if ((rc = ws_get(WS_XS, nx * sizeof(double), &dxs)) != LM_OK) return rc;
     if ((rc = ws_get(WS_YS, ny * sizeof(double), &dys)) != LM_OK) return rc;
     if ((rc = ws_get(WS_K1_WORK, 64, &dwork)) != LM_OK) return rc;
-    if (want_i32 && (rc = ws_get(WS_OUT_I32, npx * sizeof(int32_t), &dd)) != LM_OK) return rc;
+    if (want_i32 && (rc = ws_get(WS_OUT_I32, (npx + static_cast<size_t>(extra_rows) * nx) * sizeof(int32_t), &dd)) != LM_OK) return rc;
     if (dwell_f64 && (rc = ws_get(WS_OUT_F64, npx * sizeof(double), &df64)) != LM_OK) return rc;
     if (field_mode != LM_FIELD_NONE && (rc = ws_get(WS_FIELD, npx * sizeof(double), &dfield)) != LM_OK) return rc;
     job->dwork = dwork;
@@ -668,8 +668,25 @@ int32_t lm_escape_grid_f64(const double* xs, int64_t nx, const double* ys, int64
     if (stats) *stats = lm_stats{};
     if (nx == 0 || ny == 0) return LM_OK;
     lm::GridHostJob job;
-    rc = lm::grid_host_begin(xs, nx, ys, ny, max_iter, bailout, field_mode, dwell_i32, dwell_f64, field, false, &job);
+    rc = lm::grid_host_begin(xs, nx, ys, ny, max_iter, bailout, field_mode, dwell_i32, dwell_f64, field, false, 0, &job);
     if (rc != LM_OK) return rc;
+    return lm::grid_host_finish(&job, stats);
+}
+
+int32_t lm_shard_escape(const double* xs, int64_t nx, const double* ys, int64_t ny, int32_t max_iter,
+                        int32_t* dwell_i32, int64_t halo_rows, int32_t** dwell_dev_out, lm_stats* stats) {
+    int32_t rc = lm::require_device();
+    if (rc != LM_OK) return rc;
+    rc = check_grid_args("lm_shard_escape", xs, nx, ys, ny, max_iter, 2.0);
+    if (rc != LM_OK) return rc;
+    LM_REQUIRE(halo_rows >= 0 && dwell_dev_out, "lm_shard_escape: bad halo_rows / NULL dwell_dev_out");
+    if (stats) *stats = lm_stats{};
+    *dwell_dev_out = nullptr;
+    if (nx == 0 || ny == 0) return LM_OK;
+    lm::GridHostJob job;
+    rc = lm::grid_host_begin(xs, nx, ys, ny, max_iter, 2.0, LM_FIELD_NONE, dwell_i32, nullptr, nullptr, true, halo_rows, &job);
+    if (rc != LM_OK) return rc;
+    *dwell_dev_out = job.dwell_dev;
     return lm::grid_host_finish(&job, stats);
 }
 

@@ -262,10 +262,21 @@ __global__ void __launch_bounds__(ROOTS_THREADS) roots_kernel(const RootsArgs A)
         while (!all_done && sweeps < MAX_SWEEPS) {
             ++sweeps;
             bool mine_done = true;
+            // compact the roots that are still moving into act[] (the hull array is free after the initial
+            // guesses), so late sweeps with a few stragglers take one round instead of ceil(d/G)
+            int nact = 0;
             for (int r0 = 0; r0 < d; r0 += G) {
                 const int i = r0 + l;
+                const bool live = (i < d) && !frozen[i];
+                const unsigned bal = tile.ballot(live);
+                if (live) hull[nact + __popc(bal & ((1u << l) - 1u))] = i;
+                nact += __popc(bal);
+            }
+            tile.sync();
+            for (int r0 = 0; r0 < nact; r0 += G) {
+                const bool active = r0 + l < nact;
+                const int i = active ? hull[r0 + l] : 0;
                 cplx znew = {0.0, 0.0};
-                const bool active = (i < d) && !frozen[i];
                 bool freeze = false, stagnant = false;
                 if (active) {
                     const double2 zi2 = zz[i];

@@ -114,3 +114,41 @@ def test_fused_boundary_sample(gpu, oracle):
     assert st["work_units"] == int(np.minimum(out.astype(np.int64) + 1, 200).sum())
     best = gpu.contour.longest(lines)
     assert np.array_equal(best[0], best[-1]) and len(best) > 20000
+
+
+def test_shard_escape_keeps_block_for_halo_exchange(gpu):
+    """The N > 1 e2e path on one device: two row shards computed through lm_shard_escape (host copy + HBM-resident
+    block with a halo slot), the lower shard's halo filled with the upper shard's first row, K2 per shard from the
+    resident block, records concatenated and linked -> identical to the single-call result."""
+    import ctypes as C
+    from helpers import lines_equal
+    shim = gpu.shim
+    xs = np.linspace(-2.1, 0.9, 700); ys = np.linspace(-1.5, 1.5, 640)
+    mi, lvl = 300, 0.96 * 300
+    want_lines, _ = gpu.contour.boundary_sample(xs, ys, mi, lvl)
+    full, _, _ = gpu.escape.escape_grid(xs, ys, mi)
+    cut = 290
+    recs = []
+    upper_first = None
+    for (r0, r1, has_halo) in ((cut, ys.size, False), (0, cut, True)):          # upper shard first: it owns the halo row
+        rows = r1 - r0
+        out = np.empty((rows, xs.size), dtype=np.int32)
+        blk = C.c_void_p()
+        st = shim.Stats()
+        ys_rows = np.ascontiguousarray(ys[r0:r1])
+        shim.call("lm_shard_escape", shim.ptr(xs), xs.size, shim.ptr(ys_rows), rows, mi, shim.ptr(out), 1, C.byref(blk), C.byref(st))
+        assert np.array_equal(out, full[r0:r1]) and blk.value
+        assert st.work_units == int(np.minimum(out.astype(np.int64) + 1, mi).sum())
+        if not has_halo:
+            upper_first = out[0].copy()
+        else:
+            shim.call("lm_memcpy_h2d", C.c_void_p(blk.value + rows * xs.size * 4), shim.ptr(upper_first), upper_first.nbytes, None)
+        ys_blk = np.ascontiguousarray(ys[r0:r1 + (1 if has_halo else 0)])
+        cap = 1 << 16
+        buf = np.empty((cap, 8), dtype=np.int64); n = C.c_int64(0)
+        shim.call("lm_contour_classify_dev", blk, shim.ptr(xs), xs.size, shim.ptr(ys_blk), ys_blk.size, r0, float(lvl),
+                  shim.ptr(buf), cap, C.byref(n), None)
+        recs.append((r0, buf[: n.value].copy()))
+    allrec = np.concatenate([r for _, r in sorted(recs, key=lambda t: t[0])])
+    got = gpu.contour.link_records(allrec, xs, ys, lvl)
+    assert lines_equal(got, want_lines)
