@@ -369,7 +369,7 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dist.all_reduce(ww, op=dist.ReduceOp.SUM)
-        n_vertices = int(max((len(l) for l in lines), default=0)) if lines else 0
+        n_vertices = int(lines.lengths().max()) if lines is not None and len(lines) else 0
         e2e = {"value": int(ww[0]) / float(tt[0]) / 1e9, "unit": "Gpixel-iter/s",
                "h2d_bytes_per_step": int((nx + rows) * 8),
                "d2h_bytes_per_step": int(rows * nx * 4 + n_rec.value * 64), "ms_per_step": 1e3 * float(tt[0]) / args.steps,

@@ -10,6 +10,7 @@ GPU (liblm_b200.so), the ordered chaining follows contourpy's mpl2014 rules.
 from __future__ import annotations
 
 import ctypes as C
+from collections.abc import Sequence
 
 import numpy as np
 
@@ -29,12 +30,43 @@ def _as_dwell_i32(Z) -> np.ndarray:
     return Zi
 
 
-def _split(verts: np.ndarray, offs: np.ndarray, nv: int, nl: int):
-    """(N,2) array per line; one compact copy of the used vertices, the lines are views into it."""
+class Polylines(Sequence):
+    """The lines of one level as a read-only sequence of (N,2) arrays (what cs.allsegs[0] is in the reference),
+    stored as one vertex array plus line offsets; the per-line arrays are views made on access, so a level with
+    10^4 lines costs nothing until somebody iterates over it."""
+
+    def __init__(self, verts: np.ndarray, offsets: np.ndarray):
+        self.verts = verts              # [n_vertices, 2]
+        self.offsets = offsets          # [n_lines + 1]
+
+    def __len__(self) -> int:
+        return int(self.offsets.size) - 1
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self[i] for i in range(*k.indices(len(self)))]
+        n = len(self)
+        if k < 0:
+            k += n
+        if not 0 <= k < n:
+            raise IndexError("line index out of range")
+        return self.verts[self.offsets[k]:self.offsets[k + 1]]
+
+    def lengths(self) -> np.ndarray:
+        return np.diff(self.offsets)
+
+    def longest(self):
+        """The first of the lines with most vertices (max(paths, key=len) in the reference), or None."""
+        if len(self) == 0:
+            return None
+        return self[int(np.argmax(self.lengths()))]
+
+
+def _split(verts: np.ndarray, offs: np.ndarray, nv: int, nl: int) -> Polylines:
+    """One compact copy of the used vertices + offsets; the lines are views into it."""
     if nl == 0:
-        return []
-    used = verts[:nv].copy()
-    return np.split(used, offs[1:nl])
+        return Polylines(np.empty((0, 2), dtype=np.float64), np.zeros(1, dtype=np.int64))
+    return Polylines(verts[:nv].copy(), offs[:nl + 1].copy())
 
 
 def _call_with_growing_buffers(fn_name: str, head_args: tuple, level: float, n_pixels: int, tail_args: tuple = ()):
@@ -105,6 +137,8 @@ def boundary_sample(xs, ys, max_iter: int, level: float, dwell_out: np.ndarray |
 
 def longest(lines):
     """max(paths, key=#vertices): the first of the longest lines (mandelbrot_boundary_sample.py:53)."""
+    if isinstance(lines, Polylines):
+        return lines.longest()
     if not lines:
         return None
     return max(lines, key=lambda a: a.shape[0])

@@ -34,6 +34,9 @@
 #include <climits>
 #include <cmath>
 #include <cstring>
+#include <chrono>
+#include <cstdlib>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -518,12 +521,51 @@ struct Linker {
         }
         return (lo < n && quad(lo) == q) ? lo : -1;
     }
+    // nxt[2k + s]: record reached through the exit edge of segment s of record k; -1 = the line leaves the
+    // grid there, -2 = the neighbour record is missing (inconsistent input).  Filled by all host threads
+    // before the (inherently sequential) walk, so the walk itself is pointer chasing.
+    std::vector<long long> nxt;
+    void build_next_range(long long k_lo, long long k_hi) {
+        for (long long k = k_lo; k < k_hi; ++k) {
+            const unsigned m = meta(k);
+            const int nseg = static_cast<int>((m >> 16) & 3u);
+            const long long q = quad(k);
+            long long j = -1, i = -1;                      // row / column only when a vertical move needs them
+            for (int sg = 0; sg < 2; ++sg) {
+                long long r = -2;
+                if (sg < nseg) {
+                    const int ex = static_cast<int>((m >> (10 + 4 * sg)) & 3u);
+                    if (j < 0) { j = q / nx; i = q - j * nx; }
+                    switch (ex) {
+                        case EDGE_E: r = (i == nx - 2) ? -1 : ((k + 1 < n && quad(k + 1) == q + 1) ? k + 1 : -2); break;
+                        case EDGE_W: r = (i == 0) ? -1 : ((k > 0 && quad(k - 1) == q - 1) ? k - 1 : -2); break;
+                        case EDGE_N: r = (j == ny - 2) ? -1 : find_in_row(q + nx, j + 1, k); if (r < -1) r = -2; break;
+                        default:     r = (j == 0) ? -1 : find_in_row(q - nx, j - 1, k); if (r < -1) r = -2; break;
+                    }
+                    if ((ex == EDGE_N && j != ny - 2 && r == -1) || (ex == EDGE_S && j != 0 && r == -1)) r = -2;
+                }
+                nxt[static_cast<size_t>(2 * k + sg)] = r;
+            }
+        }
+    }
+    void build_next() {
+        nxt.assign(static_cast<size_t>(2 * n), -2);
+        unsigned hw = std::thread::hardware_concurrency();
+        int nthreads = static_cast<int>(hw ? hw : 1);
+        if (nthreads > 16) nthreads = 16;
+        if (n < 20000) nthreads = 1;
+        if (nthreads <= 1) { build_next_range(0, n); return; }
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthreads; ++t) {
+            const long long lo = n * t / nthreads, hi = n * (t + 1) / nthreads;
+            pool.emplace_back([this, lo, hi] { build_next_range(lo, hi); });
+        }
+        for (auto& th : pool) th.join();
+    }
     // returns false on an inconsistent record set (missing neighbour)
     bool follow(long long k, int edge, bool want_initial, bool closed) {
         const long long k0 = k; const int e0 = edge;
         if (want_initial) push_edge_vertex(k, edge);
-        long long q = quad(k);
-        long long j = q / nx, i = q - j * nx;           // tracked incrementally along the line
         for (;;) {
             const unsigned m = meta(k);
             const unsigned cfg = m & 15u;
@@ -543,23 +585,27 @@ struct Linker {
             memcpy(v, &rec[k * REC_WORDS + 4 + 2 * seg], sizeof(v));
             verts.push_back(v[0]);
             verts.push_back(v[1]);
-            int en;
-            switch (ex) {
-                case EDGE_E: if (i == nx - 2) return true; q += 1;  ++i; en = EDGE_W; break;
-                case EDGE_N: if (j == ny - 2) return true; q += nx; ++j; en = EDGE_S; break;
-                case EDGE_W: if (i == 0) return true;      q -= 1;  --i; en = EDGE_E; break;
-                default:     if (j == 0) return true;      q -= nx; --j; en = EDGE_N; break;
-            }
-            const long long kn = find_in_row(q, j, k);
+            const long long kn = nxt[static_cast<size_t>(2 * k + seg)];
+            if (kn == -1) return true;                      // left the grid
             if (kn < 0) return false;
-            k = kn; edge = en;
+            k = kn; edge = (ex + 2) & 3;                    // enter the neighbour through the opposite edge
             if (closed && k == k0 && edge == e0) return true;
         }
     }
     bool run() {
         for (long long k = 1; k < n; ++k)
             if (quad(k) <= quad(k - 1)) return false;       // records must be in raster order
+        const bool dbg = getenv("LM_LINK_DEBUG") != nullptr;
+        auto t0 = std::chrono::steady_clock::now();
         build_row_index();
+        auto t1 = std::chrono::steady_clock::now();
+        build_next();
+        auto t2 = std::chrono::steady_clock::now();
+        if (dbg) fprintf(stderr, "[link] n=%lld row_index %.2f ms, next %.2f ms\n", n,
+                         std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                         std::chrono::duration<double, std::milli>(t2 - t1).count());
+        struct Report { bool on; std::chrono::steady_clock::time_point t; ~Report() { if (on) fprintf(stderr, "[link] walk %.2f ms\n",
+                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count()); } } rep{dbg, t2};
         flags.assign(static_cast<size_t>(n), 0);
         verts.clear(); offsets.clear();
         // lines that start and end on the boundary (edges tested S, W, N, E).  Only quads on the grid border can
