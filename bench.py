@@ -237,6 +237,10 @@ def run_ours(args):
     xs_d = torch.from_numpy(xs).to(dev)
     ys_d = torch.from_numpy(ys_block).to(dev)
     dwell_d = torch.empty((rows + 1, nx), dtype=torch.int32, device=dev)      # +1: halo row slot
+    # BASELINE.json configs[1] asks for the smooth potential with the dwell grid; at N > 1 the final field is
+    # all-gathered so that every GPU holds it (north_star)
+    with_pot = args.workload == "cfg2"
+    field_d = torch.empty((rows, nx), dtype=torch.float64, device=dev) if with_pot else None
     work_d = torch.zeros(1, dtype=torch.int64, device=dev)
     rec_cap = max(int(0.01 * rows * nx) + 4096, 1 << 16)
     records = np.empty((rec_cap, 8), dtype=np.int64)
@@ -245,7 +249,8 @@ def run_ours(args):
 
     def k1():
         _shim.call("lm_escape_grid_f64_dev", C.c_void_p(xs_d.data_ptr()), nx, C.c_void_p(ys_d.data_ptr()), rows,
-                   max_iter, 2.0, 0, C.c_void_p(dwell_d.data_ptr()), None, None, C.c_void_p(work_d.data_ptr()), stream)
+                   max_iter, 2.0, 1 if with_pot else 0, C.c_void_p(dwell_d.data_ptr()), None,
+                   C.c_void_p(field_d.data_ptr()) if with_pot else None, C.c_void_p(work_d.data_ptr()), stream)
         launches["n"] += 1
 
     def classify(block_ptr, nrows_k2):
@@ -261,11 +266,15 @@ def run_ours(args):
         launches["n"] += 3 if n_rec.value else 2
         return records[: n_rec.value]
 
+    full_field = {"t": None}
+
     def k2():
         if world > 1:
             firsts = sharding.exchange_first_rows(dwell_d[0])
             if has_halo:
                 dwell_d[rows].copy_(firsts[rank + 1])
+            if with_pot:
+                full_field["t"] = sharding.allgather_rows(field_d, cuts)
         return classify(C.c_void_p(dwell_d.data_ptr()), rows + (1 if has_halo else 0))
 
     def barrier():
@@ -277,12 +286,13 @@ def run_ours(args):
     peak_tflops = C.c_double(0.0); mix = C.c_double(0.0)
     _shim.call("lm_probe_fp64_peak", 2000, C.byref(peak_tflops), C.byref(mix))
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()             # before the warm-up (same load): nvidia-smi needs ~0.2 s for its first sample and
+                                    # the small workloads finish their timed region in ~0.1 s
     for _ in range(args.warmup):
         k1(); k2()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches["n"] = 0
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 + 2 * args.steps)]
     work_steps = []
@@ -313,7 +323,7 @@ def run_ours(args):
     k1_gpi = my_work / (k1_ms * 1e-3) / 1e9
     achieved_tflops = k1_gpi * 1e9 * FLOPS_PER_PIXEL_ITER / 1e12
     roofline = {
-        "bound": "fp64", "kernel": "lm_escape_kernel<grid, dwell>", "achieved": achieved_tflops, "peak": peak_tflops.value,
+        "bound": "fp64", "kernel": "lm_escape_kernel<grid, dwell + potential>" if with_pot else "lm_escape_kernel<grid, dwell>", "achieved": achieved_tflops, "peak": peak_tflops.value,
         "unit": "TFLOP/s", "frac": achieved_tflops / peak_tflops.value,
         "peak_source": "lm_probe_fp64_peak (dependent-free DFMA loop, 2 flops/DFMA), measured live; "
                        "MEASURED_PEAKS.json has no FP64 entry",
@@ -330,20 +340,24 @@ def run_ours(args):
         ys_p = _shim.pinned_empty(rows, np.float64); ys_p[:] = ys[r0:r1]
         st = _shim.Stats()
         edge_d = torch.empty(nx, dtype=torch.int32, device=dev)
+        pot_p = _shim.pinned_empty((rows, nx), np.float64) if with_pot else None
 
         def e2e_step():
             if world == 1:
                 # the fused host-buffer call (compute_grid + extract_contour of the script's main()):
                 # H2D of xs/ys, chunked K1, dwell grid copied back to the pinned host buffer while
                 # K1/K2 still run, K2 records -> ordered polylines on the host
-                lines, stx = contour.boundary_sample(xs_p, ys_p, max_iter, level, dwell_out=out)
+                lines, stx = contour.boundary_sample(xs_p, ys_p, max_iter, level, dwell_out=out, potential_out=pot_p)
                 return stx["work_units"], lines
             # N > 1: K1 on this rank's rows through the host-buffer shard call (dwell block returned to the pinned
             # host buffer by the copy stream AND kept in HBM), shard-edge rows all-gathered over NCCL straight
             # from / into that block, K2 on it, records gathered and linked on rank 0
-            dev_block = C.c_void_p()
-            _shim.call("lm_shard_escape", _shim.ptr(xs_p), nx, _shim.ptr(ys_p), rows, max_iter, _shim.ptr(out), 1,
-                       C.byref(dev_block), C.byref(st))
+            dev_block = C.c_void_p(); pot_block = C.c_void_p()
+            _shim.call("lm_shard_escape", _shim.ptr(xs_p), nx, _shim.ptr(ys_p), rows, max_iter, _shim.ptr(out), _shim.ptr(pot_p), 1,
+                       C.byref(dev_block), C.byref(pot_block), C.byref(st))
+            if with_pot:        # final potential field on every GPU: all-gather straight from the resident block
+                _shim.call("lm_memcpy_d2d", C.c_void_p(field_d.data_ptr()), pot_block, rows * nx * 8, stream)
+                full_field["t"] = sharding.allgather_rows(field_d, cuts)
             _shim.call("lm_memcpy_d2d", C.c_void_p(edge_d.data_ptr()), dev_block, nx * 4, stream)
             firsts = sharding.exchange_first_rows(edge_d)
             if has_halo:
@@ -372,7 +386,7 @@ def run_ours(args):
         n_vertices = int(lines.lengths().max()) if lines is not None and len(lines) else 0
         e2e = {"value": int(ww[0]) / float(tt[0]) / 1e9, "unit": "Gpixel-iter/s",
                "h2d_bytes_per_step": int((nx + rows) * 8),
-               "d2h_bytes_per_step": int(rows * nx * 4 + n_rec.value * 64), "ms_per_step": 1e3 * float(tt[0]) / args.steps,
+               "d2h_bytes_per_step": int(rows * nx * (12 if with_pot else 4) + n_rec.value * 64), "ms_per_step": 1e3 * float(tt[0]) / args.steps,
                "boundary_vertices": n_vertices,
                "api": ("lm_boundary_sample (pinned numpy buffers in, dwell grid + ordered boundary polylines out)" if world == 1 else
                        "lm_shard_escape (pinned numpy buffers; block kept in HBM) + NCCL edge rows + lm_contour_classify_dev + lm_contour_link")}
@@ -405,7 +419,8 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(w), "pixel_iters_per_step": total_work // args.steps,
-                       "step": "K1 dwell grid + K2 crossing records" + (" + NCCL all-gather of shard-edge rows" if world > 1 else ""),
+                       "step": "K1 dwell grid" + (" + smooth potential" if with_pot else "") + " + K2 crossing records" +
+                               ((" + NCCL all-gather of shard-edge rows" + (" and of the potential field" if with_pot else "")) if world > 1 else ""),
                        "sharding": f"contiguous row blocks at equal estimated work, cuts={cuts}, balance={balance:.3f}",
                        "l2": "FP64-bound; per step every rank writes its dwell block (>= L2 for cfg2/cfg3) and reads 2*res coordinates"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,

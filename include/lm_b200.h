@@ -163,10 +163,13 @@ int32_t lm_escape_grid_f64_dev(const double* xs, int64_t nx, const double* ys, i
  * stays in HBM with room for `halo_rows` more rows behind it.  *dwell_dev_out is that device block
  * ([ny + halo_rows] x nx, library owned, valid until the next grid call on this device): the caller
  * exchanges shard-edge rows over NCCL straight from / into it (lm_memcpy_d2d) and then runs
- * lm_contour_classify_dev on it, so nothing is uploaded twice.
+ * lm_contour_classify_dev on it, so nothing is uploaded twice.  With potential != NULL the same pass
+ * also produces the smooth potential (LM_FIELD_GREEN) of the shard's rows: returned to the host
+ * buffer and kept in HBM (*potential_dev_out, [ny] x nx) for the all-gather of the final field.
  */
 int32_t lm_shard_escape(const double* xs, int64_t nx, const double* ys, int64_t ny, int32_t max_iter,
-                        int32_t* dwell_i32, int64_t halo_rows, int32_t** dwell_dev_out, lm_stats* stats);
+                        int32_t* dwell_i32, double* potential, int64_t halo_rows,
+                        int32_t** dwell_dev_out, double** potential_dev_out, lm_stats* stats);
 
 /* fp32 variant of the dwell grid (no reference counterpart; validated against the
  * fp64 kernel by mismatch fraction).                                                 */
@@ -240,6 +243,16 @@ int32_t lm_boundary_sample(const double* xs, int64_t nx, const double* ys, int64
                            double* verts, int64_t cap_verts, int64_t* n_verts,
                            int64_t* line_offsets, int64_t cap_lines, int64_t* n_lines,
                            lm_stats* stats);
+
+/* The same with the smooth (Green) potential g = log|z_k| * 2^-k of the escaping iterate (0 inside; the a-7
+ * definition of lucas_equipotential_test_v3.py:140-149 on the grid, BASELINE.json config 2) produced by the
+ * same K1 pass and returned to potential[ny*nx] by the copy stream.                                       */
+int32_t lm_boundary_sample_potential(const double* xs, int64_t nx, const double* ys, int64_t ny,
+                                     int32_t max_iter, double level,
+                                     int32_t* dwell_i32, double* dwell_f64, double* potential,
+                                     double* verts, int64_t cap_verts, int64_t* n_verts,
+                                     int64_t* line_offsets, int64_t cap_lines, int64_t* n_lines,
+                                     lm_stats* stats);
 
 /*
  * Multi-GPU building block: classify the quads of rows [0, ny-1) of a dwell block on the

@@ -112,10 +112,12 @@ def contour_lines_dev(dwell_dev_ptr: int, xs, ys, level: float):
                                       level, xs.size * ys.size)
 
 
-def boundary_sample(xs, ys, max_iter: int, level: float, dwell_out: np.ndarray | None = None):
+def boundary_sample(xs, ys, max_iter: int, level: float, dwell_out: np.ndarray | None = None,
+                    potential_out: np.ndarray | None = None):
     """compute_grid + plt.contour in one host-buffer call (lm_boundary_sample): the dwell grid never
     leaves the GPU between K1 and K2.  dwell_out: optional int32 or float64 [ny, nx] array that
-    receives the dwell grid (copied back while the GPU is still computing).
+    receives the dwell grid (copied back while the GPU is still computing); potential_out: optional
+    float64 [ny, nx] array for the smooth potential log|z_k| 2^-k of the same pass (config 2).
     Returns (lines, stats) with lines as in contour_lines."""
     xs = np.ascontiguousarray(xs, dtype=np.float64).ravel()
     ys = np.ascontiguousarray(ys, dtype=np.float64).ravel()
@@ -129,6 +131,15 @@ def boundary_sample(xs, ys, max_iter: int, level: float, dwell_out: np.ndarray |
             d64 = dwell_out
         else:
             raise ValueError("dwell_out must be int32 or float64")
+    if potential_out is not None:
+        if (potential_out.shape != (ys.size, xs.size) or not potential_out.flags["C_CONTIGUOUS"]
+                or potential_out.dtype != np.float64):
+            raise ValueError("potential_out must be a C-contiguous float64 [len(ys), len(xs)] array")
+        lines = _call_with_growing_buffers("lm_boundary_sample_potential",
+                                           (_shim.ptr(xs), xs.size, _shim.ptr(ys), ys.size, int(max_iter)),
+                                           level, xs.size * ys.size,
+                                           tail_args=(_shim.ptr(d32), _shim.ptr(d64), _shim.ptr(potential_out)))
+        return lines, last_stats
     lines = _call_with_growing_buffers("lm_boundary_sample",
                                        (_shim.ptr(xs), xs.size, _shim.ptr(ys), ys.size, int(max_iter)),
                                        level, xs.size * ys.size, tail_args=(_shim.ptr(d32), _shim.ptr(d64)))

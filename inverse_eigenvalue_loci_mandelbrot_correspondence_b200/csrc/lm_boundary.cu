@@ -6,14 +6,14 @@
 // transfer overlaps the FP64 work and the contour kernels.
 #include "lm_common.cuh"
 
-extern "C" {
+namespace {
 
-int32_t lm_boundary_sample(const double* xs, int64_t nx, const double* ys, int64_t ny,
-                           int32_t max_iter, double level,
-                           int32_t* dwell_i32, double* dwell_f64,
-                           double* verts, int64_t cap_verts, int64_t* n_verts,
-                           int64_t* line_offsets, int64_t cap_lines, int64_t* n_lines,
-                           lm_stats* stats) {
+int32_t boundary_sample_impl(const double* xs, int64_t nx, const double* ys, int64_t ny,
+                             int32_t max_iter, double level, int32_t field_mode, double* field,
+                             int32_t* dwell_i32, double* dwell_f64,
+                             double* verts, int64_t cap_verts, int64_t* n_verts,
+                             int64_t* line_offsets, int64_t cap_lines, int64_t* n_lines,
+                             lm_stats* stats) {
     int32_t rc = lm::require_device();
     if (rc != LM_OK) return rc;
     LM_REQUIRE(xs && ys, "lm_boundary_sample: xs/ys is NULL");
@@ -25,7 +25,7 @@ int32_t lm_boundary_sample(const double* xs, int64_t nx, const double* ys, int64
     *n_verts = 0; *n_lines = 0; line_offsets[0] = 0;
     if (nx == 0 || ny == 0) return LM_OK;
     lm::GridHostJob job;
-    rc = lm::grid_host_begin(xs, nx, ys, ny, max_iter, 2.0, LM_FIELD_NONE, dwell_i32, dwell_f64, nullptr, true, 0, &job);
+    rc = lm::grid_host_begin(xs, nx, ys, ny, max_iter, 2.0, field_mode, dwell_i32, dwell_f64, field, true, 0, &job);
     if (rc != LM_OK) return rc;
     float k2_ms = 0.f;
     int k2_launches = 0;
@@ -38,6 +38,31 @@ int32_t lm_boundary_sample(const double* xs, int64_t nx, const double* ys, int64
         stats->launches += k2_launches;
     }
     return rc != LM_OK ? rc : rc2;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t lm_boundary_sample(const double* xs, int64_t nx, const double* ys, int64_t ny,
+                           int32_t max_iter, double level,
+                           int32_t* dwell_i32, double* dwell_f64,
+                           double* verts, int64_t cap_verts, int64_t* n_verts,
+                           int64_t* line_offsets, int64_t cap_lines, int64_t* n_lines,
+                           lm_stats* stats) {
+    return boundary_sample_impl(xs, nx, ys, ny, max_iter, level, LM_FIELD_NONE, nullptr, dwell_i32, dwell_f64,
+                                verts, cap_verts, n_verts, line_offsets, cap_lines, n_lines, stats);
+}
+
+int32_t lm_boundary_sample_potential(const double* xs, int64_t nx, const double* ys, int64_t ny,
+                                     int32_t max_iter, double level,
+                                     int32_t* dwell_i32, double* dwell_f64, double* potential,
+                                     double* verts, int64_t cap_verts, int64_t* n_verts,
+                                     int64_t* line_offsets, int64_t cap_lines, int64_t* n_lines,
+                                     lm_stats* stats) {
+    LM_REQUIRE(potential != nullptr, "lm_boundary_sample_potential: potential is NULL");
+    return boundary_sample_impl(xs, nx, ys, ny, max_iter, level, LM_FIELD_GREEN, potential, dwell_i32, dwell_f64,
+                                verts, cap_verts, n_verts, line_offsets, cap_lines, n_lines, stats);
 }
 
 }  // extern "C"

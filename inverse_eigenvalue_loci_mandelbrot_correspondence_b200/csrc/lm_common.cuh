@@ -67,6 +67,7 @@ struct GridHostJob {
     std::vector<cudaEvent_t> ev_chunk;
     void* dwork = nullptr;            // device: [0] work counter, [1] overflow flag
     int32_t* dwell_dev = nullptr;     // device int32 dwell grid (when produced)
+    double* field_dev = nullptr;      // device field (when produced)
     int launches = 0;
     size_t npx = 0;
     void release_events();

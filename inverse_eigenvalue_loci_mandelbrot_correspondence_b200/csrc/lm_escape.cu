@@ -564,6 +564,7 @@ int32_t grid_host_begin(const double* xs, int64_t nx, const double* ys, int64_t 
     if (field_mode != LM_FIELD_NONE && (rc = ws_get(WS_FIELD, npx * sizeof(double), &dfield)) != LM_OK) return rc;
     job->dwork = dwork;
     job->dwell_dev = static_cast<int32_t*>(dd);
+    job->field_dev = static_cast<double*>(dfield);
     LM_CUDA_TRY(cudaMemcpyAsync(dxs, xs, nx * sizeof(double), cudaMemcpyHostToDevice, s_compute));
     LM_CUDA_TRY(cudaMemcpyAsync(dys, ys, ny * sizeof(double), cudaMemcpyHostToDevice, s_compute));
     LM_CUDA_TRY(cudaMemsetAsync(dwork, 0, 64, s_compute));
@@ -674,7 +675,8 @@ int32_t lm_escape_grid_f64(const double* xs, int64_t nx, const double* ys, int64
 }
 
 int32_t lm_shard_escape(const double* xs, int64_t nx, const double* ys, int64_t ny, int32_t max_iter,
-                        int32_t* dwell_i32, int64_t halo_rows, int32_t** dwell_dev_out, lm_stats* stats) {
+                        int32_t* dwell_i32, double* potential, int64_t halo_rows,
+                        int32_t** dwell_dev_out, double** potential_dev_out, lm_stats* stats) {
     int32_t rc = lm::require_device();
     if (rc != LM_OK) return rc;
     rc = check_grid_args("lm_shard_escape", xs, nx, ys, ny, max_iter, 2.0);
@@ -682,11 +684,14 @@ int32_t lm_shard_escape(const double* xs, int64_t nx, const double* ys, int64_t 
     LM_REQUIRE(halo_rows >= 0 && dwell_dev_out, "lm_shard_escape: bad halo_rows / NULL dwell_dev_out");
     if (stats) *stats = lm_stats{};
     *dwell_dev_out = nullptr;
+    if (potential_dev_out) *potential_dev_out = nullptr;
     if (nx == 0 || ny == 0) return LM_OK;
     lm::GridHostJob job;
-    rc = lm::grid_host_begin(xs, nx, ys, ny, max_iter, 2.0, LM_FIELD_NONE, dwell_i32, nullptr, nullptr, true, halo_rows, &job);
+    rc = lm::grid_host_begin(xs, nx, ys, ny, max_iter, 2.0, potential ? LM_FIELD_GREEN : LM_FIELD_NONE, dwell_i32, nullptr,
+                             potential, true, halo_rows, &job);
     if (rc != LM_OK) return rc;
     *dwell_dev_out = job.dwell_dev;
+    if (potential_dev_out) *potential_dev_out = job.field_dev;
     return lm::grid_host_finish(&job, stats);
 }
 

@@ -123,3 +123,40 @@ def allreduce_field_sums(sums, n_points_local: int, group=None):
         dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
     return sums, int(cnt.item())
+
+
+# ---- potential field of a row-sharded grid: all-gather of the row blocks, halo rows for the stencils ----
+def allgather_rows(block, cuts, group=None):
+    """All-gather the row blocks of a row-sharded field ([rows_r, nx] on rank r, rows cut at `cuts`) into the
+    full [ny, nx] field on every rank (NCCL all-gather of equal-size padded blocks).  This is how the final
+    potential field reaches every GPU for K4 / K4a."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return block
+    rows = [b - a for a, b in zip(cuts[:-1], cuts[1:])]
+    nx = block.shape[1]
+    pad = max(rows)
+    mine = torch.zeros((pad, nx), dtype=block.dtype, device=block.device)
+    mine[: block.shape[0]] = block
+    gathered = torch.empty((world, pad, nx), dtype=block.dtype, device=block.device)
+    dist.all_gather_into_tensor(gathered, mine.view(1, pad, nx), group=group)
+    return torch.cat([gathered[r, : rows[r]] for r in range(world)], dim=0)
+
+
+def exchange_halo_rows(block, periodic: bool, group=None):
+    """Halo rows of a row-sharded field for the 5-point stencils: returns (row_above, row_below) for this rank,
+    taken from the neighbours' last / first rows (one all-gather of 2 rows per rank).  periodic=True wraps
+    first <-> last rank (np.roll semantics of laplacian, Laplacian_C-M.py:49-59); otherwise the outer ranks get
+    None (interior stencil with copied border, variograms_construct_mandelbrot.py:169-173)."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    nx = block.shape[1]
+    edges = torch.stack([block[0], block[-1]]).contiguous()               # [2, nx]: my first and last row
+    allv = torch.empty((world, 2, nx), dtype=block.dtype, device=block.device)
+    dist.all_gather_into_tensor(allv, edges.view(1, 2, nx), group=group)
+    above = allv[(rank - 1) % world, 1] if (periodic or rank > 0) else None
+    below = allv[(rank + 1) % world, 0] if (periodic or rank < world - 1) else None
+    return above, below

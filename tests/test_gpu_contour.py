@@ -136,8 +136,13 @@ def test_shard_escape_keeps_block_for_halo_exchange(gpu):
         blk = C.c_void_p()
         st = shim.Stats()
         ys_rows = np.ascontiguousarray(ys[r0:r1])
-        shim.call("lm_shard_escape", shim.ptr(xs), xs.size, shim.ptr(ys_rows), rows, mi, shim.ptr(out), 1, C.byref(blk), C.byref(st))
-        assert np.array_equal(out, full[r0:r1]) and blk.value
+        pot = np.empty((rows, xs.size)); pblk = C.c_void_p()
+        shim.call("lm_shard_escape", shim.ptr(xs), xs.size, shim.ptr(ys_rows), rows, mi, shim.ptr(out), shim.ptr(pot), 1,
+                  C.byref(blk), C.byref(pblk), C.byref(st))
+        assert np.array_equal(out, full[r0:r1]) and blk.value and pblk.value
+        back = np.empty_like(pot)
+        shim.call("lm_memcpy_d2h", shim.ptr(back), pblk, back.nbytes, None); shim.call("lm_stream_synchronize", None)
+        assert np.array_equal(back, pot) and np.array_equal(pot, gpu.escape.escape_grid(xs, ys_rows, mi, field_mode=1)[1])
         assert st.work_units == int(np.minimum(out.astype(np.int64) + 1, mi).sum())
         if not has_halo:
             upper_first = out[0].copy()
@@ -152,3 +157,19 @@ def test_shard_escape_keeps_block_for_halo_exchange(gpu):
     allrec = np.concatenate([r for _, r in sorted(recs, key=lambda t: t[0])])
     got = gpu.contour.link_records(allrec, xs, ys, lvl)
     assert lines_equal(got, want_lines)
+
+
+def test_boundary_sample_with_potential(gpu, oracle):
+    """config 2's stage in one call: dwell grid + smooth potential + ordered boundary from one K1 pass."""
+    from helpers import lines_equal
+    xs = np.linspace(-2.1, 0.9, 333); ys = np.linspace(-1.5, 1.5, 301)
+    mi = 400
+    d = np.empty((ys.size, xs.size), dtype=np.int32); g = np.empty((ys.size, xs.size))
+    lines, st = gpu.contour.boundary_sample(xs, ys, mi, 0.96 * mi, dwell_out=d, potential_out=g)
+    d_o, g_o = oracle.potential_grid(xs, ys, mi, 2.0, oracle.FIELD_GREEN)
+    assert np.array_equal(d, d_o)
+    np.testing.assert_allclose(g, g_o, rtol=1e-14, atol=0)
+    assert lines_equal(lines, oracle.contour_lines(xs, ys, d_o.astype(float), 0.96 * mi))
+    plain, _ = gpu.contour.boundary_sample(xs, ys, mi, 0.96 * mi)
+    assert lines_equal(lines, plain)
+    assert gpu.contour.longest(lines).shape == oracle.extract_contour(xs, ys, d_o.astype(float), mi, 0.96).shape

@@ -163,3 +163,58 @@ def test_sharded_cloud_field_gloo(oracle, world):
         p.join(timeout=60)
     for rank, ok, err in results:
         assert ok, f"rank {rank}: {err}"
+
+
+def _field_worker(rank: int, world: int, port: int, q):
+    try:
+        sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+        import torch
+        import torch.distributed as dist
+        from oracle import oracle
+        from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import sharding
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        xs = np.linspace(-2.1, 0.9, 90); ys = np.linspace(-1.5, 1.5, 77)
+        cuts = sharding.balanced_row_cuts(np.ones(ys.size) + (np.arange(ys.size) % 7), world)     # ragged blocks
+        r0, r1 = cuts[rank], cuts[rank + 1]
+        _, mine = oracle.potential_grid(xs, ys[r0:r1], 120, 2.0, oracle.FIELD_GREEN)       # this rank's K1 field rows
+        _, full = oracle.potential_grid(xs, ys, 120, 2.0, oracle.FIELD_GREEN)
+        block = torch.from_numpy(mine.copy())
+        got = sharding.allgather_rows(block, cuts).numpy()
+        ok = np.array_equal(got, full)
+        h = float(xs[1] - xs[0])
+        # periodic Laplacian of the sharded field through halo rows == rows of the Laplacian of the full field
+        above, below = sharding.exchange_halo_rows(block, periodic=True)
+        ext = np.vstack([above.numpy()[None], mine, below.numpy()[None]])
+        ok = ok and np.array_equal(oracle.laplacian(ext, h)[1:-1], oracle.laplacian(full, h)[r0:r1])
+        # interior 5-point average: the outer ranks have no halo on the outside (copied border)
+        above, below = sharding.exchange_halo_rows(block, periodic=False)
+        parts = ([above.numpy()[None]] if above is not None else []) + [mine] + ([below.numpy()[None]] if below is not None else [])
+        sm = oracle.smooth5(np.vstack(parts))
+        sm = sm[(1 if above is not None else 0): sm.shape[0] - (1 if below is not None else 0)]
+        ok = ok and np.array_equal(sm, oracle.smooth5(full)[r0:r1])
+        ok = ok and (above is None) == (rank == 0) and (below is None) == (rank == world - 1)
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, bool(ok), ""))
+    except Exception:          # pragma: no cover
+        import traceback
+        q.put((rank, False, traceback.format_exc()))
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_potential_field_gloo(oracle, world):
+    """The final potential field of a row-sharded grid: all-gather of ragged row blocks, and the halo rows that
+    let each rank apply the 5-point stencils to its own block (periodic wrap across the first / last rank)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_field_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok, err in results:
+        assert ok, f"rank {rank}: {err}"
