@@ -226,6 +226,24 @@ def run_ours(args):
     if world > 1:
         profile = sharding.coarse_row_profile(xs, ys, max_iter)
         cuts = sharding.balanced_row_cuts(profile, world)
+        # measured rebalancing (untimed set-up): run K1 on the estimated blocks, time every rank with CUDA events,
+        # rescale the profile block by block to the measured times and cut again
+        for _ in range(2):
+            ra, rb = cuts[rank], cuts[rank + 1]
+            cal_ys = torch.from_numpy(np.ascontiguousarray(ys[ra:rb])).to(dev)
+            cal_xs = torch.from_numpy(xs).to(dev)
+            cal_d = torch.empty((rb - ra, nx), dtype=torch.int32, device=dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); dist.barrier()
+            e0.record()
+            _shim.call("lm_escape_grid_f64_dev", C.c_void_p(cal_xs.data_ptr()), nx, C.c_void_p(cal_ys.data_ptr()), rb - ra,
+                       max_iter, 2.0, 0, C.c_void_p(cal_d.data_ptr()), None, None, None, stream)
+            e1.record(); torch.cuda.synchronize()
+            t_all = torch.zeros(world, dtype=torch.float64, device=dev)
+            t_all[rank] = e0.elapsed_time(e1)
+            dist.all_reduce(t_all)
+            cuts = sharding.refine_cuts(profile, cuts, t_all.cpu().numpy())
+            del cal_d, cal_ys, cal_xs
         balance = sharding.parallel_efficiency(profile, cuts)
     else:
         cuts, balance = [0, ny], 1.0
@@ -424,7 +442,8 @@ def run_ours(args):
             "config": {"workload": workload_name(w), "pixel_iters_per_step": total_work // args.steps,
                        "step": "K1 dwell grid" + (" + smooth potential" if with_pot else "") + " + K2 crossing records" +
                                ((" + NCCL all-gather of shard-edge rows" + (" and of the potential field" if with_pot else "")) if world > 1 else ""),
-                       "sharding": f"contiguous row blocks at equal estimated work, cuts={cuts}, balance={balance:.3f}",
+                       "sharding": (f"contiguous row blocks at equal estimated work" + (", refined twice from measured per-rank K1 times" if world > 1 else "") +
+                                    f", cuts={cuts}, estimated balance={balance:.3f}"),
                        "l2": "FP64-bound; per step every rank writes its dwell block (>= L2 for cfg2/cfg3) and reads 2*res coordinates"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
             "k1_ms_per_step_max_rank": k1_ms_max / args.steps, "lucas_roots": lucas_roots,

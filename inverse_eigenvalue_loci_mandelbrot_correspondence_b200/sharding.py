@@ -67,6 +67,21 @@ def coarse_row_profile(xs, ys, max_iter: int, rows: int = 2048, cols: int = 2048
     return interpolate_row_profile(ri, work, ys.size)
 
 
+def refine_cuts(row_work, cuts, measured) -> list[int]:
+    """One step of measured rebalancing: rescale the estimated work of every block so that its total equals the
+    time (or any cost) MEASURED for that block, then cut again.  The iteration-count profile misses per-pixel
+    overheads (exterior rows are cheap in iterations but not free), the measurement does not."""
+    w = np.asarray(row_work, dtype=np.float64).ravel().copy()
+    measured = np.asarray(measured, dtype=np.float64).ravel()
+    if measured.size != len(cuts) - 1:
+        raise ValueError("one measurement per block expected")
+    for k, (a, b) in enumerate(zip(cuts[:-1], cuts[1:])):
+        tot = w[a:b].sum()
+        if tot > 0 and measured[k] > 0:
+            w[a:b] *= measured[k] / tot
+    return balanced_row_cuts(w, len(cuts) - 1)
+
+
 # ---- collectives (torch.distributed; backend-agnostic) -------------------------------------
 def exchange_first_rows(first_row, group=None):
     """All-gather every rank's first dwell row; returns the [world, nx] tensor.
