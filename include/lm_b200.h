@@ -308,6 +308,11 @@ int32_t lm_roots_batched_dev(const double* toprows_dev, const int32_t* deg_dev, 
 int32_t lm_cloud_compact_dev(const double* re_dev, const double* im_dev, const int32_t* n_kept_dev,
                              int64_t npoly, int32_t maxdeg, double* px_dev, double* py_dev,
                              int64_t cap_points, int64_t* n_points_dev, void* stream);
+/* Chunked form: appends this chunk's points behind the *n_points_inout_dev points already in px_dev / py_dev
+ * and adds their number to it (lets a batch stream through the device chunk by chunk).                        */
+int32_t lm_cloud_append_dev(const double* re_dev, const double* im_dev, const int32_t* n_kept_dev,
+                            int64_t npoly, int32_t maxdeg, double* px_dev, double* py_dev,
+                            int64_t cap_points, int64_t* n_points_inout_dev, void* stream);
 
 /*
  * The Lucas-Loci field stage (BASELINE.json config 5) as one host-buffer call:

@@ -8,9 +8,13 @@
 //   K4a  log-potential of the cloud on a grid         log_potential, Potentials.py:19-27 (or another LM_LOGPOT_* variant)
 //   K4   5-point periodic Laplacian of that field     laplacian, Laplacian_C-M.py:49-59
 // which is what the reference does through files (construct_points.csv -> Potentials.py /
-// Laplacian_C-M.py).  Built on the library's own _dev entry points; one stream, one sync for
-// the cloud size, event-timed stages.
+// Laplacian_C-M.py).  Built on the library's own _dev entry points.  The batch streams through the
+// device in chunks of 2^20 polynomials on three streams (upload of chunk c+1 | K3 + compaction of
+// chunk c | download of chunk c-1's cloud points), so with page-locked host buffers the PCIe
+// transfers hide behind the solver; the field stages follow on the compute stream, event-timed.
 #include "lm_common.cuh"
+
+#include <vector>
 
 extern "C" {
 
@@ -33,7 +37,6 @@ int32_t lm_lucas_cloud_fields(const double* toprows, const int32_t* deg, int64_t
     LM_REQUIRE(!want_pot || (pot_max_iter >= 1 && pot_radius > 0.0), "lm_lucas_cloud_fields: bad potential parameters");
     if (stats) *stats = lm_cloud_stats{};
     *n_points = 0;
-    cudaStream_t s = nullptr;
     const size_t ncoef = static_cast<size_t>(npoly) * maxdeg;
     void *dtop, *ddeg, *dre, *dim, *dkept, *dstat, *dpx, *dpy;
     if ((rc = lm::ws_get(lm::WS_IN_A, ncoef * sizeof(double), &dtop)) != LM_OK) return rc;
@@ -41,7 +44,11 @@ int32_t lm_lucas_cloud_fields(const double* toprows, const int32_t* deg, int64_t
     if ((rc = lm::ws_get(lm::WS_OUT_A, ncoef * sizeof(double), &dre)) != LM_OK) return rc;
     if ((rc = lm::ws_get(lm::WS_OUT_B, ncoef * sizeof(double), &dim)) != LM_OK) return rc;
     if ((rc = lm::ws_get(lm::WS_OUT_C, static_cast<size_t>(npoly) * sizeof(int), &dkept)) != LM_OK) return rc;
-    if ((rc = lm::ws_get(lm::WS_SCRATCH, 64, &dstat)) != LM_OK) return rc;
+    // the batch streams through the device in chunks: upload of chunk c+1, K3 + compaction of chunk c and the
+    // download of chunk c-1's cloud points run on three streams
+    constexpr int64_t CHUNK = int64_t(1) << 20;
+    const int nchunks = static_cast<int>(npoly ? (npoly + CHUNK - 1) / CHUNK : 0);
+    if ((rc = lm::ws_get(lm::WS_SCRATCH, 64 + 16 * static_cast<size_t>(nchunks + 1), &dstat)) != LM_OK) return rc;
     // the cloud has at most sum(deg) <= npoly * maxdeg points; size the packed buffers by the host sum
     uint64_t nroots = 0;
     for (int64_t k = 0; k < npoly; ++k) nroots += static_cast<uint64_t>(deg[k] > 0 ? deg[k] : 0);
@@ -49,37 +56,92 @@ int32_t lm_lucas_cloud_fields(const double* toprows, const int32_t* deg, int64_t
     if ((rc = lm::ws_get(lm::WS_CLOUD_A, pb, &dpx)) != LM_OK) return rc;
     if ((rc = lm::ws_get(lm::WS_CLOUD_B, pb, &dpy)) != LM_OK) return rc;
 
+    static cudaStream_t s = nullptr, s_in = nullptr, s_out = nullptr;
+    static int s_dev = -1;
+    static long long* h_note = nullptr;          // pinned: [c] running cloud size after chunk c, then 2 flags per chunk
+    static int h_note_cap = 0;
+    int dev = 0;
+    LM_CUDA_TRY(cudaGetDevice(&dev));
+    if (s_dev != dev) {
+        if (s) { cudaStreamDestroy(s); cudaStreamDestroy(s_in); cudaStreamDestroy(s_out); }
+        LM_CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        LM_CUDA_TRY(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+        LM_CUDA_TRY(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+        s_dev = dev;
+    }
+    if (h_note_cap < 2 * (nchunks + 1)) {
+        if (h_note) cudaFreeHost(h_note);
+        h_note = nullptr; h_note_cap = 0;
+        LM_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&h_note), sizeof(long long) * 2 * (nchunks + 8), cudaHostAllocDefault));
+        h_note_cap = 2 * (nchunks + 8);
+    }
+    LM_CUDA_TRY(cudaDeviceSynchronize());        // earlier default-stream work may still use the workspaces
+
     cudaEvent_t ev[6];
     for (auto& e : ev) LM_CUDA_TRY(cudaEventCreate(&e));
-    struct EvGuard { cudaEvent_t* e; ~EvGuard() { for (int k = 0; k < 6; ++k) cudaEventDestroy(e[k]); } } guard{ev};
+    std::vector<cudaEvent_t> ev_in(nchunks, nullptr), ev_done(nchunks, nullptr);
+    struct Guard {
+        cudaEvent_t* e; std::vector<cudaEvent_t>*a, *b; cudaStream_t s0, s1, s2;
+        ~Guard() {
+            cudaStreamSynchronize(s0); cudaStreamSynchronize(s1); cudaStreamSynchronize(s2);   // nothing in flight on exit
+            for (int k = 0; k < 6; ++k) cudaEventDestroy(e[k]);
+            for (cudaEvent_t x : *a) if (x) cudaEventDestroy(x);
+            for (cudaEvent_t x : *b) if (x) cudaEventDestroy(x);
+        }
+    } guard{ev, &ev_in, &ev_done, s, s_in, s_out};
 
-    if (npoly) {
-        LM_CUDA_TRY(cudaMemcpyAsync(dtop, toprows, ncoef * sizeof(double), cudaMemcpyHostToDevice, s));
-        LM_CUDA_TRY(cudaMemcpyAsync(ddeg, deg, static_cast<size_t>(npoly) * sizeof(int), cudaMemcpyHostToDevice, s));
-    }
-    int32_t* dflags = static_cast<int32_t*>(dstat);                       // [0] no-convergence, [1] bad degree
-    int64_t* dcount = reinterpret_cast<int64_t*>(static_cast<char*>(dstat) + 16);
-    uint64_t* dwork = reinterpret_cast<uint64_t*>(static_cast<char*>(dstat) + 32);
+    int64_t* dcount = reinterpret_cast<int64_t*>(static_cast<char*>(dstat));                 // running cloud size
+    uint64_t* dwork = reinterpret_cast<uint64_t*>(static_cast<char*>(dstat) + 16);
+    int32_t* dflags = reinterpret_cast<int32_t*>(static_cast<char*>(dstat) + 64);            // 2 per chunk (+ padding)
+    int32_t* h_flags = reinterpret_cast<int32_t*>(h_note + (nchunks + 4));
+    LM_CUDA_TRY(cudaMemsetAsync(dstat, 0, 64 + 16 * static_cast<size_t>(nchunks + 1), s));
     LM_CUDA_TRY(cudaEventRecord(ev[0], s));
-    rc = lm_roots_batched_dev(static_cast<double*>(dtop), static_cast<int32_t*>(ddeg), npoly, maxdeg, 1, tol,
-                              static_cast<double*>(dre), static_cast<double*>(dim), static_cast<int32_t*>(dkept), nullptr,
-                              dflags, s);
-    if (rc != LM_OK) return rc;
+    const bool want_cloud = cloud_re || cloud_im;
+    int64_t done_points = 0;                     // cloud points already handed to the download stream
+    auto download_upto = [&](int c) -> int32_t {  // chunk c is complete: its points can go back
+        LM_CUDA_TRY(cudaEventSynchronize(ev_done[c]));
+        const int64_t upto = h_note[c];
+        if ((want_cloud || want_pot) && upto > cap_points)
+            return lm::fail(LM_E_CAP, "lm_lucas_cloud_fields: the cloud has more than %lld points (capacity %lld)",
+                            static_cast<long long>(upto), static_cast<long long>(cap_points));
+        if (want_cloud && upto > done_points) {
+            const size_t off = static_cast<size_t>(done_points), nb = static_cast<size_t>(upto - done_points) * sizeof(double);
+            if (cloud_re) LM_CUDA_TRY(cudaMemcpyAsync(cloud_re + off, static_cast<double*>(dpx) + off, nb, cudaMemcpyDeviceToHost, s_out));
+            if (cloud_im) LM_CUDA_TRY(cudaMemcpyAsync(cloud_im + off, static_cast<double*>(dpy) + off, nb, cudaMemcpyDeviceToHost, s_out));
+        }
+        done_points = upto;
+        return LM_OK;
+    };
+    for (int c = 0; c < nchunks; ++c) {
+        const int64_t p0 = static_cast<int64_t>(c) * CHUNK, pn = (p0 + CHUNK <= npoly) ? CHUNK : npoly - p0;
+        const size_t co = static_cast<size_t>(p0) * maxdeg;
+        LM_CUDA_TRY(cudaMemcpyAsync(static_cast<double*>(dtop) + co, toprows + co, static_cast<size_t>(pn) * maxdeg * sizeof(double),
+                                    cudaMemcpyHostToDevice, s_in));
+        LM_CUDA_TRY(cudaMemcpyAsync(static_cast<int*>(ddeg) + p0, deg + p0, static_cast<size_t>(pn) * sizeof(int), cudaMemcpyHostToDevice, s_in));
+        LM_CUDA_TRY(cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming));
+        LM_CUDA_TRY(cudaEventRecord(ev_in[c], s_in));
+        LM_CUDA_TRY(cudaStreamWaitEvent(s, ev_in[c], 0));
+        rc = lm_roots_batched_dev(static_cast<double*>(dtop) + co, static_cast<int32_t*>(ddeg) + p0, pn, maxdeg, 1, tol,
+                                  static_cast<double*>(dre) + co, static_cast<double*>(dim) + co, static_cast<int32_t*>(dkept) + p0,
+                                  nullptr, dflags + 2 * c, s);
+        if (rc != LM_OK) return rc;
+        rc = lm_cloud_append_dev(static_cast<double*>(dre) + co, static_cast<double*>(dim) + co, static_cast<int32_t*>(dkept) + p0, pn,
+                                 maxdeg, static_cast<double*>(dpx), static_cast<double*>(dpy), static_cast<int64_t>(nroots), dcount, s);
+        if (rc != LM_OK) return rc;
+        LM_CUDA_TRY(cudaMemcpyAsync(&h_note[c], dcount, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        LM_CUDA_TRY(cudaMemcpyAsync(&h_flags[2 * c], dflags + 2 * c, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        LM_CUDA_TRY(cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming));
+        LM_CUDA_TRY(cudaEventRecord(ev_done[c], s));
+        if (c >= 1 && (rc = download_upto(c - 1)) != LM_OK) return rc;
+    }
     LM_CUDA_TRY(cudaEventRecord(ev[1], s));
-    rc = lm_cloud_compact_dev(static_cast<double*>(dre), static_cast<double*>(dim), static_cast<int32_t*>(dkept), npoly, maxdeg,
-                              static_cast<double*>(dpx), static_cast<double*>(dpy), static_cast<int64_t>(nroots), dcount, s);
-    if (rc != LM_OK) return rc;
     LM_CUDA_TRY(cudaEventRecord(ev[2], s));
+    if (nchunks && (rc = download_upto(nchunks - 1)) != LM_OK) return rc;
     int32_t flags[2] = {0, 0};
-    int64_t count = 0;
-    LM_CUDA_TRY(cudaMemcpyAsync(flags, dflags, sizeof(flags), cudaMemcpyDeviceToHost, s));
-    LM_CUDA_TRY(cudaMemcpyAsync(&count, dcount, sizeof(count), cudaMemcpyDeviceToHost, s));
-    LM_CUDA_TRY(cudaStreamSynchronize(s));
+    for (int c = 0; c < nchunks; ++c) { flags[0] |= h_flags[2 * c]; flags[1] |= h_flags[2 * c + 1]; }
+    const int64_t count = nchunks ? h_note[nchunks - 1] : 0;
     if (flags[1]) return lm::fail(LM_E_INVALID, "lm_lucas_cloud_fields: a degree outside [1, %d]", maxdeg);
     *n_points = count;
-    if ((cloud_re || cloud_im || want_pot) && count > cap_points)
-        return lm::fail(LM_E_CAP, "lm_lucas_cloud_fields: the cloud has %lld points, capacity %lld",
-                        static_cast<long long>(count), static_cast<long long>(cap_points));
     const size_t cb = static_cast<size_t>(count) * sizeof(double);
 
     int launches = 0;
@@ -117,17 +179,6 @@ int32_t lm_lucas_cloud_fields(const double* toprows, const int32_t* deg, int64_t
         ++launches;
     }
     LM_CUDA_TRY(cudaEventRecord(ev[5], s));
-    // the cloud goes back on a second stream while the field kernels (already enqueued) run
-    cudaStream_t s_copy = nullptr;
-    if ((cloud_re || cloud_im) && count) {
-        LM_CUDA_TRY(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
-        cudaError_t ce = cudaSuccess;
-        if (cloud_re) ce = cudaMemcpyAsync(cloud_re, dpx, cb, cudaMemcpyDeviceToHost, s_copy);
-        if (ce == cudaSuccess && cloud_im) ce = cudaMemcpyAsync(cloud_im, dpy, cb, cudaMemcpyDeviceToHost, s_copy);
-        if (ce == cudaSuccess) ce = cudaStreamSynchronize(s_copy);
-        cudaStreamDestroy(s_copy);
-        LM_CUDA_TRY(ce);
-    }
     if (want_pot && count) {
         if (g) LM_CUDA_TRY(cudaMemcpyAsync(g, dg, cb, cudaMemcpyDeviceToHost, s));
         if (it) LM_CUDA_TRY(cudaMemcpyAsync(it, dit, cb, cudaMemcpyDeviceToHost, s));
@@ -147,7 +198,7 @@ int32_t lm_lucas_cloud_fields(const double* toprows, const int32_t* deg, int64_t
         cudaEventElapsedTime(&stats->potential_ms, ev[2], ev[3]);
         cudaEventElapsedTime(&stats->logpot_ms, ev[3], ev[4]);
         cudaEventElapsedTime(&stats->stencil_ms, ev[4], ev[5]);
-        stats->launches = launches + 10;      // K3: 3 sort + up to 3 solver launches, compaction: 3
+        stats->launches = launches + nchunks * (7 + (maxdeg > 32) + (maxdeg > 128));   // per chunk: 3 sort + solver launches + 3 compaction
     }
     if (flags[0])
         return lm::fail(LM_E_NOCONV, "lm_lucas_cloud_fields: the Aberth iteration did not converge for some polynomial");

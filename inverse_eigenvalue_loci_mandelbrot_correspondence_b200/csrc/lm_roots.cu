@@ -174,9 +174,11 @@ __global__ void __launch_bounds__(SORT_THREADS) roots_scatter_kernel(const int* 
 // ---------------------------------------------------------------------------------------
 // the solver
 // ---------------------------------------------------------------------------------------
-// per-group shared-memory slice: coef[D+1] | z[D] (re, im interleaved) | logc[D+1] | int hull[D+1] | bytes frozen[D]
+// per-group shared-memory slice: coef[D+1] | z[D] (re, im interleaved) | float logc[D+1] | int hull[D+1] | bytes frozen[D]
+// (log|c_k| only places the initial guesses: single precision is plenty and keeps 8 CTAs of 32 polynomials per SM)
 __host__ __device__ inline size_t group_smem_bytes(int D) {
-    size_t b = sizeof(double) * (static_cast<size_t>(D + 2) + 2 * static_cast<size_t>(D) + (D + 1));
+    size_t b = sizeof(double) * (static_cast<size_t>(D + 2) + 2 * static_cast<size_t>(D));
+    b += sizeof(float) * static_cast<size_t>(D + 1);
     b += sizeof(int) * static_cast<size_t>(D + 1);
     b += static_cast<size_t>(D);
     b = (b + 15) & ~static_cast<size_t>(15);
@@ -184,8 +186,11 @@ __host__ __device__ inline size_t group_smem_bytes(int D) {
     return b;
 }
 
+#ifndef LM_K3_MIN_CTAS
+#define LM_K3_MIN_CTAS 8
+#endif
 template <int G>
-__global__ void __launch_bounds__(ROOTS_THREADS) roots_kernel(const RootsArgs A) {
+__global__ void __launch_bounds__(ROOTS_THREADS, LM_K3_MIN_CTAS) roots_kernel(const RootsArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     cg::thread_block block = cg::this_thread_block();
     cg::thread_block_tile<G> tile = cg::tiled_partition<G>(block);
@@ -196,7 +201,7 @@ __global__ void __launch_bounds__(ROOTS_THREADS) roots_kernel(const RootsArgs A)
     unsigned char* base = smem + static_cast<size_t>(gid) * group_smem_bytes(D);
     double* coef = reinterpret_cast<double*>(base);            // coef[k] multiplies x^(d-k); coef[0] = 1
     double2* zz = reinterpret_cast<double2*>(coef + ((D + 2) & ~1));
-    double* logc = reinterpret_cast<double*>(zz + D);
+    float* logc = reinterpret_cast<float*>(zz + D);
     int* hull = reinterpret_cast<int*>(logc + (D + 1));
     unsigned char* frozen = reinterpret_cast<unsigned char*>(hull + (D + 1));
     const long long first = A.plan->bounds[A.cls], last = A.plan->bounds[A.cls + 1];
@@ -219,7 +224,7 @@ __global__ void __launch_bounds__(ROOTS_THREADS) roots_kernel(const RootsArgs A)
         for (int k = l; k <= d; k += G) {
             const double c = (k == 0) ? 1.0 : -top[k - 1];
             coef[k] = c;
-            logc[k] = (c != 0.0) ? log(fabs(c)) : -INFINITY;
+            logc[k] = (c != 0.0) ? static_cast<float>(log(fabs(c))) : -INFINITY;
         }
         tile.sync();
 
@@ -247,7 +252,7 @@ __global__ void __launch_bounds__(ROOTS_THREADS) roots_kernel(const RootsArgs A)
             while (e + 2 < nh && hull[e + 1] <= k) ++e;
             const int i1 = hull[e], i2 = hull[e + 1];
             const int m = i2 - i1;
-            const double radius = exp((logc[d - i1] - logc[d - i2]) / m);
+            const double radius = exp((static_cast<double>(logc[d - i1]) - static_cast<double>(logc[d - i2])) / m);
             const double ang = TWO_PI * (k - i1) / m + TWO_PI * e / d + 0.7;
             double sn, cs;
             sincos(ang, &sn, &cs);
@@ -469,12 +474,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) kept_block_sums_kernel(const int
     }
 }
 
-// exclusive scan of the block sums in place (single CTA), total -> *total_out
+// exclusive scan of the block sums in place (single CTA), total -> *total_out.  append != 0: the scan starts
+// at the value *total_out already holds (the cloud of the previous chunks) and adds to it.
 __global__ void __launch_bounds__(1024) kept_scan_sums_kernel(unsigned long long* __restrict__ block_sums, long long nblocks,
-                                                              long long* __restrict__ total_out) {
+                                                              long long* __restrict__ total_out, int append) {
     __shared__ unsigned long long part[1024];
     __shared__ unsigned long long carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
+    if (threadIdx.x == 0) carry_s = append ? static_cast<unsigned long long>(*total_out) : 0ULL;
     __syncthreads();
     for (long long base = 0; base < nblocks; base += 1024) {
         const long long idx = base + threadIdx.x;
@@ -553,9 +559,30 @@ int32_t lm_roots_batched_dev(const double* toprows_dev, const int32_t* deg_dev, 
     return LM_OK;
 }
 
+namespace {
+int32_t cloud_compact_impl(const double* re_dev, const double* im_dev, const int32_t* n_kept_dev, int64_t npoly,
+                           int32_t maxdeg, double* px_dev, double* py_dev, int64_t cap_points,
+                           int64_t* n_points_dev, int append, void* stream);
+}
+
 int32_t lm_cloud_compact_dev(const double* re_dev, const double* im_dev, const int32_t* n_kept_dev, int64_t npoly,
                              int32_t maxdeg, double* px_dev, double* py_dev, int64_t cap_points,
                              int64_t* n_points_dev, void* stream) {
+    return cloud_compact_impl(re_dev, im_dev, n_kept_dev, npoly, maxdeg, px_dev, py_dev, cap_points, n_points_dev, 0, stream);
+}
+
+int32_t lm_cloud_append_dev(const double* re_dev, const double* im_dev, const int32_t* n_kept_dev, int64_t npoly,
+                            int32_t maxdeg, double* px_dev, double* py_dev, int64_t cap_points,
+                            int64_t* n_points_inout_dev, void* stream) {
+    return cloud_compact_impl(re_dev, im_dev, n_kept_dev, npoly, maxdeg, px_dev, py_dev, cap_points, n_points_inout_dev, 1, stream);
+}
+
+}  // extern "C"
+
+namespace {
+int32_t cloud_compact_impl(const double* re_dev, const double* im_dev, const int32_t* n_kept_dev, int64_t npoly,
+                           int32_t maxdeg, double* px_dev, double* py_dev, int64_t cap_points,
+                           int64_t* n_points_dev, int append, void* stream) {
     int32_t rc = lm::require_device();
     if (rc != LM_OK) return rc;
     LM_REQUIRE(npoly >= 0 && maxdeg >= 1 && cap_points >= 0, "lm_cloud_compact_dev: bad sizes");
@@ -564,7 +591,7 @@ int32_t lm_cloud_compact_dev(const double* re_dev, const double* im_dev, const i
                "lm_cloud_compact_dev: NULL buffer");
     cudaStream_t s = lm::as_stream(stream);
     if (npoly == 0) {
-        LM_CUDA_TRY(cudaMemsetAsync(n_points_dev, 0, sizeof(int64_t), s));
+        if (!append) LM_CUDA_TRY(cudaMemsetAsync(n_points_dev, 0, sizeof(int64_t), s));
         return LM_OK;
     }
     const long long per_block = SCAN_THREADS * SCAN_ITEMS;
@@ -573,12 +600,15 @@ int32_t lm_cloud_compact_dev(const double* re_dev, const double* im_dev, const i
     if ((rc = lm::ws_get(lm::WS_CLOUD_SCAN, static_cast<size_t>(nblocks) * sizeof(unsigned long long), &dsums)) != LM_OK) return rc;
     unsigned long long* sums = static_cast<unsigned long long*>(dsums);
     kept_block_sums_kernel<<<static_cast<unsigned>(nblocks), SCAN_THREADS, 0, s>>>(n_kept_dev, npoly, sums);
-    kept_scan_sums_kernel<<<1, 1024, 0, s>>>(sums, nblocks, reinterpret_cast<long long*>(n_points_dev));
+    kept_scan_sums_kernel<<<1, 1024, 0, s>>>(sums, nblocks, reinterpret_cast<long long*>(n_points_dev), append);
     cloud_gather_kernel<<<static_cast<unsigned>(nblocks), SCAN_THREADS, 0, s>>>(re_dev, im_dev, n_kept_dev, npoly, maxdeg, sums,
                                                                                 px_dev, py_dev, cap_points);
     LM_CUDA_TRY(cudaGetLastError());
     return LM_OK;
 }
+}  // namespace
+
+extern "C" {
 
 int32_t lm_roots_batched(const double* toprows, const int32_t* deg, int64_t npoly, int32_t maxdeg,
                          int32_t invert, double tol, double* out_re, double* out_im,

@@ -139,12 +139,16 @@ def construct_points_xy(maxN: int = 40) -> np.ndarray:
 
 def cloud_fields(toprows, deg, grid_x=None, grid_y=None, tol: float = 1e-12, eps: float = 1e-12,
                  variant: int = LOGPOT_SUM_SQRT, h: float | None = None, potential: tuple[int, float] | None = None,
-                 return_cloud: bool = True, laplacian: bool = True) -> dict:
+                 return_cloud: bool = True, laplacian: bool = True, cloud_out: tuple | None = None) -> dict:
     """The Lucas-Loci field stage in one call (BASELINE.json config 5), everything resident in HBM between
     the stages: roots of every polynomial (K3) -> cloud of 1/lambda in polynomial order
     (lucas_equipotential_test_v3.py:93-118) -> batch_potential at the cloud (K1d, :153-162, when
     `potential=(max_iter, R)`) -> log-potential on the grid (K4a, Potentials.py:19-27 by default) -> periodic
     5-point Laplacian (K4, Laplacian_C-M.py:49-59; h defaults to the x spacing as there).
+
+    cloud_out=(re, im): optional preallocated float64 arrays (e.g. page-locked, `_shim.pinned_empty`) of at least
+    sum(deg) entries that receive the cloud; "cloud" is then the pair of views (re[:n], im[:n]) instead of a
+    complex array (no extra host pass).  Page-locked `toprows` / `deg` make the upload run at PCIe speed too.
 
     Returns {"cloud", "g", "it", "U", "lapU", "stats"}; entries not asked for are None.
     """
@@ -157,8 +161,15 @@ def cloud_fields(toprows, deg, grid_x=None, grid_y=None, tol: float = 1e-12, eps
         raise ValueError("deg must have one entry per polynomial")
     cap = int(np.clip(deg, 0, None).sum())
     want_pts = return_cloud or potential is not None
-    cre = np.empty(cap, dtype=np.float64) if return_cloud else None
-    cim = np.empty(cap, dtype=np.float64) if return_cloud else None
+    if cloud_out is not None:
+        cre, cim = cloud_out
+        if (cre.dtype != np.float64 or cim.dtype != np.float64 or cre.size < cap or cim.size < cap
+                or not cre.flags["C_CONTIGUOUS"] or not cim.flags["C_CONTIGUOUS"]):
+            raise ValueError("cloud_out must be two C-contiguous float64 arrays with at least sum(deg) entries")
+        return_cloud = True
+    else:
+        cre = np.empty(cap, dtype=np.float64) if return_cloud else None
+        cim = np.empty(cap, dtype=np.float64) if return_cloud else None
     g = np.empty(cap, dtype=np.float64) if potential is not None else None
     it = np.empty(cap, dtype=np.int64) if potential is not None else None
     U = lap = gx = gy = None
@@ -181,7 +192,9 @@ def cloud_fields(toprows, deg, grid_x=None, grid_y=None, tol: float = 1e-12, eps
                _shim.ptr(U), _shim.ptr(lap), C.byref(st))
     k = int(n.value)
     cloud = None
-    if return_cloud:
+    if cloud_out is not None:
+        cloud = (cre[:k], cim[:k])
+    elif return_cloud:
         cloud = np.empty(k, dtype=np.complex128)
         cloud.real = cre[:k]; cloud.imag = cim[:k]
     return {"cloud": cloud, "g": None if g is None else g[:k], "it": None if it is None else it[:k],
