@@ -30,6 +30,8 @@
 // segment 1, bits 16-17 number of segments.  Edges: E=0, N=1, W=2, S=3.
 #include "lm_common.cuh"
 
+#include <cuda/ptx>
+
 #include <algorithm>
 #include <climits>
 #include <cmath>
@@ -109,23 +111,33 @@ __host__ __device__ inline void edge_corners(int edge, int& dj1, int& di1, int& 
 //   X = (L ^ L') | (H ^ H') | (L ^ H),  L' / H' = the row words shifted by one column
 // (the funnel shift pulls in the first bit of the next chunk / the strip's edge column).
 // ------------------------------------------------------------------------------------
-constexpr int MARK_ROWS = 4;
+#ifndef LM_K2_MARK_ROWS
+#define LM_K2_MARK_ROWS 4
+#endif
+constexpr int MARK_ROWS = LM_K2_MARK_ROWS;
 
-template <bool SAFE>
-__device__ __forceinline__ void mark_strip(const int* __restrict__ row0, const long long nx, const long long ny,
+// one dwell value: through the read-only path from global memory, or from the staged tile in shared memory
+template <bool SMEM>
+__device__ __forceinline__ int dwell_at(const int* q) { return SMEM ? *q : __ldg(q); }
+
+// `strip0` points at column c0 of dwell row j0 (in global memory with row stride nx, or in the staged
+// shared-memory tile with its own row stride)
+template <bool SAFE, bool SMEM>
+__device__ __forceinline__ void mark_strip(const int* __restrict__ strip0, const long long stride,
+                                           const long long nx, const long long ny,
                                            const long long j0, const long long c0, const int ilevel, const int lane,
                                            unsigned* __restrict__ mrow0, const long long words_per_row,
                                            unsigned (&cnt)[MARK_ROWS]) {
     unsigned M[MARK_ROWS + 1][4];
     unsigned E;                                       // bit r: corner right of the strip in dwell row j0 + r
-    const int* p = row0 + c0 + lane;
+    const int* p = strip0 + lane;
     if (SAFE) {
         int z[MARK_ROWS + 1][4];
 #pragma unroll
         for (int r = 0; r <= MARK_ROWS; ++r)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) z[r][k] = __ldg(p + r * nx + 32 * k);
-        const int ze = (lane <= MARK_ROWS) ? __ldg(row0 + lane * nx + c0 + STRIP) : INT_MIN;
+            for (int k = 0; k < 4; ++k) z[r][k] = dwell_at<SMEM>(p + r * stride + 32 * k);
+        const int ze = (lane <= MARK_ROWS) ? dwell_at<SMEM>(strip0 + lane * stride + STRIP) : INT_MIN;
 #pragma unroll
         for (int r = 0; r <= MARK_ROWS; ++r)
 #pragma unroll
@@ -137,11 +149,11 @@ __device__ __forceinline__ void mark_strip(const int* __restrict__ row0, const l
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const bool in = (j0 + r < ny) && (c0 + 32 * k + lane < nx);
-                const int z = in ? __ldg(p + r * nx + 32 * k) : INT_MIN;
+                const int z = in ? dwell_at<SMEM>(p + r * stride + 32 * k) : INT_MIN;
                 M[r][k] = __ballot_sync(FULL, z > ilevel);
             }
         const bool ein = (lane <= MARK_ROWS) && (j0 + lane < ny) && (c0 + STRIP < nx);
-        const int ze = ein ? __ldg(row0 + lane * nx + c0 + STRIP) : INT_MIN;
+        const int ze = ein ? dwell_at<SMEM>(strip0 + lane * stride + STRIP) : INT_MIN;
         E = __ballot_sync(FULL, ze > ilevel);
     }
     // row words shifted by one column
@@ -204,14 +216,103 @@ __global__ void __launch_bounds__(MARK_WARPS * 32) contour_mark_kernel(
 #pragma unroll
         for (int r = 0; r < MARK_ROWS; ++r) cnt[r] = 0u;
         if (j0 + MARK_ROWS < ny && sidx < safe_strips)
-            mark_strip<true>(row0, nx, ny, j0, sidx * STRIP, ilevel, lane, mrow0, words_per_row, cnt);
+            mark_strip<true, false>(row0 + sidx * STRIP, nx, nx, ny, j0, sidx * STRIP, ilevel, lane, mrow0, words_per_row, cnt);
         else
-            mark_strip<false>(row0, nx, ny, j0, sidx * STRIP, ilevel, lane, mrow0, words_per_row, cnt);
+            mark_strip<false, false>(row0 + sidx * STRIP, nx, nx, ny, j0, sidx * STRIP, ilevel, lane, mrow0, words_per_row, cnt);
         if (lane == 0) {
 #pragma unroll
             for (int r = 0; r < MARK_ROWS; ++r)
                 if (cnt[r]) atomicAdd(row_count + j0 + r, cnt[r]);
         }
+    }
+}
+
+// The same pass with the dwell rows brought in by the bulk-copy engine (cp.async.bulk -> UBLKCP) instead of
+// per-thread loads: one elected thread arms an mbarrier with the tile's byte count and issues MARK_ROWS+1
+// row copies of (MARK_WARPS*STRIP + 4) ints into shared memory; while the CTA classifies tile t from one
+// buffer the copies of tile t+1 land in the other, and with several CTAs per SM tens of KB are in flight per
+// SM all the time -- the loads no longer wait for registers or for warps to come round.
+// Needs 16-byte aligned rows: nx % 4 == 0 and a 16-byte aligned grid (the driver falls back otherwise).
+constexpr int BULK_COLS = MARK_WARPS * STRIP + 4;           // quad columns of a tile + the right edge (padded to 16 B)
+constexpr int BULK_STAGE_INTS = (MARK_ROWS + 1) * BULK_COLS;
+
+__global__ void __launch_bounds__(MARK_WARPS * 32) contour_mark_bulk_kernel(
+    const int* __restrict__ dwell, long long nx, long long ny, int ilevel,
+    unsigned* __restrict__ mask, long long words_per_row, unsigned* __restrict__ row_count) {
+    extern __shared__ __align__(128) unsigned char bulk_smem[];
+    int* tile = reinterpret_cast<int*>(bulk_smem);                                   // 2 stages
+    uint64_t* bar = reinterpret_cast<uint64_t*>(bulk_smem + 2 * BULK_STAGE_INTS * sizeof(int));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long strips_per_row = words_per_row / 4;
+    const long long ngroups = (ny - 1 + MARK_ROWS - 1) / MARK_ROWS;
+    const long long chunks_per_group = (strips_per_row + MARK_WARPS - 1) / MARK_WARPS;
+    const long long nitems = ngroups * chunks_per_group;
+    const long long safe_strips = (nx - 1) / STRIP;
+
+    if (threadIdx.x == 0) {
+        cuda::ptx::mbarrier_init(&bar[0], 1);
+        cuda::ptx::mbarrier_init(&bar[1], 1);
+        cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);       // make the initialised barriers visible to the copy engine
+    }
+    __syncthreads();
+
+    // item -> (row group, column chunk); 32-bit division whenever the item count allows it
+    const bool small = (nitems >> 31) == 0;
+    auto split = [&](long long item, long long& grp, long long& chunk) {
+        if (small) {
+            const unsigned g32 = static_cast<unsigned>(item) / static_cast<unsigned>(chunks_per_group);
+            grp = g32;
+            chunk = static_cast<unsigned>(item) - g32 * static_cast<unsigned>(chunks_per_group);
+        } else {
+            grp = item / chunks_per_group;
+            chunk = item - grp * chunks_per_group;
+        }
+    };
+    auto issue = [&](long long item, int stage) {        // elected thread only
+        long long grp, chunk;
+        split(item, grp, chunk);
+        const long long j0 = grp * MARK_ROWS, c0 = chunk * (MARK_WARPS * STRIP);
+        const long long cols = (nx - c0 < BULK_COLS) ? nx - c0 : BULK_COLS;          // multiple of 4 (nx % 4 == 0)
+        const long long rows = (ny - j0 < MARK_ROWS + 1) ? ny - j0 : MARK_ROWS + 1;
+        const uint32_t row_bytes = static_cast<uint32_t>(cols * sizeof(int));
+        cuda::ptx::mbarrier_arrive_expect_tx(cuda::ptx::sem_release, cuda::ptx::scope_cta, cuda::ptx::space_shared, &bar[stage],
+                                             row_bytes * static_cast<uint32_t>(rows));
+        int* dst = tile + stage * BULK_STAGE_INTS;
+        for (long long r = 0; r < rows; ++r)
+            cuda::ptx::cp_async_bulk(cuda::ptx::space_cluster, cuda::ptx::space_global, dst + r * BULK_COLS,
+                                     dwell + (j0 + r) * nx + c0, row_bytes, &bar[stage]);
+    };
+
+    unsigned phase[2] = {0u, 0u};
+    int stage = 0;
+    long long item = blockIdx.x;
+    if (item < nitems && threadIdx.x == 0) issue(item, 0);
+    for (; item < nitems; item += gridDim.x, stage ^= 1) {
+        const long long next = item + gridDim.x;
+        if (next < nitems && threadIdx.x == 0) issue(next, stage ^ 1);               // its last readers passed the barrier below
+        while (!cuda::ptx::mbarrier_try_wait_parity(&bar[stage], phase[stage])) {}
+        phase[stage] ^= 1u;
+        long long grp, chunk;
+        split(item, grp, chunk);
+        const long long sidx = chunk * MARK_WARPS + warp;
+        if (sidx < strips_per_row) {
+            const long long j0 = grp * MARK_ROWS;
+            unsigned* mrow0 = mask + j0 * words_per_row;
+            const int* strip0 = tile + stage * BULK_STAGE_INTS + warp * STRIP;
+            unsigned cnt[MARK_ROWS];
+#pragma unroll
+            for (int r = 0; r < MARK_ROWS; ++r) cnt[r] = 0u;
+            if (j0 + MARK_ROWS < ny && sidx < safe_strips)
+                mark_strip<true, true>(strip0, BULK_COLS, nx, ny, j0, sidx * STRIP, ilevel, lane, mrow0, words_per_row, cnt);
+            else
+                mark_strip<false, true>(strip0, BULK_COLS, nx, ny, j0, sidx * STRIP, ilevel, lane, mrow0, words_per_row, cnt);
+            if (lane == 0) {
+#pragma unroll
+                for (int r = 0; r < MARK_ROWS; ++r)
+                    if (cnt[r]) atomicAdd(row_count + j0 + r, cnt[r]);
+            }
+        }
+        __syncthreads();          // everybody is done with this buffer before it is refilled two items later
     }
 }
 
@@ -272,84 +373,119 @@ __device__ __forceinline__ void edge_vertex_dev(int edge, const int z[2][2], con
 // ------------------------------------------------------------------------------------
 // 3. emit: ordered records
 // ------------------------------------------------------------------------------------
+// one crossing quad (j, i) -> its record at rank `pos`
+__device__ __forceinline__ void emit_record(const int* __restrict__ dwell, long long nx, long long row_offset_global, double level,
+                                            const double* __restrict__ xs, const double* __restrict__ ys, long long j, long long i,
+                                            unsigned long long pos, long long* __restrict__ records) {
+    int z[2][2];
+    z[0][0] = __ldg(dwell + j * nx + i);
+    z[0][1] = __ldg(dwell + j * nx + i + 1);
+    z[1][0] = __ldg(dwell + (j + 1) * nx + i);
+    z[1][1] = __ldg(dwell + (j + 1) * nx + i + 1);
+    const bool sw = above_level(z[0][0], level), se = above_level(z[0][1], level);
+    const bool nw = above_level(z[1][0], level), ne = above_level(z[1][1], level);
+    // mean of the four corners, summed in the reference's order SW+SE+NW+NE
+    const double zmid = __dmul_rn(0.25, __dadd_rn(__dadd_rn(__dadd_rn(static_cast<double>(z[0][0]),
+                        static_cast<double>(z[0][1])), static_cast<double>(z[1][0])), static_cast<double>(z[1][1])));
+    const bool saddle_right = zmid > level;
+    int entry[2] = {0, 0}, exit_[2] = {0, 0};
+    const int nseg = quad_segments(sw, se, nw, ne, saddle_right, entry, exit_);
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    if (nseg >= 1) edge_vertex_dev(exit_[0], z, xs, ys, j, i, level, v[0], v[1]);
+    if (nseg >= 2) edge_vertex_dev(exit_[1], z, xs, ys, j, i, level, v[2], v[3]);
+    const unsigned config = (nw ? 8u : 0u) | (ne ? 4u : 0u) | (sw ? 2u : 0u) | (se ? 1u : 0u);
+    const long long meta = static_cast<long long>(config | (saddle_right ? 16u : 0u) |
+                           (static_cast<unsigned>(entry[0]) << 8) | (static_cast<unsigned>(exit_[0]) << 10) |
+                           (static_cast<unsigned>(entry[1]) << 12) | (static_cast<unsigned>(exit_[1]) << 14) |
+                           (static_cast<unsigned>(nseg) << 16));
+    longlong2* r2 = reinterpret_cast<longlong2*>(records + pos * REC_WORDS);
+    r2[0] = make_longlong2((row_offset_global + j) * nx + i,
+                           static_cast<long long>(static_cast<unsigned>(z[0][0])) |
+                           (static_cast<long long>(static_cast<unsigned>(z[0][1])) << 32));
+    r2[1] = make_longlong2(static_cast<long long>(static_cast<unsigned>(z[1][0])) |
+                           (static_cast<long long>(static_cast<unsigned>(z[1][1])) << 32), meta);
+    r2[2] = make_longlong2(__double_as_longlong(v[0]), __double_as_longlong(v[1]));
+    r2[3] = make_longlong2(__double_as_longlong(v[2]), __double_as_longlong(v[3]));
+}
+
+// A warp owns a quad row.  The row's mask words are fetched 32 x 32 at a time (32 independent coalesced
+// loads in flight), the set bits are turned into a list of crossing columns in shared memory (raster order
+// by ballot-free prefix sums), and the list is worked off 32 crossings at a time -- every lane gathers and
+// emits one record in parallel, instead of one lane walking its word while 31 wait for its DRAM round trips.
+constexpr int EMIT_LIST = 256;                 // list capacity per warp; flushed when more than EMIT_LIST - 64 are pending
 __global__ void __launch_bounds__(MARK_WARPS * 32) contour_emit_kernel(
     const int* __restrict__ dwell, long long nx, long long ny, long long row_offset_global, double level,
     const double* __restrict__ xs, const double* __restrict__ ys,   // ys indexed by local row
     const unsigned* __restrict__ mask, long long words_per_row, const unsigned* __restrict__ row_count,
     const unsigned long long* __restrict__ row_offset, long long* __restrict__ records) {
     __shared__ unsigned s_words[MARK_WARPS][32 * 32];
-    const int lane = threadIdx.x & 31;
+    __shared__ int s_list[MARK_WARPS][EMIT_LIST];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long nwarps = static_cast<long long>(gridDim.x) * MARK_WARPS;
-    for (long long j = static_cast<long long>(blockIdx.x) * MARK_WARPS + (threadIdx.x >> 5); j < ny - 1; j += nwarps) {
+    for (long long j = static_cast<long long>(blockIdx.x) * MARK_WARPS + warp; j < ny - 1; j += nwarps) {
         if (row_count[j] == 0u) continue;
-        unsigned long long running = row_offset[j];
-        // the row's mask words are fetched 32 x 32 at a time (32 independent coalesced loads in flight per
-        // warp) so the walk below does not pay one DRAM round trip per 32 words
+        unsigned long long list_pos = row_offset[j];      // rank of s_list[0]
+        int nlist = 0;                                    // pending crossings (warp-uniform)
+        auto flush = [&]() {
+            __syncwarp();
+            for (int b = 0; b < nlist; b += 32)
+                if (b + lane < nlist)
+                    emit_record(dwell, nx, row_offset_global, level, xs, ys, j, s_list[warp][b + lane], list_pos + b + lane, records);
+            list_pos += static_cast<unsigned long long>(nlist);
+            nlist = 0;
+            __syncwarp();
+        };
         for (long long s0 = 0; s0 < words_per_row; s0 += 32 * 32) {
-          {
-              unsigned wv[32];
+            {
+                unsigned wv[32];
 #pragma unroll
-              for (int t = 0; t < 32; ++t) {
-                  const long long w = s0 + t * 32 + lane;
-                  wv[t] = (w < words_per_row) ? __ldg(mask + j * words_per_row + w) : 0u;
-              }
-              __syncwarp();
+                for (int t = 0; t < 32; ++t) {
+                    const long long w = s0 + t * 32 + lane;
+                    wv[t] = (w < words_per_row) ? __ldg(mask + j * words_per_row + w) : 0u;
+                }
+                __syncwarp();
 #pragma unroll
-              for (int t = 0; t < 32; ++t) s_words[threadIdx.x >> 5][t * 32 + lane] = wv[t];
-              __syncwarp();
-          }
-          for (int t = 0; t < 32; ++t) {
-            const long long w = s0 + t * 32 + lane;
-            if (s0 + t * 32 >= words_per_row) break;
-            unsigned word = s_words[threadIdx.x >> 5][t * 32 + lane];
-            if (__ballot_sync(FULL, word != 0u) == 0u) continue;
-            const int cnt = __popc(word);
-            int incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int y = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += y;
+                for (int t = 0; t < 32; ++t) s_words[warp][t * 32 + lane] = wv[t];
+                __syncwarp();
             }
-            unsigned long long pos = running + static_cast<unsigned long long>(incl - cnt);
-            running += static_cast<unsigned long long>(__shfl_sync(FULL, incl, 31));
-            while (word) {
-                const int bit = __ffs(word) - 1;
-                word &= word - 1;
-                const long long i = w * 32 + bit;
-                int z[2][2];
-                z[0][0] = __ldg(dwell + j * nx + i);
-                z[0][1] = __ldg(dwell + j * nx + i + 1);
-                z[1][0] = __ldg(dwell + (j + 1) * nx + i);
-                z[1][1] = __ldg(dwell + (j + 1) * nx + i + 1);
-                const bool sw = above_level(z[0][0], level), se = above_level(z[0][1], level);
-                const bool nw = above_level(z[1][0], level), ne = above_level(z[1][1], level);
-                // mean of the four corners, summed in the reference's order SW+SE+NW+NE
-                const double zmid = __dmul_rn(0.25, __dadd_rn(__dadd_rn(__dadd_rn(static_cast<double>(z[0][0]),
-                                    static_cast<double>(z[0][1])), static_cast<double>(z[1][0])), static_cast<double>(z[1][1])));
-                const bool saddle_right = zmid > level;
-                int entry[2] = {0, 0}, exit_[2] = {0, 0};
-                const int nseg = quad_segments(sw, se, nw, ne, saddle_right, entry, exit_);
-                double v[4] = {0.0, 0.0, 0.0, 0.0};
-                if (nseg >= 1) edge_vertex_dev(exit_[0], z, xs, ys, j, i, level, v[0], v[1]);
-                if (nseg >= 2) edge_vertex_dev(exit_[1], z, xs, ys, j, i, level, v[2], v[3]);
-                const unsigned config = (nw ? 8u : 0u) | (ne ? 4u : 0u) | (sw ? 2u : 0u) | (se ? 1u : 0u);
-                const long long meta = static_cast<long long>(config | (saddle_right ? 16u : 0u) |
-                                       (static_cast<unsigned>(entry[0]) << 8) | (static_cast<unsigned>(exit_[0]) << 10) |
-                                       (static_cast<unsigned>(entry[1]) << 12) | (static_cast<unsigned>(exit_[1]) << 14) |
-                                       (static_cast<unsigned>(nseg) << 16));
-                long long* r = records + pos * REC_WORDS;
-                longlong2* r2 = reinterpret_cast<longlong2*>(r);
-                r2[0] = make_longlong2((row_offset_global + j) * nx + i,
-                                       static_cast<long long>(static_cast<unsigned>(z[0][0])) |
-                                       (static_cast<long long>(static_cast<unsigned>(z[0][1])) << 32));
-                r2[1] = make_longlong2(static_cast<long long>(static_cast<unsigned>(z[1][0])) |
-                                       (static_cast<long long>(static_cast<unsigned>(z[1][1])) << 32), meta);
-                r2[2] = make_longlong2(__double_as_longlong(v[0]), __double_as_longlong(v[1]));
-                r2[3] = make_longlong2(__double_as_longlong(v[2]), __double_as_longlong(v[3]));
-                ++pos;
+            for (int t = 0; t < 32; ++t) {
+                if (s0 + t * 32 >= words_per_row) break;
+                const long long w = s0 + t * 32 + lane;
+                unsigned word = s_words[warp][t * 32 + lane];
+                if (__ballot_sync(FULL, word != 0u) == 0u) continue;
+                const int cnt = __popc(word);
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int y = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += y;
+                }
+                const int total = __shfl_sync(FULL, incl, 31);
+                if (total > 64) {
+                    // a dense stretch (up to 1024 crossings in 32 words): keep the order by flushing the list, then
+                    // let every lane walk its own word
+                    flush();
+                    unsigned long long pos = list_pos + static_cast<unsigned long long>(incl - cnt);
+                    while (word) {
+                        const int bit = __ffs(word) - 1;
+                        word &= word - 1;
+                        emit_record(dwell, nx, row_offset_global, level, xs, ys, j, w * 32 + bit, pos, records);
+                        ++pos;
+                    }
+                    list_pos += static_cast<unsigned long long>(total);
+                    continue;
+                }
+                int k = nlist + incl - cnt;
+                while (word) {
+                    const int bit = __ffs(word) - 1;
+                    word &= word - 1;
+                    s_list[warp][k++] = static_cast<int>(w * 32 + bit);
+                }
+                nlist += total;
+                if (nlist > EMIT_LIST - 64) flush();
             }
-          }
         }
+        flush();
     }
 }
 
@@ -386,8 +522,28 @@ int32_t classify_device(const int* dwell_dev, const double* xs_host, long long n
     const long long strips_per_row = words_per_row / 4;
     long long blocks = ((nrows + MARK_ROWS - 1) / MARK_ROWS) * ((strips_per_row + MARK_WARPS - 1) / MARK_WARPS);
     if (blocks > cap) blocks = cap;
-    contour_mark_kernel<<<static_cast<unsigned>(blocks), MARK_WARPS * 32, 0, s>>>(
-        dwell_dev, nx, ny, ilevel, static_cast<unsigned*>(dmask), words_per_row, static_cast<unsigned*>(dcount));
+    static const bool no_bulk = getenv("LM_K2_NO_BULK") != nullptr;      // tuning / A-B switch
+    if (!no_bulk && nx % 4 == 0 && (reinterpret_cast<uintptr_t>(dwell_dev) & 15u) == 0) {
+        const size_t smem = 2 * BULK_STAGE_INTS * sizeof(int) + 2 * sizeof(uint64_t);
+        static bool attr_set = false;
+        if (!attr_set) {
+            LM_CUDA_TRY(cudaFuncSetAttribute(contour_mark_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            attr_set = true;
+        }
+        long long bblocks = blocks;
+        static int per_sm = 0;                                                       // persistent: as many CTAs as fit (5 x 41 KB)
+        if (per_sm == 0) {
+            LM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, contour_mark_bulk_kernel, MARK_WARPS * 32, smem));
+            if (per_sm < 1) per_sm = 1;
+        }
+        const long long bcap = static_cast<long long>(lm::sm_count()) * per_sm;
+        if (bblocks > bcap) bblocks = bcap;
+        contour_mark_bulk_kernel<<<static_cast<unsigned>(bblocks), MARK_WARPS * 32, smem, s>>>(
+            dwell_dev, nx, ny, ilevel, static_cast<unsigned*>(dmask), words_per_row, static_cast<unsigned*>(dcount));
+    } else {
+        contour_mark_kernel<<<static_cast<unsigned>(blocks), MARK_WARPS * 32, 0, s>>>(
+            dwell_dev, nx, ny, ilevel, static_cast<unsigned*>(dmask), words_per_row, static_cast<unsigned*>(dcount));
+    }
     LM_CUDA_TRY(cudaGetLastError());
     contour_scan_kernel<<<1, 1024, 0, s>>>(static_cast<unsigned*>(dcount), nrows, static_cast<unsigned long long*>(doff));
     LM_CUDA_TRY(cudaGetLastError());
