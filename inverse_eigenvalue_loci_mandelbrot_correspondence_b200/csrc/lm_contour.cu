@@ -228,21 +228,76 @@ __global__ void __launch_bounds__(MARK_WARPS * 32) contour_mark_kernel(
 }
 
 // The same pass with the dwell rows brought in by the bulk-copy engine (cp.async.bulk -> UBLKCP) instead of
-// per-thread loads: one elected thread arms an mbarrier with the tile's byte count and issues MARK_ROWS+1
-// row copies of (MARK_WARPS*STRIP + 4) ints into shared memory; while the CTA classifies tile t from one
-// buffer the copies of tile t+1 land in the other, and with several CTAs per SM tens of KB are in flight per
-// SM all the time -- the loads no longer wait for registers or for warps to come round.
+// per-thread loads, and with the bit arithmetic spread over the lanes.  ncu showed the register-load kernel to be
+// instruction-issue bound (~330 warp instructions per 4 x 128-quad strip, every lane repeating the same
+// warp-uniform XOR/OR/popc work), not memory bound.  Here
+//   * one elected thread arms a "full" mbarrier with the tile's byte count and issues MARK_ROWS+1 row copies of
+//     (MARK_WARPS*STRIP + 4) ints into one of two shared-memory buffers; a warp releases a buffer through an
+//     "empty" mbarrier as soon as its ballots are done, so there is no CTA-wide barrier in the loop;
+//   * the 20 ballot words (+ the edge bits) of a strip go to a 5 x 5 word scratch in shared memory and lane
+//     l < 16 alone derives crossing word (row l/4, word l%4): one coalesced 64-byte-per-row store and a
+//     4-lane shuffle reduction for the row counts.
 // Needs 16-byte aligned rows: nx % 4 == 0 and a 16-byte aligned grid (the driver falls back otherwise).
 constexpr int BULK_COLS = MARK_WARPS * STRIP + 4;           // quad columns of a tile + the right edge (padded to 16 B)
 constexpr int BULK_STAGE_INTS = (MARK_ROWS + 1) * BULK_COLS;
+constexpr int BULK_SCRATCH = (MARK_ROWS + 1) * 5 + 3;       // per warp: M[r][0..3] and the edge bit as a fifth word
+
+template <bool SAFE>
+__device__ __forceinline__ void mark_strip_tile(const int* __restrict__ strip0, unsigned* __restrict__ sm,
+                                                uint64_t* empty_bar,
+                                                const long long nx, const long long ny, const long long j0, const long long c0,
+                                                const int ilevel, const int lane,
+                                                unsigned* __restrict__ mrow0, const long long words_per_row,
+                                                unsigned* __restrict__ row_count) {
+    const int* p = strip0 + lane;
+#pragma unroll
+    for (int r = 0; r <= MARK_ROWS; ++r) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const bool in = SAFE || ((j0 + r < ny) && (c0 + 32 * k + lane < nx));
+            const int z = in ? p[r * BULK_COLS + 32 * k] : INT_MIN;
+            const unsigned b = __ballot_sync(FULL, z > ilevel);
+            if (lane == r * 4 + k) sm[r * 5 + k] = b;             // MARK_ROWS + 1 <= 8 rows: lane index < 32
+        }
+    }
+    {
+        const bool ein = (lane <= MARK_ROWS) && (SAFE || ((j0 + lane < ny) && (c0 + STRIP < nx)));
+        const int ze = ein ? strip0[lane * BULK_COLS + STRIP] : INT_MIN;
+        if (lane <= MARK_ROWS) sm[lane * 5 + 4] = (ze > ilevel) ? 1u : 0u;
+    }
+    __syncwarp();
+    if (lane == 0) cuda::ptx::mbarrier_arrive(empty_bar);         // this warp no longer reads the tile
+    unsigned x = 0u;
+    const int r = lane >> 2, k = lane & 3;
+    if (lane < 4 * MARK_ROWS && (SAFE || j0 + r < ny - 1)) {
+        const unsigned a = sm[r * 5 + k], an = sm[r * 5 + k + 1];
+        const unsigned b = sm[(r + 1) * 5 + k], bn = sm[(r + 1) * 5 + k + 1];
+        const unsigned sa = __funnelshift_r(a, an, 1), sb = __funnelshift_r(b, bn, 1);   // the rows shifted by one column
+        x = (a ^ sa) | (b ^ sb) | (a ^ b);
+        if (!SAFE) {
+            const long long left = (nx - 1) - (c0 + 32 * k);       // quads exist for columns < nx - 1
+            x &= (left >= 32) ? 0xffffffffu : ((left <= 0) ? 0u : ((1u << left) - 1u));
+        }
+        mrow0[r * words_per_row + (c0 >> 5) + k] = x;
+    }
+    unsigned cnt = __popc(x);
+    cnt += __shfl_xor_sync(FULL, cnt, 1);
+    cnt += __shfl_xor_sync(FULL, cnt, 2);
+    if (k == 0 && lane < 4 * MARK_ROWS && cnt) atomicAdd(row_count + j0 + r, cnt);
+    __syncwarp();                                                  // scratch is reused by the next strip
+}
 
 __global__ void __launch_bounds__(MARK_WARPS * 32) contour_mark_bulk_kernel(
     const int* __restrict__ dwell, long long nx, long long ny, int ilevel,
     unsigned* __restrict__ mask, long long words_per_row, unsigned* __restrict__ row_count) {
+    static_assert(4 * (MARK_ROWS + 1) <= 32, "one lane per ballot word");
     extern __shared__ __align__(128) unsigned char bulk_smem[];
     int* tile = reinterpret_cast<int*>(bulk_smem);                                   // 2 stages
-    uint64_t* bar = reinterpret_cast<uint64_t*>(bulk_smem + 2 * BULK_STAGE_INTS * sizeof(int));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(bulk_smem + 2 * BULK_STAGE_INTS * sizeof(int));
+    uint64_t* empty_bar = full_bar + 2;
+    unsigned* scratch = reinterpret_cast<unsigned*>(empty_bar + 2);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned* sm = scratch + warp * BULK_SCRATCH;
     const long long strips_per_row = words_per_row / 4;
     const long long ngroups = (ny - 1 + MARK_ROWS - 1) / MARK_ROWS;
     const long long chunks_per_group = (strips_per_row + MARK_WARPS - 1) / MARK_WARPS;
@@ -250,8 +305,10 @@ __global__ void __launch_bounds__(MARK_WARPS * 32) contour_mark_bulk_kernel(
     const long long safe_strips = (nx - 1) / STRIP;
 
     if (threadIdx.x == 0) {
-        cuda::ptx::mbarrier_init(&bar[0], 1);
-        cuda::ptx::mbarrier_init(&bar[1], 1);
+        cuda::ptx::mbarrier_init(&full_bar[0], 1);
+        cuda::ptx::mbarrier_init(&full_bar[1], 1);
+        cuda::ptx::mbarrier_init(&empty_bar[0], MARK_WARPS);
+        cuda::ptx::mbarrier_init(&empty_bar[1], MARK_WARPS);
         cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);       // make the initialised barriers visible to the copy engine
     }
     __syncthreads();
@@ -268,30 +325,33 @@ __global__ void __launch_bounds__(MARK_WARPS * 32) contour_mark_bulk_kernel(
             chunk = item - grp * chunks_per_group;
         }
     };
+    unsigned empty_phase[2] = {1u, 1u};                   // a fresh barrier passes a wait on parity 1: both buffers start free
     auto issue = [&](long long item, int stage) {        // elected thread only
+        while (!cuda::ptx::mbarrier_try_wait_parity(&empty_bar[stage], empty_phase[stage])) {}   // all warps released it
+        empty_phase[stage] ^= 1u;
         long long grp, chunk;
         split(item, grp, chunk);
         const long long j0 = grp * MARK_ROWS, c0 = chunk * (MARK_WARPS * STRIP);
         const long long cols = (nx - c0 < BULK_COLS) ? nx - c0 : BULK_COLS;          // multiple of 4 (nx % 4 == 0)
         const long long rows = (ny - j0 < MARK_ROWS + 1) ? ny - j0 : MARK_ROWS + 1;
         const uint32_t row_bytes = static_cast<uint32_t>(cols * sizeof(int));
-        cuda::ptx::mbarrier_arrive_expect_tx(cuda::ptx::sem_release, cuda::ptx::scope_cta, cuda::ptx::space_shared, &bar[stage],
+        cuda::ptx::mbarrier_arrive_expect_tx(cuda::ptx::sem_release, cuda::ptx::scope_cta, cuda::ptx::space_shared, &full_bar[stage],
                                              row_bytes * static_cast<uint32_t>(rows));
         int* dst = tile + stage * BULK_STAGE_INTS;
         for (long long r = 0; r < rows; ++r)
             cuda::ptx::cp_async_bulk(cuda::ptx::space_cluster, cuda::ptx::space_global, dst + r * BULK_COLS,
-                                     dwell + (j0 + r) * nx + c0, row_bytes, &bar[stage]);
+                                     dwell + (j0 + r) * nx + c0, row_bytes, &full_bar[stage]);
     };
 
-    unsigned phase[2] = {0u, 0u};
+    unsigned full_phase[2] = {0u, 0u};
     int stage = 0;
     long long item = blockIdx.x;
     if (item < nitems && threadIdx.x == 0) issue(item, 0);
     for (; item < nitems; item += gridDim.x, stage ^= 1) {
         const long long next = item + gridDim.x;
-        if (next < nitems && threadIdx.x == 0) issue(next, stage ^ 1);               // its last readers passed the barrier below
-        while (!cuda::ptx::mbarrier_try_wait_parity(&bar[stage], phase[stage])) {}
-        phase[stage] ^= 1u;
+        if (next < nitems && threadIdx.x == 0) issue(next, stage ^ 1);
+        while (!cuda::ptx::mbarrier_try_wait_parity(&full_bar[stage], full_phase[stage])) {}
+        full_phase[stage] ^= 1u;
         long long grp, chunk;
         split(item, grp, chunk);
         const long long sidx = chunk * MARK_WARPS + warp;
@@ -299,20 +359,13 @@ __global__ void __launch_bounds__(MARK_WARPS * 32) contour_mark_bulk_kernel(
             const long long j0 = grp * MARK_ROWS;
             unsigned* mrow0 = mask + j0 * words_per_row;
             const int* strip0 = tile + stage * BULK_STAGE_INTS + warp * STRIP;
-            unsigned cnt[MARK_ROWS];
-#pragma unroll
-            for (int r = 0; r < MARK_ROWS; ++r) cnt[r] = 0u;
             if (j0 + MARK_ROWS < ny && sidx < safe_strips)
-                mark_strip<true, true>(strip0, BULK_COLS, nx, ny, j0, sidx * STRIP, ilevel, lane, mrow0, words_per_row, cnt);
+                mark_strip_tile<true>(strip0, sm, &empty_bar[stage], nx, ny, j0, sidx * STRIP, ilevel, lane, mrow0, words_per_row, row_count);
             else
-                mark_strip<false, true>(strip0, BULK_COLS, nx, ny, j0, sidx * STRIP, ilevel, lane, mrow0, words_per_row, cnt);
-            if (lane == 0) {
-#pragma unroll
-                for (int r = 0; r < MARK_ROWS; ++r)
-                    if (cnt[r]) atomicAdd(row_count + j0 + r, cnt[r]);
-            }
+                mark_strip_tile<false>(strip0, sm, &empty_bar[stage], nx, ny, j0, sidx * STRIP, ilevel, lane, mrow0, words_per_row, row_count);
+        } else if (lane == 0) {
+            cuda::ptx::mbarrier_arrive(&empty_bar[stage]);         // nothing to read for this warp: release at once
         }
-        __syncthreads();          // everybody is done with this buffer before it is refilled two items later
     }
 }
 
@@ -524,7 +577,7 @@ int32_t classify_device(const int* dwell_dev, const double* xs_host, long long n
     if (blocks > cap) blocks = cap;
     static const bool no_bulk = getenv("LM_K2_NO_BULK") != nullptr;      // tuning / A-B switch
     if (!no_bulk && nx % 4 == 0 && (reinterpret_cast<uintptr_t>(dwell_dev) & 15u) == 0) {
-        const size_t smem = 2 * BULK_STAGE_INTS * sizeof(int) + 2 * sizeof(uint64_t);
+        const size_t smem = 2 * BULK_STAGE_INTS * sizeof(int) + 4 * sizeof(uint64_t) + MARK_WARPS * BULK_SCRATCH * sizeof(unsigned);
         static bool attr_set = false;
         if (!attr_set) {
             LM_CUDA_TRY(cudaFuncSetAttribute(contour_mark_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
