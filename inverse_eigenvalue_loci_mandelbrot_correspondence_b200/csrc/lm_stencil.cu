@@ -40,6 +40,12 @@ __device__ __forceinline__ double combine(double c, double up, double dn, double
 }
 
 // vectorised kernel: nx even, pointers 16-byte aligned
+#ifndef LM_K4_PF_LAP
+#define LM_K4_PF_LAP 2
+#endif
+#ifndef LM_K4_PF_SMOOTH
+#define LM_K4_PF_SMOOTH 2
+#endif
 template <int OP>
 __global__ void __launch_bounds__(ST_THREADS) stencil_vec_kernel(const double* __restrict__ in,
                                                                  double* __restrict__ out,
@@ -59,30 +65,65 @@ __global__ void __launch_bounds__(ST_THREADS) stencil_vec_kernel(const double* _
         if (!live) return make_double2(0.0, 0.0);
         return *reinterpret_cast<const double2*>(in + j * nx + c0);
     };
+    // neighbours across a warp edge (lanes 0 / 31, and the row ends): one scalar each, fetched with the rows
+    auto load_edges = [&](long long j, double& l, double& r) {
+        l = (live && edge_l) ? __ldg(in + j * nx + cl) : 0.0;
+        r = (live && edge_r) ? __ldg(in + j * nx + cr) : 0.0;
+    };
     const long long jup0 = (r0 == 0) ? ny - 1 : r0 - 1;
     double2 up = load_row(jup0);
     double2 ce = load_row(r0);
-    for (long long j = r0; j < r1; ++j) {
-        const long long jdn = (j == ny - 1) ? 0 : j + 1;
-        const double2 dn = load_row(jdn);
-        double lf = __shfl_up_sync(FULL, ce.y, 1);
-        double rt = __shfl_down_sync(FULL, ce.x, 1);
-        if (live) {
-            if (edge_l) lf = __ldg(in + j * nx + cl);
-            if (edge_r) rt = __ldg(in + j * nx + cr);
-            double2 o;
-            if (OP == OP_LAPLACIAN) {
-                o.x = combine<OP>(ce.x, up.x, dn.x, lf, ce.y, h2);
-                o.y = combine<OP>(ce.y, up.y, dn.y, ce.x, rt, h2);
-            } else {
-                const bool row_border = (j == 0) || (j == ny - 1);
-                o.x = (row_border || c0 == 0) ? ce.x : combine<OP>(ce.x, up.x, dn.x, lf, ce.y, h2);
-                o.y = (row_border || c0 + 1 == nx - 1) ? ce.y : combine<OP>(ce.y, up.y, dn.y, ce.x, rt, h2);
-            }
-            *reinterpret_cast<double2*>(out + j * nx + c0) = o;
+    // software pipeline: the PF rows below the current batch (and the batch's edge values) are requested one
+    // batch ahead, so PF row loads per thread are in flight while PF rows are being combined
+    constexpr int PF = (OP == OP_LAPLACIAN) ? LM_K4_PF_LAP : LM_K4_PF_SMOOTH;   // rows per batch (measured best)
+    double2 nxt[PF];
+    double el[PF], er[PF];
+#pragma unroll
+    for (int k = 0; k < PF; ++k) {
+        nxt[k] = make_double2(0.0, 0.0); el[k] = 0.0; er[k] = 0.0;
+        if (r0 + k < r1) {
+            const long long jd = r0 + k + 1;
+            nxt[k] = load_row(jd == ny ? 0 : jd);
+            load_edges(r0 + k, el[k], er[k]);
         }
-        up = ce;
-        ce = dn;
+    }
+    for (long long jb = r0; jb < r1; jb += PF) {
+        double2 cur[PF];
+        double cel[PF], cer[PF];
+#pragma unroll
+        for (int k = 0; k < PF; ++k) { cur[k] = nxt[k]; cel[k] = el[k]; cer[k] = er[k]; }
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
+            const long long j = jb + PF + k;               // row of the next batch
+            if (j < r1) {
+                nxt[k] = load_row(j + 1 == ny ? 0 : j + 1);
+                load_edges(j, el[k], er[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
+            const long long j = jb + k;
+            if (j >= r1) break;
+            const double2 dn = cur[k];
+            double lf = __shfl_up_sync(FULL, ce.y, 1);
+            double rt = __shfl_down_sync(FULL, ce.x, 1);
+            if (live) {
+                if (edge_l) lf = cel[k];
+                if (edge_r) rt = cer[k];
+                double2 o;
+                if (OP == OP_LAPLACIAN) {
+                    o.x = combine<OP>(ce.x, up.x, dn.x, lf, ce.y, h2);
+                    o.y = combine<OP>(ce.y, up.y, dn.y, ce.x, rt, h2);
+                } else {
+                    const bool row_border = (j == 0) || (j == ny - 1);
+                    o.x = (row_border || c0 == 0) ? ce.x : combine<OP>(ce.x, up.x, dn.x, lf, ce.y, h2);
+                    o.y = (row_border || c0 + 1 == nx - 1) ? ce.y : combine<OP>(ce.y, up.y, dn.y, ce.x, rt, h2);
+                }
+                *reinterpret_cast<double2*>(out + j * nx + c0) = o;
+            }
+            up = ce;
+            ce = dn;
+        }
     }
 }
 
