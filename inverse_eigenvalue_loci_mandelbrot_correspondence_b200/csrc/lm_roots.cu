@@ -252,11 +252,15 @@ __global__ void __launch_bounds__(ROOTS_THREADS, LM_K3_MIN_CTAS) roots_kernel(co
             while (e + 2 < nh && hull[e + 1] <= k) ++e;
             const int i1 = hull[e], i2 = hull[e + 1];
             const int m = i2 - i1;
-            const double radius = exp((static_cast<double>(logc[d - i1]) - static_cast<double>(logc[d - i2])) / m);
-            const double ang = TWO_PI * (k - i1) / m + TWO_PI * e / d + 0.7;
-            double sn, cs;
-            sincos(ang, &sn, &cs);
-            zz[k] = make_double2(radius * cs, radius * sn);
+            // starting points only need a few digits: single-precision hardware exp / sincos (the double versions
+            // cost as much as a whole Aberth sweep of a small polynomial)
+            const float lr = (logc[d - i1] - logc[d - i2]) / static_cast<float>(m);
+            const double radius = (fabsf(lr) < 80.0f) ? static_cast<double>(__expf(lr)) : exp(static_cast<double>(lr));
+            const float ang = static_cast<float>(TWO_PI) * (static_cast<float>(k - i1) / static_cast<float>(m) +
+                                                            static_cast<float>(e) / static_cast<float>(d)) + 0.7f;
+            float sn, cs;
+            __sincosf(ang, &sn, &cs);
+            zz[k] = make_double2(radius * static_cast<double>(cs), radius * static_cast<double>(sn));
             frozen[k] = 0;
         }
         tile.sync();
