@@ -363,6 +363,14 @@ int32_t lm_log_potential_sums_dev(const double* px_dev, const double* py_dev, in
 int32_t lm_log_potential_finish_dev(const double* sums_dev, int64_t ncells, int64_t n_total_points,
                                     int32_t variant, double* U_dev, void* stream);
 
+/* ---- nearest-neighbour matching of two point sets (tracker module) -- */
+/* index[k] = first j minimising |x_k - y_j| (sqrt(dx*dx + dy*dy), unfused): what
+ * argmax(exp(-cdist(X, Y)/const), axis=1) selects in entropic_ot_alignment,
+ * tci_construct_mandelbrot_v002_fixed.py:62-71.  distance (may be NULL) receives the minimum.   */
+int32_t lm_nearest_match(const double* x_re, const double* x_im, int64_t n,
+                         const double* y_re, const double* y_im, int64_t m,
+                         int64_t* index, double* distance, lm_stats* stats);
+
 /* ---- measurement probes -------------------------------------------------------- */
 /* Dependent-free DFMA loop on every SM: FP64 peak (TFLOP/s, 2 flops per DFMA) and a
  * DMUL/DADD-only variant (the unfused mix K1 needs).  Used by bench.py for the

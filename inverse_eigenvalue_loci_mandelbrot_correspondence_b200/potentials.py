@@ -85,3 +85,19 @@ def mandelbrot_distance_estimator(c: complex, max_iter: int = 200, bailout: floa
     """Scalar drop-in for construct_stage1_clean.py:50-58."""
     d, _ = distance_grid([complex(c).real], [complex(c).imag], max_iter, bailout, 1e-16, DE_SCALAR)
     return float(d[0, 0])
+
+
+def nearest_match(X, Y):
+    """For every X (complex) the FIRST index of the nearest Y and that distance: the selection
+    argmax(exp(-cdist(X, Y)/const), axis=1) makes in entropic_ot_alignment
+    (tci_construct_mandelbrot_v002_fixed.py:62-71).  Returns (index int64[n], distance float64[n])."""
+    X = np.asarray(X, dtype=np.complex128).ravel(); Y = np.asarray(Y, dtype=np.complex128).ravel()
+    xr = np.ascontiguousarray(X.real); xi = np.ascontiguousarray(X.imag)
+    yr = np.ascontiguousarray(Y.real); yi = np.ascontiguousarray(Y.imag)
+    idx = np.empty(X.size, dtype=np.int64); dist = np.empty(X.size, dtype=np.float64)
+    st = Stats()
+    _shim.call("lm_nearest_match", _shim.ptr(xr), _shim.ptr(xi), X.size, _shim.ptr(yr), _shim.ptr(yi), Y.size,
+               _shim.ptr(idx), _shim.ptr(dist), C.byref(st))
+    global last_stats
+    last_stats = st.as_dict()
+    return idx, dist

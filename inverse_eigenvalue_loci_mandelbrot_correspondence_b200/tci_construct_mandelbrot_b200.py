@@ -12,9 +12,11 @@ signatures and moves the two generators onto the B200:
   mandelbrot_distance_estimator   -> K1b lm_distance_grid_f64, LM_DE_FINAL_DZ (…_v002_fixed.py:35-47)
   sample_mandelbrot_boundary()    -> K1b + the same quantile mask / np.random.choice on the host
                                      (…_v002_fixed.py:49-59), so a seeded run draws the same sample
+  entropic_ot_alignment(X, Y)     -> lm_nearest_match: the argmax of exp(-cdist/const) is the nearest
+                                     point (…_v002_fixed.py:62-71), same np.random.choice subsampling
 
-The matching / Procrustes / histogram helpers are host numpy on <= 4*10^4 points, as in the stock
-module.  Differences a user can see: inside one n the cloud is sorted by (re, im) instead of in
+The Procrustes / histogram helpers are host numpy on <= 4*10^4 points, as in the stock module.
+Differences a user can see: inside one n the cloud is sorted by (re, im) instead of in
 LAPACK's order, and `mandelbrot_distance_estimator` wants a meshgrid (`X + 1j*Y`) and returns
 `last = None` (z of the first escape stays on the device).
 """
@@ -86,21 +88,19 @@ def sample_mandelbrot_boundary():
 
 
 def entropic_ot_alignment(X, Y):
-    """The stock module's 'simplified Sinkhorn': equalise the sizes by random subsampling, then match every
-    X to the Y with the largest exp(-dist/(mean dist * sinkhorn_eps)), i.e. its nearest Y (first index on
-    ties).  Done in row blocks so the n x m distance matrix is never materialised."""
+    """The stock module's 'simplified Sinkhorn': equalise the sizes by random subsampling (same draws from
+    numpy's global stream), then match every X to the Y with the largest exp(-dist/(mean dist * sinkhorn_eps)),
+    i.e. its nearest Y, first index on ties -- on the GPU (lm_nearest_match), so the n x m distance matrix the
+    stock module builds (5 GB at 25 000 points) never exists."""
     X = np.asarray(X); Y = np.asarray(Y)
     n, m = len(X), len(Y)
     if n > m:
         X = np.random.choice(X, m, replace=False)
     if m > n:
         Y = np.random.choice(Y, n, replace=False)
-    yr, yi = Y.real[None, :], Y.imag[None, :]
-    match = np.empty(len(X), dtype=np.int64)
-    step = max(1, (1 << 24) // max(len(Y), 1))
-    for s in range(0, len(X), step):
-        xr = X.real[s:s + step, None]; xi = X.imag[s:s + step, None]
-        match[s:s + step] = np.argmin(np.sqrt((xr - yr) ** 2 + (xi - yi) ** 2), axis=1)
+    if len(X) == 0:
+        return Y[:0], X
+    match, _ = _potentials.nearest_match(X, Y)
     return Y[match], X
 
 

@@ -62,6 +62,8 @@ def lib() -> C.CDLL:
         L.oracle_log_potential.restype = None
         L.oracle_log_potential.argtypes = [_f64p, _f64p, C.c_int64, _f64p, C.c_int64, _f64p, C.c_int64,
                                            C.c_double, C.c_int32, _f64p]
+        L.oracle_nearest_match.restype = None
+        L.oracle_nearest_match.argtypes = [_f64p, _f64p, C.c_int64, _f64p, _f64p, C.c_int64, _i64p, _f64p]
         L.oracle_contour_lines.restype = C.c_int
         L.oracle_contour_lines.argtypes = [_f64p, C.c_int64, _f64p, C.c_int64, _f64p, C.c_double,
                                            _f64p, C.c_int64, C.POINTER(C.c_int64),
@@ -155,6 +157,16 @@ def log_potential(points, grid_x, grid_y, eps: float, variant: int):
     U = np.empty((gy.size, gx.size), dtype=np.float64)
     lib().oracle_log_potential(px, py, px.size, gx, gx.size, gy, gy.size, float(eps), int(variant), U)
     return U
+
+
+def nearest_match(X, Y):
+    """First index of the nearest Y for every X (complex arrays): the selection rule of entropic_ot_alignment,
+    tci_construct_mandelbrot_v002_fixed.py:62-71.  Returns (index int64[n], distance float64[n])."""
+    X = np.asarray(X, dtype=np.complex128).ravel(); Y = np.asarray(Y, dtype=np.complex128).ravel()
+    idx = np.empty(X.size, dtype=np.int64); dist = np.empty(X.size, dtype=np.float64)
+    lib().oracle_nearest_match(_c(X.real, np.float64), _c(X.imag, np.float64), X.size,
+                               _c(Y.real, np.float64), _c(Y.imag, np.float64), Y.size, idx, dist)
+    return idx, dist
 
 
 # ---- K2 -------------------------------------------------------------------------------

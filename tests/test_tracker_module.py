@@ -27,12 +27,10 @@ def test_module_contract_cpu(shim):
                "KL", "to_prob", "tci_flow", "mandelbrot_distance_estimator", "lucas_companion"):
         assert callable(getattr(mod, fn))
     assert mod.domain == (-2.25, 1.25, -1.75, 1.75) and mod.eps == 1e-12 and mod.mandelbrot_grid == 600
-    # host helpers: nearest-neighbour matching, rigid alignment, histogram probabilities, KL
+    # host helpers: rigid alignment, histogram probabilities, KL
     rng = np.random.default_rng(3)
     Y = rng.standard_normal(50) + 1j * rng.standard_normal(50)
     X = Y[rng.permutation(50)] + 1e-3
-    Ym, Xs = mod.entropic_ot_alignment(X, Y)
-    assert np.allclose(Ym, Xs - 1e-3)
     back = mod.procrustes_align_no_scale(Y + (2 - 1j), Y)                # pure translation is undone
     assert np.allclose(back, Y, atol=1e-12)
     moved = mod.procrustes_align_no_scale(Y * np.exp(0.3j) + (2 - 1j), Y)  # always a rigid motion onto Y's centroid
@@ -46,6 +44,21 @@ def test_module_contract_cpu(shim):
     if shim.device_count() < 1:          # no CPU fallback behind the module either
         with pytest.raises(RuntimeError):
             mod.construct_points([3])
+        with pytest.raises(RuntimeError):
+            mod.entropic_ot_alignment(X, Y)
+
+
+def test_nearest_match_oracle_is_the_reference_rule(oracle):
+    """The oracle's nearest_match against the stock module's own expression
+    argmax(exp(-cdist/mean/eps), axis=1) (tci_construct_mandelbrot_v002_fixed.py:66-70), restated with numpy."""
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal(300) + 1j * rng.standard_normal(300)
+    Y = np.concatenate([rng.standard_normal(200) + 1j * rng.standard_normal(200), X[:40], X[:40]])   # exact ties
+    M = np.sqrt((X.real[:, None] - Y.real[None, :]) ** 2 + (X.imag[:, None] - Y.imag[None, :]) ** 2)
+    K = np.nan_to_num(np.exp(-(M / M.mean()) / 0.8))
+    idx, dist = oracle.nearest_match(X, Y)
+    assert np.array_equal(idx, np.argmax(K, axis=1))
+    assert np.array_equal(dist, M[np.arange(300), idx])
 
 
 @pytest.mark.gpu
@@ -69,6 +82,16 @@ def test_tracker_levels(gpu, golden):
     np.random.seed(7); a = mod.sample_mandelbrot_boundary()
     np.random.seed(7); b = mod.sample_mandelbrot_boundary()
     assert a.size == 500 and np.array_equal(a, b)
+    # the matching rule on the GPU: first index of the nearest point, bit-identical to the oracle (exact ties included)
+    rng = np.random.default_rng(9)
+    X = rng.standard_normal(5000) + 1j * rng.standard_normal(5000)
+    Y = np.concatenate([rng.standard_normal(3000) + 1j * rng.standard_normal(3000), X[:500], X[:500]])
+    from oracle import oracle as orc
+    gi, gd = gpu.potentials.nearest_match(X, Y)
+    oi, od = orc.nearest_match(X, Y)
+    assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+    Ym, Xs = mod.entropic_ot_alignment(X[:2000], Y[:2000])          # equal sizes: no subsampling
+    assert np.array_equal(Ym, Y[:2000][orc.nearest_match(X[:2000], Y[:2000])[0]]) and np.array_equal(Xs, X[:2000])
     # one tracker level end to end
     mod.mandelbrot_grid = 600; mod.mandelbrot_samples = 25000
     np.random.seed(7)
