@@ -371,6 +371,18 @@ int32_t lm_nearest_match(const double* x_re, const double* x_im, int64_t n,
                          const double* y_re, const double* y_im, int64_t m,
                          int64_t* index, double* distance, lm_stats* stats);
 
+/* ---- dense boundary-integral (Nystrom) sums, SURVEY 8f-2 ------------------------ */
+/* out[m] = sum_n weight[n] * log(|z_m - node_n| + eps): the O(M*N) part of g_real,
+ * lucas_to_cardioid_v40_reference.py:240-257 (log(abs(z[:,None]-bdy[None,:]) + 1e-300) @ (sigma*ds)).  */
+int32_t lm_weighted_log_sum(const double* z_re, const double* z_im, int64_t M,
+                            const double* node_re, const double* node_im, const double* weight, int64_t N,
+                            double eps, double* out, lm_stats* stats);
+/* out[m] = sum_n weight[n] / dz_mn with dz_mn = z_m - node_n replaced by dz_eps + 0j where |dz_mn| < dz_eps:
+ * the integral term of dPhi, lucas_to_cardioid_v40_reference.py:201-211.                                 */
+int32_t lm_weighted_cauchy_sum(const double* z_re, const double* z_im, int64_t M,
+                               const double* node_re, const double* node_im, const double* weight, int64_t N,
+                               double dz_eps, double* out_re, double* out_im, lm_stats* stats);
+
 /* ---- measurement probes -------------------------------------------------------- */
 /* Dependent-free DFMA loop on every SM: FP64 peak (TFLOP/s, 2 flops per DFMA) and a
  * DMUL/DADD-only variant (the unfused mix K1 needs).  Used by bench.py for the

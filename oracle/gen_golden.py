@@ -163,6 +163,24 @@ def main() -> None:
                      "mandelbrot_grid": 150, "mandelbrot_samples": 10 ** 9})
     g["tci_fixed_boundary_sample_grid150"] = fxm["sample_mandelbrot_boundary"]()
 
+    # ---- boundary-integral Green function (lucas_to_cardioid_v40_reference.py:184-257): g_real and dPhi of the
+    # reference's own dataclass on a synthetic closed boundary (an ellipse with a smooth density)
+    rm = load_defs("lucas_to_cardioid_v40_reference.py", ["gauss_legendre_01", "RiemannMapDisk_GreenModulus"],
+                   {"PATH_GAUSS_N": 16, "EPS_POLE": 1e-6, "DZ_EPS": 1e-14, "G_CHUNK": 600})
+    nb = 257
+    th = 2 * np.pi * (np.arange(nb) + 0.5) / nb
+    bdy = 1.3 * np.cos(th) + 0.8j * np.sin(th) + 0.1
+    dsb = np.abs(np.roll(bdy, -1) - bdy)
+    sig = 0.5 + 0.2 * np.cos(3 * th) + 0.05 * np.sin(th)
+    obj = rm["RiemannMapDisk_GreenModulus"](bdy_z=bdy, ds=dsb, sigma=sig, a=0.15 + 0.05j, C=0.3, g_shift=-0.07)
+    rng = np.random.default_rng(11)
+    zt = np.concatenate([rng.uniform(-2, 2, 700) + 1j * rng.uniform(-1.5, 1.5, 700), bdy[:5], [0.15 + 0.05j]])
+    g["green_bdy"] = bdy; g["green_ds"] = dsb; g["green_sigma"] = sig
+    g["green_params"] = np.array([0.15, 0.05, 0.3, -0.07])
+    g["green_targets"] = zt
+    g["green_g_real"] = obj.g_real(zt)
+    g["green_dPhi"] = obj.dPhi(zt)
+
     OUT.parent.mkdir(parents=True, exist_ok=True)
     np.savez_compressed(OUT, **g)
     print(f"wrote {OUT} ({OUT.stat().st_size / 1024:.1f} KiB, {len(g)} arrays)")

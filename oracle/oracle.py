@@ -169,6 +169,22 @@ def nearest_match(X, Y):
     return idx, dist
 
 
+def weighted_log_sum(z, nodes, weights, eps: float = 1e-300):
+    """sum_n w_n log(|z_m - zeta_n| + eps): the matrix-vector product inside g_real,
+    lucas_to_cardioid_v40_reference.py:252-253, written as one numpy expression."""
+    z = np.asarray(z, dtype=np.complex128).ravel(); b = np.asarray(nodes, dtype=np.complex128).ravel()
+    return np.log(np.abs(z[:, None] - b[None, :]) + eps) @ np.asarray(weights, dtype=np.float64)
+
+
+def weighted_cauchy_sum(z, nodes, weights, dz_eps: float = 1e-14):
+    """sum_n w_n / dz with short differences clamped to dz_eps + 0j: the integral term of dPhi,
+    lucas_to_cardioid_v40_reference.py:207-211."""
+    z = np.asarray(z, dtype=np.complex128).ravel(); b = np.asarray(nodes, dtype=np.complex128).ravel()
+    DZ = z[:, None] - b[None, :]
+    DZ = np.where(np.abs(DZ) < dz_eps, dz_eps + 0j, DZ)
+    return (np.asarray(weights, dtype=np.float64)[None, :] / DZ).sum(axis=1)
+
+
 # ---- K2 -------------------------------------------------------------------------------
 def contour_lines(xs, ys, Z, level: float):
     """plt.contour(xs, ys, Z, levels=[level]).allsegs[0] restated (mpl2014) -> list of (N,2) arrays."""

@@ -77,3 +77,26 @@ def test_distance_estimator_tracker_module(gpu, oracle, golden):
         o, oesc = oracle.distance_grid(golden[tag + "_x"], golden[tag + "_y"], 250, 250.0, 1e-12, 2)
         assert np.array_equal(esc, oesc)
         np.testing.assert_allclose(got, o, rtol=1e-13, atol=0)
+
+
+def test_green_function_sums(gpu, oracle, golden):
+    """g_real / dPhi (lucas_to_cardioid_v40_reference.py:201-257) with the O(M*N) sums on the GPU, against the
+    reference's own outputs and the oracle; targets ON boundary nodes exercise the eps / dz_eps clamps."""
+    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import nystrom
+    bdy, ds, sig, z = golden["green_bdy"], golden["green_ds"], golden["green_sigma"], golden["green_targets"]
+    ar, ai, Cc, sh = golden["green_params"]
+    a = complex(ar, ai)
+    g = nystrom.g_real(z, bdy, sig, ds, a, Cc, sh)
+    np.testing.assert_allclose(g, golden["green_g_real"], rtol=1e-12, atol=1e-13)
+    dphi = nystrom.dPhi(z, bdy, sig, ds, a)
+    np.testing.assert_allclose(dphi, golden["green_dPhi"], rtol=1e-12, atol=1e-12 * np.abs(golden["green_dPhi"]).max())
+    # the reference's production size: 2*10^4 targets x 2000 nodes
+    rng = np.random.default_rng(4)
+    zz = rng.uniform(-2, 2, 20000) + 1j * rng.uniform(-2, 2, 20000)
+    nodes = np.exp(2j * np.pi * np.arange(2000) / 2000) * (1 + 0.3 * np.cos(5 * 2 * np.pi * np.arange(2000) / 2000))
+    w = rng.uniform(0.0, 0.01, 2000)
+    np.testing.assert_allclose(nystrom.weighted_log_sum(zz, nodes, w), oracle.weighted_log_sum(zz, nodes, w), rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(nystrom.weighted_cauchy_sum(zz, nodes, w), oracle.weighted_cauchy_sum(zz, nodes, w), rtol=1e-11, atol=1e-13)
+    assert nystrom.weighted_log_sum(np.zeros(0, complex), nodes, w).shape == (0,)
+    with pytest.raises(ValueError):
+        nystrom.weighted_log_sum(zz, nodes, w[:-1])

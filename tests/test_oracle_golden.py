@@ -129,3 +129,17 @@ def test_known_answers(oracle, golden):
     # shipped artefact: 2400 points for n = 20..300 step 20 (v3_T25_sigma3_dense.csv:2)
     assert int(golden["tci_construct_points_count"][0]) == 2400
     assert sum(range(20, 301, 20)) == 2400
+
+
+def test_green_function_sums(oracle, golden):
+    """The oracle's Nystrom sums against g_real / dPhi of the reference's own RiemannMapDisk_GreenModulus
+    (lucas_to_cardioid_v40_reference.py:184-257) on a synthetic boundary."""
+    bdy, ds, sig, z = golden["green_bdy"], golden["green_ds"], golden["green_sigma"], golden["green_targets"]
+    ar, ai, Cc, sh = golden["green_params"]
+    a = complex(ar, ai)
+    got = -np.log(np.abs(z - a) + 1e-300) + oracle.weighted_log_sum(z, bdy, sig * ds) + Cc + sh
+    np.testing.assert_allclose(got, golden["green_g_real"], rtol=1e-12, atol=1e-13)
+    DZ0 = np.where(np.abs(z - a) < 1e-14, 1e-14 + 0j, z - a)
+    got = -1.0 / DZ0 + oracle.weighted_cauchy_sum(z, bdy, sig * ds, 1e-14)
+    np.testing.assert_allclose(got, golden["green_dPhi"], rtol=1e-12, atol=1e-12 * np.abs(golden["green_dPhi"]).max())
+    assert np.isfinite(golden["green_g_real"][:-1]).all()
