@@ -29,10 +29,7 @@
 // Horner evaluation.  Parity with LAPACK is tolerance based (sorted roots, 1e-10 relative).
 #include "lm_common.cuh"
 
-#include <cooperative_groups.h>
 #include <math.h>
-
-namespace cg = cooperative_groups;
 
 namespace {
 
@@ -192,8 +189,22 @@ __host__ __device__ inline size_t group_smem_bytes(int D) {
 template <int G>
 __global__ void __launch_bounds__(ROOTS_THREADS, LM_K3_MIN_CTAS) roots_kernel(const RootsArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
-    cg::thread_block block = cg::this_thread_block();
-    cg::thread_block_tile<G> tile = cg::tiled_partition<G>(block);
+    // group-of-G primitives on raw warp intrinsics with the group's lane mask (ncu: the cooperative-groups tile
+    // collectives showed up as VOTE/ENDCOLLECTIVE/BSYNC sequences worth 12 % of the stall samples)
+    struct Tile {
+        unsigned mask; int shift, rank;
+        __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+        __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(mask, p) & mask) >> shift; }
+        __device__ __forceinline__ bool all(bool p) const { return (__ballot_sync(mask, p) & mask) == mask; }
+        __device__ __forceinline__ int shfl(int v, int src) const { return __shfl_sync(mask, v, shift + src); }
+        __device__ __forceinline__ int shfl_xor(int v, int o) const { return __shfl_xor_sync(mask, v, o); }
+        __device__ __forceinline__ int thread_rank() const { return rank; }
+    };
+    const int lane_in_warp = threadIdx.x & 31;
+    Tile tile;
+    tile.shift = lane_in_warp & ~(G - 1);
+    tile.rank = lane_in_warp & (G - 1);
+    tile.mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << tile.shift);
     const int groups_per_cta = blockDim.x / G;
     const int gid = threadIdx.x / G;
     const int l = tile.thread_rank();
