@@ -14,8 +14,9 @@
 //
 // Mapping: a group of G lanes owns one polynomial (G = 4 for degree <= 32, 8 up to 128, 32
 // above); coefficients and the current root estimates are staged in shared memory; lane l
-// updates roots l, l+G, ... (Gauss-Seidel between rounds); group-wide decisions use tile
-// shuffles/ballots.  The batch is counting-sorted by degree ON THE DEVICE first (histogram,
+// updates roots l, l+G, ... (Gauss-Seidel between rounds); group-wide decisions use masked warp
+// shuffles/ballots.  For degree <= 32 a warp processes its 8 polynomials as one generation
+// (roots_pool_kernel below).  The batch is counting-sorted by degree ON THE DEVICE first (histogram,
 // scan, scatter), so the groups that share a warp hold polynomials of the same degree and run
 // the same trip counts; the solver launches read their index ranges from device memory, so
 // the whole pipeline is asynchronous on one stream (lm_roots_batched_dev).
@@ -49,6 +50,7 @@ struct RootsPlan {
     long long bounds[4];                 // index ranges of the three classes: [bounds[c], bounds[c+1])
     int fail_flag;                       // some polynomial did not converge
     int bad_degree;                      // some deg[k] outside [1, maxdeg]
+    unsigned long long cursor;           // next unclaimed polynomial of class 0 (pool kernel, work stealing)
     unsigned long long hist[HIST_BINS];  // per-degree counts, then running cursors
 };
 
@@ -186,225 +188,348 @@ __host__ __device__ inline size_t group_smem_bytes(int D) {
 #ifndef LM_K3_MIN_CTAS
 #define LM_K3_MIN_CTAS 8
 #endif
+
+// group-of-G primitives on raw warp intrinsics with the group's lane mask
+struct Tile {
+    unsigned mask; int shift, rank;
+    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+    __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(mask, p) & mask) >> shift; }
+    __device__ __forceinline__ bool all(bool p) const { return (__ballot_sync(mask, p) & mask) == mask; }
+    __device__ __forceinline__ int shfl(int v, int src) const { return __shfl_sync(mask, v, shift + src); }
+    __device__ __forceinline__ int shfl_xor(int v, int o) const { return __shfl_xor_sync(mask, v, o); }
+};
+template <int G>
+__device__ __forceinline__ Tile make_tile() {
+    const int lane = threadIdx.x & 31;
+    Tile t;
+    t.shift = lane & ~(G - 1);
+    t.rank = lane & (G - 1);
+    t.mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << t.shift);
+    return t;
+}
+
+// one polynomial's shared-memory slice
+struct Slot {
+    double* coef;            // coef[k] multiplies x^(d-k); coef[0] = 1
+    double2* zz;             // current estimates
+    float* logc;             // log|coef| (initial guesses only)
+    int* hull;               // Newton polygon, later the per-sweep list of roots still moving
+    unsigned char* frozen;
+};
+__device__ __forceinline__ Slot make_slot(unsigned char* base, int D) {
+    Slot s;
+    s.coef = reinterpret_cast<double*>(base);
+    s.zz = reinterpret_cast<double2*>(s.coef + ((D + 2) & ~1));
+    s.logc = reinterpret_cast<float*>(s.zz + D);
+    s.hull = reinterpret_cast<int*>(s.logc + (D + 1));
+    s.frozen = reinterpret_cast<unsigned char*>(s.hull + (D + 1));
+    return s;
+}
+
+// Load polynomial `pid` into the slot (deflating trailing zero coefficients: roots at 0) and place the initial
+// guesses by Bini's rule.  Returns the deflated degree; nzero = number of zero roots.  Called by the G lanes of a group.
+template <int G>
+__device__ __forceinline__ int load_and_init(const Tile& tile, const Slot& S, const RootsArgs& A, long long pid, int& nzero) {
+    const int l = tile.rank;
+    const int d_full = A.deg[pid];
+    const double* top = A.toprows + pid * A.maxdeg;
+    int d;
+    {
+        int last_nz = 0;
+        for (int k = l; k < d_full; k += G)
+            if (top[k] != 0.0) last_nz = k + 1;
+        for (int o = G / 2; o > 0; o >>= 1) last_nz = max(last_nz, tile.shfl_xor(last_nz, o));
+        d = last_nz;
+    }
+    nzero = d_full - d;
+    for (int k = l; k <= d; k += G) {
+        const double c = (k == 0) ? 1.0 : -top[k - 1];
+        S.coef[k] = c;
+        S.logc[k] = (c != 0.0) ? static_cast<float>(log(fabs(c))) : -INFINITY;
+    }
+    tile.sync();
+    // Work with ascending powers: a_i = coef[d-i].  Upper convex hull of (i, log|a_i|), i = 0..d
+    // (a_0 = coef[d] != 0 after deflation, a_d = 1).
+    int nh = 0;
+    if (l == 0 && d > 0) {
+        for (int i = 0; i <= d; ++i) {
+            const double yi = S.logc[d - i];
+            if (yi == -INFINITY) continue;
+            while (nh >= 2) {
+                const int i1 = S.hull[nh - 2], i2 = S.hull[nh - 1];
+                const double y1 = S.logc[d - i1], y2 = S.logc[d - i2];
+                // keep i2 only if it lies strictly above the chord i1 -> i
+                if ((y2 - y1) * (i - i1) <= (yi - y1) * (i2 - i1)) --nh; else break;
+            }
+            S.hull[nh++] = i;
+        }
+    }
+    nh = tile.shfl(nh, 0);
+    tile.sync();
+    for (int k = l; k < d; k += G) {
+        // root k belongs to the hull edge [hull[e], hull[e+1]) that contains k
+        int e = 0;
+        while (e + 2 < nh && S.hull[e + 1] <= k) ++e;
+        const int i1 = S.hull[e], i2 = S.hull[e + 1];
+        const int m = i2 - i1;
+        // starting points only need a few digits: single-precision hardware exp / sincos (the double versions
+        // cost as much as a whole Aberth sweep of a small polynomial)
+        const float lr = (S.logc[d - i1] - S.logc[d - i2]) / static_cast<float>(m);
+        const double radius = (fabsf(lr) < 80.0f) ? static_cast<double>(__expf(lr)) : exp(static_cast<double>(lr));
+        const float ang = static_cast<float>(TWO_PI) * (static_cast<float>(k - i1) / static_cast<float>(m) +
+                                                        static_cast<float>(e) / static_cast<float>(d)) + 0.7f;
+        float sn, cs;
+        __sincosf(ang, &sn, &cs);
+        S.zz[k] = make_double2(radius * static_cast<double>(cs), radius * static_cast<double>(sn));
+        S.frozen[k] = 0;
+    }
+    tile.sync();
+    return d;
+}
+
+// One Aberth-Ehrlich update of root i from the slot's current estimates (read only).  freeze: |p(z)| is below
+// the rounding bound of its own evaluation (z is kept); stagnant: the correction no longer changes z.
+__device__ __forceinline__ void aberth_update(const Slot& S, int d, int i, cplx& znew, bool& freeze, bool& stagnant) {
+    const double2 zi2 = S.zz[i];
+    const cplx z = {zi2.x, zi2.y};
+    const double az2 = z.r * z.r + z.i * z.i;
+    const double az = sqrt(az2);
+    // One Horner loop for both regimes, so lanes inside and outside the unit circle do not diverge:
+    // |z| <= 1 evaluates p at w = z from coef[0] up;  |z| > 1 evaluates the reversed polynomial
+    // q(w) = sum_k coef[k] w^k at w = 1/z from coef[d] down (p(z) = z^d q(1/z)).
+    const bool inside = az <= 1.0;
+    const double iz2 = rcp_fast<2>(inside ? 1.0 : az2);
+    const cplx w = inside ? z : cplx{z.r * iz2, -z.i * iz2};
+    const double aw = inside ? az : az * iz2;
+    const int k_first = inside ? 0 : d, k_step = inside ? 1 : -1;
+    cplx b = {S.coef[k_first], 0.0}, bp = {0.0, 0.0};
+    double s = fabs(b.r);
+    for (int k = 1, idx = k_first + k_step; k <= d; ++k, idx += k_step) {
+        const double ck = S.coef[idx];
+        bp = {fma(bp.r, w.r, fma(-bp.i, w.i, b.r)), fma(bp.r, w.i, fma(bp.i, w.r, b.i))};
+        b = {fma(b.r, w.r, fma(-b.i, w.i, ck)), fma(b.r, w.i, b.i * w.r)};
+        s = fma(s, aw, fabs(ck));
+    }
+    const double ab2 = b.r * b.r + b.i * b.i;
+    const double bound = EPS * s * (d + 1);
+    freeze = ab2 <= bound * bound;
+    stagnant = false;
+    znew = z;
+    if (freeze) return;
+    // inside:  p/p' = b / bp;   outside:  p/p' = z / (d - w q'(w)/q(w)) = z b / (d b - w bp)
+    cplx num, den;
+    if (inside) { num = b; den = bp; }
+    else {
+        const cplx wbp = cmul(w, bp);
+        num = cmul(z, b);
+        den = {fma(static_cast<double>(d), b.r, -wbp.r), fma(static_cast<double>(d), b.i, -wbp.i)};
+    }
+    const double dd = den.r * den.r + den.i * den.i;
+    const cplx newton = (dd > 1e-290 && dd < 1e290) ? cmul(num, cinv_fast(den))
+                      : (dd > 0.0 ? cmul(num, cinv(den)) : cplx{1e-3 * (az + 1e-3), 1e-3 * (az + 1e-3)});
+    double Sr = 0.0, Si = 0.0;
+#pragma unroll 4
+    for (int j = 0; j < d; ++j) {
+        const double2 zj = S.zz[j];
+        const double dr = z.r - zj.x, di = z.i - zj.y;
+        const double q = fma(dr, dr, di * di);
+        // j == i (q == 0) and coinciding estimates contribute nothing; the reciprocal's NaN/Inf for q == 0 is
+        // discarded by the select
+        const double inv = (q > 1e-300) ? rcp_fast<1>(q) : 0.0;
+        Sr = fma(dr, inv, Sr);
+        Si = fma(-di, inv, Si);
+    }
+    const cplx ns = cmul(newton, cplx{Sr, Si});
+    const cplx den2 = {1.0 - ns.r, -ns.i};
+    const double d2 = den2.r * den2.r + den2.i * den2.i;
+    const cplx corr = (d2 > 1e-290 && d2 < 1e290) ? cmul(newton, cinv_fast(den2))
+                    : (d2 > 0.0 ? cmul(newton, cinv(den2)) : newton);
+    znew = {z.r - corr.r, z.i - corr.i};
+    if (!(isfinite(znew.r) && isfinite(znew.i))) znew = {z.r * 0.5 + 1e-3, z.i * 0.5 - 1e-3};
+    // stagnation: the correction is below the resolution of z -> it is frozen with the new value
+    if (corr.r * corr.r + corr.i * corr.i <= (4.0 * EPS * EPS) * az2) stagnant = true;
+}
+
+// [zero roots] + computed roots, optionally inverted / filtered / compacted, NaN padding, counters
+template <int G>
+__device__ __forceinline__ void write_output(const Tile& tile, const Slot& S, const RootsArgs& A, long long pid, int d, int nzero,
+                                             int sweeps, bool converged) {
+    const int l = tile.rank;
+    double* ore = A.out_re + pid * A.maxdeg;
+    double* oim = A.out_im + pid * A.maxdeg;
+    int kept = 0;
+    const int total = d + nzero;
+    for (int r0 = 0; r0 < total; r0 += G) {
+        const int i = r0 + l;
+        bool keep = false;
+        cplx v = {0.0, 0.0};
+        if (i < total) {
+            cplx z = {0.0, 0.0};
+            if (i < d) { const double2 t = S.zz[i]; z = {t.x, t.y}; }
+            if (A.invert) {
+                const double az = sqrt(z.r * z.r + z.i * z.i);
+                keep = az > A.tol;
+                if (keep) v = cinv(z);
+            } else {
+                keep = true;
+                v = z;
+            }
+        }
+        const unsigned bal = tile.ballot(keep);
+        if (keep) {
+            const int pos = kept + __popc(bal & ((1u << l) - 1u));
+            ore[pos] = v.r;
+            oim[pos] = v.i;
+        }
+        kept += __popc(bal);
+    }
+    for (int k = kept + l; k < A.maxdeg; k += G) { ore[k] = nan(""); oim[k] = nan(""); }
+    if (l == 0) {
+        if (A.n_kept) A.n_kept[pid] = kept;
+        if (A.iters) A.iters[pid] = converged ? sweeps : -sweeps;
+        if (!converged) atomicExch(&A.plan->fail_flag, 1);
+    }
+    tile.sync();
+}
+
+// ---- group kernel: G lanes own one polynomial from start to end (degrees above CLASS_SMALL_MAX) ----
 template <int G>
 __global__ void __launch_bounds__(ROOTS_THREADS, LM_K3_MIN_CTAS) roots_kernel(const RootsArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
-    // group-of-G primitives on raw warp intrinsics with the group's lane mask (ncu: the cooperative-groups tile
-    // collectives showed up as VOTE/ENDCOLLECTIVE/BSYNC sequences worth 12 % of the stall samples)
-    struct Tile {
-        unsigned mask; int shift, rank;
-        __device__ __forceinline__ void sync() const { __syncwarp(mask); }
-        __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(mask, p) & mask) >> shift; }
-        __device__ __forceinline__ bool all(bool p) const { return (__ballot_sync(mask, p) & mask) == mask; }
-        __device__ __forceinline__ int shfl(int v, int src) const { return __shfl_sync(mask, v, shift + src); }
-        __device__ __forceinline__ int shfl_xor(int v, int o) const { return __shfl_xor_sync(mask, v, o); }
-        __device__ __forceinline__ int thread_rank() const { return rank; }
-    };
-    const int lane_in_warp = threadIdx.x & 31;
-    Tile tile;
-    tile.shift = lane_in_warp & ~(G - 1);
-    tile.rank = lane_in_warp & (G - 1);
-    tile.mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << tile.shift);
+    const Tile tile = make_tile<G>();
     const int groups_per_cta = blockDim.x / G;
     const int gid = threadIdx.x / G;
-    const int l = tile.thread_rank();
+    const int l = tile.rank;
     const int D = A.smem_deg;
-    unsigned char* base = smem + static_cast<size_t>(gid) * group_smem_bytes(D);
-    double* coef = reinterpret_cast<double*>(base);            // coef[k] multiplies x^(d-k); coef[0] = 1
-    double2* zz = reinterpret_cast<double2*>(coef + ((D + 2) & ~1));
-    float* logc = reinterpret_cast<float*>(zz + D);
-    int* hull = reinterpret_cast<int*>(logc + (D + 1));
-    unsigned char* frozen = reinterpret_cast<unsigned char*>(hull + (D + 1));
+    const Slot S = make_slot(smem + static_cast<size_t>(gid) * group_smem_bytes(D), D);
     const long long first = A.plan->bounds[A.cls], last = A.plan->bounds[A.cls + 1];
 
     for (long long item = first + static_cast<long long>(blockIdx.x) * groups_per_cta + gid; item < last;
          item += static_cast<long long>(gridDim.x) * groups_per_cta) {
         const long long pid = A.index[item];
-        const int d_full = A.deg[pid];
-        const double* top = A.toprows + pid * A.maxdeg;
-        // trailing zero coefficients are roots at 0: deflate
-        int d = d_full;
-        {
-            int last_nz = 0;
-            for (int k = l; k < d_full; k += G)
-                if (top[k] != 0.0) last_nz = k + 1;
-            for (int o = G / 2; o > 0; o >>= 1) last_nz = max(last_nz, tile.shfl_xor(last_nz, o));
-            d = last_nz;
-        }
-        const int nzero = d_full - d;
-        for (int k = l; k <= d; k += G) {
-            const double c = (k == 0) ? 1.0 : -top[k - 1];
-            coef[k] = c;
-            logc[k] = (c != 0.0) ? static_cast<float>(log(fabs(c))) : -INFINITY;
-        }
-        tile.sync();
-
-        // ---- initial guesses: Bini's rule.  Work with ascending powers: a_i = coef[d-i].
-        // Upper convex hull of (i, log|a_i|), i = 0..d (a_0 = coef[d] != 0 after deflation, a_d = 1).
-        int nh = 0;
-        if (l == 0 && d > 0) {
-            for (int i = 0; i <= d; ++i) {
-                const double yi = logc[d - i];
-                if (yi == -INFINITY) continue;
-                while (nh >= 2) {
-                    const int i1 = hull[nh - 2], i2 = hull[nh - 1];
-                    const double y1 = logc[d - i1], y2 = logc[d - i2];
-                    // keep i2 only if it lies strictly above the chord i1 -> i
-                    if ((y2 - y1) * (i - i1) <= (yi - y1) * (i2 - i1)) --nh; else break;
-                }
-                hull[nh++] = i;
-            }
-        }
-        nh = tile.shfl(nh, 0);
-        tile.sync();
-        for (int k = l; k < d; k += G) {
-            // root k belongs to the hull edge [hull[e], hull[e+1]) that contains k
-            int e = 0;
-            while (e + 2 < nh && hull[e + 1] <= k) ++e;
-            const int i1 = hull[e], i2 = hull[e + 1];
-            const int m = i2 - i1;
-            // starting points only need a few digits: single-precision hardware exp / sincos (the double versions
-            // cost as much as a whole Aberth sweep of a small polynomial)
-            const float lr = (logc[d - i1] - logc[d - i2]) / static_cast<float>(m);
-            const double radius = (fabsf(lr) < 80.0f) ? static_cast<double>(__expf(lr)) : exp(static_cast<double>(lr));
-            const float ang = static_cast<float>(TWO_PI) * (static_cast<float>(k - i1) / static_cast<float>(m) +
-                                                            static_cast<float>(e) / static_cast<float>(d)) + 0.7f;
-            float sn, cs;
-            __sincosf(ang, &sn, &cs);
-            zz[k] = make_double2(radius * static_cast<double>(cs), radius * static_cast<double>(sn));
-            frozen[k] = 0;
-        }
-        tile.sync();
-
-        // ---- Aberth sweeps
+        int nzero = 0;
+        const int d = load_and_init<G>(tile, S, A, pid, nzero);
         int sweeps = 0;
         bool all_done = (d == 0);
         while (!all_done && sweeps < MAX_SWEEPS) {
             ++sweeps;
             bool mine_done = true;
-            // compact the roots that are still moving into act[] (the hull array is free after the initial
-            // guesses), so late sweeps with a few stragglers take one round instead of ceil(d/G)
+            // compact the roots that are still moving into the (now free) hull array, so late sweeps with a few
+            // stragglers take one round instead of ceil(d/G)
             int nact = 0;
             for (int r0 = 0; r0 < d; r0 += G) {
                 const int i = r0 + l;
-                const bool live = (i < d) && !frozen[i];
+                const bool live = (i < d) && !S.frozen[i];
                 const unsigned bal = tile.ballot(live);
-                if (live) hull[nact + __popc(bal & ((1u << l) - 1u))] = i;
+                if (live) S.hull[nact + __popc(bal & ((1u << l) - 1u))] = i;
                 nact += __popc(bal);
             }
             tile.sync();
             for (int r0 = 0; r0 < nact; r0 += G) {
                 const bool active = r0 + l < nact;
-                const int i = active ? hull[r0 + l] : 0;
+                const int i = active ? S.hull[r0 + l] : 0;
                 cplx znew = {0.0, 0.0};
                 bool freeze = false, stagnant = false;
                 if (active) {
-                    const double2 zi2 = zz[i];
-                    const cplx z = {zi2.x, zi2.y};
-                    const double az2 = z.r * z.r + z.i * z.i;
-                    const double az = sqrt(az2);
-                    cplx newton;           // p/p'
-                    // One Horner loop for both regimes, so lanes inside and outside the unit circle do not
-                    // diverge:  |z| <= 1 evaluates p at w = z from coef[0] up;  |z| > 1 evaluates the reversed
-                    // polynomial q(w) = sum_k coef[k] w^k at w = 1/z from coef[d] down (p(z) = z^d q(1/z)).
-                    const bool inside = az <= 1.0;
-                    const double iz2 = rcp_fast<2>(inside ? 1.0 : az2);
-                    const cplx w = inside ? z : cplx{z.r * iz2, -z.i * iz2};
-                    const double aw = inside ? az : az * iz2;
-                    const int k_first = inside ? 0 : d, k_step = inside ? 1 : -1;
-                    cplx b = {coef[k_first], 0.0}, bp = {0.0, 0.0};
-                    double s = fabs(b.r);
-                    for (int k = 1, idx = k_first + k_step; k <= d; ++k, idx += k_step) {
-                        const double ck = coef[idx];
-                        bp = {fma(bp.r, w.r, fma(-bp.i, w.i, b.r)), fma(bp.r, w.i, fma(bp.i, w.r, b.i))};
-                        b = {fma(b.r, w.r, fma(-b.i, w.i, ck)), fma(b.r, w.i, b.i * w.r)};
-                        s = fma(s, aw, fabs(ck));
-                    }
-                    const double ab2 = b.r * b.r + b.i * b.i;
-                    const double bound = EPS * s * (d + 1);
-                    freeze = ab2 <= bound * bound;
-                    // inside:  p/p' = b / bp;   outside:  p/p' = z / (d - w q'(w)/q(w)) = z b / (d b - w bp)
-                    cplx num, den;
-                    if (inside) { num = b; den = bp; }
-                    else {
-                        const cplx wbp = cmul(w, bp);
-                        num = cmul(z, b);
-                        den = {fma(static_cast<double>(d), b.r, -wbp.r), fma(static_cast<double>(d), b.i, -wbp.i)};
-                    }
-                    const double dd = den.r * den.r + den.i * den.i;
-                    newton = (dd > 1e-290 && dd < 1e290) ? cmul(num, cinv_fast(den))
-                           : (dd > 0.0 ? cmul(num, cinv(den)) : cplx{1e-3 * (az + 1e-3), 1e-3 * (az + 1e-3)});
-                    if (!freeze) {
-                        double Sr = 0.0, Si = 0.0;
-#pragma unroll 4
-                        for (int j = 0; j < d; ++j) {
-                            const double2 zj = zz[j];
-                            const double dr = z.r - zj.x, di = z.i - zj.y;
-                            const double q = fma(dr, dr, di * di);
-                            // j == i (q == 0) and coinciding estimates contribute nothing; the
-                            // reciprocal's NaN/Inf for q == 0 is discarded by the select
-                            const double inv = (q > 1e-300) ? rcp_fast<1>(q) : 0.0;
-                            Sr = fma(dr, inv, Sr);
-                            Si = fma(-di, inv, Si);
-                        }
-                        const cplx ns = cmul(newton, cplx{Sr, Si});
-                        const cplx den = {1.0 - ns.r, -ns.i};
-                        const double dd = den.r * den.r + den.i * den.i;
-                        const cplx corr = (dd > 1e-290 && dd < 1e290) ? cmul(newton, cinv_fast(den))
-                                        : (dd > 0.0 ? cmul(newton, cinv(den)) : newton);
-                        znew = {z.r - corr.r, z.i - corr.i};
-                        if (!(isfinite(znew.r) && isfinite(znew.i))) znew = {z.r * 0.5 + 1e-3, z.i * 0.5 - 1e-3};
-                        // stagnation: the correction is below the resolution of z -> next sweep freezes it
-                        if (corr.r * corr.r + corr.i * corr.i <= (4.0 * EPS * EPS) * az2) stagnant = true;
-                        mine_done = false;
-                    }
+                    aberth_update(S, d, i, znew, freeze, stagnant);
+                    if (!freeze) mine_done = false;
                 }
                 tile.sync();               // everybody has read the old estimates of this round
                 if (active) {
-                    if (freeze) frozen[i] = 1;
-                    else { zz[i] = make_double2(znew.r, znew.i); if (stagnant) frozen[i] = 1; }
+                    if (freeze) S.frozen[i] = 1;
+                    else { S.zz[i] = make_double2(znew.r, znew.i); if (stagnant) S.frozen[i] = 1; }
                 }
                 tile.sync();
             }
             all_done = tile.all(mine_done);
         }
-        if (!all_done && l == 0) atomicExch(&A.plan->fail_flag, 1);
+        write_output<G>(tile, S, A, pid, d, nzero, sweeps, all_done);
+    }
+}
 
-        // ---- output: [zero roots] + computed roots, optionally inverted / filtered / compacted
-        double* ore = A.out_re + pid * A.maxdeg;
-        double* oim = A.out_im + pid * A.maxdeg;
-        int kept = 0;
-        const int total = d + nzero;
-        for (int r0 = 0; r0 < total; r0 += G) {
-            const int i = r0 + l;
-            bool keep = false;
-            cplx v = {0.0, 0.0};
-            if (i < total) {
-                cplx z = {0.0, 0.0};
-                if (i < d) { const double2 t = zz[i]; z = {t.x, t.y}; }
-                if (A.invert) {
-                    const double az = sqrt(z.r * z.r + z.i * z.i);
-                    keep = az > A.tol;
-                    if (keep) v = cinv(z);
-                } else {
-                    keep = true;
-                    v = z;
+// ---- generation kernel (degree <= CLASS_SMALL_MAX): a warp takes 8 polynomials at a time (one generation, claimed
+// with an atomic cursor over the degree-sorted batch), one per 4-lane group.  The groups load and initialise their
+// polynomials at the same time, walk through the sweeps side by side, and write their results together.  In the
+// first version every group ran on its own schedule and ncu showed the sequential Newton-polygon scan of a new
+// polynomial running on ONE lane while the other 31 waited (13 % of all instructions at 1.4 active threads); in a
+// generation 8 scans run side by side.  Every slot keeps its own lanes and its own update schedule (rounds of 4
+// roots, Gauss-Seidel between rounds), so the result of a polynomial does not depend on which polynomials share
+// its warp: runs are bit-reproducible.  (A variant that pooled the 32 lanes over all (polynomial, root) pairs still
+// moving was measured too: same speed, but the update schedule -- and with it the last bits of ill-conditioned
+// roots -- then depends on the neighbours, so it was dropped.)
+constexpr int POOL_SLOTS = 8;
+constexpr int POOL_WARPS = ROOTS_THREADS / 32;
+
+__global__ void __launch_bounds__(ROOTS_THREADS, LM_K3_MIN_CTAS) roots_pool_kernel(const RootsArgs A) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const Tile tile = make_tile<4>();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, l = tile.rank;                   // my slot (for load / output), my rank in its group
+    const int D = A.smem_deg;
+    const size_t slot_bytes = group_smem_bytes(D);
+    unsigned char* warp_base = smem + static_cast<size_t>(warp) * POOL_SLOTS * slot_bytes;
+    const Slot S = make_slot(warp_base + static_cast<size_t>(g) * slot_bytes, D);
+    const long long first = A.plan->bounds[A.cls], last = A.plan->bounds[A.cls + 1];
+
+    while (true) {
+        // ---- claim a generation of 8 polynomials
+        unsigned long long gen = 0;
+        if (lane == 0) gen = atomicAdd(&A.plan->cursor, static_cast<unsigned long long>(POOL_SLOTS));
+        gen = __shfl_sync(0xffffffffu, gen, 0);
+        const long long item = first + static_cast<long long>(gen) + g;
+        if (first + static_cast<long long>(gen) >= last) break;
+        const bool occupied = item < last;
+        long long pid = -1;
+        int d = 0, nzero = 0, sweeps = 0;
+        if (occupied) {
+            pid = A.index[item];
+            d = load_and_init<4>(tile, S, A, pid, nzero);
+        }
+        __syncwarp();
+        bool moving = occupied && d > 0;          // some root of my slot was still updated in its last sweep
+        bool gave_up = false;
+
+        // ---- sweeps over the whole generation
+        // a slot that has converged waits for the generation to finish
+        while (__ballot_sync(0xffffffffu, moving) != 0u) {
+            if (moving) {
+                if (sweeps >= MAX_SWEEPS) { moving = false; gave_up = true; }
+                else {
+                    ++sweeps;
+                    int nact = 0;
+                    for (int r0 = 0; r0 < d; r0 += 4) {
+                        const int i = r0 + l;
+                        const bool live = (i < d) && !S.frozen[i];
+                        const unsigned bal = tile.ballot(live);
+                        if (live) S.hull[nact + __popc(bal & ((1u << l) - 1u))] = i;
+                        nact += __popc(bal);
+                    }
+                    tile.sync();
+                    bool mine_done = true;
+                    for (int r0 = 0; r0 < nact; r0 += 4) {
+                        const bool active = r0 + l < nact;
+                        const int i = active ? S.hull[r0 + l] : 0;
+                        cplx znew = {0.0, 0.0};
+                        bool freeze = false, stagnant = false;
+                        if (active) {
+                            aberth_update(S, d, i, znew, freeze, stagnant);
+                            if (!freeze) mine_done = false;
+                        }
+                        tile.sync();               // everybody has read the old estimates of this round
+                        if (active) {
+                            if (freeze) S.frozen[i] = 1;
+                            else { S.zz[i] = make_double2(znew.r, znew.i); if (stagnant) S.frozen[i] = 1; }
+                        }
+                        tile.sync();
+                    }
+                    if (tile.all(mine_done)) moving = false;
                 }
             }
-            const unsigned bal = tile.ballot(keep);
-            if (keep) {
-                const int pos = kept + __popc(bal & ((1u << l) - 1u));
-                ore[pos] = v.r;
-                oim[pos] = v.i;
-            }
-            kept += __popc(bal);
         }
-        for (int k = kept + l; k < A.maxdeg; k += G) { ore[k] = nan(""); oim[k] = nan(""); }
-        if (l == 0) {
-            if (A.n_kept) A.n_kept[pid] = kept;
-            if (A.iters) A.iters[pid] = all_done ? sweeps : -sweeps;
-        }
-        tile.sync();
+
+        // ---- the generation's results
+        if (occupied) write_output<4>(tile, S, A, pid, d, nzero, sweeps, !gave_up);
+        __syncwarp();
     }
 }
 
@@ -449,7 +574,22 @@ int32_t roots_enqueue(const double* toprows, const int* deg, long long npoly, in
     A.out_re = out_re; A.out_im = out_im; A.n_kept = n_kept; A.iters = iters;
     int n = 3;
     A.cls = 0; A.smem_deg = maxdeg < CLASS_SMALL_MAX ? maxdeg : CLASS_SMALL_MAX;
-    if ((rc = launch_roots<4>(A, npoly, s)) != LM_OK) return rc;
+    {
+        const size_t smem = group_smem_bytes(A.smem_deg) * POOL_SLOTS * POOL_WARPS;
+        static int per_sm = 0;
+        static size_t per_sm_smem = 0;
+        if (per_sm == 0 || per_sm_smem != smem) {
+            LM_CUDA_TRY(cudaFuncSetAttribute(roots_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            LM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, roots_pool_kernel, ROOTS_THREADS, smem));
+            if (per_sm < 1) per_sm = 1;
+            per_sm_smem = smem;
+        }
+        long long blocks = (npoly + POOL_SLOTS * POOL_WARPS - 1) / (POOL_SLOTS * POOL_WARPS);
+        const long long cap = static_cast<long long>(lm::sm_count()) * per_sm;      // persistent CTAs, polynomials by work stealing
+        if (blocks > cap) blocks = cap;
+        roots_pool_kernel<<<static_cast<unsigned>(blocks), ROOTS_THREADS, smem, s>>>(A);
+        LM_CUDA_TRY(cudaGetLastError());
+    }
     ++n;
     if (maxdeg > CLASS_SMALL_MAX) {
         A.cls = 1; A.smem_deg = maxdeg < CLASS_MID_MAX ? maxdeg : CLASS_MID_MAX;
