@@ -383,6 +383,15 @@ int32_t lm_weighted_cauchy_sum(const double* z_re, const double* z_im, int64_t M
                                const double* node_re, const double* node_im, const double* weight, int64_t N,
                                double dz_eps, double* out_re, double* out_im, lm_stats* stats);
 
+/* ---- local-polynomial curvature of an ordered boundary ------------- */
+/* compute_curvature_localpoly(P, neighbors, closed, stride=1), boundary_curvature_localpoly.py:133-184:
+ * per point a least-squares quadratic in arclength over the window i-neighbors..i+neighbors (wrapped when
+ * closed != 0, clamped otherwise); kappa_signed = (x'y'' - y'x'') / (|(x',y')| + 1e-16)^3.  x, y: the n
+ * ordered points (the two columns of <prefix>_boundary.csv).  xprime..y2 may be NULL.                   */
+int32_t lm_curvature_localpoly(const double* x, const double* y, int64_t n, int32_t neighbors, int32_t closed,
+                               double* kappa, double* kappa_signed, double* speed,
+                               double* xprime, double* yprime, double* x2, double* y2, lm_stats* stats);
+
 /* ---- measurement probes -------------------------------------------------------- */
 /* Dependent-free DFMA loop on every SM: FP64 peak (TFLOP/s, 2 flops per DFMA) and a
  * DMUL/DADD-only variant (the unfused mix K1 needs).  Used by bench.py for the

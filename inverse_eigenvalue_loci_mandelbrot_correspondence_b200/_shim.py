@@ -33,7 +33,7 @@ EXPORTS = (
     "lm_roots_batched", "lm_roots_batched_dev", "lm_cloud_compact_dev", "lm_cloud_append_dev", "lm_lucas_cloud_fields", "lm_escape_points_f64_dev",
     "lm_laplacian5_periodic", "lm_laplacian5_periodic_dev", "lm_smooth5_interior", "lm_smooth5_interior_dev",
     "lm_log_potential", "lm_log_potential_sums_dev", "lm_log_potential_finish_dev",
-    "lm_nearest_match", "lm_weighted_log_sum", "lm_weighted_cauchy_sum",
+    "lm_nearest_match", "lm_weighted_log_sum", "lm_weighted_cauchy_sum", "lm_curvature_localpoly",
     "lm_probe_fp64_peak", "lm_probe_fp64_latency", "lm_probe_k1_loop", "lm_probe_hbm_copy",
 )
 
@@ -121,6 +121,7 @@ _SIGNATURES = {
     "lm_nearest_match": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _pStats]),
     "lm_weighted_log_sum": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _f64, _vp, _pStats]),
     "lm_weighted_cauchy_sum": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _f64, _vp, _vp, _pStats]),
+    "lm_curvature_localpoly": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _pStats]),
     "lm_probe_fp64_peak": (_i32, [_i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "lm_probe_fp64_latency": (_i32, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "lm_probe_k1_loop": (_i32, [_i32, _i32, _i32, C.POINTER(C.c_double)]),

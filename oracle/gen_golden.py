@@ -181,6 +181,22 @@ def main() -> None:
     g["green_g_real"] = obj.g_real(zt)
     g["green_dPhi"] = obj.dPhi(zt)
 
+    # ---- boundary consumer: local-polynomial curvature (boundary_curvature_localpoly.py:65-184) on a closed and an
+    # open curve at pixel-like spacing, including a repeated closing vertex like <prefix>_boundary.csv has
+    cv = load_defs("boundary_curvature_localpoly.py",
+                   ["local_arclength_parameters", "quadratic_design", "fit_quadratic", "curvature_from_param_quadratic",
+                    "index_window", "compute_curvature_localpoly"])
+    tt = np.linspace(0, 2 * np.pi, 181)
+    loop = np.c_[-0.75 + 3e-3 * (1 + 0.3 * np.cos(5 * tt)) * np.cos(tt), 0.1 + 3e-3 * (1 + 0.3 * np.cos(5 * tt)) * np.sin(tt)]
+    loop[-1] = loop[0]                                       # closed polyline repeats its first vertex
+    k, ks, sp, aux = cv["compute_curvature_localpoly"](loop, neighbors=7, closed=True, stride=1)
+    g["curv_closed_P"] = loop
+    g["curv_closed_out"] = np.c_[k, ks, sp, aux["xprime"], aux["yprime"], aux["x2"], aux["y2"]]
+    arc = np.c_[np.linspace(-1, 1, 90), 0.3 * np.linspace(-1, 1, 90) ** 3]
+    k, ks, sp, aux = cv["compute_curvature_localpoly"](arc, neighbors=4, closed=False, stride=3)
+    g["curv_open_P"] = arc
+    g["curv_open_out"] = np.c_[k, ks, sp, aux["xprime"], aux["yprime"], aux["x2"], aux["y2"]]
+
     OUT.parent.mkdir(parents=True, exist_ok=True)
     np.savez_compressed(OUT, **g)
     print(f"wrote {OUT} ({OUT.stat().st_size / 1024:.1f} KiB, {len(g)} arrays)")

@@ -169,6 +169,31 @@ def nearest_match(X, Y):
     return idx, dist
 
 
+def curvature_localpoly(P, neighbors: int = 7, closed: bool = True):
+    """compute_curvature_localpoly with stride 1 (boundary_curvature_localpoly.py:65-184), restated: window indices,
+    signed arclength from the centre, np.linalg.lstsq quadratics, curvature formula.  Returns [N, 7] columns
+    kappa, kappa_signed, speed, x', y', x'', y''."""
+    P = np.asarray(P, dtype=np.float64)
+    N, m = P.shape[0], int(neighbors)
+    out = np.zeros((N, 7))
+    for i in range(N):
+        idx = [(i + dlt) % N if closed else min(max(i + dlt, 0), N - 1) for dlt in range(-m, m + 1)]
+        XY = P[idx]
+        s = np.zeros(2 * m + 1)
+        for k in range(m + 1, 2 * m + 1):
+            s[k] = s[k - 1] + np.linalg.norm(XY[k] - XY[k - 1])
+        for k in range(m - 1, -1, -1):
+            s[k] = s[k + 1] - np.linalg.norm(XY[k + 1] - XY[k])
+        A = np.c_[np.ones_like(s), s, s ** 2]
+        ax = np.linalg.lstsq(A, XY[:, 0], rcond=None)[0]
+        bx = np.linalg.lstsq(A, XY[:, 1], rcond=None)[0]
+        x1, x2, y1, y2 = ax[1], 2.0 * ax[2], bx[1], 2.0 * bx[2]
+        sp = np.sqrt(x1 * x1 + y1 * y1) + 1e-16
+        ks = (x1 * y2 - y1 * x2) / sp ** 3
+        out[i] = [abs(ks), ks, sp, x1, y1, x2, y2]
+    return out
+
+
 def weighted_log_sum(z, nodes, weights, eps: float = 1e-300):
     """sum_n w_n log(|z_m - zeta_n| + eps): the matrix-vector product inside g_real,
     lucas_to_cardioid_v40_reference.py:252-253, written as one numpy expression."""

@@ -73,3 +73,11 @@ def lines_equal(a, b) -> bool:
     if len(a) != len(b):
         return False
     return all(x.shape == y.shape and np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def assert_columns_close(got, want, rtol: float, afrac: float, cols=None) -> None:
+    """Column-wise allclose with an absolute floor proportional to each column's largest magnitude."""
+    got = np.asarray(got); want = np.asarray(want)
+    for j in (range(want.shape[1]) if cols is None else cols):
+        np.testing.assert_allclose(got[:, j], want[:, j], rtol=rtol, atol=afrac * float(np.abs(want[:, j]).max()),
+                                   err_msg=f"column {j}")

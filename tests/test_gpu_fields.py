@@ -100,3 +100,30 @@ def test_green_function_sums(gpu, oracle, golden):
     assert nystrom.weighted_log_sum(np.zeros(0, complex), nodes, w).shape == (0,)
     with pytest.raises(ValueError):
         nystrom.weighted_log_sum(zz, nodes, w[:-1])
+
+
+def test_curvature_localpoly(gpu, oracle, golden):
+    """the boundary consumer.  The fit is ill-conditioned in arclength at pixel spacing (cond ~ 1e6), so the
+    GPU's scaled QR and LAPACK's SVD agree to ~1e-8 relative on the second derivatives; first derivatives and
+    speed to 1e-11."""
+    from helpers import assert_columns_close
+    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import curvature
+    for tag, m, closed, stride in (("curv_closed", 7, True, 1), ("curv_open", 4, False, 3)):
+        P, want = golden[tag + "_P"], golden[tag + "_out"]
+        k, ks, sp, aux = curvature.compute_curvature_localpoly(P, neighbors=m, closed=closed, stride=stride)
+        got = np.c_[k, ks, sp, aux["xprime"], aux["yprime"], aux["x2"], aux["y2"]]
+        assert_columns_close(got, want, 1e-10, 1e-11, cols=(2, 3, 4))
+        assert_columns_close(got, want, 1e-7, 1e-8, cols=(0, 1, 5, 6))
+    # a circle of radius r has curvature 1/r; the real boundary of config 1 through the whole chain
+    th = np.linspace(0, 2 * np.pi, 4000, endpoint=False)
+    k, ks, sp, _ = curvature.compute_curvature_localpoly(np.c_[2.5 * np.cos(th), 2.5 * np.sin(th)], neighbors=7, closed=True)
+    np.testing.assert_allclose(k, 0.4, rtol=1e-4)            # chord discretisation of the local fit
+    assert (ks > 0).all()                                    # counter-clockwise: positive signed curvature
+    xs = np.linspace(-2.1, 0.9, 600); ys = np.linspace(-1.5, 1.5, 600)
+    lines, _ = gpu.contour.boundary_sample(xs, ys, 300, 288.0)
+    B = gpu.contour.longest(lines)
+    k, ks, sp, _ = curvature.compute_curvature_localpoly(B, neighbors=7, closed=True)
+    want = oracle.curvature_localpoly(B[:400], 7, False)      # interior of an open window: same fits away from its ends
+    np.testing.assert_allclose(ks[20:380], want[20:380, 1], rtol=1e-6, atol=1e-6 * np.abs(want[:, 1]).max())
+    with pytest.raises(ValueError):
+        curvature.compute_curvature_localpoly(B, neighbors=1)

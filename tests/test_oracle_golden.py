@@ -143,3 +143,13 @@ def test_green_function_sums(oracle, golden):
     got = -1.0 / DZ0 + oracle.weighted_cauchy_sum(z, bdy, sig * ds, 1e-14)
     np.testing.assert_allclose(got, golden["green_dPhi"], rtol=1e-12, atol=1e-12 * np.abs(golden["green_dPhi"]).max())
     assert np.isfinite(golden["green_g_real"][:-1]).all()
+
+
+def test_curvature_localpoly(oracle, golden):
+    """The oracle's restatement against compute_curvature_localpoly of the reference (boundary_curvature_localpoly.py)."""
+    from helpers import assert_columns_close
+    got = oracle.curvature_localpoly(golden["curv_closed_P"], 7, True)
+    assert_columns_close(got, golden["curv_closed_out"], 1e-9, 1e-9)
+    got = oracle.curvature_localpoly(golden["curv_open_P"], 4, False)
+    want = golden["curv_open_out"]                         # stride 3: every third point is a fit, the rest interpolated
+    assert_columns_close(got[::3], want[::3], 1e-9, 1e-9)
