@@ -470,8 +470,10 @@ def cpu_roots_pass(npoly_sample: int, procs: int):
     """numpy (LAPACK dgeev) on the first npoly_sample polynomials of chunk 0, `procs` worker processes.
     -> (roots, seconds)"""
     import multiprocessing as mp
-    top, deg = cfg5_chunk(0)
-    top, deg = top[:npoly_sample], deg[:npoly_sample]
+    per_chunk = CFG5["npoly"] // CFG5["chunks"]
+    parts = [cfg5_chunk(k) for k in range(min(CFG5["chunks"], (npoly_sample + per_chunk - 1) // per_chunk))]
+    top = np.concatenate([p[0] for p in parts])[:npoly_sample]
+    deg = np.concatenate([p[1] for p in parts])[:npoly_sample]
     jobs = []
     for d in range(2, CFG5["maxdeg"] + 1):
         sel = np.where(deg == d)[0]
@@ -491,7 +493,7 @@ def cpu_roots_baseline(target_s: float = 10.0) -> dict:
     procs = os.cpu_count() or 1
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
     roots, dt = cpu_roots_pass(4000 * procs, procs)
-    n = int(min(max(4000 * procs * target_s / max(dt, 1e-3), 4000 * procs), CFG5["npoly"] // CFG5["chunks"]))
+    n = int(min(max(4000 * procs * target_s / max(dt, 1e-3), 4000 * procs), CFG5["npoly"] // 2))
     roots, dt = cpu_roots_pass(n, procs)
     return {"value": roots / dt / 1e6, "unit": "Mroots/s", "cores": procs, "kind": "reference",
             "sample": f"np.linalg.eigvals on the stacked companion matrices of the first {n} polynomials of the "
