@@ -362,6 +362,7 @@ def run_ours(args):
         st = _shim.Stats()
         edge_d = torch.empty(nx, dtype=torch.int32, device=dev)
         pot_p = _shim.pinned_empty((rows, nx), np.float64) if with_pot else None
+        job = sharding.ShardedBoundary(xs, ys, max_iter, level, device=dev, with_potential=with_pot, cuts=cuts) if world > 1 else None
 
         def e2e_step():
             if world == 1:
@@ -370,24 +371,12 @@ def run_ours(args):
                 # K1/K2 still run, K2 records -> ordered polylines on the host
                 lines, stx = contour.boundary_sample(xs_p, ys_p, max_iter, level, dwell_out=out, potential_out=pot_p)
                 return stx["work_units"], lines
-            # N > 1: K1 on this rank's rows through the host-buffer shard call (dwell block returned to the pinned
-            # host buffer by the copy stream AND kept in HBM), shard-edge rows all-gathered over NCCL straight
-            # from / into that block, K2 on it, records gathered and linked on rank 0
-            dev_block = C.c_void_p(); pot_block = C.c_void_p()
-            _shim.call("lm_shard_escape", _shim.ptr(xs_p), nx, _shim.ptr(ys_p), rows, max_iter, _shim.ptr(out), _shim.ptr(pot_p), 1,
-                       C.byref(dev_block), C.byref(pot_block), C.byref(st))
-            if with_pot:        # final potential field on every GPU: all-gather straight from the resident block
-                _shim.call("lm_memcpy_d2d", C.c_void_p(field_d.data_ptr()), pot_block, rows * nx * 8, stream)
-                full_field["t"] = sharding.allgather_rows(field_d, cuts)
-            _shim.call("lm_memcpy_d2d", C.c_void_p(edge_d.data_ptr()), dev_block, nx * 4, stream)
-            firsts = sharding.exchange_first_rows(edge_d)
-            if has_halo:
-                _shim.call("lm_memcpy_d2d", C.c_void_p(dev_block.value + rows * nx * 4), C.c_void_p(firsts[rank + 1].data_ptr()),
-                           nx * 4, stream)
-            recs_local = classify(dev_block, rows + (1 if has_halo else 0))
-            allrec = sharding.gather_records(recs_local, dev, 0)
-            lines = contour.link_records(allrec, xs, ys, level) if rank == 0 else None
-            return st.work_units, lines
+            # N > 1: the package's sharded boundary stage (sharding.ShardedBoundary.run): K1 on this rank's rows
+            # through the host-buffer shard call (block returned to pinned host memory AND kept in HBM), shard-edge
+            # rows all-gathered over NCCL straight from / into those blocks, K2 on them, records gathered and
+            # linked on rank 0
+            lines = job.run(stream)
+            return job.last_work_units, lines
 
         e2e_step()
         barrier()
@@ -407,10 +396,10 @@ def run_ours(args):
         n_vertices = int(lines.lengths().max()) if lines is not None and len(lines) else 0
         e2e = {"value": int(ww[0]) / float(tt[0]) / 1e9, "unit": "Gpixel-iter/s",
                "h2d_bytes_per_step": int((nx + rows) * 8),
-               "d2h_bytes_per_step": int(rows * nx * (12 if with_pot else 4) + n_rec.value * 64), "ms_per_step": 1e3 * float(tt[0]) / args.steps,
+               "d2h_bytes_per_step": int(rows * nx * (12 if with_pot else 4) + (job.n_records if job else n_rec.value) * 64), "ms_per_step": 1e3 * float(tt[0]) / args.steps,
                "boundary_vertices": n_vertices,
                "api": ("lm_boundary_sample (pinned numpy buffers in, dwell grid + ordered boundary polylines out)" if world == 1 else
-                       "lm_shard_escape (pinned numpy buffers; block kept in HBM) + NCCL edge rows + lm_contour_classify_dev + lm_contour_link")}
+                       "sharding.ShardedBoundary.run: lm_shard_escape (pinned numpy buffers; block kept in HBM) + NCCL edge rows + lm_contour_classify_dev + lm_contour_link")}
 
     # ---- the other half of BASELINE.json's metric: Lucas roots/s (K3) on the config-5 batch, sharded by polynomial
     lucas_roots = None

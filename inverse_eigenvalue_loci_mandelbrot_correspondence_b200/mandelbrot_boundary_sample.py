@@ -11,6 +11,11 @@ Outputs (mandelbrot_boundary_sample.py:71-90):
 
 compute_grid and extract_contour keep the reference signatures; the dwell grid stays on the
 GPU between the two stages when main() drives them (only the boundary polyline comes back).
+
+Several GPUs: launch the same module with torchrun, one process per GPU --
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+        -m inverse_eigenvalue_loci_mandelbrot_correspondence_b200.mandelbrot_boundary_sample --res 32768 ...
+the rows are sharded over the ranks (sharding.ShardedBoundary), rank 0 writes the three files.
 """
 from __future__ import annotations
 
@@ -27,9 +32,23 @@ FAIL_MSG = "Failed to extract a usable contour. Try different --level or higher 
 
 
 def boundary_from_window(xlim, ylim, res: int, max_iter: int, level_frac: float):
-    """compute_grid + extract_contour with the dwell grid kept resident on the device."""
+    """compute_grid + extract_contour with the dwell grid kept resident on the device.  Under torchrun
+    (WORLD_SIZE > 1) the rows are sharded over the ranks; the contour comes back on rank 0 (None elsewhere)."""
     xs = np.linspace(xlim[0], xlim[1], res)
     ys = np.linspace(ylim[0], ylim[1], res)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch
+        import torch.distributed as dist
+        from . import _shim, sharding
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local); _shim.set_device(local)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        job = sharding.ShardedBoundary(xs, ys, max_iter, level_frac * max_iter)
+        lines = job.run()
+        dist.barrier()
+        dist.destroy_process_group()
+        return xs, ys, (_contour.longest(lines) if lines is not None else None)
     lines, _ = _contour.boundary_sample(xs, ys, max_iter, level_frac * max_iter)
     return xs, ys, _contour.longest(lines)
 
@@ -69,6 +88,8 @@ def main(argv=None):
     args = ap.parse_args(argv)
 
     _, _, contour = boundary_from_window(args.xlim, args.ylim, args.res, args.max_iter, args.level)
+    if int(os.environ.get("RANK", "0")) != 0:
+        return                                   # sharded run: rank 0 holds the contour and writes the files
     if contour is None or contour.shape[0] < 50:
         raise SystemExit(FAIL_MSG)
     out_csv, out_png, out_meta = save_outputs(contour, args.output_prefix, args.xlim, args.ylim, args.res,

@@ -175,3 +175,116 @@ def exchange_halo_rows(block, periodic: bool, group=None):
     above = allv[(rank - 1) % world, 1] if (periodic or rank > 0) else None
     below = allv[(rank + 1) % world, 0] if (periodic or rank < world - 1) else None
     return above, below
+
+
+# ---- the boundary stage of the script on N GPUs (one process per GPU, torch.distributed initialised) ----
+class ShardedBoundary:
+    """compute_grid + extract_contour (mandelbrot_boundary_sample.py:66-67) with the rows sharded over the ranks.
+
+    Every rank computes K1 on its row block through the host-buffer shard call (the block comes back to a pinned
+    host array AND stays in HBM with a halo slot), the first dwell row of every block is all-gathered over NCCL
+    straight from / into those blocks, K2 classifies each block on the device, the records are gathered to
+    rank 0 and linked once.  Cuts come from a coarse K1 pre-pass; `refine()` re-cuts from measured block times.
+    Works with world size 1 too (then it is just the fused single-GPU call)."""
+
+    def __init__(self, xs, ys, max_iter: int, level: float, device=None, with_potential: bool = False, cuts=None):
+        import torch
+        import torch.distributed as dist
+        from . import _shim
+        self.xs = np.ascontiguousarray(xs, dtype=np.float64).ravel()
+        self.ys = np.ascontiguousarray(ys, dtype=np.float64).ravel()
+        self.max_iter, self.level, self.with_potential = int(max_iter), float(level), bool(with_potential)
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if cuts is None:
+            if self.world > 1:
+                self.profile = coarse_row_profile(self.xs, self.ys, self.max_iter)
+                cuts = balanced_row_cuts(self.profile, self.world)
+            else:
+                self.profile = np.ones(self.ys.size)
+                cuts = [0, self.ys.size]
+        else:
+            self.profile = np.ones(self.ys.size)
+        self._set_cuts(cuts)
+        self._shim = _shim
+        self.last_work_units = 0
+
+    def _set_cuts(self, cuts):
+        from . import _shim
+        import torch
+        self.cuts = [int(c) for c in cuts]
+        self.r0, self.r1 = self.cuts[self.rank], self.cuts[self.rank + 1]
+        self.rows = self.r1 - self.r0
+        self.has_halo = self.rank < self.world - 1
+        nx = self.xs.size
+        self.dwell = _shim.pinned_empty((self.rows, nx), np.int32)             # this rank's rows, page-locked
+        self.potential = _shim.pinned_empty((self.rows, nx), np.float64) if self.with_potential else None
+        self.ys_rows = np.ascontiguousarray(self.ys[self.r0:self.r1])
+        self.ys_block = np.ascontiguousarray(self.ys[self.r0:self.r1 + (1 if self.has_halo else 0)])
+        self._edge = torch.empty(nx, dtype=torch.int32, device=self.device)
+        self._field = (torch.empty((self.rows, nx), dtype=torch.float64, device=self.device)
+                       if (self.with_potential and self.world > 1) else None)
+        self._records = np.empty((max(int(0.01 * self.rows * nx) + 4096, 1 << 16), 8), dtype=np.int64)
+        self.full_potential = None
+
+    def refine(self, rounds: int = 2):
+        """Measured rebalancing: time K1 on the current blocks on every rank, rescale the profile, cut again."""
+        import time
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return self.cuts
+        for _ in range(rounds):
+            st = self._shim.Stats()
+            blk = C.c_void_p(); pblk = C.c_void_p()
+            dist.barrier()
+            self._shim.call("lm_shard_escape", self._shim.ptr(self.xs), self.xs.size, self._shim.ptr(self.ys_rows), self.rows,
+                            self.max_iter, None, None, 1, C.byref(blk), C.byref(pblk), C.byref(st))
+            t_all = torch.zeros(self.world, dtype=torch.float64, device=self.device)
+            t_all[self.rank] = float(st.kernel_ms)
+            dist.all_reduce(t_all)
+            self._set_cuts(refine_cuts(self.profile, self.cuts, t_all.cpu().numpy()))
+        return self.cuts
+
+    def run(self, stream=None):
+        """One pass.  Returns the polylines on rank 0 (None elsewhere); self.dwell / self.potential hold this rank's
+        rows, self.full_potential the all-gathered field (device tensor) when asked for."""
+        import ctypes as C
+        from . import contour
+        shim = self._shim
+        nx = self.xs.size
+        if self.world == 1:
+            lines, st = contour.boundary_sample(self.xs, self.ys, self.max_iter, self.level, dwell_out=self.dwell,
+                                                potential_out=self.potential)
+            self.last_work_units = int(st["work_units"])
+            return lines
+        st = shim.Stats()
+        blk = C.c_void_p(); pblk = C.c_void_p()
+        shim.call("lm_shard_escape", shim.ptr(self.xs), nx, shim.ptr(self.ys_rows), self.rows, self.max_iter,
+                  shim.ptr(self.dwell), shim.ptr(self.potential), 1, C.byref(blk), C.byref(pblk), C.byref(st))
+        self.last_work_units = int(st.work_units)
+        if self.with_potential:     # final potential field on every GPU: all-gather straight from the resident block
+            shim.call("lm_memcpy_d2d", C.c_void_p(self._field.data_ptr()), pblk, self.rows * nx * 8, stream)
+            self.full_potential = allgather_rows(self._field, self.cuts)
+        shim.call("lm_memcpy_d2d", C.c_void_p(self._edge.data_ptr()), blk, nx * 4, stream)
+        firsts = exchange_first_rows(self._edge)
+        if self.has_halo:
+            shim.call("lm_memcpy_d2d", C.c_void_p(blk.value + self.rows * nx * 4), C.c_void_p(firsts[self.rank + 1].data_ptr()),
+                      nx * 4, stream)
+        n_rec = C.c_int64(0)
+        lib = shim.load()
+        while True:
+            rc = lib.lm_contour_classify_dev(blk, shim.ptr(self.xs), nx, shim.ptr(self.ys_block), self.ys_block.size, self.r0,
+                                             self.level, shim.ptr(self._records), self._records.shape[0], C.byref(n_rec), stream)
+            if rc == shim.LM_E_CAP:
+                self._records = np.empty((n_rec.value + 1024, 8), dtype=np.int64)
+                continue
+            shim.check(rc)
+            break
+        self.n_records = int(n_rec.value)
+        allrec = gather_records(self._records[: n_rec.value], self.device, 0)
+        if self.rank != 0:
+            return None
+        return contour.link_records(allrec, self.xs, self.ys, self.level)
