@@ -288,3 +288,55 @@ class ShardedBoundary:
         if self.rank != 0:
             return None
         return contour.link_records(allrec, self.xs, self.ys, self.level)
+
+
+def sharded_cloud_fields(toprows_local, deg_local, grid_x, grid_y, tol: float = 1e-12, eps: float = 1e-12, variant: int = 0,
+                         h: float | None = None, potential: tuple | None = None, device=None, stream=None) -> dict:
+    """lucas.cloud_fields with the polynomials sharded over the ranks (one process per GPU): every rank passes ITS
+    slice of the batch (see item_slices), runs K3 -> cloud -> K1d -> K4a partial sums on it, the per-cell sums and
+    the cloud sizes are all-reduced (NCCL), and every rank ends with the same U and Laplacian.
+    Returns {"cloud" (this rank's points, complex), "g", "it" (this rank's), "U", "lapU", "n_points_total"}."""
+    import ctypes as C
+    import torch
+    from . import _shim
+    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    P = lambda t: C.c_void_p(t.data_ptr())
+    top_h = np.ascontiguousarray(toprows_local, dtype=np.float64)
+    deg_h = np.ascontiguousarray(deg_local, dtype=np.int32).reshape(-1)
+    npoly, maxdeg = top_h.shape
+    nroots = int(np.clip(deg_h, 0, None).sum())
+    top = torch.from_numpy(top_h).to(dev); deg = torch.from_numpy(deg_h).to(dev)
+    re = torch.empty((max(npoly, 1), maxdeg), dtype=torch.float64, device=dev); im = torch.empty_like(re)
+    kept = torch.empty(max(npoly, 1), dtype=torch.int32, device=dev)
+    status = torch.zeros(2, dtype=torch.int32, device=dev)
+    px = torch.empty(max(nroots, 1), dtype=torch.float64, device=dev); py = torch.empty_like(px)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    _shim.call("lm_roots_batched_dev", P(top), P(deg), npoly, maxdeg, 1, float(tol), P(re), P(im), P(kept), None, P(status), stream)
+    _shim.call("lm_cloud_compact_dev", P(re), P(im), P(kept), npoly, maxdeg, P(px), P(py), nroots, P(cnt), stream)
+    n_local = int(cnt.item())
+    flags = status.cpu().numpy()
+    if flags[1]:
+        raise ValueError("a degree outside [1, maxdeg]")
+    out = {"cloud": px[:n_local].cpu().numpy() + 1j * py[:n_local].cpu().numpy(), "g": None, "it": None}
+    if potential is not None:
+        g = torch.empty(max(n_local, 1), dtype=torch.float64, device=dev)
+        it = torch.empty(max(n_local, 1), dtype=torch.int64, device=dev)
+        _shim.call("lm_escape_points_f64_dev", P(px), P(py), n_local, int(potential[0]), float(potential[1]), P(g), P(it),
+                   None, None, None, stream)
+        out["g"], out["it"] = g[:n_local].cpu().numpy(), it[:n_local].cpu().numpy()
+    gx = torch.from_numpy(np.ascontiguousarray(grid_x, dtype=np.float64).ravel()).to(dev)
+    gy = torch.from_numpy(np.ascontiguousarray(grid_y, dtype=np.float64).ravel()).to(dev)
+    nx, ny = gx.numel(), gy.numel()
+    sums = torch.empty(nx * ny, dtype=torch.float64, device=dev)
+    _shim.call("lm_log_potential_sums_dev", P(px), P(py), n_local, P(gx), nx, P(gy), ny, float(eps), int(variant), P(sums), stream)
+    _, n_total = allreduce_field_sums(sums, n_local)
+    U = torch.empty_like(sums); lap = torch.empty_like(sums)
+    _shim.call("lm_log_potential_finish_dev", P(sums), nx * ny, n_total, int(variant), P(U), stream)
+    if h is None:
+        h = float(gx[1] - gx[0]) if nx > 1 else 1.0
+    _shim.call("lm_laplacian5_periodic_dev", P(U), ny, nx, float(h), P(lap), stream)
+    out["U"] = U.cpu().numpy().reshape(ny, nx); out["lapU"] = lap.cpu().numpy().reshape(ny, nx)
+    out["n_points_total"] = n_total
+    if flags[0]:
+        raise RuntimeError("the Aberth iteration did not converge for some polynomial")
+    return out

@@ -132,3 +132,16 @@ def test_degree_sort_mixed_classes(gpu, oracle):
     assert list(kept) == degs and (iters > 0).all()
     for k, d in enumerate(degs):
         assert match_sorted_complex(vals[k, :d], oracle.inverse_eigenvalues_toprow(np.ones(d), 1e-10)) < 1e-9
+
+
+def test_sharded_cloud_fields_world1(gpu, oracle):
+    """The multi-GPU cloud stage (sharding.sharded_cloud_fields) at world size 1: same fields as the fused single call."""
+    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import sharding
+    top, deg = _batch(800, seed=5)
+    gx = np.linspace(-2, 2, 40); gy = np.linspace(-2, 2, 36)
+    a = gpu.lucas.cloud_fields(top, deg, gx, gy, potential=(700, 2.0))
+    b = sharding.sharded_cloud_fields(top, deg, gx, gy, potential=(700, 2.0))
+    assert b["n_points_total"] == a["n_points"] and np.array_equal(b["cloud"], a["cloud"])
+    assert np.array_equal(b["it"], a["it"]) and np.array_equal(b["g"], a["g"])
+    np.testing.assert_allclose(b["U"], a["U"], rtol=1e-13, atol=1e-14)
+    assert np.array_equal(b["lapU"], oracle.laplacian(b["U"], gx[1] - gx[0]))
