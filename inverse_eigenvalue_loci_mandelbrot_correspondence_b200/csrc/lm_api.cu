@@ -72,7 +72,15 @@ int32_t ws_get(WsSlot slot, size_t bytes, void** out) {
     return LM_OK;
 }
 
+static void (*g_hooks[16])() = {};
+static int g_nhooks = 0;
+void register_release_hook(void (*fn)()) {
+    for (int i = 0; i < g_nhooks; ++i) if (g_hooks[i] == fn) return;
+    if (g_nhooks < 16) g_hooks[g_nhooks++] = fn;
+}
+
 void ws_release_all() {
+    for (int i = 0; i < g_nhooks; ++i) g_hooks[i]();
     int cur = 0;
     if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); return; }
     for (int i = 0; i < WS_NSLOTS; ++i) {

@@ -60,6 +60,10 @@ int32_t lm_lucas_cloud_fields(const double* toprows, const int32_t* deg, int64_t
     static int s_dev = -1;
     static long long* h_note = nullptr;          // pinned: [c] running cloud size after chunk c, then 2 flags per chunk
     static int h_note_cap = 0;
+    lm::register_release_hook([] {
+        if (s) { cudaStreamDestroy(s); cudaStreamDestroy(s_in); cudaStreamDestroy(s_out); s = s_in = s_out = nullptr; s_dev = -1; }
+        if (h_note) { cudaFreeHost(h_note); h_note = nullptr; h_note_cap = 0; }
+    });
     int dev = 0;
     LM_CUDA_TRY(cudaGetDevice(&dev));
     if (s_dev != dev) {

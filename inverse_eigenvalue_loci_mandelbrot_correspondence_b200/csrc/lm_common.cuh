@@ -47,6 +47,9 @@ enum WsSlot {
 };
 int32_t ws_get(WsSlot slot, size_t bytes, void** out);
 void    ws_release_all();
+// Translation units that cache page-locked staging buffers / streams of their own register a hook that
+// lm_release_workspace() runs before the device workspaces are freed.
+void    register_release_hook(void (*fn)());
 
 // RAII-free helper for event timing on a stream.
 struct Timer {

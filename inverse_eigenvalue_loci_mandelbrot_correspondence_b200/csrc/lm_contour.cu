@@ -622,6 +622,7 @@ int32_t classify_device(const int* dwell_dev, const double* xs_host, long long n
         // page-locked staging buffer, cached across calls (records are read by the host linker)
         static long long* h_stage = nullptr;
         static size_t h_cap = 0;
+        lm::register_release_hook([] { if (h_stage) { cudaFreeHost(h_stage); h_stage = nullptr; h_cap = 0; } });
         const size_t need = static_cast<size_t>(total) * REC_WORDS * sizeof(long long);
         if (need > h_cap) {
             if (h_stage) cudaFreeHost(h_stage);

@@ -542,6 +542,9 @@ int32_t grid_host_begin(const double* xs, int64_t nx, const double* ys, int64_t 
     job->npx = npx;
     static cudaStream_t s_compute = nullptr, s_copy = nullptr;
     static int s_dev = -1;
+    lm::register_release_hook([] {
+        if (s_compute) { cudaStreamDestroy(s_compute); cudaStreamDestroy(s_copy); s_compute = s_copy = nullptr; s_dev = -1; }
+    });
     int dev = 0;
     LM_CUDA_TRY(cudaGetDevice(&dev));
     if (s_dev != dev) {      // (re)create the two pipeline streams on the current device

@@ -164,3 +164,18 @@ def test_full_size_properties_config2(gpu):
     mirrored, _, _ = gpu.escape.escape_grid(xs, -ys[4000:4016], mi)
     assert np.array_equal(mirrored, strip)
     assert 0.16 < (d == mi).mean() < 0.175
+
+
+def test_release_workspace_and_reuse(gpu, oracle):
+    """lm_release_workspace frees the cached device buffers, page-locked staging buffers and pipeline streams; the
+    next calls re-create them."""
+    xs = np.linspace(-2.1, 0.9, 300); ys = np.linspace(-1.5, 1.5, 200)
+    want, _ = oracle.dwell_grid(xs, ys, 150)
+    for _ in range(2):
+        lines, _ = gpu.contour.boundary_sample(xs, ys, 150, 144.0)
+        d, _, _ = gpu.escape.escape_grid(xs, ys, 150)
+        assert np.array_equal(d, want) and len(lines) > 0
+        top = np.ones((5, 6)); deg = np.arange(2, 7, dtype=np.int32)
+        top[np.arange(6)[None, :] >= deg[:, None]] = 0.0
+        assert gpu.lucas.cloud_fields(top, deg)["n_points"] == int(deg.sum())
+        gpu.shim.call("lm_release_workspace")
