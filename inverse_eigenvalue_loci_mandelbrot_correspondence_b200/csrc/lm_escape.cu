@@ -51,10 +51,13 @@ namespace {
 #define LM_K1_MIN_CTAS 3
 #endif
 #ifndef LM_K1_FB
-#define LM_K1_FB 32
+#define LM_K1_FB 64
 #endif
 #ifndef LM_K1_COOL_MIN
-#define LM_K1_COOL_MIN 16
+#define LM_K1_COOL_MIN 4
+#endif
+#ifndef LM_K1_REDO_ESCAPED_ONLY
+#define LM_K1_REDO_ESCAPED_ONLY 1
 #endif
 
 constexpr int TILE = 128;          // pixels per tile (one int4 per lane)
@@ -303,7 +306,35 @@ __global__ void __launch_bounds__(CTA_THREADS, LM_K1_MIN_CTAS) lm_escape_kernel(
 #pragma unroll
                 for (int k = 0; k < FB; ++k) LM_STEP6();
                 const double m = __dadd_rn(a, b);
-                if (__any_sync(FULL, !(m <= A.thr2))) {
+                const bool esc = !(m <= A.thr2);
+#if LM_K1_REDO_ESCAPED_ONLY
+                if (__any_sync(FULL, esc)) {
+                    // Some lane escaped inside this block.  The lanes that did not keep the FB iterations they
+                    // just made (their end-of-block test proves no earlier escape); only the escaped lanes go
+                    // back to the saved state and repeat the block with the exact per-iteration test to find
+                    // their first-escape index.
+                    if (esc) {
+                        zr = szr; zi = szi; a = sa; b = sb;
+                        int k = 0;
+#pragma unroll 1
+                        for (; k < FB - 1; ++k) {
+                            LM_STEP6();
+                            if (__dadd_rn(a, b) > A.thr2) break;
+                        }
+                        if (k == FB - 1) LM_STEP6();          // not found earlier: it is the block's last iterate
+                        done = true; n_fin = n + k + 1;
+                        if (FIELD || HYPOT || POINTS) { ze_r = zr; ze_i = zi; }
+                    }
+                    n += FB;
+                    safe -= FB;
+                    break;                                      // to the handler: retire and refill
+                }
+                n += FB;
+                safe -= FB;
+                if (safe == 0) break;
+                continue;
+#else
+                if (__any_sync(FULL, esc)) {
                     zr = szr; zi = szi; a = sa; b = sb;     // some lane escaped in here: redo carefully
                     cool = 0;
                 } else {
@@ -312,6 +343,7 @@ __global__ void __launch_bounds__(CTA_THREADS, LM_K1_MIN_CTAS) lm_escape_kernel(
                     if (safe == 0) break;
                     continue;
                 }
+#endif
             }
             // ---- careful block: CB iterations with the exact test (first escape kept per lane)
             int cnt;

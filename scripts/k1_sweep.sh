@@ -1,10 +1,9 @@
 #!/bin/bash
-# Tuning sweep for K1 on the GPU box: rebuild with different -D tunables and time cfg3/cfg2.
-set -u
-cd "$(dirname "$0")/.."
-for defs in "" "-DLM_K1_FB=64" "-DLM_K1_FB=48" "-DLM_K1_FB=64 -DLM_K1_COOL_MIN=8" "-DLM_K1_MIN_CTAS=2" "-DLM_K1_WARPS=4 -DLM_K1_MIN_CTAS=6"; do
+# K1 tunables sweep (rebuilds the library with -D overrides; see csrc/lm_escape.cu)
+for defs in "-DLM_K1_FB=64 -DLM_K1_COOL_MIN=4" "-DLM_K1_FB=96 -DLM_K1_COOL_MIN=4" "-DLM_K1_FB=128 -DLM_K1_COOL_MIN=4" "-DLM_K1_FB=128 -DLM_K1_COOL_MIN=8" "-DLM_K1_FB=64 -DLM_K1_COOL_MIN=16" "-DLM_K1_FB=64 -DLM_K1_COOL_MIN=8"; do
   echo "=== defs: '$defs'"
-  LM_NVCC_DEFS="$defs" python -m inverse_eigenvalue_loci_mandelbrot_correspondence_b200.build > /dev/null 2>&1 || echo BUILD FAILED
-  LM_NVCC_DEFS="$defs" python scripts/k1_run.py --res 32768 --max_iter 10000 --reps 2 | tail -1
+  LM_NVCC_DEFS="$defs" python -m inverse_eigenvalue_loci_mandelbrot_correspondence_b200.build --force > /dev/null || { echo build failed; continue; }
   LM_NVCC_DEFS="$defs" python scripts/k1_run.py --res 8192 --max_iter 2000 --reps 3 | tail -1
+  LM_NVCC_DEFS="$defs" python scripts/k2_run.py --res 32768 --max_iter 10000 --reps 1 > /dev/null
+  LM_NVCC_DEFS="$defs" python bench.py --no-roots --no-cpu-baseline --no-e2e --steps 3 2>&1 | tail -1 | cut -c1-110
 done

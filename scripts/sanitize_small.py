@@ -1,0 +1,29 @@
+"""Small instances of every kernel family, for compute-sanitizer (one --tool per gpurun call)."""
+import sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import numpy as np
+from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import contour, curvature, escape, lucas, nystrom, potentials, stencils
+
+rng = np.random.default_rng(0)
+xs = np.linspace(-2.1, 0.9, 256); ys = np.linspace(-1.5, 1.5, 200)
+lines, st = contour.boundary_sample(xs, ys, 120, 115.2)                       # K1 chunked + bulk-copy mark + emit + link
+d, f, _ = escape.escape_grid(np.linspace(-2.1, 0.9, 301), ys, 120, 2.0, 1)    # field mode, ragged width
+l2 = contour.contour_lines(np.linspace(-2.1, 0.9, 301), ys, d, 115.2)         # register-load mark kernel
+pts = rng.uniform(-2.2, 1.0, 20000) + 1j * rng.uniform(-1.5, 1.5, 20000)
+g, it, phi = escape.batch_potential(pts, 600, 2.0)                            # two-pass point schedule
+deg = rng.integers(2, 26, size=2000).astype(np.int32)
+top = rng.integers(0, 3, size=(2000, 25)).astype(np.float64)
+top[np.arange(25)[None, :] >= deg[:, None]] = 0.0
+top[np.arange(2000), deg - 1] = np.maximum(top[np.arange(2000), deg - 1], 1.0)
+gx = np.linspace(-2, 2, 50)
+out = lucas.cloud_fields(top, deg, gx, gx, potential=(300, 2.0))              # K3 generations, compaction, K1d, K4a, K4
+hi = lucas.construct_points([40, 130])                                        # 8-lane and 32-lane solver classes
+U = potentials._logpot(pts.real[:3000], pts.imag[:3000], gx, gx, 1e-6, 3)     # general-eps K4a path
+L = stencils.laplacian(rng.standard_normal((64, 96)), 0.1); S = stencils.smooth5(rng.standard_normal((33, 41)))
+dd, esc = potentials.distance_grid(xs[:100], ys[:80], 100, 250.0, 1e-12, 2)
+i, dist = potentials.nearest_match(pts[:3000], pts[3000:5000])
+w = nystrom.weighted_log_sum(pts[:500], pts[500:900], rng.uniform(0, 1, 400))
+c = nystrom.weighted_cauchy_sum(pts[:500], pts[500:900], rng.uniform(0, 1, 400))
+k = curvature.compute_curvature_localpoly(contour.longest(lines), 7, True)
+print("sanitize_small ok:", len(lines), len(l2), int(it.sum()), out["n_points"], hi.size, float(U.sum()), i[:3], float(w[0]))
