@@ -349,8 +349,8 @@ def run_ours(args):
         "fp64_pipe_instr_util": k1_gpi * 1e9 * 6 / (peak_tflops.value * 1e12 / 2),
         "k1_gpixel_iter_per_s": k1_gpi,
         # dram__bytes_read.sum + dram__bytes_write.sum of this launch from one ncu --set full capture
-        # (profiles/r01_k1_escape_cfg3_ncu_full.csv: 0.105 GB read + 4.319 GB written; algorithmic output 4.295 GB)
-        "traffic": 4.4234e9 if (args.workload == "cfg3" and world == 1) else None,
+        # (profiles/r01_k1_escape_cfg3_ncu_full_v2.csv: 0.066 GB read + 4.263 GB written; algorithmic output 4.295 GB)
+        "traffic": 4.3289e9 if (args.workload == "cfg3" and world == 1) else None,
     }
 
     # ---- e2e through the host-buffer C ABI
