@@ -129,3 +129,22 @@ def test_png_and_csv_writers(tmp_path, shim):
     assert np.array_equal(back, contour)                       # %.18e round-trips binary64
     assert Path(png).read_bytes()[:8] == b"\x89PNG\r\n\x1a\n"
     assert Path(meta).read_text() == "xlim=[-2.1, 0.9]\nylim=[-1.5, 1.5]\nres=2000\nmax_iter=500\nlevel=0.96\n"
+
+
+def test_polylines_container():
+    """contour.Polylines: the lines of a level as a lazy sequence of views (what cs.allsegs[0] is to the reference)."""
+    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200.contour import Polylines, longest
+    verts = np.arange(20, dtype=np.float64).reshape(10, 2)
+    L = Polylines(verts, np.array([0, 3, 3, 7, 10], dtype=np.int64))
+    assert len(L) == 4 and [len(a) for a in L] == [3, 0, 4, 3]
+    assert np.array_equal(L[2], verts[3:7]) and np.array_equal(L[-1], verts[7:10])
+    assert [a.shape for a in L[1:3]] == [(0, 2), (4, 2)]
+    with pytest.raises(IndexError):
+        L[4]
+    assert np.array_equal(L.longest(), verts[3:7]) and np.array_equal(longest(L), verts[3:7])
+    assert np.array_equal(longest([verts[:2], verts[2:8], verts[8:]]), verts[2:8])     # plain lists still work
+    E = Polylines(np.empty((0, 2)), np.zeros(1, dtype=np.int64))
+    assert len(E) == 0 and not E and E.longest() is None and longest(E) is None and longest([]) is None
+    # ties: the FIRST of the longest lines, like max(paths, key=len)
+    T = Polylines(verts, np.array([0, 5, 10], dtype=np.int64))
+    assert np.array_equal(T.longest(), verts[:5])
