@@ -30,7 +30,10 @@
 namespace {
 
 constexpr int LP_THREADS = 256;
-constexpr int LP_CPT = 4;            // cells per thread, consecutive in x
+#ifndef LM_K4A_CPT
+#define LM_K4A_CPT 4
+#endif
+constexpr int LP_CPT = LM_K4A_CPT;   // cells per thread, consecutive in x (they share dy^2)
 constexpr int LP_CHUNK = 1024;       // points staged in shared memory per round
 constexpr int LP_GROUP = 16;         // terms per group product (range check / exponent extraction once per group)
 
