@@ -662,8 +662,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) cloud_gather_kernel(const double
                                                                     const unsigned long long* __restrict__ block_offsets,
                                                                     double* __restrict__ px, double* __restrict__ py,
                                                                     long long cap) {
+    // phase 1: exclusive offsets of the block's SCAN_THREADS * SCAN_ITEMS polynomials (thread t owns SCAN_ITEMS
+    // consecutive ones) into shared memory; phase 2: a warp per polynomial, lane r copies kept root r, so both
+    // the padded rows and the packed cloud are touched in contiguous runs
     __shared__ unsigned long long wsum[SCAN_THREADS / 32];
-    const long long base = static_cast<long long>(blockIdx.x) * (SCAN_THREADS * SCAN_ITEMS) + threadIdx.x * SCAN_ITEMS;
+    __shared__ unsigned long long s_pos[SCAN_THREADS * SCAN_ITEMS];
+    __shared__ int s_cnt[SCAN_THREADS * SCAN_ITEMS];
+    const long long block_base = static_cast<long long>(blockIdx.x) * (SCAN_THREADS * SCAN_ITEMS);
+    const long long base = block_base + threadIdx.x * SCAN_ITEMS;
     int cnt[SCAN_ITEMS];
     unsigned long long mine = 0;
 #pragma unroll
@@ -681,10 +687,18 @@ __global__ void __launch_bounds__(SCAN_THREADS) cloud_gather_kernel(const double
     unsigned long long pos = before + incl - mine;
 #pragma unroll
     for (int t = 0; t < SCAN_ITEMS; ++t) {
-        const long long pid = base + t;
-        for (int r = 0; r < cnt[t]; ++r) {
-            if (static_cast<long long>(pos) < cap) { px[pos] = re[pid * maxdeg + r]; py[pos] = im[pid * maxdeg + r]; }
-            ++pos;
+        s_pos[threadIdx.x * SCAN_ITEMS + t] = pos;
+        s_cnt[threadIdx.x * SCAN_ITEMS + t] = cnt[t];
+        pos += cnt[t];
+    }
+    __syncthreads();
+    for (int q = warp; q < SCAN_THREADS * SCAN_ITEMS; q += SCAN_THREADS / 32) {
+        const long long pid = block_base + q;
+        if (pid >= npoly) break;
+        const int c = s_cnt[q];
+        const unsigned long long p0 = s_pos[q];
+        for (int r = lane; r < c; r += 32) {
+            if (static_cast<long long>(p0 + r) < cap) { px[p0 + r] = re[pid * maxdeg + r]; py[p0 + r] = im[pid * maxdeg + r]; }
         }
     }
 }
