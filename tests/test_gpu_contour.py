@@ -46,7 +46,9 @@ def test_records_match_numpy_restatement(gpu, oracle):
     assert np.array_equal(recs[: n.value], want)
 
 
-@pytest.mark.parametrize("shape", [(2, 2), (2, 300), (300, 2), (3, 129), (5, 130)])
+@pytest.mark.parametrize("shape", [(2, 2), (2, 300), (300, 2), (3, 129), (5, 130),
+                                   # widths that are multiples of 4 take the bulk-copy mark kernel: tile / strip / row-group edges
+                                   (2, 4), (3, 8), (6, 1024), (9, 1028), (5, 1032), (7, 2052), (4, 132), (11, 128), (13, 2048)])
 def test_contour_small_and_ragged(gpu, oracle, shape):
     rng = np.random.default_rng(shape[0] * 1000 + shape[1])
     ny, nx = shape
