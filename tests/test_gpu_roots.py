@@ -118,3 +118,26 @@ def test_high_degree(gpu, oracle):
         ref = oracle.inverse_eigenvalues_toprow(np.ones(n), 1e-10)
         assert len(got) == n
         assert match_sorted_complex(got, ref) < 1e-9
+
+
+def test_generation_kernel_edge_batches(gpu, oracle):
+    """Batches whose size is no multiple of the 8-polynomial generation, degree-1 and all-zero polynomials (x^d:
+    d zero eigenvalues, nothing kept when inverting), and one-polynomial batches."""
+    for npoly in (1, 7, 8, 9, 17):
+        rng = np.random.default_rng(npoly)
+        deg = rng.integers(1, 9, size=npoly).astype(np.int32)
+        top = np.zeros((npoly, 8))
+        for k in range(npoly):
+            top[k, :deg[k]] = rng.integers(0, 3, size=deg[k])
+        top[0, :] = 0.0                                         # x^d
+        vals, kept, iters = gpu.lucas.roots_batched(top, deg, invert=False)
+        assert list(kept) == list(deg)
+        assert np.all(vals[0, :deg[0]] == 0)
+        for k in range(1, npoly):
+            ref = oracle.eigvals_toprow(top[k, :deg[k]])
+            assert match_sorted_complex(vals[k, :deg[k]], ref) < 1e-7      # tiny degrees with repeated roots: sqrt(eps) accuracy
+        v2, k2, _ = gpu.lucas.roots_batched(top, deg, invert=True, tol=1e-12)
+        assert k2[0] == 0 and np.isnan(v2[0].real).all()
+        for k in range(1, npoly):
+            nz = int((np.abs(oracle.eigvals_toprow(top[k, :deg[k]])) > 1e-12).sum())
+            assert k2[k] == nz
