@@ -648,7 +648,11 @@ int32_t classify_device(const int* dwell_dev, const double* xs_host, long long n
 struct Linker {
     const long long* rec; long long n;
     const double *xs, *ys; long long nx, ny; double level;
-    std::vector<unsigned char> flags;          // 1 visited, 2 saddle seen, 4 start-SW
+    // per record, one 16-byte entry (one cache line access per step of the walk): the records reached through the exit
+    // edges of its (up to two) segments -- -1 = the line leaves the grid there, -2 = the neighbour record is
+    // missing (inconsistent input) -- and the visit flags: 1 visited, 2 saddle seen, 4 start-SW
+    struct alignas(16) Aux { int nxt[2]; int flags; int pad; };
+    std::vector<Aux> aux;
     std::vector<double> verts;                 // x, y interleaved
     std::vector<long long> offsets;            // line starts (+ end)
 
@@ -707,7 +711,7 @@ struct Linker {
         verts.push_back(ay + by);
     }
     int start_edge(long long k) const {
-        const bool saddle = (flags[k] & 2) != 0, start_sw = (flags[k] & 4) != 0;
+        const bool saddle = (aux[k].flags & 2) != 0, start_sw = (aux[k].flags & 4) != 0;
         switch (config(k)) {
             case 1: return EDGE_E;   case 2: return EDGE_S;   case 3: return EDGE_E;
             case 4: return EDGE_N;   case 5: return EDGE_N;
@@ -734,7 +738,6 @@ struct Linker {
     // nxt[2k + s]: record reached through the exit edge of segment s of record k; -1 = the line leaves the
     // grid there, -2 = the neighbour record is missing (inconsistent input).  Filled by all host threads
     // before the (inherently sequential) walk, so the walk itself is pointer chasing.
-    std::vector<long long> nxt;
     void build_next_range(long long k_lo, long long k_hi) {
         for (long long k = k_lo; k < k_hi; ++k) {
             const unsigned m = meta(k);
@@ -754,12 +757,12 @@ struct Linker {
                     }
                     if ((ex == EDGE_N && j != ny - 2 && r == -1) || (ex == EDGE_S && j != 0 && r == -1)) r = -2;
                 }
-                nxt[static_cast<size_t>(2 * k + sg)] = r;
+                aux[static_cast<size_t>(k)].nxt[sg] = static_cast<int>(r);
             }
         }
     }
     void build_next() {
-        nxt.assign(static_cast<size_t>(2 * n), -2);
+        aux.assign(static_cast<size_t>(n), Aux{{-2, -2}, 0, 0});
         unsigned hw = std::thread::hardware_concurrency();
         int nthreads = static_cast<int>(hw ? hw : 1);
         if (nthreads > 16) nthreads = 16;
@@ -780,10 +783,10 @@ struct Linker {
             const unsigned m = meta(k);
             const unsigned cfg = m & 15u;
             if (cfg == 6u || cfg == 9u) {
-                if (flags[k] & 2) flags[k] |= 1;
-                else { flags[k] |= 2; if (edge == EDGE_N || edge == EDGE_E) flags[k] |= 4; }
+                if (aux[k].flags & 2) aux[k].flags |= 1;
+                else { aux[k].flags |= 2; if (edge == EDGE_N || edge == EDGE_E) aux[k].flags |= 4; }
             } else {
-                flags[k] |= 1;
+                aux[k].flags |= 1;
             }
             const int nseg = static_cast<int>((m >> 16) & 3u);
             int seg = -1;
@@ -795,7 +798,7 @@ struct Linker {
             memcpy(v, &rec[k * REC_WORDS + 4 + 2 * seg], sizeof(v));
             verts.push_back(v[0]);
             verts.push_back(v[1]);
-            const long long kn = nxt[static_cast<size_t>(2 * k + seg)];
+            const long long kn = aux[static_cast<size_t>(k)].nxt[seg];
             if (kn == -1) return true;                      // left the grid
             if (kn < 0) return false;
             k = kn; edge = (ex + 2) & 3;                    // enter the neighbour through the opposite edge
@@ -816,14 +819,13 @@ struct Linker {
                          std::chrono::duration<double, std::milli>(t2 - t1).count());
         struct Report { bool on; std::chrono::steady_clock::time_point t; ~Report() { if (on) fprintf(stderr, "[link] walk %.2f ms\n",
                          std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count()); } } rep{dbg, t2};
-        flags.assign(static_cast<size_t>(n), 0);
         verts.clear(); offsets.clear();
         // lines that start and end on the boundary (edges tested S, W, N, E).  Only quads on the grid border can
         // start one: every record of the first and last quad row, and the first / last record of the rows between
         // (visited in raster order, like a scan over all records would).
-        verts.reserve(static_cast<size_t>(n) * 2 + 64);
+        verts.reserve(static_cast<size_t>(n) * 8 + 64);      // <= 2 segments per record + start / closing vertices per line
         auto try_boundary_start = [&](long long k, long long i, long long j) -> bool {
-            if (flags[k] & 1) return true;
+            if (aux[k].flags & 1) return true;
             const unsigned c = config(k);
             const bool nw = c & 8u, ne = c & 4u, sw = c & 2u, se = c & 1u;
             const bool cond[4] = {i == nx - 2 && se && !ne, j == ny - 2 && ne && !nw, i == 0 && nw && !sw, j == 0 && sw && !se};
@@ -833,7 +835,7 @@ struct Linker {
                 if (!cond[e]) continue;
                 offsets.push_back(static_cast<long long>(verts.size() / 2));
                 if (!follow(k, e, true, false)) return false;
-                if (flags[k] & 1) break;
+                if (aux[k].flags & 1) break;
             }
             return true;
         };
@@ -851,7 +853,7 @@ struct Linker {
         }
         // interior closed loops
         for (long long k = 0; k < n; ++k) {
-            if (flags[k] & 1) continue;
+            if (aux[k].flags & 1) continue;
             const int se = start_edge(k);
             if (se == EDGE_NONE) continue;
             const bool ignore_first = (se == EDGE_N);
@@ -863,7 +865,7 @@ struct Linker {
                 verts.push_back(fx);
                 verts.push_back(fy);
             }
-            if ((flags[k] & 2) && !(flags[k] & 1)) --k;      // second pass through the saddle
+            if ((aux[k].flags & 2) && !(aux[k].flags & 1)) --k;      // second pass through the saddle
         }
         offsets.push_back(static_cast<long long>(verts.size() / 2));
         return true;
@@ -878,6 +880,7 @@ int32_t link_and_export(const long long* records, long long n_records, const dou
                         const double* ys, long long ny, double level,
                         double* verts, long long cap_verts, long long* n_verts,
                         long long* line_offsets, long long cap_lines, long long* n_lines) {
+    LM_REQUIRE(n_records < (1LL << 31), "lm_contour_link: more than 2^31 crossing records");
     Linker L{records, n_records, xs, ys, nx, ny, level, {}, {}, {}, {}};
     if (!L.run())
         return lm::fail(LM_E_INVALID, "lm_contour_link: inconsistent crossing records (not in raster order, or a neighbour quad is missing)");
