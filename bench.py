@@ -260,8 +260,8 @@ def run_ours(args):
     with_pot = args.workload == "cfg2"
     field_d = torch.empty((rows, nx), dtype=torch.float64, device=dev) if with_pot else None
     work_d = torch.zeros(1, dtype=torch.int64, device=dev)
-    rec_cap = max(int(0.01 * rows * nx) + 4096, 1 << 16)
-    records = np.empty((rec_cap, 8), dtype=np.int64)
+    rec_cap = max(int(0.002 * rows * nx) + 4096, 1 << 16)
+    records = _shim.pinned_empty((rec_cap, 8), np.int64)          # page-locked: the records land in it straight from the device
     n_rec = C.c_int64(0)
     launches = {"n": 0}
 
@@ -277,7 +277,7 @@ def run_ours(args):
             rc = lib.lm_contour_classify_dev(block_ptr, _shim.ptr(xs), nx, _shim.ptr(ys_block), nrows_k2,
                                              r0, float(level), _shim.ptr(records), records.shape[0], C.byref(n_rec), stream)
             if rc == _shim.LM_E_CAP:
-                records = np.empty((n_rec.value + 1024, 8), dtype=np.int64)
+                records = _shim.pinned_empty((n_rec.value + 1024, 8), np.int64)
                 continue
             _shim.check(rc)
             break

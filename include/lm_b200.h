@@ -261,7 +261,8 @@ int32_t lm_boundary_sample_potential(const double* xs, int64_t nx, const double*
  * consecutive row blocks are concatenated and chained by lm_contour_link.
  * A record is 8 x int64: {quad = (row_offset + j)*nx + i, SW | SE<<32, NW | NE<<32 (corner
  * dwell values), meta, exit vertex of segment 0 (x, y as binary64), exit vertex of
- * segment 1 (saddle quads)}; meta is described in csrc/lm_contour.cu.
+ * segment 1 (saddle quads)}; meta is described in csrc/lm_contour.cu.  A page-locked `records`
+ * buffer (lm_host_alloc) is filled straight from the device, a pageable one through a staging copy.
  */
 int32_t lm_contour_classify_dev(const int32_t* dwell_dev, const double* xs_host, int64_t nx,
                                 const double* ys_host, int64_t ny, int64_t row_offset, double level,

@@ -545,9 +545,12 @@ __global__ void __launch_bounds__(MARK_WARPS * 32) contour_emit_kernel(
 // ------------------------------------------------------------------------------------
 // device side driver: dwell block on the device -> ordered records on the host
 // ------------------------------------------------------------------------------------
+// direct_dst / direct_cap: a caller buffer that is page-locked and large enough receives the records straight from
+// the device (no staging copy); *records_out then points at it.
 int32_t classify_device(const int* dwell_dev, const double* xs_host, long long nx,
                         const double* ys_host, long long ny, long long row_offset, double level,
-                        const long long** records_out, long long* n_out, float* kernel_ms, cudaStream_t s) {
+                        const long long** records_out, long long* n_out, float* kernel_ms, cudaStream_t s,
+                        long long* direct_dst = nullptr, long long direct_cap = 0) {
     *records_out = nullptr; *n_out = 0;
     if (nx < 2 || ny < 2) return LM_OK;
     const long long nrows = ny - 1;
@@ -618,6 +621,18 @@ int32_t classify_device(const int* dwell_dev, const double* xs_host, long long n
     float ms = 0.f;
     if ((rc = tm.end(s, &ms)) != LM_OK) return rc;
     if (kernel_ms) *kernel_ms = ms;
+    if (total && direct_dst && static_cast<long long>(total) <= direct_cap) {
+        cudaPointerAttributes attr{};
+        if (cudaPointerGetAttributes(&attr, direct_dst) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+            const size_t need = static_cast<size_t>(total) * REC_WORDS * sizeof(long long);
+            LM_CUDA_TRY(cudaMemcpyAsync(direct_dst, drec, need, cudaMemcpyDeviceToHost, s));
+            LM_CUDA_TRY(cudaStreamSynchronize(s));
+            *records_out = direct_dst;
+            *n_out = static_cast<long long>(total);
+            return LM_OK;
+        }
+        cudaGetLastError();           // pageable memory: not an error, take the staged path
+    }
     if (total) {
         // page-locked staging buffer, cached across calls (records are read by the host linker)
         static long long* h_stage = nullptr;
@@ -956,14 +971,16 @@ int32_t lm_contour_classify_dev(const int32_t* dwell_dev, const double* xs_host,
     LM_REQUIRE(nx >= 0 && ny >= 0 && cap_records >= 0, "lm_contour_classify_dev: negative size");
     const long long* recs = nullptr;
     long long n = 0;
-    rc = classify_device(dwell_dev, xs_host, nx, ys_host, ny, row_offset, level, &recs, &n, nullptr, lm::as_stream(stream));
+    rc = classify_device(dwell_dev, xs_host, nx, ys_host, ny, row_offset, level, &recs, &n, nullptr, lm::as_stream(stream),
+                         reinterpret_cast<long long*>(records), cap_records);
     if (rc != LM_OK) return rc;
     *n_records = n;
     if (n > cap_records)
         return lm::fail(LM_E_CAP, "lm_contour_classify_dev: need room for %lld records (got %lld)", n,
                         static_cast<long long>(cap_records));
     LM_REQUIRE(records || n == 0, "lm_contour_classify_dev: records is NULL");
-    if (n) memcpy(records, recs, static_cast<size_t>(n) * REC_WORDS * sizeof(long long));
+    if (n && recs != reinterpret_cast<const long long*>(records))      // page-locked caller buffers were filled directly
+        memcpy(records, recs, static_cast<size_t>(n) * REC_WORDS * sizeof(long long));
     return LM_OK;
 }
 

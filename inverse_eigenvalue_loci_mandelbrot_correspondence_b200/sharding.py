@@ -225,7 +225,7 @@ class ShardedBoundary:
         self._edge = torch.empty(nx, dtype=torch.int32, device=self.device)
         self._field = (torch.empty((self.rows, nx), dtype=torch.float64, device=self.device)
                        if (self.with_potential and self.world > 1) else None)
-        self._records = np.empty((max(int(0.01 * self.rows * nx) + 4096, 1 << 16), 8), dtype=np.int64)
+        self._records = _shim.pinned_empty((max(int(0.002 * self.rows * nx) + 4096, 1 << 16), 8), np.int64)   # page-locked
         self.full_potential = None
 
     def refine(self, rounds: int = 2):
@@ -279,7 +279,7 @@ class ShardedBoundary:
             rc = lib.lm_contour_classify_dev(blk, shim.ptr(self.xs), nx, shim.ptr(self.ys_block), self.ys_block.size, self.r0,
                                              self.level, shim.ptr(self._records), self._records.shape[0], C.byref(n_rec), stream)
             if rc == shim.LM_E_CAP:
-                self._records = np.empty((n_rec.value + 1024, 8), dtype=np.int64)
+                self._records = shim.pinned_empty((n_rec.value + 1024, 8), np.int64)
                 continue
             shim.check(rc)
             break
