@@ -62,34 +62,27 @@ class Polylines(Sequence):
         return self[int(np.argmax(self.lengths()))]
 
 
-def _split(verts: np.ndarray, offs: np.ndarray, nv: int, nl: int) -> Polylines:
-    """One compact copy of the used vertices + offsets; the lines are views into it."""
-    if nl == 0:
-        return Polylines(np.empty((0, 2), dtype=np.float64), np.zeros(1, dtype=np.int64))
-    return Polylines(verts[:nv].copy(), offs[:nl + 1].copy())
-
-
-def _call_with_growing_buffers(fn_name: str, head_args: tuple, level: float, n_pixels: int, tail_args: tuple = ()):
-    cap_v = max(4096, min(int(0.002 * n_pixels), 1 << 22))
-    cap_l = max(1024, cap_v // 16)
+def _call_then_fetch(fn_name: str, head_args: tuple, level: float, tail_args: tuple = ()) -> Polylines:
+    """Run a contour entry point with zero output capacity -- the library links the lines, keeps them and reports
+    their sizes (LM_E_CAP) -- then fetch them into arrays of exactly that size: one copy, no over-allocation."""
     st = Stats()
-    verts = np.empty((cap_v, 2), dtype=np.float64)
-    offs = np.empty(cap_l + 1, dtype=np.int64)
     nv = C.c_int64(0); nl = C.c_int64(0)
+    first = np.zeros(1, dtype=np.int64)
     lib = _shim.load()
     with _shim._lock:
-        rc = getattr(lib, fn_name)(*head_args, float(level), *tail_args, _shim.ptr(verts), cap_v, C.byref(nv),
-                                   _shim.ptr(offs), cap_l, C.byref(nl), C.byref(st))
+        rc = getattr(lib, fn_name)(*head_args, float(level), *tail_args, None, 0, C.byref(nv),
+                                   _shim.ptr(first), 0, C.byref(nl), C.byref(st))
         if rc == _shim.LM_E_CAP:
-            # the library kept the linked result: fetch it into buffers of the reported size
-            cap_v, cap_l = nv.value + 1, nl.value + 1
-            verts = np.empty((cap_v, 2), dtype=np.float64)
-            offs = np.empty(cap_l + 1, dtype=np.int64)
-            rc = lib.lm_contour_fetch_last(_shim.ptr(verts), cap_v, C.byref(nv), _shim.ptr(offs), cap_l, C.byref(nl))
+            verts = np.empty((nv.value, 2), dtype=np.float64)
+            offs = np.empty(nl.value + 1, dtype=np.int64)
+            rc = lib.lm_contour_fetch_last(_shim.ptr(verts), nv.value, C.byref(nv), _shim.ptr(offs), nl.value, C.byref(nl))
+        else:
+            verts = np.empty((0, 2), dtype=np.float64)
+            offs = np.zeros(1, dtype=np.int64)
     _shim.check(rc)
     global last_stats
     last_stats = st.as_dict()
-    return _split(verts, offs, nv.value, nl.value)
+    return Polylines(verts, offs)
 
 
 def contour_lines(xs, ys, Z, level: float):
@@ -99,17 +92,15 @@ def contour_lines(xs, ys, Z, level: float):
     d = _as_dwell_i32(Z)
     if d.shape != (ys.size, xs.size):
         raise ValueError("Z must have shape (len(ys), len(xs))")
-    return _call_with_growing_buffers("lm_contour_level", (_shim.ptr(d), _shim.ptr(xs), xs.size, _shim.ptr(ys), ys.size),
-                                      level, d.size)
+    return _call_then_fetch("lm_contour_level", (_shim.ptr(d), _shim.ptr(xs), xs.size, _shim.ptr(ys), ys.size), level)
 
 
 def contour_lines_dev(dwell_dev_ptr: int, xs, ys, level: float):
     """Same with the int32 dwell grid already resident on the current device."""
     xs = np.ascontiguousarray(xs, dtype=np.float64).ravel()
     ys = np.ascontiguousarray(ys, dtype=np.float64).ravel()
-    return _call_with_growing_buffers("lm_contour_level_dev",
-                                      (C.c_void_p(dwell_dev_ptr), _shim.ptr(xs), xs.size, _shim.ptr(ys), ys.size),
-                                      level, xs.size * ys.size)
+    return _call_then_fetch("lm_contour_level_dev",
+                            (C.c_void_p(dwell_dev_ptr), _shim.ptr(xs), xs.size, _shim.ptr(ys), ys.size), level)
 
 
 def boundary_sample(xs, ys, max_iter: int, level: float, dwell_out: np.ndarray | None = None,
@@ -135,14 +126,12 @@ def boundary_sample(xs, ys, max_iter: int, level: float, dwell_out: np.ndarray |
         if (potential_out.shape != (ys.size, xs.size) or not potential_out.flags["C_CONTIGUOUS"]
                 or potential_out.dtype != np.float64):
             raise ValueError("potential_out must be a C-contiguous float64 [len(ys), len(xs)] array")
-        lines = _call_with_growing_buffers("lm_boundary_sample_potential",
-                                           (_shim.ptr(xs), xs.size, _shim.ptr(ys), ys.size, int(max_iter)),
-                                           level, xs.size * ys.size,
-                                           tail_args=(_shim.ptr(d32), _shim.ptr(d64), _shim.ptr(potential_out)))
+        lines = _call_then_fetch("lm_boundary_sample_potential",
+                                 (_shim.ptr(xs), xs.size, _shim.ptr(ys), ys.size, int(max_iter)), level,
+                                 tail_args=(_shim.ptr(d32), _shim.ptr(d64), _shim.ptr(potential_out)))
         return lines, last_stats
-    lines = _call_with_growing_buffers("lm_boundary_sample",
-                                       (_shim.ptr(xs), xs.size, _shim.ptr(ys), ys.size, int(max_iter)),
-                                       level, xs.size * ys.size, tail_args=(_shim.ptr(d32), _shim.ptr(d64)))
+    lines = _call_then_fetch("lm_boundary_sample", (_shim.ptr(xs), xs.size, _shim.ptr(ys), ys.size, int(max_iter)), level,
+                             tail_args=(_shim.ptr(d32), _shim.ptr(d64)))
     return lines, last_stats
 
 
@@ -167,10 +156,18 @@ def link_records(records: np.ndarray, xs, ys, level: float):
     ys = np.ascontiguousarray(ys, dtype=np.float64).ravel()
     records = np.ascontiguousarray(records, dtype=np.int64).reshape(-1, 8)
     n = records.shape[0]
-    cap_v, cap_l = 4 * n + 16, n + 16
-    verts = np.empty((cap_v, 2), dtype=np.float64)
-    offs = np.empty(cap_l + 1, dtype=np.int64)
     nv = C.c_int64(0); nl = C.c_int64(0)
-    _shim.call("lm_contour_link", _shim.ptr(records), n, _shim.ptr(xs), xs.size, _shim.ptr(ys), ys.size, float(level),
-               _shim.ptr(verts), cap_v, C.byref(nv), _shim.ptr(offs), cap_l, C.byref(nl))
-    return _split(verts, offs, nv.value, nl.value)
+    first = np.zeros(1, dtype=np.int64)
+    lib = _shim.load()
+    with _shim._lock:
+        rc = lib.lm_contour_link(_shim.ptr(records), n, _shim.ptr(xs), xs.size, _shim.ptr(ys), ys.size, float(level),
+                                 None, 0, C.byref(nv), _shim.ptr(first), 0, C.byref(nl))
+        if rc == _shim.LM_E_CAP:
+            verts = np.empty((nv.value, 2), dtype=np.float64)
+            offs = np.empty(nl.value + 1, dtype=np.int64)
+            rc = lib.lm_contour_fetch_last(_shim.ptr(verts), nv.value, C.byref(nv), _shim.ptr(offs), nl.value, C.byref(nl))
+        else:
+            verts = np.empty((0, 2), dtype=np.float64)
+            offs = np.zeros(1, dtype=np.int64)
+    _shim.check(rc)
+    return Polylines(verts, offs)
