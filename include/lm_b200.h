@@ -87,6 +87,11 @@ extern "C" {
 /* U = (1/N) sum_p log(1/(|z-p| + eps))               variograms_construct_mandelbrot.py:128-146 */
 #define LM_LOGPOT_LOG_INV      3
 
+/* ---- per-pair weight of the binned pair statistics (lm_pair_histogram) ---------- */
+#define LM_PAIR_W_NONE          0   /* counts only (pair_correlation, ripley_K)                     */
+#define LM_PAIR_W_VALUE_SQDIFF  1   /* (value_i - value_j)^2 (empirical_variogram_field)            */
+#define LM_PAIR_W_DIST_SQ       2   /* d_ij^2 (empirical_variogram_coords)                          */
+
 /* ---- plain-old-data structs ---------------------------------------------------- */
 typedef struct lm_device_info {
     int32_t  device;            /* CUDA ordinal                                       */
@@ -392,6 +397,58 @@ int32_t lm_weighted_cauchy_sum(const double* z_re, const double* z_im, int64_t M
 int32_t lm_curvature_localpoly(const double* x, const double* y, int64_t n, int32_t neighbors, int32_t closed,
                                double* kappa, double* kappa_signed, double* speed,
                                double* xprime, double* yprime, double* x2, double* y2, lm_stats* stats);
+
+/* ---- binned statistics over all point pairs ----------------------- */
+/* counts[k] = #{ i < j : lo[k] <= d_ij < hi[k] },  sums[k] = sum of w_ij over those pairs, with
+ * d_ij = sqrt(dx*dx + dy*dy) in unfused binary64 (= scipy pdist / distance_matrix / np.linalg.norm(axis=1)) and
+ * w_ij chosen by weight_mode (LM_PAIR_W_*).  One call is the O(N^2) part of
+ *   empirical_variogram_field, empirical_variogram_coords   Variogram-Mandelbrot-Construct.py:106-152
+ *       (lo = bins[:-1], hi = bins[1:] of np.linspace(0, max_dist, nbins+1); gamma = 0.5*sums/counts)
+ *   empirical_variogram_from_field_locs                     Iterative_Variogram_Laplacian.py:53-86
+ *   pair_correlation (lo = r_vals, hi = r_vals + dr), ripley_K (cumulated counts)   spatial_stats_phase2.py:9-47
+ * without materialising the N(N-1)/2 distances.  Edges: lo strictly increasing, hi[k] <= lo[k+2] (a shell may
+ * overlap its neighbour, as r+dr can exceed the next r by an ulp; such a pair is counted in both, like the
+ * reference's masks do); hi may be +inf.  1 <= nbins <= 2048.  value is read only for LM_PAIR_W_VALUE_SQDIFF;
+ * sums may be NULL for LM_PAIR_W_NONE.  Coordinates must be finite.  n < 2 gives all-zero outputs.            */
+int32_t lm_pair_histogram(const double* x, const double* y, const double* value, int64_t n,
+                          const double* lo, const double* hi, int32_t nbins, int32_t weight_mode,
+                          uint64_t* counts, double* sums, lm_stats* stats);
+/* *dmax = max_{i<j} d_ij: the D.max() behind the default max_dist = 0.5 * D.max()
+ * (Variogram-Mandelbrot-Construct.py:118-119, Iterative_Variogram_Laplacian.py:60-61).  0 for n < 2.          */
+int32_t lm_pair_max_distance(const double* x, const double* y, int64_t n, double* dmax, lm_stats* stats);
+
+/* ---- the tracker's density stage: histogram, blur, divergences, GI flow -------- */
+/* H[ix*nby + iy] = np.histogram2d(x, y, bins=(nbx, nby), range=...)[0]: xedges[nbx+1] / yedges[nby+1] are the caller's
+ * np.linspace edges; a sample is in bin k when edges[k] <= v < edges[k+1] (np.searchsorted side="right"), the last
+ * edge closed, everything else (NaN included) dropped.  gi_assumption_tracker_v3.py:110-114,
+ * tci_construct_mandelbrot_v002_fixed.py:78-82 (to_prob).                                                        */
+int32_t lm_histogram2d(const double* x, const double* y, int64_t n, const double* xedges, int32_t nbx,
+                       const double* yedges, int32_t nby, double* H, lm_stats* stats);
+/* mollified_histogram, gi_assumption_tracker_v3.py:109-127, in one device pass:
+ * histogram2d -> max(H, eps) -> [radius > 0: scipy.ndimage.gaussian_filter(mode="nearest") with the given normalised
+ * symmetric weights[2*radius+1] (axis 0, then axis 1) -> max(H, eps)] -> H / H.sum() (numpy's pairwise order).
+ * Bit-identical to the numpy / scipy chain.                                                                      */
+int32_t lm_mollified_histogram(const double* x, const double* y, int64_t n, const double* xedges, int32_t nbx,
+                               const double* yedges, int32_t nby, double eps, const double* weights, int32_t radius,
+                               double* P, lm_stats* stats);
+/* scipy.ndimage.gaussian_filter(in[n0, n1], mode="nearest") given its 1-D weights (correlate1d, symmetric path).  */
+int32_t lm_gaussian_filter_nearest(const double* in, int64_t n0, int64_t n1, const double* weights, int32_t radius,
+                                   double* out, lm_stats* stats);
+/* *out = np.sum(a) for a contiguous float64 array, in numpy's pairwise summation order (bit-identical).            */
+int32_t lm_sum_pairwise(const double* a, int64_t n, double* out, lm_stats* stats);
+/* One pass over two densities: sum|p-q| (tv_distance = 0.5 * it), sum min(p,q) (overlap_mass) and
+ * KL(p, q) = sum p_ (log p_ - log q_) with p_ = max(p, eps), q_ = max(q, eps).
+ * gi_assumption_tracker_v3.py:91-96, tci_construct_mandelbrot_v002_fixed.py:84-86.  Outputs may be NULL.          */
+int32_t lm_density_compare(const double* p, const double* q, int64_t n, double eps,
+                           double* sum_abs_diff, double* sum_min, double* kl_pq, lm_stats* stats);
+/* gi_flow_to_threshold (fixed_T == 0) / gi_flow_fixed_T (fixed_T != 0, T = max_steps), gi_assumption_tracker_v3.py:130-151,
+ * with the stock module's KL: X <- (1-alpha) X + alpha P (unfused), KL(P, X) after every sweep, stop at the first
+ * t >= max(min_steps, 1) with KL <= kl_threshold.  X_out[n] = X_T (bit-identical to numpy), *steps_out = T,
+ * *kl_initial = KL(P, X0), *kl_final = KL(P, X_T); kl_history (may be NULL) receives max_steps+1 slots, filled 0..T. */
+int32_t lm_gi_flow(const double* P, const double* X0, int64_t n, double alpha, double eps,
+                   int32_t max_steps, int32_t min_steps, double kl_threshold, int32_t fixed_T,
+                   double* X_out, int32_t* steps_out, double* kl_initial, double* kl_final,
+                   double* kl_history, lm_stats* stats);
 
 /* ---- measurement probes -------------------------------------------------------- */
 /* Dependent-free DFMA loop on every SM: FP64 peak (TFLOP/s, 2 flops per DFMA) and a

@@ -21,6 +21,7 @@ LM_OK, LM_E_INVALID, LM_E_CUDA, LM_E_CAP, LM_E_NOMEM, LM_E_NODEV, LM_E_NOCONV, L
 FIELD_NONE, FIELD_GREEN, FIELD_POW2_ALWAYS, FIELD_INV_K, FIELD_POW2_FIRST = 0, 1, 2, 3, 4
 DE_SCALAR, DE_FIRST_ESCAPE, DE_FINAL_DZ = 0, 1, 2
 LOGPOT_SUM_SQRT, LOGPOT_NEG_PERTERM, LOGPOT_SUM_HYPOT, LOGPOT_LOG_INV = 0, 1, 2, 3
+PAIR_W_NONE, PAIR_W_VALUE_SQDIFF, PAIR_W_DIST_SQ = 0, 1, 2
 
 # every symbol include/lm_b200.h declares (tests check the library exports all of them)
 EXPORTS = (
@@ -34,6 +35,8 @@ EXPORTS = (
     "lm_laplacian5_periodic", "lm_laplacian5_periodic_dev", "lm_smooth5_interior", "lm_smooth5_interior_dev",
     "lm_log_potential", "lm_log_potential_sums_dev", "lm_log_potential_finish_dev",
     "lm_nearest_match", "lm_weighted_log_sum", "lm_weighted_cauchy_sum", "lm_curvature_localpoly",
+    "lm_pair_histogram", "lm_pair_max_distance",
+    "lm_histogram2d", "lm_mollified_histogram", "lm_gaussian_filter_nearest", "lm_sum_pairwise", "lm_density_compare", "lm_gi_flow",
     "lm_probe_fp64_peak", "lm_probe_fp64_latency", "lm_probe_k1_loop", "lm_probe_hbm_copy",
 )
 
@@ -122,6 +125,15 @@ _SIGNATURES = {
     "lm_weighted_log_sum": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _f64, _vp, _pStats]),
     "lm_weighted_cauchy_sum": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _f64, _vp, _vp, _pStats]),
     "lm_curvature_localpoly": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _pStats]),
+    "lm_pair_histogram": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _pStats]),
+    "lm_pair_max_distance": (_i32, [_vp, _vp, _i64, C.POINTER(C.c_double), _pStats]),
+    "lm_histogram2d": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp, _i32, _vp, _pStats]),
+    "lm_mollified_histogram": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp, _i32, _f64, _vp, _i32, _vp, _pStats]),
+    "lm_gaussian_filter_nearest": (_i32, [_vp, _i64, _i64, _vp, _i32, _vp, _pStats]),
+    "lm_sum_pairwise": (_i32, [_vp, _i64, C.POINTER(C.c_double), _pStats]),
+    "lm_density_compare": (_i32, [_vp, _vp, _i64, _f64, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), _pStats]),
+    "lm_gi_flow": (_i32, [_vp, _vp, _i64, _f64, _f64, _i32, _i32, _f64, _i32, _vp, C.POINTER(C.c_int32),
+                          C.POINTER(C.c_double), C.POINTER(C.c_double), _vp, _pStats]),
     "lm_probe_fp64_peak": (_i32, [_i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "lm_probe_fp64_latency": (_i32, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "lm_probe_k1_loop": (_i32, [_i32, _i32, _i32, C.POINTER(C.c_double)]),

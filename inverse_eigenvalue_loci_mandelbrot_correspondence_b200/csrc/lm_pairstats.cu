@@ -1,0 +1,326 @@
+// lm_pairstats.cu -- binned statistics over all N(N-1)/2 point pairs (FP64 pipe).
+//
+// The reference materialises every pairwise distance on the host (scipy pdist / distance_matrix: 8 B per pair,
+// 5.7 GB for the 37 820-point cloud of the tracker) and then bins it:
+//   empirical_variogram_field / _coords        Variogram-Mandelbrot-Construct.py:106-152   (np.digitize on linspace bins)
+//   empirical_variogram_from_field_locs        Iterative_Variogram_Laplacian.py:53-86      ((D >= b[k]) & (D < b[k+1]))
+//   pair_correlation, ripley_K                 spatial_stats_phase2.py:9-47                (shells [r, r+dr), counts d < r)
+// Every one of them is "count the pairs i<j with lo[k] <= d_ij < hi[k] and sum a per-pair weight", with
+// d_ij = sqrt(dx*dx + dy*dy) in unfused binary64 (probe: scipy pdist, distance_matrix and np.linalg.norm(axis=1) all
+// return exactly that).  Here nothing is materialised: a tile loop over the upper triangle, one i per thread, the j
+// tile staged in shared memory, and the bin of every pair located EXACTLY against the caller's edge arrays (a
+// reciprocal-width guess, then comparisons with the real edges), so the counts are bit-identical to the reference's.
+// Weights are summed per thread in runs of equal bin, per warp in a private shared-memory histogram, per block in
+// a partial row, and across blocks in block order by a finishing kernel (the reference's np.mean is a pairwise
+// sum: parity of the sums is 1e-12, of the counts exact).
+#include "lm_common.cuh"
+
+#include <math.h>
+
+namespace {
+
+constexpr int PS_THREADS = 128;          // threads per block = i's per tile
+constexpr int PS_TILE = 128;             // j's per tile
+constexpr int PS_WARPS = PS_THREADS / 32;
+constexpr int PS_PRIVATE_MAX_BINS = 512; // up to here every warp owns a histogram copy
+constexpr int PS_MAX_BINS = 2048;
+constexpr int PS_BLOCKS_PER_SM = 8;
+
+// tile t of the row-major upper triangle (bi <= bj) of a T x T tile grid
+__device__ __forceinline__ void decode_tile(long long t, long long T, int* bi, int* bj) {
+    // rows before bi hold bi*T - bi*(bi-1)/2 tiles; solve with a double sqrt and repair
+    const double b = 2.0 * static_cast<double>(T) + 1.0;
+    long long r = static_cast<long long>((b - sqrt(b * b - 8.0 * static_cast<double>(t))) * 0.5);
+    if (r < 0) r = 0;
+    if (r > T - 1) r = T - 1;
+    while (r > 0 && r * T - r * (r - 1) / 2 > t) --r;
+    while (r + 1 < T && (r + 1) * T - (r + 1) * r / 2 <= t) ++r;
+    *bi = static_cast<int>(r);
+    *bj = static_cast<int>(r + (t - (r * T - r * (r - 1) / 2)));
+}
+
+struct RunCache {
+    int k = -1;
+    unsigned cnt = 0;
+    double sum = 0.0;
+};
+
+template <int WMODE>
+__device__ __forceinline__ void flush_run(RunCache& rc, unsigned long long* hc, double* hs) {
+    if (rc.k >= 0) {
+        atomicAdd(&hc[rc.k], static_cast<unsigned long long>(rc.cnt));
+        if (WMODE != LM_PAIR_W_NONE) atomicAdd(&hs[rc.k], rc.sum);
+    }
+}
+
+// WMODE: LM_PAIR_W_NONE counts only, LM_PAIR_W_VALUE_SQDIFF (v_i - v_j)^2, LM_PAIR_W_DIST_SQ d^2
+template <int WMODE>
+__global__ void __launch_bounds__(PS_THREADS) pair_hist_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                                                               const double* __restrict__ v, long long n,
+                                                               const double* __restrict__ lo, const double* __restrict__ hi, int nb,
+                                                               double lo0, double inv_w, int copies, long long T, long long total_tiles,
+                                                               unsigned long long* __restrict__ part_counts,
+                                                               double* __restrict__ part_sums) {
+    extern __shared__ __align__(16) unsigned char ps_smem[];
+    double* slo = reinterpret_cast<double*>(ps_smem);
+    double* shi = slo + nb;
+    double* ssum = shi + nb;                                                   // [copies][nb]
+    unsigned long long* scnt = reinterpret_cast<unsigned long long*>(ssum + static_cast<size_t>(copies) * nb);
+    __shared__ double sx[PS_TILE], sy[PS_TILE], sv[PS_TILE];
+
+    const int tid = threadIdx.x;
+    for (int k = tid; k < nb; k += PS_THREADS) { slo[k] = lo[k]; shi[k] = hi[k]; }
+    for (int k = tid; k < copies * nb; k += PS_THREADS) { ssum[k] = 0.0; scnt[k] = 0ull; }
+    const int copy = copies > 1 ? (tid >> 5) : 0;
+    unsigned long long* hc = scnt + static_cast<size_t>(copy) * nb;
+    double* hs = ssum + static_cast<size_t>(copy) * nb;
+    RunCache run;
+
+    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int bi, bj;
+        decode_tile(t, T, &bi, &bj);
+        const long long i = static_cast<long long>(bi) * PS_TILE + tid;
+        const long long j0 = static_cast<long long>(bj) * PS_TILE;
+        const bool live = i < n;
+        const double xi = live ? x[i] : 0.0, yi = live ? y[i] : 0.0;
+        double vi = 0.0;
+        if (WMODE == LM_PAIR_W_VALUE_SQDIFF) vi = live ? v[i] : 0.0;
+        __syncthreads();                                   // previous tile consumed (and the zero fill on the first pass)
+        if (j0 + tid < n) {
+            sx[tid] = x[j0 + tid]; sy[tid] = y[j0 + tid];
+            if (WMODE == LM_PAIR_W_VALUE_SQDIFF) sv[tid] = v[j0 + tid];
+        }
+        __syncthreads();
+        if (!live) continue;
+        const int jn = static_cast<int>(n - j0 < PS_TILE ? n - j0 : PS_TILE);
+        const int jfirst = (bi == bj) ? tid + 1 : 0;      // strict upper triangle on diagonal tiles
+#pragma unroll 2
+        for (int j = jfirst; j < jn; ++j) {
+            const double dx = __dsub_rn(xi, sx[j]), dy = __dsub_rn(yi, sy[j]);
+            const double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+            // k = largest index with lo[k] <= d (or -1): guess from the mean width, repair against the real edges
+            int k = static_cast<int>(fmin(fmax((d - lo0) * inv_w, 0.0), static_cast<double>(nb - 1)));
+            while (k >= 0 && d < slo[k]) --k;
+            while (k + 1 < nb && slo[k + 1] <= d) ++k;
+            if (k < 0) continue;
+            double w = 0.0;
+            if (WMODE == LM_PAIR_W_VALUE_SQDIFF) { const double dv = __dsub_rn(vi, sv[j]); w = __dmul_rn(dv, dv); }
+            if (WMODE == LM_PAIR_W_DIST_SQ) w = __dmul_rn(d, d);
+            if (d < shi[k]) {
+                if (k == run.k) { ++run.cnt; run.sum += w; }
+                else { flush_run<WMODE>(run, hc, hs); run.k = k; run.cnt = 1; run.sum = w; }
+            }
+            if (k >= 1 && d < shi[k - 1]) {               // shells whose upper edge overshoots the next lower edge by an ulp
+                atomicAdd(&hc[k - 1], 1ull);
+                if (WMODE != LM_PAIR_W_NONE) atomicAdd(&hs[k - 1], w);
+            }
+        }
+    }
+    flush_run<WMODE>(run, hc, hs);
+    __syncthreads();
+    for (int k = tid; k < nb; k += PS_THREADS) {
+        unsigned long long c = 0ull;
+        double s = 0.0;
+        for (int q = 0; q < copies; ++q) { c += scnt[static_cast<size_t>(q) * nb + k]; s += ssum[static_cast<size_t>(q) * nb + k]; }
+        part_counts[static_cast<size_t>(blockIdx.x) * nb + k] = c;
+        if (WMODE != LM_PAIR_W_NONE) part_sums[static_cast<size_t>(blockIdx.x) * nb + k] = s;
+    }
+}
+
+__global__ void pair_hist_finish_kernel(const unsigned long long* __restrict__ part_counts, const double* __restrict__ part_sums,
+                                        int blocks, int nb, int with_sums, unsigned long long* __restrict__ counts,
+                                        double* __restrict__ sums) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nb) return;
+    unsigned long long c = 0ull;
+    double s = 0.0;
+    for (int b = 0; b < blocks; ++b) {                    // block order: the same sum on every run
+        c += part_counts[static_cast<size_t>(b) * nb + k];
+        if (with_sums) s += part_sums[static_cast<size_t>(b) * nb + k];
+    }
+    counts[k] = c;
+    sums[k] = s;
+}
+
+// max over pairs of dx*dx + dy*dy (sqrt is monotone: sqrt of the maximum is the maximum distance, D.max())
+__global__ void __launch_bounds__(PS_THREADS) pair_max_kernel(const double* __restrict__ x, const double* __restrict__ y, long long n,
+                                                              long long T, long long total_tiles, unsigned long long* __restrict__ out_bits) {
+    __shared__ double sx[PS_TILE], sy[PS_TILE];
+    const int tid = threadIdx.x;
+    double best = 0.0;
+    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int bi, bj;
+        decode_tile(t, T, &bi, &bj);
+        const long long i = static_cast<long long>(bi) * PS_TILE + tid;
+        const long long j0 = static_cast<long long>(bj) * PS_TILE;
+        const bool live = i < n;
+        const double xi = live ? x[i] : 0.0, yi = live ? y[i] : 0.0;
+        __syncthreads();
+        if (j0 + tid < n) { sx[tid] = x[j0 + tid]; sy[tid] = y[j0 + tid]; }
+        __syncthreads();
+        if (!live) continue;
+        const int jn = static_cast<int>(n - j0 < PS_TILE ? n - j0 : PS_TILE);
+        const int jfirst = (bi == bj) ? tid + 1 : 0;
+#pragma unroll 4
+        for (int j = jfirst; j < jn; ++j) {
+            const double dx = __dsub_rn(xi, sx[j]), dy = __dsub_rn(yi, sy[j]);
+            const double s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+            best = s > best ? s : best;                   // NaN pairs never win, like np.max would propagate: inputs must be finite
+        }
+    }
+    unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(best));   // non-negative doubles order like integers
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, bits, o);
+        bits = other > bits ? other : bits;
+    }
+    if ((tid & 31) == 0) atomicMax(out_bits, bits);
+}
+
+struct TileGrid {
+    long long T = 0, total = 0;
+    unsigned blocks = 0;
+};
+
+TileGrid tile_grid(int64_t n) {
+    TileGrid g;
+    g.T = (n + PS_TILE - 1) / PS_TILE;
+    g.total = g.T * (g.T + 1) / 2;
+    const long long cap = static_cast<long long>(lm::sm_count()) * PS_BLOCKS_PER_SM;
+    g.blocks = static_cast<unsigned>(g.total < cap ? g.total : cap);
+    return g;
+}
+
+int32_t all_finite(const double* a, int64_t n, const char* what) {
+    for (int64_t i = 0; i < n; ++i)
+        if (!isfinite(a[i])) return lm::fail(LM_E_INVALID, "lm_pair: %s[%lld] is not finite", what, static_cast<long long>(i));
+    return LM_OK;
+}
+
+template <int WMODE>
+void launch_hist(const TileGrid& g, size_t smem, cudaStream_t s, const double* x, const double* y, const double* v, int64_t n,
+                 const double* lo, const double* hi, int nb, double lo0, double inv_w, int copies, unsigned long long* pc, double* psum) {
+    cudaFuncSetAttribute(pair_hist_kernel<WMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    pair_hist_kernel<WMODE><<<g.blocks, PS_THREADS, smem, s>>>(x, y, v, n, lo, hi, nb, lo0, inv_w, copies, g.T, g.total, pc, psum);
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t lm_pair_histogram(const double* x, const double* y, const double* value, int64_t n,
+                          const double* lo, const double* hi, int32_t nbins, int32_t weight_mode,
+                          uint64_t* counts, double* sums, lm_stats* stats) {
+    int32_t rc = lm::require_device();
+    if (rc != LM_OK) return rc;
+    LM_REQUIRE(n >= 0, "lm_pair_histogram: negative size");
+    LM_REQUIRE(nbins >= 1 && nbins <= PS_MAX_BINS, "lm_pair_histogram: nbins must be in [1, %d]", PS_MAX_BINS);
+    LM_REQUIRE(weight_mode == LM_PAIR_W_NONE || weight_mode == LM_PAIR_W_VALUE_SQDIFF || weight_mode == LM_PAIR_W_DIST_SQ,
+               "lm_pair_histogram: unknown weight_mode %d", weight_mode);
+    LM_REQUIRE(lo && hi && counts, "lm_pair_histogram: NULL edge / count buffer");
+    LM_REQUIRE(weight_mode == LM_PAIR_W_NONE || sums, "lm_pair_histogram: sums is NULL");
+    LM_REQUIRE(n == 0 || (x && y), "lm_pair_histogram: NULL coordinate buffer");
+    LM_REQUIRE(weight_mode != LM_PAIR_W_VALUE_SQDIFF || n == 0 || value, "lm_pair_histogram: value is NULL");
+    for (int k = 0; k < nbins; ++k) {
+        LM_REQUIRE(isfinite(lo[k]) && !isnan(hi[k]), "lm_pair_histogram: bad edge at bin %d", k);
+        LM_REQUIRE(k == 0 || lo[k] > lo[k - 1], "lm_pair_histogram: lower edges must increase (bin %d)", k);
+        LM_REQUIRE(k + 2 >= nbins || hi[k] <= lo[k + 2], "lm_pair_histogram: bin %d overlaps bin %d", k, k + 2);
+    }
+    if ((rc = all_finite(x, n, "x")) != LM_OK) return rc;
+    if ((rc = all_finite(y, n, "y")) != LM_OK) return rc;
+    if (stats) *stats = lm_stats{};
+    for (int k = 0; k < nbins; ++k) { counts[k] = 0; if (sums) sums[k] = 0.0; }
+    if (n < 2) return LM_OK;
+
+    cudaStream_t s = nullptr;
+    const size_t pb = static_cast<size_t>(n) * sizeof(double), eb = static_cast<size_t>(nbins) * sizeof(double);
+    const TileGrid g = tile_grid(n);
+    void *dx, *dy, *dv, *dlo, *dhi, *dpc, *dps, *dfin;
+    if ((rc = lm::ws_get(lm::WS_IN_A, pb, &dx)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_IN_B, pb, &dy)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_IN_C, pb, &dv)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_OUT_A, eb, &dlo)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_OUT_B, eb, &dhi)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_OUT_C, eb * g.blocks, &dpc)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_OUT_D, eb * g.blocks, &dps)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_SCRATCH, 2 * eb + 64, &dfin)) != LM_OK) return rc;
+    LM_CUDA_TRY(cudaMemcpyAsync(dx, x, pb, cudaMemcpyHostToDevice, s));
+    LM_CUDA_TRY(cudaMemcpyAsync(dy, y, pb, cudaMemcpyHostToDevice, s));
+    if (weight_mode == LM_PAIR_W_VALUE_SQDIFF) LM_CUDA_TRY(cudaMemcpyAsync(dv, value, pb, cudaMemcpyHostToDevice, s));
+    LM_CUDA_TRY(cudaMemcpyAsync(dlo, lo, eb, cudaMemcpyHostToDevice, s));
+    LM_CUDA_TRY(cudaMemcpyAsync(dhi, hi, eb, cudaMemcpyHostToDevice, s));
+
+    const int copies = nbins <= PS_PRIVATE_MAX_BINS ? PS_WARPS : 1;
+    const size_t smem = static_cast<size_t>(nbins) * 16 + static_cast<size_t>(copies) * nbins * 16;
+    const double span = lo[nbins - 1] - lo[0];
+    const double inv_w = (nbins > 1 && span > 0.0) ? static_cast<double>(nbins - 1) / span : 0.0;
+    unsigned long long* pc = static_cast<unsigned long long*>(dpc);
+    double* psum = static_cast<double*>(dps);
+    unsigned long long* fin_c = static_cast<unsigned long long*>(dfin);
+    double* fin_s = reinterpret_cast<double*>(fin_c + nbins);
+
+    lm::Timer tm;
+    if ((rc = tm.begin(s)) != LM_OK) return rc;
+    const double *cx = static_cast<double*>(dx), *cy = static_cast<double*>(dy), *cv = static_cast<double*>(dv);
+    const double *clo = static_cast<double*>(dlo), *chi = static_cast<double*>(dhi);
+    if (weight_mode == LM_PAIR_W_NONE) launch_hist<LM_PAIR_W_NONE>(g, smem, s, cx, cy, cv, n, clo, chi, nbins, lo[0], inv_w, copies, pc, psum);
+    else if (weight_mode == LM_PAIR_W_VALUE_SQDIFF) launch_hist<LM_PAIR_W_VALUE_SQDIFF>(g, smem, s, cx, cy, cv, n, clo, chi, nbins, lo[0], inv_w, copies, pc, psum);
+    else launch_hist<LM_PAIR_W_DIST_SQ>(g, smem, s, cx, cy, cv, n, clo, chi, nbins, lo[0], inv_w, copies, pc, psum);
+    LM_CUDA_TRY(cudaGetLastError());
+    pair_hist_finish_kernel<<<(nbins + 127) / 128, 128, 0, s>>>(pc, psum, static_cast<int>(g.blocks), nbins,
+                                                               weight_mode != LM_PAIR_W_NONE, fin_c, fin_s);
+    LM_CUDA_TRY(cudaGetLastError());
+    float ms = 0.f;
+    if ((rc = tm.end(s, &ms)) != LM_OK) return rc;
+    LM_CUDA_TRY(cudaMemcpyAsync(counts, fin_c, eb, cudaMemcpyDeviceToHost, s));
+    if (sums) LM_CUDA_TRY(cudaMemcpyAsync(sums, fin_s, eb, cudaMemcpyDeviceToHost, s));
+    LM_CUDA_TRY(cudaStreamSynchronize(s));
+    if (stats) {
+        stats->items = static_cast<uint64_t>(n);
+        stats->work_units = static_cast<uint64_t>(n) * static_cast<uint64_t>(n - 1) / 2;
+        stats->kernel_ms = ms;
+        stats->launches = 2;
+    }
+    return LM_OK;
+}
+
+int32_t lm_pair_max_distance(const double* x, const double* y, int64_t n, double* dmax, lm_stats* stats) {
+    int32_t rc = lm::require_device();
+    if (rc != LM_OK) return rc;
+    LM_REQUIRE(n >= 0 && dmax, "lm_pair_max_distance: bad arguments");
+    LM_REQUIRE(n == 0 || (x && y), "lm_pair_max_distance: NULL coordinate buffer");
+    if ((rc = all_finite(x, n, "x")) != LM_OK) return rc;
+    if ((rc = all_finite(y, n, "y")) != LM_OK) return rc;
+    if (stats) *stats = lm_stats{};
+    *dmax = 0.0;
+    if (n < 2) return LM_OK;
+    cudaStream_t s = nullptr;
+    const size_t pb = static_cast<size_t>(n) * sizeof(double);
+    const TileGrid g = tile_grid(n);
+    void *dx, *dy, *dout;
+    if ((rc = lm::ws_get(lm::WS_IN_A, pb, &dx)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_IN_B, pb, &dy)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_SCRATCH, 64, &dout)) != LM_OK) return rc;
+    LM_CUDA_TRY(cudaMemcpyAsync(dx, x, pb, cudaMemcpyHostToDevice, s));
+    LM_CUDA_TRY(cudaMemcpyAsync(dy, y, pb, cudaMemcpyHostToDevice, s));
+    LM_CUDA_TRY(cudaMemsetAsync(dout, 0, 8, s));
+    lm::Timer tm;
+    if ((rc = tm.begin(s)) != LM_OK) return rc;
+    pair_max_kernel<<<g.blocks, PS_THREADS, 0, s>>>(static_cast<double*>(dx), static_cast<double*>(dy), n, g.T, g.total,
+                                                    static_cast<unsigned long long*>(dout));
+    LM_CUDA_TRY(cudaGetLastError());
+    float ms = 0.f;
+    if ((rc = tm.end(s, &ms)) != LM_OK) return rc;
+    double s2 = 0.0;
+    LM_CUDA_TRY(cudaMemcpyAsync(&s2, dout, 8, cudaMemcpyDeviceToHost, s));
+    LM_CUDA_TRY(cudaStreamSynchronize(s));
+    *dmax = sqrt(s2);
+    if (stats) {
+        stats->items = static_cast<uint64_t>(n);
+        stats->work_units = static_cast<uint64_t>(n) * static_cast<uint64_t>(n - 1) / 2;
+        stats->kernel_ms = ms;
+        stats->launches = 1;
+    }
+    return LM_OK;
+}
+
+}  // extern "C"

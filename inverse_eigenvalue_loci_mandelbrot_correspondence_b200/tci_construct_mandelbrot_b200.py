@@ -14,8 +14,10 @@ signatures and moves the two generators onto the B200:
                                      (…_v002_fixed.py:49-59), so a seeded run draws the same sample
   entropic_ot_alignment(X, Y)     -> lm_nearest_match: the argmax of exp(-cdist/const) is the nearest
                                      point (…_v002_fixed.py:62-71), same np.random.choice subsampling
+  to_prob(cloud, bins), KL(P, X)  -> lm_mollified_histogram / lm_density_compare (…_v002_fixed.py:78-86);
+                                     KL carries `lm_eps`, so tracker.gi_flow_* run the GI flow on the device
 
-The Procrustes / histogram helpers are host numpy on <= 4*10^4 points, as in the stock module.
+The Procrustes helper is host numpy on <= 4*10^4 points, as in the stock module.
 Differences a user can see: inside one n the cloud is sorted by (re, im) instead of in
 LAPACK's order, and `mandelbrot_distance_estimator` wants a meshgrid (`X + 1j*Y`) and returns
 `last = None` (z of the first escape stays on the device).
@@ -33,6 +35,7 @@ if str(_ROOT) not in sys.path:           # loaded by file path, not as a package
 
 from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import lucas as _lucas  # noqa: E402
 from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import potentials as _potentials  # noqa: E402
+from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import tracker as _tracker  # noqa: E402
 
 # ---------- CONFIG (names and defaults of tci_construct_mandelbrot_v002_fixed.py:12-22) ----------
 np.random.seed(7)
@@ -113,16 +116,23 @@ def procrustes_align_no_scale(Xc, Yc):
     return out[:, 0] + 1j * out[:, 1]
 
 
+class _Self:
+    """what tracker.mollified_histogram reads from a module: the current `domain` and `eps` of this one"""
+    domain = property(lambda self: domain)
+    eps = property(lambda self: eps)
+
+
 def to_prob(cloud, bins=grid_bins):
-    H, _, _ = np.histogram2d(cloud.real, cloud.imag, bins=(bins, bins),
-                             range=[[domain[0], domain[1]], [domain[2], domain[3]]])
-    H = np.maximum(H, eps)
-    return H / H.sum()
+    """histogram2d -> max(eps) -> / sum on the device (…_v002_fixed.py:78-82; bit-identical to numpy)."""
+    return _tracker.mollified_histogram(_Self(), cloud, bins, 0.0)
 
 
 def KL(P, X):
-    p = np.clip(P, eps, None); x = np.clip(X, eps, None)
-    return float(np.sum(p * (np.log(p) - np.log(x))))
+    """sum P_ (log P_ - log X_) with both clipped at eps, on the device (…_v002_fixed.py:84-86)."""
+    return _tracker.density_compare(P, X, eps)[2]
+
+
+KL.lm_eps = lambda: eps      # lets tracker.gi_flow_* run the whole flow on the device with this module's KL
 
 
 def tci_flow(P, X0):

@@ -197,6 +197,68 @@ def main() -> None:
     g["curv_open_P"] = arc
     g["curv_open_out"] = np.c_[k, ks, sp, aux["xprime"], aux["yprime"], aux["x2"], aux["y2"]]
 
+    # ---- pair statistics: variograms and pair correlation of a small cloud, plus a lattice whose
+    # distances fall exactly on bin edges (3-4-5 triangles against integer edges)
+    from scipy.spatial.distance import pdist
+    from scipy.spatial import distance_matrix
+    import warnings
+    warnings.simplefilter("ignore", DeprecationWarning)
+    vm = load_defs("Variogram-Mandelbrot-Construct.py", ["empirical_variogram_field", "empirical_variogram_coords"],
+                   {"pdist": pdist, "MAX_DIST_FACTOR": 0.5})
+    iv = load_defs("Iterative_Variogram_Laplacian.py", ["empirical_variogram_from_field_locs"], {"pdist": pdist})
+    sp2 = load_defs("spatial_stats_phase2.py", ["pair_correlation", "ripley_K"], {"distance_matrix": distance_matrix})
+    pc = np.column_stack([cloud.real, cloud.imag])[::2]                    # 410 points of the Lucas cloud
+    pv = np.hypot(pc[:, 0] + 0.25, pc[:, 1]) + 0.1 * np.sin(7 * pc[:, 0])   # a smooth "matching distance"-like field
+    g["pair_cloud"] = pc; g["pair_values"] = pv
+    for tag, out in [("field", vm["empirical_variogram_field"](pc, pv, nbins=60)),
+                     ("field_maxd", vm["empirical_variogram_field"](pc, pv, nbins=17, max_dist=0.9)),
+                     ("coords", vm["empirical_variogram_coords"](pc, nbins=60)),
+                     ("iter_values", iv["empirical_variogram_from_field_locs"](pc, values=pv, nbins=50)),
+                     ("iter_coords", iv["empirical_variogram_from_field_locs"](pc, values=None, nbins=50))]:
+        g[f"pair_vario_{tag}"] = np.vstack([out[0], out[1], out[2].astype(np.float64)])
+    r_pc, g_pc = sp2["pair_correlation"](pc, 1.5, 0.01)
+    r_k, K_k = sp2["ripley_K"](pc, 1.5, 0.01)
+    g["pair_correlation_r1.5_dr0.01"] = np.vstack([r_pc, g_pc])
+    g["pair_ripley_r1.5_dr0.01"] = np.vstack([r_k, K_k])
+    lat = np.array([[i, j] for i in range(13) for j in range(11)], dtype=np.float64)
+    g["pair_lattice"] = lat
+    lv = (lat[:, 0] * 3 - lat[:, 1] * 2) % 7
+    g["pair_lattice_values"] = lv
+    out = vm["empirical_variogram_field"](lat, lv, nbins=16, max_dist=16.0)    # edges 0, 1, 2, ...: d = 5, 10, 13 sit on edges
+    g["pair_lattice_vario"] = np.vstack([out[0], out[1], out[2].astype(np.float64)])
+    r_l, g_l = sp2["pair_correlation"](lat, 8.0, 0.5)
+    r_lk, K_l = sp2["ripley_K"](lat, 8.0, 0.5)
+    g["pair_lattice_correlation"] = np.vstack([r_l, g_l])
+    g["pair_lattice_ripley"] = np.vstack([r_lk, K_l])
+
+    # ---- the tracker's density stage (gi_assumption_tracker_v3.py:91-151) with the stock module's KL
+    # (tci_construct_mandelbrot_v002_fixed.py:84-86): Lucas cloud vs the module's boundary sample, as main() pairs them
+    from scipy.ndimage import gaussian_filter
+    from typing import Tuple
+    trk = load_defs("gi_assumption_tracker_v3.py",
+                    ["tv_distance", "overlap_mass", "fraction_outside_domain", "mollified_histogram", "gi_flow_fixed_T",
+                     "gi_flow_to_threshold"], {"gaussian_filter": gaussian_filter, "Tuple": Tuple})
+    kmod = load_defs("tci_construct_mandelbrot_v002_fixed.py", ["KL"], {"eps": 1e-12})
+
+    class _Mod:
+        domain = (-2.2, 1.2, -1.6, 1.6)         # the tracker's default --domain
+        eps = 1e-12
+    Mb = g["tci_fixed_boundary_sample_grid150"]
+    g["density_domain_eps"] = np.array([*_Mod.domain, _Mod.eps])
+    g["density_cloud_C"] = cloud
+    for bins, sig in [(64, 1.0), (64, 0.0), (50, 2.5)]:
+        tag = f"b{bins}_s{sig}"
+        P_C = trk["mollified_histogram"](_Mod, cloud, bins, sig)
+        P_M = trk["mollified_histogram"](_Mod, Mb, bins, sig)
+        g[f"density_PC_{tag}"] = P_C; g[f"density_PM_{tag}"] = P_M
+        X_T, Tn, kl0, klT = trk["gi_flow_to_threshold"](kmod["KL"], P_M, P_C, 0.1, 1e-6, 800, 5)
+        X_F, TF, kl0f, klF = trk["gi_flow_fixed_T"](kmod["KL"], P_M, P_C, 0.1, 25)
+        g[f"density_flow_XT_{tag}"] = X_T; g[f"density_flow_XF_{tag}"] = X_F
+        g[f"density_scalars_{tag}"] = np.array([trk["tv_distance"](P_C, P_M), trk["overlap_mass"](P_C, P_M), kmod["KL"](P_M, P_C),
+                                                Tn, kl0, klT, TF, kl0f, klF, trk["tv_distance"](X_T, P_M),
+                                                trk["fraction_outside_domain"](cloud, _Mod.domain),
+                                                trk["fraction_outside_domain"](Mb, _Mod.domain)])
+
     OUT.parent.mkdir(parents=True, exist_ok=True)
     np.savez_compressed(OUT, **g)
     print(f"wrote {OUT} ({OUT.stat().st_size / 1024:.1f} KiB, {len(g)} arrays)")

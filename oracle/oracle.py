@@ -64,6 +64,9 @@ def lib() -> C.CDLL:
                                            C.c_double, C.c_int32, _f64p]
         L.oracle_nearest_match.restype = None
         L.oracle_nearest_match.argtypes = [_f64p, _f64p, C.c_int64, _f64p, _f64p, C.c_int64, _i64p, _f64p]
+        L.oracle_pair_histogram.restype = C.c_double
+        L.oracle_pair_histogram.argtypes = [_f64p, _f64p, C.c_void_p, C.c_int64, _f64p, _f64p, C.c_int32, C.c_int32,
+                                            np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS"), _f64p]
         L.oracle_contour_lines.restype = C.c_int
         L.oracle_contour_lines.argtypes = [_f64p, C.c_int64, _f64p, C.c_int64, _f64p, C.c_double,
                                            _f64p, C.c_int64, C.POINTER(C.c_int64),
@@ -208,6 +211,125 @@ def weighted_cauchy_sum(z, nodes, weights, dz_eps: float = 1e-14):
     DZ = z[:, None] - b[None, :]
     DZ = np.where(np.abs(DZ) < dz_eps, dz_eps + 0j, DZ)
     return (np.asarray(weights, dtype=np.float64)[None, :] / DZ).sum(axis=1)
+
+
+# ---- pair statistics --------------------------------------------------
+def pair_histogram(locs, lo, hi, values=None, weight: str = "none"):
+    """counts / weight sums of the pairs i<j with lo[k] <= d_ij < hi[k] (every pair tested against every bin, like the
+    reference's masks) -> (counts uint64[nb], sums float64[nb], D.max()).  weight: "none" | "value" | "dist2"."""
+    P = np.asarray(locs, dtype=np.float64).reshape(-1, 2)
+    x = _c(P[:, 0], np.float64); y = _c(P[:, 1], np.float64)
+    lo = _c(lo, np.float64); hi = _c(hi, np.float64)
+    wmode = {"none": 0, "value": 1, "dist2": 2}[weight]
+    v = _c(values, np.float64) if wmode == 1 else None
+    counts = np.zeros(lo.size, dtype=np.uint64); sums = np.zeros(lo.size, dtype=np.float64)
+    dmax = lib().oracle_pair_histogram(x, y, v.ctypes.data if v is not None else None, x.size, lo, hi, lo.size, wmode,
+                                       counts, sums)
+    return counts, sums, float(dmax)
+
+
+def _variogram_from_bins(locs, nbins, max_dist, factor, values, weight):
+    P = np.asarray(locs, dtype=np.float64).reshape(-1, 2)
+    if max_dist is None:
+        _, _, dmax = pair_histogram(P, [0.0], [np.inf])
+        max_dist = factor * dmax
+    bins = np.linspace(0.0, max_dist, nbins + 1)
+    centers = 0.5 * (bins[:-1] + bins[1:])
+    counts, sums, _ = pair_histogram(P, bins[:-1], bins[1:], values, weight)
+    gamma = np.full(nbins, np.nan)
+    nz = counts > 0
+    gamma[nz] = 0.5 * (sums[nz] / counts[nz])
+    return centers, gamma, counts.astype(int)
+
+
+def empirical_variogram_field(locs, values, nbins: int = 50, max_dist=None, max_dist_factor: float = 0.5):
+    """empirical_variogram_field, Variogram-Mandelbrot-Construct.py:106-130 (= empirical_variogram_from_field_locs with
+    values, Iterative_Variogram_Laplacian.py:53-86)."""
+    if np.asarray(locs).shape[0] < 2:
+        return np.array([]), np.array([]), np.array([])
+    return _variogram_from_bins(locs, nbins, max_dist, max_dist_factor, np.asarray(values, dtype=np.float64), "value")
+
+
+def empirical_variogram_coords(locs, nbins: int = 50, max_dist=None, max_dist_factor: float = 0.5):
+    """empirical_variogram_coords, Variogram-Mandelbrot-Construct.py:132-152."""
+    return _variogram_from_bins(locs, nbins, max_dist, max_dist_factor, None, "dist2")
+
+
+def pair_correlation(points, r_max: float, dr: float):
+    """pair_correlation, spatial_stats_phase2.py:9-28."""
+    P = np.asarray(points, dtype=np.float64)
+    N = len(P)
+    area = (np.max(P[:, 0]) - np.min(P[:, 0])) * (np.max(P[:, 1]) - np.min(P[:, 1]))
+    rho = N / area
+    r_vals = np.arange(0, r_max, dr)
+    counts, _, _ = pair_histogram(P, r_vals, r_vals + dr)
+    g_r = []
+    for r, count in zip(r_vals, counts.astype(np.int64)):
+        norm = 2 * np.pi * r * dr * N * rho
+        g_r.append(count / norm if norm > 0 else 0)
+    return r_vals, np.array(g_r)
+
+
+def ripley_K(points, r_max: float, dr: float):
+    """ripley_K, spatial_stats_phase2.py:30-47: count(d < r) = pairs in the bins [r_j, r_{j+1}) below r."""
+    P = np.asarray(points, dtype=np.float64)
+    N = len(P)
+    area = (np.max(P[:, 0]) - np.min(P[:, 0])) * (np.max(P[:, 1]) - np.min(P[:, 1]))
+    rho = N / area
+    r_vals = np.arange(0, r_max, dr)
+    counts, _, _ = pair_histogram(P, r_vals, np.append(r_vals[1:], np.inf))
+    below = np.concatenate([[0], np.cumsum(counts.astype(np.int64))[:-1]])
+    return r_vals, np.array([(2 * c) / (N * rho) for c in below])
+
+
+# ---- the tracker's density stage (SURVEY 8f-1) ------------------------------------------
+def mollified_histogram(domain, eps: float, cloud, bins: int, sigma_bins: float) -> np.ndarray:
+    """mollified_histogram, gi_assumption_tracker_v3.py:109-127 (mod.domain / mod.eps passed explicitly): the same
+    numpy / scipy calls -- they are the reference's arithmetic for this function."""
+    cloud = np.asarray(cloud, dtype=np.complex128)
+    H, _, _ = np.histogram2d(cloud.real, cloud.imag, bins=(bins, bins),
+                             range=[[domain[0], domain[1]], [domain[2], domain[3]]])
+    H = np.maximum(H, eps)
+    if sigma_bins and sigma_bins > 0:
+        from scipy.ndimage import gaussian_filter
+        H = gaussian_filter(H, sigma=float(sigma_bins), mode="nearest")
+        H = np.maximum(H, eps)
+    return H / H.sum()
+
+
+def tv_distance(p, q) -> float:
+    """gi_assumption_tracker_v3.py:91-92."""
+    return 0.5 * float(np.sum(np.abs(p - q)))
+
+
+def overlap_mass(p, q) -> float:
+    """gi_assumption_tracker_v3.py:95-96."""
+    return float(np.sum(np.minimum(p, q)))
+
+
+def KL(P, X, eps: float = 1e-12) -> float:
+    """KL of the stock module, tci_construct_mandelbrot_v002_fixed.py:84-86."""
+    P_ = np.clip(P, eps, None); X_ = np.clip(X, eps, None)
+    return float(np.sum(P_ * (np.log(P_) - np.log(X_))))
+
+
+def gi_flow(P_target, X0, alpha: float, max_steps: int, min_steps: int = 1, kl_threshold=None, eps: float = 1e-12):
+    """gi_flow_to_threshold (kl_threshold given) / gi_flow_fixed_T (None: exactly max_steps sweeps),
+    gi_assumption_tracker_v3.py:130-151 -> (X_T, T, kl0, klT)."""
+    X = np.array(X0, dtype=np.float64, copy=True)
+    kl0 = KL(P_target, X, eps)
+    kl, T = kl0, 0
+    for t in range(1, int(max_steps) + 1):
+        X = (1.0 - alpha) * X + alpha * P_target
+        T = t
+        if kl_threshold is None:
+            continue
+        kl = KL(P_target, X, eps)
+        if t >= int(min_steps) and kl <= float(kl_threshold):
+            break
+    if kl_threshold is None:
+        kl = KL(P_target, X, eps)
+    return X, T, kl0, kl
 
 
 # ---- K2 -------------------------------------------------------------------------------

@@ -153,3 +153,50 @@ def test_curvature_localpoly(oracle, golden):
     got = oracle.curvature_localpoly(golden["curv_open_P"], 4, False)
     want = golden["curv_open_out"]                         # stride 3: every third point is a fit, the rest interpolated
     assert_columns_close(got[::3], want[::3], 1e-9, 1e-9)
+
+
+def _check_vario(out, ref):
+    centers, gamma, counts = out
+    assert np.array_equal(centers, ref[0])
+    assert np.array_equal(counts, ref[2].astype(int))              # pair counts per bin: exact
+    assert np.array_equal(np.isnan(gamma), np.isnan(ref[1]))
+    np.testing.assert_allclose(gamma, ref[1], rtol=1e-12)          # the reference's np.mean is a pairwise sum
+
+
+def test_pair_statistics(oracle, golden):
+    """the pair-histogram restatement against the reference's variogram / pair-correlation functions
+    (Variogram-Mandelbrot-Construct.py:106-152, Iterative_Variogram_Laplacian.py:53-86, spatial_stats_phase2.py:9-47)."""
+    pc, pv = golden["pair_cloud"], golden["pair_values"]
+    _check_vario(oracle.empirical_variogram_field(pc, pv, 60), golden["pair_vario_field"])
+    _check_vario(oracle.empirical_variogram_field(pc, pv, 17, 0.9), golden["pair_vario_field_maxd"])
+    _check_vario(oracle.empirical_variogram_coords(pc, 60), golden["pair_vario_coords"])
+    _check_vario(oracle.empirical_variogram_field(pc, pv, 50), golden["pair_vario_iter_values"])
+    _check_vario(oracle.empirical_variogram_coords(pc, 50), golden["pair_vario_iter_coords"])
+    for pts, rmax, dr, kc, kk in [(pc, 1.5, 0.01, "pair_correlation_r1.5_dr0.01", "pair_ripley_r1.5_dr0.01"),
+                                  (golden["pair_lattice"], 8.0, 0.5, "pair_lattice_correlation", "pair_lattice_ripley")]:
+        r, g_r = oracle.pair_correlation(pts, rmax, dr)
+        assert np.array_equal(r, golden[kc][0]) and np.array_equal(g_r, golden[kc][1])      # integer counts / same norm
+        r, K = oracle.ripley_K(pts, rmax, dr)
+        assert np.array_equal(r, golden[kk][0]) and np.array_equal(K, golden[kk][1])
+    # distances exactly on the integer bin edges (3-4-5 triangles): [lo, hi) semantics of np.digitize
+    _check_vario(oracle.empirical_variogram_field(golden["pair_lattice"], golden["pair_lattice_values"], 16, 16.0),
+                 golden["pair_lattice_vario"])
+
+
+def test_tracker_density_stage(oracle, golden):
+    """mollified_histogram / tv / overlap / KL / GI flows restated (gi_assumption_tracker_v3.py:91-151,
+    tci_construct_mandelbrot_v002_fixed.py:84-86) against the reference's own functions."""
+    dom = tuple(golden["density_domain_eps"][:4]); eps = float(golden["density_domain_eps"][4])
+    Cc, Mb = golden["density_cloud_C"], golden["tci_fixed_boundary_sample_grid150"]
+    for bins, sig in [(64, 1.0), (64, 0.0), (50, 2.5)]:
+        tag = f"b{bins}_s{sig}"
+        P_C = oracle.mollified_histogram(dom, eps, Cc, bins, sig)
+        P_M = oracle.mollified_histogram(dom, eps, Mb, bins, sig)
+        assert np.array_equal(P_C, golden[f"density_PC_{tag}"]) and np.array_equal(P_M, golden[f"density_PM_{tag}"])
+        sc = golden[f"density_scalars_{tag}"]
+        assert oracle.tv_distance(P_C, P_M) == sc[0] and oracle.overlap_mass(P_C, P_M) == sc[1]
+        assert oracle.KL(P_M, P_C, eps) == sc[2]
+        X, T, kl0, klT = oracle.gi_flow(P_M, P_C, 0.1, 800, 5, 1e-6, eps)
+        assert T == int(sc[3]) and kl0 == sc[4] and klT == sc[5] and np.array_equal(X, golden[f"density_flow_XT_{tag}"])
+        X, T, kl0, klT = oracle.gi_flow(P_M, P_C, 0.1, 25, eps=eps)
+        assert T == int(sc[6]) and kl0 == sc[7] and klT == sc[8] and np.array_equal(X, golden[f"density_flow_XF_{tag}"])

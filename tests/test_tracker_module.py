@@ -36,16 +36,16 @@ def test_module_contract_cpu(shim):
     moved = mod.procrustes_align_no_scale(Y * np.exp(0.3j) + (2 - 1j), Y)  # always a rigid motion onto Y's centroid
     assert abs(moved.mean() - Y.mean()) < 1e-12
     assert np.allclose(np.abs(moved[:, None] - moved[None, :]), np.abs(Y[:, None] - Y[None, :]), atol=1e-12)
-    P = mod.to_prob(Y, 16); Q = mod.to_prob(X, 16)
-    assert P.shape == (16, 16) and abs(P.sum() - 1) < 1e-12
-    assert mod.KL(P, P) == 0.0 and mod.KL(P, Q) > 0
-    kls, traj = mod.tci_flow(P, Q)
-    assert len(kls) == mod.T + 1 and kls[-1] < kls[0] * 1e-4 and np.all(np.diff(kls) < 0)
+    assert mod.KL.lm_eps() == mod.eps                                    # what tracker.gi_flow_* read
     if shim.device_count() < 1:          # no CPU fallback behind the module either
         with pytest.raises(RuntimeError):
             mod.construct_points([3])
         with pytest.raises(RuntimeError):
             mod.entropic_ot_alignment(X, Y)
+        with pytest.raises(RuntimeError):
+            mod.to_prob(Y, 16)
+        with pytest.raises(RuntimeError):
+            mod.KL(np.full((4, 4), 1 / 16), np.full((4, 4), 1 / 16))
 
 
 def test_nearest_match_oracle_is_the_reference_rule(oracle):
@@ -100,3 +100,14 @@ def test_tracker_levels(gpu, golden):
     Cal = mod.procrustes_align_no_scale(Csub, Mmatch)
     assert Cal.size == 2400 and Mmatch.size == 2400
     assert np.isfinite(mod.KL(mod.to_prob(Mmatch, 64), mod.to_prob(Cal, 64)))
+    # histogram probabilities, KL and the module's own flow (device KL)
+    rng = np.random.default_rng(3)
+    Y = rng.standard_normal(50) + 1j * rng.standard_normal(50)
+    X = Y[rng.permutation(50)] + 1e-3
+    P = mod.to_prob(Y, 16); Q = mod.to_prob(X, 16)
+    assert P.shape == (16, 16) and abs(P.sum() - 1) < 1e-12
+    H = np.maximum(np.histogram2d(Y.real, Y.imag, bins=(16, 16), range=[[-2.25, 1.25], [-1.75, 1.75]])[0], mod.eps)
+    assert np.array_equal(P, H / H.sum())
+    assert mod.KL(P, P) == 0.0 and mod.KL(P, Q) > 0
+    kls, traj = mod.tci_flow(P, Q)
+    assert len(kls) == mod.T + 1 and kls[-1] < kls[0] * 1e-4 and np.all(np.diff(kls) < 0)
