@@ -8,8 +8,12 @@
 // Every one of them is "count the pairs i<j with lo[k] <= d_ij < hi[k] and sum a per-pair weight", with
 // d_ij = sqrt(dx*dx + dy*dy) in unfused binary64 (probe: scipy pdist, distance_matrix and np.linalg.norm(axis=1) all
 // return exactly that).  Here nothing is materialised: a tile loop over the upper triangle, one i per thread, the j
-// tile staged in shared memory, and the bin of every pair located EXACTLY against the caller's edge arrays (a
-// reciprocal-width guess, then comparisons with the real edges), so the counts are bit-identical to the reference's.
+// tile staged in shared memory, and the bin of every pair located EXACTLY against the caller's edges, so the counts
+// are bit-identical to the reference's.  The comparison runs in the squared domain: sqrt_rn is monotone, so
+//     sqrt_rn(s) >= L   <=>   s >= T(L),   T(L) = the smallest binary64 s whose correctly rounded root reaches L
+// (found on the host per edge by stepping around fl(L*L)), which keeps the FP64 square root out of the per-pair path
+// (it is only taken for the d*d weight).  The bin is guessed from an FP32 root and checked against T(lo[k]), T(lo[k+1]);
+// a wrong guess (a pair within an FP32 ulp of an edge, or non-uniform edges) falls into a linear repair loop.
 // Weights are summed per thread in runs of equal bin, per warp in a private shared-memory histogram, per block in
 // a partial row, and across blocks in block order by a finishing kernel (the reference's np.mean is a pairwise
 // sum: parity of the sums is 1e-12, of the counts exact).
@@ -17,14 +21,16 @@
 
 #include <math.h>
 
+#include <vector>
+
 namespace {
 
 constexpr int PS_THREADS = 128;          // threads per block = i's per tile
 constexpr int PS_TILE = 128;             // j's per tile
 constexpr int PS_WARPS = PS_THREADS / 32;
-constexpr int PS_PRIVATE_MAX_BINS = 512; // up to here every warp owns a histogram copy
+constexpr size_t PS_HIST_BYTES = 16384;  // shared-memory budget of the per-block histogram copies
 constexpr int PS_MAX_BINS = 2048;
-constexpr int PS_BLOCKS_PER_SM = 8;
+constexpr int PS_BLOCKS_PER_SM = 16;         // upper bound of resident 128-thread blocks per SM (2048 threads)
 
 // tile t of the row-major upper triangle (bi <= bj) of a T x T tile grid
 __device__ __forceinline__ void decode_tile(long long t, long long T, int* bi, int* bj) {
@@ -37,6 +43,13 @@ __device__ __forceinline__ void decode_tile(long long t, long long T, int* bi, i
     while (r + 1 < T && (r + 1) * T - (r + 1) * r / 2 <= t) ++r;
     *bi = static_cast<int>(r);
     *bj = static_cast<int>(r + (t - (r * T - r * (r - 1) / 2)));
+}
+
+// MUFU.SQRT: the guess only has to be close, the exact check follows
+__device__ __forceinline__ float approx_sqrtf(float a) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
 }
 
 struct RunCache {
@@ -53,28 +66,35 @@ __device__ __forceinline__ void flush_run(RunCache& rc, unsigned long long* hc, 
     }
 }
 
-// WMODE: LM_PAIR_W_NONE counts only, LM_PAIR_W_VALUE_SQDIFF (v_i - v_j)^2, LM_PAIR_W_DIST_SQ d^2
-template <int WMODE>
+// WMODE: LM_PAIR_W_NONE counts only, LM_PAIR_W_VALUE_SQDIFF (v_i - v_j)^2, LM_PAIR_W_DIST_SQ d^2.
+// PARTITION: hi[k] == lo[k+1] for every k (np.digitize bins, Ripley's cumulated counts): no upper-edge array needed.
+// tlo[nb + 1]: T(lo[k]) with a +inf sentinel; thi[nb]: T(hi[k]) (general shells only).
+template <int WMODE, bool PARTITION>
 __global__ void __launch_bounds__(PS_THREADS) pair_hist_kernel(const double* __restrict__ x, const double* __restrict__ y,
                                                                const double* __restrict__ v, long long n,
-                                                               const double* __restrict__ lo, const double* __restrict__ hi, int nb,
-                                                               double lo0, double inv_w, int copies, long long T, long long total_tiles,
-                                                               unsigned long long* __restrict__ part_counts,
+                                                               const double* __restrict__ tlo, const double* __restrict__ thi, int nb,
+                                                               float lo0, float inv_w, double thi_last, int copies, int stride, long long T,
+                                                               long long total_tiles, unsigned long long* __restrict__ part_counts,
                                                                double* __restrict__ part_sums) {
     extern __shared__ __align__(16) unsigned char ps_smem[];
-    double* slo = reinterpret_cast<double*>(ps_smem);
-    double* shi = slo + nb;
-    double* ssum = shi + nb;                                                   // [copies][nb]
-    unsigned long long* scnt = reinterpret_cast<unsigned long long*>(ssum + static_cast<size_t>(copies) * nb);
-    __shared__ double sx[PS_TILE], sy[PS_TILE], sv[PS_TILE];
+    double* slo = reinterpret_cast<double*>(ps_smem);                          // [nb + 1]
+    double* shi = slo + (nb + 1);                                              // [nb] (unused when PARTITION)
+    double* ssum = shi + (PARTITION ? 0 : nb);                                 // [copies][stride], stride odd (bank spread)
+    unsigned long long* scnt = reinterpret_cast<unsigned long long*>(ssum + static_cast<size_t>(copies) * stride);
+    __shared__ double2 sxy[PS_TILE];
+    __shared__ double sv[PS_TILE];
 
     const int tid = threadIdx.x;
-    for (int k = tid; k < nb; k += PS_THREADS) { slo[k] = lo[k]; shi[k] = hi[k]; }
-    for (int k = tid; k < copies * nb; k += PS_THREADS) { ssum[k] = 0.0; scnt[k] = 0ull; }
-    const int copy = copies > 1 ? (tid >> 5) : 0;
-    unsigned long long* hc = scnt + static_cast<size_t>(copy) * nb;
-    double* hs = ssum + static_cast<size_t>(copy) * nb;
+    for (int k = tid; k <= nb; k += PS_THREADS) slo[k] = tlo[k];
+    if (!PARTITION) for (int k = tid; k < nb; k += PS_THREADS) shi[k] = thi[k];
+    for (int k = tid; k < copies * stride; k += PS_THREADS) { ssum[k] = 0.0; scnt[k] = 0ull; }
+    // neighbouring lanes look at neighbouring points and tend to flush the same bin at the same time: consecutive
+    // lanes own different histogram copies (copies is a power of two), so those atomics do not serialise
+    const int copy = tid & (copies - 1);
+    unsigned long long* hc = scnt + static_cast<size_t>(copy) * stride;
+    double* hs = ssum + static_cast<size_t>(copy) * stride;
     RunCache run;
+    const float kmax = static_cast<float>(nb - 1);
 
     for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         int bi, bj;
@@ -87,7 +107,7 @@ __global__ void __launch_bounds__(PS_THREADS) pair_hist_kernel(const double* __r
         if (WMODE == LM_PAIR_W_VALUE_SQDIFF) vi = live ? v[i] : 0.0;
         __syncthreads();                                   // previous tile consumed (and the zero fill on the first pass)
         if (j0 + tid < n) {
-            sx[tid] = x[j0 + tid]; sy[tid] = y[j0 + tid];
+            sxy[tid] = make_double2(x[j0 + tid], y[j0 + tid]);
             if (WMODE == LM_PAIR_W_VALUE_SQDIFF) sv[tid] = v[j0 + tid];
         }
         __syncthreads();
@@ -96,21 +116,25 @@ __global__ void __launch_bounds__(PS_THREADS) pair_hist_kernel(const double* __r
         const int jfirst = (bi == bj) ? tid + 1 : 0;      // strict upper triangle on diagonal tiles
 #pragma unroll 2
         for (int j = jfirst; j < jn; ++j) {
-            const double dx = __dsub_rn(xi, sx[j]), dy = __dsub_rn(yi, sy[j]);
-            const double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
-            // k = largest index with lo[k] <= d (or -1): guess from the mean width, repair against the real edges
-            int k = static_cast<int>(fmin(fmax((d - lo0) * inv_w, 0.0), static_cast<double>(nb - 1)));
-            while (k >= 0 && d < slo[k]) --k;
-            while (k + 1 < nb && slo[k + 1] <= d) ++k;
-            if (k < 0) continue;
+            const double2 pj = sxy[j];
+            const double dx = __dsub_rn(xi, pj.x), dy = __dsub_rn(yi, pj.y);
+            const double s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));          // d = sqrt_rn(s)
+            // k = largest index with lo[k] <= d, i.e. T(lo[k]) <= s: FP32 guess, exact check, rare repair
+            int k = static_cast<int>(fminf(fmaxf((approx_sqrtf(static_cast<float>(s)) - lo0) * inv_w, 0.f), kmax));
+            if (s < slo[k] || s >= slo[k + 1]) {
+                while (k >= 0 && s < slo[k]) --k;
+                while (k + 1 < nb && slo[k + 1] <= s) ++k;
+                if (k < 0) continue;
+            }
             double w = 0.0;
             if (WMODE == LM_PAIR_W_VALUE_SQDIFF) { const double dv = __dsub_rn(vi, sv[j]); w = __dmul_rn(dv, dv); }
-            if (WMODE == LM_PAIR_W_DIST_SQ) w = __dmul_rn(d, d);
-            if (d < shi[k]) {
+            if (WMODE == LM_PAIR_W_DIST_SQ) { const double d = __dsqrt_rn(s); w = __dmul_rn(d, d); }
+            const bool inside = PARTITION ? (k < nb - 1 || s < thi_last) : (s < shi[k]);
+            if (inside) {
                 if (k == run.k) { ++run.cnt; run.sum += w; }
                 else { flush_run<WMODE>(run, hc, hs); run.k = k; run.cnt = 1; run.sum = w; }
             }
-            if (k >= 1 && d < shi[k - 1]) {               // shells whose upper edge overshoots the next lower edge by an ulp
+            if (!PARTITION && k >= 1 && s < shi[k - 1]) {  // shells whose upper edge overshoots the next lower edge by an ulp
                 atomicAdd(&hc[k - 1], 1ull);
                 if (WMODE != LM_PAIR_W_NONE) atomicAdd(&hs[k - 1], w);
             }
@@ -120,10 +144,10 @@ __global__ void __launch_bounds__(PS_THREADS) pair_hist_kernel(const double* __r
     __syncthreads();
     for (int k = tid; k < nb; k += PS_THREADS) {
         unsigned long long c = 0ull;
-        double s = 0.0;
-        for (int q = 0; q < copies; ++q) { c += scnt[static_cast<size_t>(q) * nb + k]; s += ssum[static_cast<size_t>(q) * nb + k]; }
+        double sm = 0.0;
+        for (int q = 0; q < copies; ++q) { c += scnt[static_cast<size_t>(q) * stride + k]; sm += ssum[static_cast<size_t>(q) * stride + k]; }
         part_counts[static_cast<size_t>(blockIdx.x) * nb + k] = c;
-        if (WMODE != LM_PAIR_W_NONE) part_sums[static_cast<size_t>(blockIdx.x) * nb + k] = s;
+        if (WMODE != LM_PAIR_W_NONE) part_sums[static_cast<size_t>(blockIdx.x) * nb + k] = sm;
     }
 }
 
@@ -196,11 +220,49 @@ int32_t all_finite(const double* a, int64_t n, const char* what) {
     return LM_OK;
 }
 
-template <int WMODE>
-void launch_hist(const TileGrid& g, size_t smem, cudaStream_t s, const double* x, const double* y, const double* v, int64_t n,
-                 const double* lo, const double* hi, int nb, double lo0, double inv_w, int copies, unsigned long long* pc, double* psum) {
-    cudaFuncSetAttribute(pair_hist_kernel<WMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    pair_hist_kernel<WMODE><<<g.blocks, PS_THREADS, smem, s>>>(x, y, v, n, lo, hi, nb, lo0, inv_w, copies, g.T, g.total, pc, psum);
+// T(L): the smallest s >= 0 with sqrt_rn(s) >= L (sqrt_rn monotone => d >= L <=> s >= T(L)).
+double sq_threshold(double L) {
+    if (!(L > 0.0)) return 0.0;
+    if (isinf(L)) return INFINITY;
+    double c = L * L;
+    if (isinf(c)) c = 1.7976931348623157e308;
+    while (c > 0.0 && sqrt(c) >= L) c = nextafter(c, 0.0);
+    while (sqrt(c) < L) {
+        const double up = nextafter(c, INFINITY);
+        if (isinf(up)) return INFINITY;                 // no finite s has a root that large
+        c = up;
+    }
+    return c;
+}
+
+struct HistArgs {
+    const double *x, *y, *v, *tlo, *thi;
+    int64_t n; int nb; float lo0, inv_w; double thi_last; int copies, stride;
+    unsigned long long* pc; double* psum;
+};
+
+// persistent grid: exactly the blocks that are resident at once (tiles are dealt round-robin, so a partial second
+// wave would leave most SMs idle at the end); returns the grid size used (= rows of the partial arrays)
+template <int WMODE, bool PARTITION>
+unsigned launch_hist(const TileGrid& g, size_t smem, cudaStream_t s, const HistArgs& a) {
+    cudaFuncSetAttribute(pair_hist_kernel<WMODE, PARTITION>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pair_hist_kernel<WMODE, PARTITION>, PS_THREADS, smem) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 1;
+    }
+    const long long resident = static_cast<long long>(lm::sm_count()) * per_sm;
+    const unsigned blocks = static_cast<unsigned>(g.total < resident ? g.total : resident);
+    pair_hist_kernel<WMODE, PARTITION><<<blocks, PS_THREADS, smem, s>>>(a.x, a.y, a.v, a.n, a.tlo, a.thi, a.nb, a.lo0, a.inv_w, a.thi_last,
+                                                                         a.copies, a.stride, g.T, g.total, a.pc, a.psum);
+    return blocks;
+}
+
+template <bool PARTITION>
+unsigned launch_hist_mode(int weight_mode, const TileGrid& g, size_t smem, cudaStream_t s, const HistArgs& a) {
+    if (weight_mode == LM_PAIR_W_NONE) return launch_hist<LM_PAIR_W_NONE, PARTITION>(g, smem, s, a);
+    if (weight_mode == LM_PAIR_W_VALUE_SQDIFF) return launch_hist<LM_PAIR_W_VALUE_SQDIFF, PARTITION>(g, smem, s, a);
+    return launch_hist<LM_PAIR_W_DIST_SQ, PARTITION>(g, smem, s, a);
 }
 
 }  // namespace
@@ -238,7 +300,7 @@ int32_t lm_pair_histogram(const double* x, const double* y, const double* value,
     if ((rc = lm::ws_get(lm::WS_IN_A, pb, &dx)) != LM_OK) return rc;
     if ((rc = lm::ws_get(lm::WS_IN_B, pb, &dy)) != LM_OK) return rc;
     if ((rc = lm::ws_get(lm::WS_IN_C, pb, &dv)) != LM_OK) return rc;
-    if ((rc = lm::ws_get(lm::WS_OUT_A, eb, &dlo)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_OUT_A, eb + sizeof(double), &dlo)) != LM_OK) return rc;
     if ((rc = lm::ws_get(lm::WS_OUT_B, eb, &dhi)) != LM_OK) return rc;
     if ((rc = lm::ws_get(lm::WS_OUT_C, eb * g.blocks, &dpc)) != LM_OK) return rc;
     if ((rc = lm::ws_get(lm::WS_OUT_D, eb * g.blocks, &dps)) != LM_OK) return rc;
@@ -246,13 +308,23 @@ int32_t lm_pair_histogram(const double* x, const double* y, const double* value,
     LM_CUDA_TRY(cudaMemcpyAsync(dx, x, pb, cudaMemcpyHostToDevice, s));
     LM_CUDA_TRY(cudaMemcpyAsync(dy, y, pb, cudaMemcpyHostToDevice, s));
     if (weight_mode == LM_PAIR_W_VALUE_SQDIFF) LM_CUDA_TRY(cudaMemcpyAsync(dv, value, pb, cudaMemcpyHostToDevice, s));
-    LM_CUDA_TRY(cudaMemcpyAsync(dlo, lo, eb, cudaMemcpyHostToDevice, s));
-    LM_CUDA_TRY(cudaMemcpyAsync(dhi, hi, eb, cudaMemcpyHostToDevice, s));
+    std::vector<double> tlo(static_cast<size_t>(nbins) + 1), thi(static_cast<size_t>(nbins));
+    bool partition = true;
+    for (int k = 0; k < nbins; ++k) {
+        tlo[k] = sq_threshold(lo[k]);
+        thi[k] = sq_threshold(hi[k]);
+        if (k + 1 < nbins && hi[k] != lo[k + 1]) partition = false;
+    }
+    tlo[nbins] = INFINITY;                                  // sentinel: the exact check reads slo[k + 1]
+    LM_CUDA_TRY(cudaMemcpyAsync(dlo, tlo.data(), eb + sizeof(double), cudaMemcpyHostToDevice, s));
+    LM_CUDA_TRY(cudaMemcpyAsync(dhi, thi.data(), eb, cudaMemcpyHostToDevice, s));
 
-    const int copies = nbins <= PS_PRIVATE_MAX_BINS ? PS_WARPS : 1;
-    const size_t smem = static_cast<size_t>(nbins) * 16 + static_cast<size_t>(copies) * nbins * 16;
+    const int stride = nbins | 1;
+    int copies = 1;
+    while (copies < PS_THREADS && static_cast<size_t>(2 * copies) * stride * 16 <= PS_HIST_BYTES) copies *= 2;
+    const size_t smem = (static_cast<size_t>(nbins) + 1 + (partition ? 0 : nbins)) * 8 + static_cast<size_t>(copies) * stride * 16;
     const double span = lo[nbins - 1] - lo[0];
-    const double inv_w = (nbins > 1 && span > 0.0) ? static_cast<double>(nbins - 1) / span : 0.0;
+    const double inv_w = (nbins > 1 && span > 0.0 && isfinite(span)) ? static_cast<double>(nbins - 1) / span : 0.0;
     unsigned long long* pc = static_cast<unsigned long long*>(dpc);
     double* psum = static_cast<double*>(dps);
     unsigned long long* fin_c = static_cast<unsigned long long*>(dfin);
@@ -260,13 +332,11 @@ int32_t lm_pair_histogram(const double* x, const double* y, const double* value,
 
     lm::Timer tm;
     if ((rc = tm.begin(s)) != LM_OK) return rc;
-    const double *cx = static_cast<double*>(dx), *cy = static_cast<double*>(dy), *cv = static_cast<double*>(dv);
-    const double *clo = static_cast<double*>(dlo), *chi = static_cast<double*>(dhi);
-    if (weight_mode == LM_PAIR_W_NONE) launch_hist<LM_PAIR_W_NONE>(g, smem, s, cx, cy, cv, n, clo, chi, nbins, lo[0], inv_w, copies, pc, psum);
-    else if (weight_mode == LM_PAIR_W_VALUE_SQDIFF) launch_hist<LM_PAIR_W_VALUE_SQDIFF>(g, smem, s, cx, cy, cv, n, clo, chi, nbins, lo[0], inv_w, copies, pc, psum);
-    else launch_hist<LM_PAIR_W_DIST_SQ>(g, smem, s, cx, cy, cv, n, clo, chi, nbins, lo[0], inv_w, copies, pc, psum);
+    HistArgs a{static_cast<double*>(dx), static_cast<double*>(dy), static_cast<double*>(dv), static_cast<double*>(dlo),
+               static_cast<double*>(dhi), n, nbins, static_cast<float>(lo[0]), static_cast<float>(inv_w), thi[nbins - 1], copies, stride, pc, psum};
+    const unsigned blocks = partition ? launch_hist_mode<true>(weight_mode, g, smem, s, a) : launch_hist_mode<false>(weight_mode, g, smem, s, a);
     LM_CUDA_TRY(cudaGetLastError());
-    pair_hist_finish_kernel<<<(nbins + 127) / 128, 128, 0, s>>>(pc, psum, static_cast<int>(g.blocks), nbins,
+    pair_hist_finish_kernel<<<(nbins + 127) / 128, 128, 0, s>>>(pc, psum, static_cast<int>(blocks), nbins,
                                                                weight_mode != LM_PAIR_W_NONE, fin_c, fin_s);
     LM_CUDA_TRY(cudaGetLastError());
     float ms = 0.f;
