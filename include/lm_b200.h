@@ -337,6 +337,15 @@ int32_t lm_lucas_cloud_fields(const double* toprows, const int32_t* deg, int64_t
                               const double* gx, int64_t nx, const double* gy, int64_t ny,
                               double eps, int32_t variant, double h, double* U, double* lapU,
                               lm_cloud_stats* stats);
+/* Same call with the first rows as int8 (generalized-Lucas rows are small integers -- family_toprow,
+ * lucas_equipotential_test_v3.py:76-91 -- and int8 -> binary64 is exact): 1 byte per coefficient over PCIe
+ * instead of 8, widened on the device; results are bit-identical to the float64 call.                       */
+int32_t lm_lucas_cloud_fields_i8(const int8_t* toprows_i8, const int32_t* deg, int64_t npoly, int32_t maxdeg, double tol,
+                                 double* cloud_re, double* cloud_im, int64_t cap_points, int64_t* n_points,
+                                 int32_t pot_max_iter, double pot_radius, double* g, int64_t* it,
+                                 const double* gx, int64_t nx, const double* gy, int64_t ny,
+                                 double eps, int32_t variant, double h, double* U, double* lapU,
+                                 lm_cloud_stats* stats);
 
 /* ---- K4: 5-point stencils ------------------------------------------------------ */
 /* lap = (((((-4 U) + U[j-1]) + U[j+1]) + U[:,i-1]) + U[:,i+1]) / (h*h), periodic wrap.

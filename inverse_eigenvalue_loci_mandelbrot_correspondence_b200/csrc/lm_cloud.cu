@@ -16,18 +16,26 @@
 
 #include <vector>
 
-extern "C" {
+namespace {
 
-int32_t lm_lucas_cloud_fields(const double* toprows, const int32_t* deg, int64_t npoly, int32_t maxdeg, double tol,
-                              double* cloud_re, double* cloud_im, int64_t cap_points, int64_t* n_points,
-                              int32_t pot_max_iter, double pot_radius, double* g, int64_t* it,
-                              const double* gx, int64_t nx, const double* gy, int64_t ny,
-                              double eps, int32_t variant, double h, double* U, double* lapU,
-                              lm_cloud_stats* stats) {
+// first rows handed over as int8 (generalized-Lucas rows are small integers: family_toprow,
+// lucas_equipotential_test_v3.py:76-91) are widened on the device: 1 byte instead of 8 per coefficient over PCIe
+__global__ void widen_i8_kernel(const signed char* __restrict__ in, long long n, double* __restrict__ out) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = static_cast<double>(in[i]);
+}
+
+// toprows (float64) or toprows_i8 (int8): exactly one of them is non-NULL when npoly > 0
+int32_t cloud_fields_impl(const double* toprows, const signed char* toprows_i8, const int32_t* deg, int64_t npoly, int32_t maxdeg, double tol,
+                          double* cloud_re, double* cloud_im, int64_t cap_points, int64_t* n_points,
+                          int32_t pot_max_iter, double pot_radius, double* g, int64_t* it,
+                          const double* gx, int64_t nx, const double* gy, int64_t ny,
+                          double eps, int32_t variant, double h, double* U, double* lapU,
+                          lm_cloud_stats* stats) {
     int32_t rc = lm::require_device();
     if (rc != LM_OK) return rc;
     LM_REQUIRE(npoly >= 0 && maxdeg >= 1 && cap_points >= 0, "lm_lucas_cloud_fields: bad sizes");
-    LM_REQUIRE(npoly == 0 || (toprows && deg), "lm_lucas_cloud_fields: NULL polynomial buffers");
+    LM_REQUIRE(npoly == 0 || ((toprows || toprows_i8) && deg), "lm_lucas_cloud_fields: NULL polynomial buffers");
     LM_REQUIRE(n_points != nullptr, "lm_lucas_cloud_fields: n_points is NULL");
     LM_REQUIRE(nx >= 0 && ny >= 0, "lm_lucas_cloud_fields: negative grid size");
     const bool want_field = (U != nullptr || lapU != nullptr) && nx * ny > 0;
@@ -44,15 +52,18 @@ int32_t lm_lucas_cloud_fields(const double* toprows, const int32_t* deg, int64_t
     if ((rc = lm::ws_get(lm::WS_OUT_A, ncoef * sizeof(double), &dre)) != LM_OK) return rc;
     if ((rc = lm::ws_get(lm::WS_OUT_B, ncoef * sizeof(double), &dim)) != LM_OK) return rc;
     if ((rc = lm::ws_get(lm::WS_OUT_C, static_cast<size_t>(npoly) * sizeof(int), &dkept)) != LM_OK) return rc;
+    void* dtop8 = nullptr;
+    if (toprows_i8 && (rc = lm::ws_get(lm::WS_IN_C, ncoef, &dtop8)) != LM_OK) return rc;
     // the batch streams through the device in chunks: upload of chunk c+1, K3 + compaction of chunk c and the
     // download of chunk c-1's cloud points run on three streams
     constexpr int64_t CHUNK = int64_t(1) << 20;
     const int nchunks = static_cast<int>(npoly ? (npoly + CHUNK - 1) / CHUNK : 0);
     if ((rc = lm::ws_get(lm::WS_SCRATCH, 64 + 16 * static_cast<size_t>(nchunks + 1), &dstat)) != LM_OK) return rc;
-    // the cloud has at most sum(deg) <= npoly * maxdeg points; size the packed buffers by the host sum
+    // the cloud has at most sum(deg) <= npoly * maxdeg points: the packed buffers are sized by that bound, and the
+    // exact sum (for the report) is accumulated chunk by chunk below, while the device works on the previous chunk
     uint64_t nroots = 0;
-    for (int64_t k = 0; k < npoly; ++k) nroots += static_cast<uint64_t>(deg[k] > 0 ? deg[k] : 0);
-    const size_t pb = static_cast<size_t>(nroots) * sizeof(double);
+    const uint64_t max_points = static_cast<uint64_t>(ncoef);
+    const size_t pb = static_cast<size_t>(max_points) * sizeof(double);
     if ((rc = lm::ws_get(lm::WS_CLOUD_A, pb, &dpx)) != LM_OK) return rc;
     if ((rc = lm::ws_get(lm::WS_CLOUD_B, pb, &dpy)) != LM_OK) return rc;
 
@@ -119,8 +130,16 @@ int32_t lm_lucas_cloud_fields(const double* toprows, const int32_t* deg, int64_t
     for (int c = 0; c < nchunks; ++c) {
         const int64_t p0 = static_cast<int64_t>(c) * CHUNK, pn = (p0 + CHUNK <= npoly) ? CHUNK : npoly - p0;
         const size_t co = static_cast<size_t>(p0) * maxdeg;
-        LM_CUDA_TRY(cudaMemcpyAsync(static_cast<double*>(dtop) + co, toprows + co, static_cast<size_t>(pn) * maxdeg * sizeof(double),
-                                    cudaMemcpyHostToDevice, s_in));
+        if (toprows_i8) {
+            const long long nc = static_cast<long long>(pn) * maxdeg;
+            LM_CUDA_TRY(cudaMemcpyAsync(static_cast<signed char*>(dtop8) + co, toprows_i8 + co, static_cast<size_t>(nc), cudaMemcpyHostToDevice, s_in));
+            widen_i8_kernel<<<static_cast<unsigned>((nc + 255) / 256), 256, 0, s_in>>>(static_cast<signed char*>(dtop8) + co, nc,
+                                                                                       static_cast<double*>(dtop) + co);
+            LM_CUDA_TRY(cudaGetLastError());
+        } else {
+            LM_CUDA_TRY(cudaMemcpyAsync(static_cast<double*>(dtop) + co, toprows + co, static_cast<size_t>(pn) * maxdeg * sizeof(double),
+                                        cudaMemcpyHostToDevice, s_in));
+        }
         LM_CUDA_TRY(cudaMemcpyAsync(static_cast<int*>(ddeg) + p0, deg + p0, static_cast<size_t>(pn) * sizeof(int), cudaMemcpyHostToDevice, s_in));
         LM_CUDA_TRY(cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming));
         LM_CUDA_TRY(cudaEventRecord(ev_in[c], s_in));
@@ -130,12 +149,13 @@ int32_t lm_lucas_cloud_fields(const double* toprows, const int32_t* deg, int64_t
                                   nullptr, dflags + 2 * c, s);
         if (rc != LM_OK) return rc;
         rc = lm_cloud_append_dev(static_cast<double*>(dre) + co, static_cast<double*>(dim) + co, static_cast<int32_t*>(dkept) + p0, pn,
-                                 maxdeg, static_cast<double*>(dpx), static_cast<double*>(dpy), static_cast<int64_t>(nroots), dcount, s);
+                                 maxdeg, static_cast<double*>(dpx), static_cast<double*>(dpy), static_cast<int64_t>(max_points), dcount, s);
         if (rc != LM_OK) return rc;
         LM_CUDA_TRY(cudaMemcpyAsync(&h_note[c], dcount, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
         LM_CUDA_TRY(cudaMemcpyAsync(&h_flags[2 * c], dflags + 2 * c, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
         LM_CUDA_TRY(cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming));
         LM_CUDA_TRY(cudaEventRecord(ev_done[c], s));
+        for (int64_t k = p0; k < p0 + pn; ++k) nroots += static_cast<uint64_t>(deg[k] > 0 ? deg[k] : 0);
         if (c >= 1 && (rc = download_upto(c - 1)) != LM_OK) return rc;
     }
     LM_CUDA_TRY(cudaEventRecord(ev[1], s));
@@ -207,6 +227,30 @@ int32_t lm_lucas_cloud_fields(const double* toprows, const int32_t* deg, int64_t
     if (flags[0])
         return lm::fail(LM_E_NOCONV, "lm_lucas_cloud_fields: the Aberth iteration did not converge for some polynomial");
     return LM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t lm_lucas_cloud_fields(const double* toprows, const int32_t* deg, int64_t npoly, int32_t maxdeg, double tol,
+                              double* cloud_re, double* cloud_im, int64_t cap_points, int64_t* n_points,
+                              int32_t pot_max_iter, double pot_radius, double* g, int64_t* it,
+                              const double* gx, int64_t nx, const double* gy, int64_t ny,
+                              double eps, int32_t variant, double h, double* U, double* lapU,
+                              lm_cloud_stats* stats) {
+    return cloud_fields_impl(toprows, nullptr, deg, npoly, maxdeg, tol, cloud_re, cloud_im, cap_points, n_points, pot_max_iter,
+                             pot_radius, g, it, gx, nx, gy, ny, eps, variant, h, U, lapU, stats);
+}
+
+int32_t lm_lucas_cloud_fields_i8(const int8_t* toprows_i8, const int32_t* deg, int64_t npoly, int32_t maxdeg, double tol,
+                                 double* cloud_re, double* cloud_im, int64_t cap_points, int64_t* n_points,
+                                 int32_t pot_max_iter, double pot_radius, double* g, int64_t* it,
+                                 const double* gx, int64_t nx, const double* gy, int64_t ny,
+                                 double eps, int32_t variant, double h, double* U, double* lapU,
+                                 lm_cloud_stats* stats) {
+    return cloud_fields_impl(nullptr, reinterpret_cast<const signed char*>(toprows_i8), deg, npoly, maxdeg, tol, cloud_re, cloud_im,
+                             cap_points, n_points, pot_max_iter, pot_radius, g, it, gx, nx, gy, ny, eps, variant, h, U, lapU, stats);
 }
 
 }  // extern "C"

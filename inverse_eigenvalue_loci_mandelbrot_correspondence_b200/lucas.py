@@ -149,25 +149,31 @@ def cloud_fields(toprows, deg, grid_x=None, grid_y=None, tol: float = 1e-12, eps
     cloud_out=(re, im): optional preallocated float64 arrays (e.g. page-locked, `_shim.pinned_empty`) of at least
     sum(deg) entries that receive the cloud; "cloud" is then the pair of views (re[:n], im[:n]) instead of a
     complex array (no extra host pass).  Page-locked `toprows` / `deg` make the upload run at PCIe speed too.
+    `toprows` of dtype int8 (generalized-Lucas rows are small integers) travel as 1 byte per coefficient and are
+    widened on the device (lm_lucas_cloud_fields_i8): same results, 8x less upload.
 
     Returns {"cloud", "g", "it", "U", "lapU", "stats"}; entries not asked for are None.
     """
-    toprows = np.ascontiguousarray(toprows, dtype=np.float64)
+    compact = np.asarray(toprows).dtype == np.int8      # small-integer first rows: 1 byte per coefficient over PCIe
+    toprows = np.ascontiguousarray(toprows, dtype=np.int8 if compact else np.float64)
     if toprows.ndim != 2:
         raise ValueError("toprows must be [npoly, maxdeg]")
     npoly, maxdeg = toprows.shape
     deg = np.ascontiguousarray(deg, dtype=np.int32).reshape(-1)
     if deg.shape[0] != npoly:
         raise ValueError("deg must have one entry per polynomial")
-    cap = int(np.clip(deg, 0, None).sum())
     want_pts = return_cloud or potential is not None
     if cloud_out is not None:
         cre, cim = cloud_out
-        if (cre.dtype != np.float64 or cim.dtype != np.float64 or cre.size < cap or cim.size < cap
+        if (cre.dtype != np.float64 or cim.dtype != np.float64
                 or not cre.flags["C_CONTIGUOUS"] or not cim.flags["C_CONTIGUOUS"]):
             raise ValueError("cloud_out must be two C-contiguous float64 arrays with at least sum(deg) entries")
+        cap = int(min(cre.size, cim.size))       # the library reports LM_E_CAP (LmError) if the cloud is larger
+        if potential is not None:
+            cap = min(cap, max(int(deg.sum(dtype=np.int64)), 0))
         return_cloud = True
     else:
+        cap = max(int(deg.sum(dtype=np.int64)), 0)   # a negative degree makes the call itself fail (LM_E_INVALID)
         cre = np.empty(cap, dtype=np.float64) if return_cloud else None
         cim = np.empty(cap, dtype=np.float64) if return_cloud else None
     g = np.empty(cap, dtype=np.float64) if potential is not None else None
@@ -186,7 +192,7 @@ def cloud_fields(toprows, deg, grid_x=None, grid_y=None, tol: float = 1e-12, eps
     st = CloudStats()
     n = C.c_int64(0)
     pmi, pR = (int(potential[0]), float(potential[1])) if potential is not None else (1, 2.0)
-    _shim.call("lm_lucas_cloud_fields", _shim.ptr(toprows), _shim.ptr(deg), npoly, maxdeg, float(tol),
+    _shim.call("lm_lucas_cloud_fields_i8" if compact else "lm_lucas_cloud_fields", _shim.ptr(toprows), _shim.ptr(deg), npoly, maxdeg, float(tol),
                _shim.ptr(cre), _shim.ptr(cim), cap if want_pts else 0, C.byref(n), pmi, pR, _shim.ptr(g), _shim.ptr(it),
                _shim.ptr(gx), nx, _shim.ptr(gy), ny, float(eps), int(variant), float(h if h is not None else 1.0),
                _shim.ptr(U), _shim.ptr(lap), C.byref(st))

@@ -145,3 +145,33 @@ def test_sharded_cloud_fields_world1(gpu, oracle):
     assert np.array_equal(b["it"], a["it"]) and np.array_equal(b["g"], a["g"])
     np.testing.assert_allclose(b["U"], a["U"], rtol=1e-13, atol=1e-14)
     assert np.array_equal(b["lapU"], oracle.laplacian(b["U"], gx[1] - gx[0]))
+
+
+def test_cloud_fields_int8_rows(gpu):
+    """lm_lucas_cloud_fields_i8: small-integer first rows handed over as int8 give bit-identical outputs, across the
+    2^20-polynomial chunk boundary of the streaming pipeline too."""
+    rng = np.random.default_rng(21)
+    npoly, maxdeg = (1 << 20) + 4097, 12
+    deg = rng.integers(2, maxdeg + 1, npoly).astype(np.int32)
+    top = rng.integers(0, 3, (npoly, maxdeg)).astype(np.float64)     # the config-5 coefficient set
+    top[np.arange(maxdeg)[None, :] >= deg[:, None]] = 0.0
+    top[np.arange(npoly), deg - 1] = rng.integers(1, 3, npoly)         # no zero eigenvalue
+    gx = np.linspace(-2, 2, 24)
+    a = gpu.lucas.cloud_fields(top, deg, gx, gx, potential=(200, 2.0))
+    b = gpu.lucas.cloud_fields(top.astype(np.int8), deg, gx, gx, potential=(200, 2.0))
+    assert a["n_points"] == b["n_points"] == int(deg.sum())
+    assert np.array_equal(a["cloud"], b["cloud"]) and np.array_equal(a["U"], b["U"]) and np.array_equal(a["lapU"], b["lapU"])
+    assert np.array_equal(a["g"], b["g"]) and np.array_equal(a["it"], b["it"])
+    small = gpu.lucas.cloud_fields(np.array([[1, 1, 0], [2, 1, 1]], dtype=np.int8), np.array([2, 3], dtype=np.int32))
+    ref = gpu.lucas.cloud_fields(np.array([[1.0, 1, 0], [2, 1, 1]]), np.array([2, 3], dtype=np.int32))
+    assert np.array_equal(small["cloud"], ref["cloud"])
+    empty = gpu.lucas.cloud_fields(np.zeros((0, 5), dtype=np.int8), np.zeros(0, dtype=np.int32))
+    assert empty["n_points"] == 0
+    # caller-provided (page-locked) cloud buffers: views of exactly n_points entries come back; too small -> LM_E_CAP
+    n = int(deg[:5000].sum())
+    cre = gpu.shim.pinned_empty(n + 7, np.float64); cim = gpu.shim.pinned_empty(n + 7, np.float64)
+    c = gpu.lucas.cloud_fields(top[:5000].astype(np.int8), deg[:5000], cloud_out=(cre, cim))
+    assert c["n_points"] == n and c["cloud"][0].size == n
+    assert np.array_equal(c["cloud"][0] + 1j * c["cloud"][1], a["cloud"][:n])
+    with pytest.raises(RuntimeError):
+        gpu.lucas.cloud_fields(top[:5000], deg[:5000], cloud_out=(cre[:n - 1], cim[:n - 1]))
