@@ -459,6 +459,16 @@ int32_t lm_gi_flow(const double* P, const double* X0, int64_t n, double alpha, d
                    double* X_out, int32_t* steps_out, double* kl_initial, double* kl_final,
                    double* kl_history, lm_stats* stats);
 
+/* ---- alpha-shape edge filter of the boundary consumers ------------- */
+/* alpha_shape_edges(P, alpha), construct_boundary_alpha.py:45-82, given the Delaunay simplices[ntri*3] of the points
+ * (the reference calls scipy.spatial.Delaunay(P).simplices): keep[t] = circumradius(t) < 1/alpha
+ * (R = abc / (4 sqrt(max(s(s-a)(s-b)(s-c), 0)) + 1e-16), inf for a degenerate triangle), boundary edges = edges used by
+ * exactly one kept triangle, as (min, max) vertex pairs in the order the reference's dict yields them (first occurrence
+ * walking the kept triangles, edges (t0,t1), (t1,t2), (t2,t0)).  keep / radius may be NULL.  LM_E_CAP (with *n_edges set)
+ * when more than cap_edges edges exist.                                                                          */
+int32_t lm_alpha_shape_edges(const double* x, const double* y, int64_t npts, const int32_t* simplices, int64_t ntri, double alpha,
+                             uint8_t* keep, double* radius, int32_t* edges, int64_t cap_edges, int64_t* n_edges, lm_stats* stats);
+
 /* ---- measurement probes -------------------------------------------------------- */
 /* Dependent-free DFMA loop on every SM: FP64 peak (TFLOP/s, 2 flops per DFMA) and a
  * DMUL/DADD-only variant (the unfused mix K1 needs).  Used by bench.py for the

@@ -259,6 +259,28 @@ def main() -> None:
                                                 trk["fraction_outside_domain"](cloud, _Mod.domain),
                                                 trk["fraction_outside_domain"](Mb, _Mod.domain)])
 
+    # ---- alpha-shape boundary of a point cloud (construct_boundary_alpha.py:45-125): the reference's functions with the
+    # Delaunay simplices recorded, so that the fixture does not depend on the Qhull build of the machine running the tests
+    from scipy.spatial import Delaunay as _Delaunay
+    seen = {}
+
+    def _recording_delaunay(P):
+        tri = _Delaunay(P)
+        seen["simplices"] = tri.simplices.copy()
+        return tri
+    ab = load_defs("construct_boundary_alpha.py", ["circumradius", "alpha_shape_edges", "order_boundary"], {"Delaunay": _recording_delaunay})
+    rng = np.random.default_rng(77)
+    tt = rng.uniform(0, 2 * np.pi, 1500)
+    rr = np.sqrt(rng.uniform(0.0, 1.0, 1500)) * (1.0 + 0.35 * np.cos(3 * tt))       # a filled trefoil-like blob
+    Pa = np.c_[rr * np.cos(tt), rr * np.sin(tt)]
+    for tag, alpha in [("a6", 6.0), ("a12", 12.0)]:
+        edges = ab["alpha_shape_edges"](Pa, alpha)
+        g[f"alpha_{tag}_edges"] = np.asarray(edges, dtype=np.int32).reshape(-1, 2)
+        g[f"alpha_{tag}_ordered"] = np.asarray(ab["order_boundary"](Pa, edges), dtype=np.int32)
+    g["alpha_points"] = Pa
+    g["alpha_simplices"] = seen["simplices"].astype(np.int32)
+    g["alpha_radius"] = np.array([ab["circumradius"](Pa[t[0]], Pa[t[1]], Pa[t[2]]) for t in seen["simplices"]])
+
     OUT.parent.mkdir(parents=True, exist_ok=True)
     np.savez_compressed(OUT, **g)
     print(f"wrote {OUT} ({OUT.stat().st_size / 1024:.1f} KiB, {len(g)} arrays)")

@@ -332,6 +332,35 @@ def gi_flow(P_target, X0, alpha: float, max_steps: int, min_steps: int = 1, kl_t
     return X, T, kl0, kl
 
 
+# ---- alpha-shape edge filter ------------------------------------------------
+def circumradius(p, q, r) -> float:
+    """circumradius, construct_boundary_alpha.py:45-55 (same numpy calls: np.linalg.norm is the reference's arithmetic)."""
+    a = np.linalg.norm(q - r)
+    b = np.linalg.norm(p - r)
+    c = np.linalg.norm(p - q)
+    s = (a + b + c) / 2.0
+    A = max(s * (s - a) * (s - b) * (s - c), 0.0)
+    if A == 0.0:
+        return np.inf
+    area = np.sqrt(A)
+    return (a * b * c) / (4.0 * area + 1e-16)
+
+
+def alpha_shape_edges(P, simplices, alpha: float):
+    """alpha_shape_edges, construct_boundary_alpha.py:57-82, for given Delaunay simplices -> (keep bool[T], radius[T],
+    boundary edges [(i, j)] in dict order)."""
+    P = np.asarray(P, dtype=np.float64)
+    inv_alpha = 1.0 / alpha
+    radius = np.array([circumradius(P[t[0]], P[t[1]], P[t[2]]) for t in simplices], dtype=np.float64).reshape(-1)
+    keep = radius < inv_alpha
+    edge_count: dict = {}
+    for t in np.asarray(simplices)[keep]:
+        for i, j in ((t[0], t[1]), (t[1], t[2]), (t[2], t[0])):
+            key = (int(i), int(j)) if i < j else (int(j), int(i))
+            edge_count[key] = edge_count.get(key, 0) + 1
+    return keep, radius, [e for e, c in edge_count.items() if c == 1]
+
+
 # ---- K2 -------------------------------------------------------------------------------
 def contour_lines(xs, ys, Z, level: float):
     """plt.contour(xs, ys, Z, levels=[level]).allsegs[0] restated (mpl2014) -> list of (N,2) arrays."""

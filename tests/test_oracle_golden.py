@@ -200,3 +200,13 @@ def test_tracker_density_stage(oracle, golden):
         assert T == int(sc[3]) and kl0 == sc[4] and klT == sc[5] and np.array_equal(X, golden[f"density_flow_XT_{tag}"])
         X, T, kl0, klT = oracle.gi_flow(P_M, P_C, 0.1, 25, eps=eps)
         assert T == int(sc[6]) and kl0 == sc[7] and klT == sc[8] and np.array_equal(X, golden[f"density_flow_XF_{tag}"])
+
+
+def test_alpha_shape_edges(oracle, golden):
+    """circumradius / alpha_shape_edges restated (construct_boundary_alpha.py:45-82) on the recorded Delaunay
+    simplices, against the reference's own outputs."""
+    P, S = golden["alpha_points"], golden["alpha_simplices"]
+    for tag, alpha in (("a6", 6.0), ("a12", 12.0)):
+        keep, radius, edges = oracle.alpha_shape_edges(P, S, alpha)
+        assert np.array_equal(radius, golden["alpha_radius"])
+        assert np.array_equal(np.asarray(edges, dtype=np.int32).reshape(-1, 2), golden[f"alpha_{tag}_edges"])
