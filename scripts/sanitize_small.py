@@ -3,7 +3,9 @@ import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import numpy as np
-from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import contour, curvature, escape, lucas, nystrom, potentials, stencils
+from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import (alpha_shape, contour, curvature, escape, lucas, nystrom, pairstats, potentials,
+                                                                    stencils, tracker)
+import types
 
 rng = np.random.default_rng(0)
 xs = np.linspace(-2.1, 0.9, 256); ys = np.linspace(-1.5, 1.5, 200)
@@ -26,4 +28,20 @@ i, dist = potentials.nearest_match(pts[:3000], pts[3000:5000])
 w = nystrom.weighted_log_sum(pts[:500], pts[500:900], rng.uniform(0, 1, 400))
 c = nystrom.weighted_cauchy_sum(pts[:500], pts[500:900], rng.uniform(0, 1, 400))
 k = curvature.compute_curvature_localpoly(contour.longest(lines), 7, True)
+out8 = lucas.cloud_fields(top.astype(np.int8), deg)                             # int8 first rows, widened on the device
+P2 = np.c_[pts.real[:1500], pts.imag[:1500]]
+e = np.linspace(0, 1.5, 61)
+for wt in ("none", "value", "dist2"):
+    pairstats.pair_histogram(P2, e[:-1], e[1:], P2[:, 0], wt)                 # partition bins
+pairstats.pair_histogram(P2, e[:-1], e[:-1] + 0.03, P2[:, 0], "value")        # overlapping shells (general edges)
+ee = np.linspace(0, 3.0, 1801)
+pairstats.pair_histogram(P2, ee[:-1], ee[1:], None, "dist2")                  # 1800 bins: a single histogram copy
+dm = pairstats.max_pair_distance(P2)
+mod = types.SimpleNamespace(domain=(-2.2, 1.2, -1.6, 1.6), eps=1e-12)
+PM = tracker.mollified_histogram(mod, pts, 96, 1.0); PC = tracker.mollified_histogram(mod, pts[:4000] * 0.9, 96, 2.5)
+XT, T, kl0, klT = tracker.gi_flow_to_threshold(tracker.KL, PM, PC, 0.1, 1e-6, 200, 5)
+tv = tracker.tv_distance(PM, PC); sm = tracker.sum_pairwise(rng.standard_normal(12345))
+tri = alpha_shape.delaunay_simplices(P2)
+edges = alpha_shape.alpha_shape_edges(P2, 8.0, simplices=tri)
+print("new rows ok:", out8["n_points"], dm, T, klT, tv, len(edges))
 print("sanitize_small ok:", len(lines), len(l2), int(it.sum()), out["n_points"], hi.size, float(U.sum()), i[:3], float(w[0]))
