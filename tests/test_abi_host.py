@@ -148,3 +148,38 @@ def test_polylines_container():
     # ties: the FIRST of the longest lines, like max(paths, key=len)
     T = Polylines(verts, np.array([0, 5, 10], dtype=np.int64))
     assert np.array_equal(T.longest(), verts[:5])
+
+
+def test_new_row_host_logic_cpu(shim, golden):
+    """Host-side pieces of the section-8f rows that need no device: scipy's gaussian kernel, the boundary walk of the alpha
+    shape (against the reference's traced loops), argument checks; and that nothing computes without a GPU."""
+    from scipy.ndimage import _filters
+    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import alpha_shape, pairstats, tracker
+    for sigma in (0.3, 1.0, 2.5, 4.0):
+        w, radius = tracker.gaussian_kernel1d(sigma)
+        assert radius == int(4.0 * sigma + 0.5)
+        assert np.array_equal(w, _filters._gaussian_kernel1d(sigma, 0, radius))
+    P = golden["alpha_points"]
+    for tag in ("a6", "a12"):
+        edges = [tuple(e) for e in golden[f"alpha_{tag}_edges"].tolist()]
+        assert np.array_equal(np.asarray(alpha_shape.order_boundary(P, edges), dtype=np.int32), golden[f"alpha_{tag}_ordered"])
+    with pytest.raises(ValueError):
+        pairstats.pair_histogram(np.zeros((4, 3)), [0.0], [1.0])
+    with pytest.raises(ValueError):
+        pairstats.pair_histogram(np.zeros((4, 2)), [0.0, 1.0], [1.0])
+    with pytest.raises(ValueError):
+        tracker.gaussian_filter(np.zeros((4, 4)), 1.0, mode="reflect")
+    with pytest.raises(TypeError):
+        tracker.gi_flow_fixed_T(lambda p, x: 0.0, np.ones((2, 2)), np.ones((2, 2)), 0.1, 2)
+    assert tracker.fraction_outside_domain(np.array([0j, 3 + 0j, 1 + 1j, -5j]), (-2.2, 1.2, -1.6, 1.6)) == 0.5
+    if shim.device_count() < 1:
+        mod = type("M", (), {"domain": (-2.2, 1.2, -1.6, 1.6), "eps": 1e-12})
+        for call in (lambda: pairstats.pair_histogram(np.zeros((4, 2)), [0.0], [1.0]),
+                     lambda: pairstats.max_pair_distance(np.zeros((4, 2))),
+                     lambda: tracker.mollified_histogram(mod, np.zeros(4, complex), 8, 1.0),
+                     lambda: tracker.KL(np.ones(4) / 4, np.ones(4) / 4),
+                     lambda: tracker.gi_flow_fixed_T(tracker.KL, np.ones(4) / 4, np.ones(4) / 4, 0.1, 2),
+                     lambda: tracker.sum_pairwise(np.ones(9)),
+                     lambda: alpha_shape.alpha_shape_edges(np.zeros((3, 2)), 1.0, simplices=[[0, 1, 2]])):
+            with pytest.raises(RuntimeError):
+                call()
