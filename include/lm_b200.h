@@ -76,6 +76,11 @@ extern "C" {
  * tci_construct_mandelbrot.py:21-39 and tci_construct_mandelbrot_v002_fixed.py:35-47 compute
  * (the module gi_assumption_tracker_v3.py loads).                                       */
 #define LM_DE_FINAL_DZ         2
+/* the same function with numpy's SIMD complex multiply restated (a*b: real = fma(ar, br, -(ai*bi)),
+ * imag = fma(ar, bi, ai*br) -- npyv_muladdsub): escape mask and d == 0 pattern bit-identical to what
+ * tci_construct_mandelbrot_v002_fixed.py:35-47 returns on an FMA-capable host, so sample_mandelbrot_boundary()
+ * (:49-59) and everything the tracker derives from it reproduce exactly.                                     */
+#define LM_DE_FINAL_DZ_NUMPY   3
 
 /* ---- log-potential variants (K4a) ---------------------------------------------- */
 /* U = (1/N) sum_p log(sqrt(dx^2+dy^2) + eps)         Potentials.py:19-27             */

@@ -19,7 +19,7 @@ LM_OK, LM_E_INVALID, LM_E_CUDA, LM_E_CAP, LM_E_NOMEM, LM_E_NODEV, LM_E_NOCONV, L
     0, -1, -2, -3, -4, -5, -6, -7)
 
 FIELD_NONE, FIELD_GREEN, FIELD_POW2_ALWAYS, FIELD_INV_K, FIELD_POW2_FIRST = 0, 1, 2, 3, 4
-DE_SCALAR, DE_FIRST_ESCAPE, DE_FINAL_DZ = 0, 1, 2
+DE_SCALAR, DE_FIRST_ESCAPE, DE_FINAL_DZ, DE_FINAL_DZ_NUMPY = 0, 1, 2, 3
 LOGPOT_SUM_SQRT, LOGPOT_NEG_PERTERM, LOGPOT_SUM_HYPOT, LOGPOT_LOG_INV = 0, 1, 2, 3
 PAIR_W_NONE, PAIR_W_VALUE_SQDIFF, PAIR_W_DIST_SQ = 0, 1, 2
 

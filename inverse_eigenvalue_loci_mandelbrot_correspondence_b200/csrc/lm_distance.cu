@@ -5,6 +5,10 @@
 //   mandelbrot_distance_estimator   tci_construct_mandelbrot.py:21-39,
 //                                   tci_construct_mandelbrot_v002_fixed.py:35-47 (LM_DE_FINAL_DZ: z from the
 //                                   first escape, dz from the END of the loop)
+//   the same function as numpy really evaluates it                            (LM_DE_FINAL_DZ_NUMPY): numpy's SIMD
+//                                   complex multiply is real = fma(ar, br, -(ai*bi)), imag = fma(ar, bi, ai*br)
+//                                   (npyv_muladdsub); with that recipe the escape mask and the d == 0 pattern of
+//                                   the stock tracker module -- hence sample_mandelbrot_boundary() -- are bit-exact
 //
 // The reference runs these on small grids (120x80 ... 912^2, max_iter <= 500), so a plain
 // one-thread-per-pixel kernel is used; the recurrences are unfused (__dmul_rn/__dadd_rn) in
@@ -14,6 +18,29 @@
 #include <math.h>
 
 namespace {
+
+// one sweep dz <- (2 z) dz + 1, z <- z z + c.  NP = false: CPython's unfused complex arithmetic; NP = true: numpy's SIMD
+// complex multiply (a * b: real = fma(ar, br, -(ai*bi)), imag = fma(ar, bi, ai*br)); 2 * z is exact for finite z.
+template <bool NP>
+__device__ __forceinline__ void de_step(double& zr, double& zi, double& dr, double& di, double cr, double ci) {
+    const double tr = __dmul_rn(2.0, zr), ti = __dmul_rn(2.0, zi);
+    double ndr, ndi, re, im;
+    if (NP) {
+        ndr = __dadd_rn(__fma_rn(tr, dr, -__dmul_rn(ti, di)), 1.0);
+        ndi = __fma_rn(tr, di, __dmul_rn(ti, dr));
+        re = __fma_rn(zr, zr, -__dmul_rn(zi, zi));
+        im = __fma_rn(zr, zi, __dmul_rn(zi, zr));
+    } else {
+        ndr = __dadd_rn(__dsub_rn(__dmul_rn(tr, dr), __dmul_rn(ti, di)), 1.0);
+        ndi = __dadd_rn(__dmul_rn(tr, di), __dmul_rn(ti, dr));
+        re = __dsub_rn(__dmul_rn(zr, zr), __dmul_rn(zi, zi));
+        const double pp = __dmul_rn(zr, zi);
+        im = __dadd_rn(pp, pp);
+    }
+    dr = ndr; di = ndi;
+    zr = __dadd_rn(re, cr);
+    zi = __dadd_rn(im, ci);
+}
 
 template <int VARIANT>
 __global__ void __launch_bounds__(256) distance_kernel(const double* __restrict__ xs, long long nx,
@@ -28,15 +55,9 @@ __global__ void __launch_bounds__(256) distance_kernel(const double* __restrict_
     double d = 0.0;
     bool esc = false;
     const double loop_thr = bailout * bailout * (1.0 - 1e-9);
+    constexpr bool NP = (VARIANT == LM_DE_FINAL_DZ_NUMPY);
     for (int n = 0; n < max_iter; ++n) {
-        const double tr = __dmul_rn(2.0, zr), ti = __dmul_rn(2.0, zi);
-        const double ndr = __dadd_rn(__dsub_rn(__dmul_rn(tr, dr), __dmul_rn(ti, di)), 1.0);
-        const double ndi = __dadd_rn(__dmul_rn(tr, di), __dmul_rn(ti, dr));
-        dr = ndr; di = ndi;
-        const double re = __dsub_rn(__dmul_rn(zr, zr), __dmul_rn(zi, zi));
-        const double pp = __dmul_rn(zr, zi);
-        zr = __dadd_rn(re, cr);
-        zi = __dadd_rn(__dadd_rn(pp, pp), ci);
+        de_step<NP>(zr, zi, dr, di, cr, ci);
         const double m = __dadd_rn(__dmul_rn(zr, zr), __dmul_rn(zi, zi));
         if (!(m <= loop_thr)) {                       // candidate (also catches overflow); hypot decides
             const double az = hypot(zr, zi);
@@ -57,20 +78,14 @@ __global__ void __launch_bounds__(256) distance_kernel(const double* __restrict_
                     // LM_DE_FINAL_DZ: keep z of this first escape, run dz (and z) on to the end of the loop
                     const double ezr = zr, ezi = zi;
                     for (int m2 = n + 1; m2 < max_iter; ++m2) {
-                        const double tr2 = __dmul_rn(2.0, zr), ti2 = __dmul_rn(2.0, zi);
-                        const double ndr2 = __dadd_rn(__dsub_rn(__dmul_rn(tr2, dr), __dmul_rn(ti2, di)), 1.0);
-                        const double ndi2 = __dadd_rn(__dmul_rn(tr2, di), __dmul_rn(ti2, dr));
-                        dr = ndr2; di = ndi2;
-                        const double re2 = __dsub_rn(__dmul_rn(zr, zr), __dmul_rn(zi, zi));
-                        const double pp2 = __dmul_rn(zr, zi);
-                        zr = __dadd_rn(re2, cr);
-                        zi = __dadd_rn(__dadd_rn(pp2, pp2), ci);
+                        de_step<NP>(zr, zi, dr, di, cr, ci);
                         if (!(isfinite(dr) && isfinite(di))) break;     // stays non-finite: d = 0
                     }
                     d = 0.0;
                     if (isfinite(dr) && isfinite(di)) {
-                        const double qr = __dsub_rn(__dmul_rn(__dmul_rn(2.0, ezr), dr), __dmul_rn(__dmul_rn(2.0, ezi), di));
-                        const double qi = __dadd_rn(__dmul_rn(__dmul_rn(2.0, ezr), di), __dmul_rn(__dmul_rn(2.0, ezi), dr));
+                        const double er = __dmul_rn(2.0, ezr), ei = __dmul_rn(2.0, ezi);
+                        const double qr = NP ? __fma_rn(er, dr, -__dmul_rn(ei, di)) : __dsub_rn(__dmul_rn(er, dr), __dmul_rn(ei, di));
+                        const double qi = NP ? __fma_rn(er, di, __dmul_rn(ei, dr)) : __dadd_rn(__dmul_rn(er, di), __dmul_rn(ei, dr));
                         const double den0 = hypot(qr, qi);
                         if (isfinite(den0)) {
                             d = __ddiv_rn(__dmul_rn(log(az), az), den0 > eps ? den0 : eps);
@@ -123,7 +138,7 @@ int32_t lm_distance_grid_f64(const double* xs, int64_t nx, const double* ys, int
     LM_REQUIRE(xs && ys && dist, "lm_distance_grid_f64: NULL buffer");
     LM_REQUIRE(nx >= 0 && ny >= 0 && max_iter >= 0, "lm_distance_grid_f64: negative size");
     LM_REQUIRE(bailout > 0.0 && bailout < 1e150, "lm_distance_grid_f64: bailout out of range");
-    LM_REQUIRE(variant >= LM_DE_SCALAR && variant <= LM_DE_FINAL_DZ, "lm_distance_grid_f64: unknown variant %d", variant);
+    LM_REQUIRE(variant >= LM_DE_SCALAR && variant <= LM_DE_FINAL_DZ_NUMPY, "lm_distance_grid_f64: unknown variant %d", variant);
     if (stats) *stats = lm_stats{};
     if (nx * ny == 0) return LM_OK;
     cudaStream_t s = nullptr;
@@ -146,6 +161,10 @@ int32_t lm_distance_grid_f64(const double* xs, int64_t nx, const double* ys, int
         distance_kernel<LM_DE_FIRST_ESCAPE><<<blocks, 256, 0, s>>>(static_cast<double*>(dxs), nx, static_cast<double*>(dys), ny,
                                                                    max_iter, bailout, eps, static_cast<double*>(dd),
                                                                    static_cast<unsigned char*>(de));
+    else if (variant == LM_DE_FINAL_DZ_NUMPY)
+        distance_kernel<LM_DE_FINAL_DZ_NUMPY><<<blocks, 256, 0, s>>>(static_cast<double*>(dxs), nx, static_cast<double*>(dys), ny,
+                                                                     max_iter, bailout, eps, static_cast<double*>(dd),
+                                                                     static_cast<unsigned char*>(de));
     else
         distance_kernel<LM_DE_FINAL_DZ><<<blocks, 256, 0, s>>>(static_cast<double*>(dxs), nx, static_cast<double*>(dys), ny,
                                                                max_iter, bailout, eps, static_cast<double*>(dd),

@@ -14,7 +14,7 @@ import ctypes as C
 import numpy as np
 
 from . import _shim
-from ._shim import (DE_FINAL_DZ, DE_FIRST_ESCAPE, DE_SCALAR, LOGPOT_LOG_INV, LOGPOT_NEG_PERTERM, LOGPOT_SUM_HYPOT,
+from ._shim import (DE_FINAL_DZ, DE_FINAL_DZ_NUMPY, DE_FIRST_ESCAPE, DE_SCALAR, LOGPOT_LOG_INV, LOGPOT_NEG_PERTERM, LOGPOT_SUM_HYPOT,
                     LOGPOT_SUM_SQRT, Stats)
 
 last_stats: dict = {}
@@ -67,7 +67,8 @@ def distance_grid(xs, ys, max_iter: int = 200, bailout: float = 1e6, eps: float 
 
     variant=DE_SCALAR: construct_stage1_clean.py:50-58 (bailout 1e6);
     variant=DE_FIRST_ESCAPE: variograms_construct_mandelbrot.py:61-88 (R=4, eps=1e-14);
-    variant=DE_FINAL_DZ: tci_construct_mandelbrot_v002_fixed.py:35-47 (R=250, eps=1e-12; dz from the end of the loop).
+    variant=DE_FINAL_DZ: tci_construct_mandelbrot_v002_fixed.py:35-47 (R=250, eps=1e-12; dz from the end of the loop);
+    variant=DE_FINAL_DZ_NUMPY: the same with numpy's SIMD complex multiply (FMA recipe) restated -- bit-exact masks.
     """
     xs = np.ascontiguousarray(xs, dtype=np.float64).ravel()
     ys = np.ascontiguousarray(ys, dtype=np.float64).ravel()

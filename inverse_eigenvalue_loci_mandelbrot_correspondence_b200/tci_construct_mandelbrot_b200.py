@@ -9,7 +9,8 @@ tci_construct_mandelbrot_v002_fixed.py; this one keeps its attribute names, defa
 signatures and moves the two generators onto the B200:
 
   construct_points(ns)            -> K3  lm_roots_batched            (…_v002_fixed.py:27-33)
-  mandelbrot_distance_estimator   -> K1b lm_distance_grid_f64, LM_DE_FINAL_DZ (…_v002_fixed.py:35-47)
+  mandelbrot_distance_estimator   -> K1b lm_distance_grid_f64, LM_DE_FINAL_DZ_NUMPY (…_v002_fixed.py:35-47 as numpy
+                                     evaluates it: FMA complex multiply; escape mask and d == 0 pattern bit-exact)
   sample_mandelbrot_boundary()    -> K1b + the same quantile mask / np.random.choice on the host
                                      (…_v002_fixed.py:49-59), so a seeded run draws the same sample
   entropic_ot_alignment(X, Y)     -> lm_nearest_match: the argmax of exp(-cdist/const) is the nearest
@@ -72,14 +73,14 @@ def _axes_of_meshgrid(c: np.ndarray):
 def mandelbrot_distance_estimator(c):
     """(escaped mask, distance estimate, None) on the meshgrid c; module-level max_iter/escape_R/eps apply."""
     xs, ys = _axes_of_meshgrid(c)
-    d, esc = _potentials.distance_grid(xs, ys, int(max_iter), float(escape_R), float(eps), _potentials.DE_FINAL_DZ)
+    d, esc = _potentials.distance_grid(xs, ys, int(max_iter), float(escape_R), float(eps), _potentials.DE_FINAL_DZ_NUMPY)
     return esc, d, None
 
 
 def sample_mandelbrot_boundary():
     xs = np.linspace(domain[0], domain[1], mandelbrot_grid)
     ys = np.linspace(domain[2], domain[3], mandelbrot_grid)
-    d, esc = _potentials.distance_grid(xs, ys, int(max_iter), float(escape_R), float(eps), _potentials.DE_FINAL_DZ)
+    d, esc = _potentials.distance_grid(xs, ys, int(max_iter), float(escape_R), float(eps), _potentials.DE_FINAL_DZ_NUMPY)
     if not esc.any():
         raise RuntimeError("No escape points")
     q = np.quantile(d[esc], 0.25)
