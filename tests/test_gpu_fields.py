@@ -77,6 +77,20 @@ def test_distance_estimator_tracker_module(gpu, oracle, golden):
         o, oesc = oracle.distance_grid(golden[tag + "_x"], golden[tag + "_y"], 250, 250.0, 1e-12, 2)
         assert np.array_equal(esc, oesc)
         np.testing.assert_allclose(got, o, rtol=1e-13, atol=0)
+        # LM_DE_FINAL_DZ_NUMPY: numpy's FMA complex multiply restated -> the reference's masks exactly, values to rounding
+        got3, esc3 = gpu.potentials.distance_grid(golden[tag + "_x"], golden[tag + "_y"], 250, 250.0, 1e-12, 3)
+        assert np.array_equal(esc3, want_esc) and np.array_equal(got3 != 0, want != 0)
+        np.testing.assert_allclose(got3, want, rtol=4e-15, atol=0)
+        o3, oesc3 = oracle.distance_grid(golden[tag + "_x"], golden[tag + "_y"], 250, 250.0, 1e-12, 3)
+        assert np.array_equal(esc3, oesc3)
+        np.testing.assert_allclose(got3, o3, rtol=4e-15, atol=0)
+    # the tracker's grid sizes: mask and zero pattern of the two variants against the oracle's numpy recipe
+    for grid in (600, 912):
+        xs = np.linspace(-2.2, 1.2, grid); ys = np.linspace(-1.6, 1.6, grid)
+        got3, esc3 = gpu.potentials.distance_grid(xs, ys, 250, 250.0, 1e-12, 3)
+        o3, oesc3 = oracle.distance_grid(xs, ys, 250, 250.0, 1e-12, 3)
+        assert np.array_equal(esc3, oesc3) and np.array_equal(got3 != 0, o3 != 0)
+        np.testing.assert_allclose(got3, o3, rtol=4e-15, atol=0)
 
 
 def test_green_function_sums(gpu, oracle, golden):

@@ -92,6 +92,17 @@ def test_distance_estimator_tracker_module(oracle, golden):
         m = want != 0
         np.testing.assert_allclose(d[m], want[m], rtol=1e-4)
     assert (golden["tci_fixed_zoom_dist"] != 0).sum() >= 10
+    # variant 3 restates numpy's SIMD complex multiply (fma(ar, br, -(ai*bi)), fma(ar, bi, ai*br)): the same fixtures to
+    # rounding (log / hypot of numpy vs libm), masks exact, and the stock module's boundary sample as an exact set
+    for tag in ("tci_fixed", "tci_fixed_zoom"):
+        d, esc = oracle.distance_grid(golden[tag + "_x"], golden[tag + "_y"], 250, 250.0, 1e-12, 3)
+        want, want_esc = golden[tag + "_dist"], golden[tag + "_escaped"]
+        assert np.array_equal(esc, want_esc) and np.array_equal(d != 0, want != 0)
+        np.testing.assert_allclose(d, want, rtol=2e-15, atol=0)
+    xs = np.linspace(-2.25, 1.25, 150); ys = np.linspace(-1.75, 1.75, 150)
+    d, esc = oracle.distance_grid(xs, ys, 250, 250.0, 1e-12, 3)
+    jj, ii = np.nonzero(esc & (d <= np.quantile(d[esc], 0.25)))
+    assert np.array_equal(xs[ii] + 1j * ys[jj], golden["tci_fixed_boundary_sample_grid150"])
 
 
 def test_stencils_bit_exact(oracle, golden):
