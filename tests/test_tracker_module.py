@@ -61,6 +61,21 @@ def test_nearest_match_oracle_is_the_reference_rule(oracle):
     assert np.array_equal(dist, M[np.arange(300), idx])
 
 
+def test_exp_rule_near_ties_pick_the_first_index(oracle):
+    """Known gap: exp() maps scaled distances that differ by an ulp to the same double, so the stock
+    module's argmax(exp(-M/mean/eps)) returns the FIRST of two near-equidistant points, while nearest_match returns the
+    true minimum.  The four pairs below are the ones where the two rules differ in the reference's own level-4 run
+    (real-axis cloud points against the mirror pair of boundary samples -1.2483 +- 0.0509i, captured from that run)."""
+    X = np.array([-1.0183764595711713 - 0j, -1.0110099247483106 - 0j, -1.0078593635360475 - 0j, -1.0068756134485202 - 0j])
+    pair = np.array([-1.248298572996707 + 0.05093304061470927j, -1.248298572996707 - 0.050933040614709046j])   # first: 1 ulp farther
+    Y = np.concatenate([pair, 2.0 * np.array([0.9 + 0.7j, -1.2 - 1.3j, 0.1 + 1.1j, 1.0 - 0.9j])])
+    M = np.sqrt((X.real[:, None] - Y.real[None, :]) ** 2 + (X.imag[:, None] - Y.imag[None, :]) ** 2)
+    assert np.all(M[:, 1] < M[:, 0]) and np.all(M[:, 0] - M[:, 1] < 1e-16)
+    K = np.nan_to_num(np.exp(-(M / M.mean()) / 0.8))
+    assert np.sum(np.argmax(K, axis=1) == 0) >= 3            # the reference's rule: first index of the tied maximum
+    assert np.array_equal(oracle.nearest_match(X, Y)[0], [1, 1, 1, 1])      # true nearest
+
+
 @pytest.mark.gpu
 def test_tracker_levels(gpu, golden):
     mod = load_module(MODULE)
