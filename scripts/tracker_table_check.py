@@ -1,6 +1,6 @@
 """Run the packaged tracker with the settings of the reference's published tables and print, per row, the largest relative
 difference over the float columns and whether the integer columns agree (tests/golden/tracker_tables.json)."""
-import json, sys, time
+import sys, time
 from pathlib import Path
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))

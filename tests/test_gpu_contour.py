@@ -1,6 +1,5 @@
 """GPU: K2 (level set) through the C ABI against the mpl2014 restatement (bit-exact vertices, same
 line order) and the full drop-in script."""
-import re
 from pathlib import Path
 
 import numpy as np
