@@ -35,7 +35,7 @@ def _args(table: str, bins_max: int):
 
 
 def _compare(rows, table: str, rtol: float):
-    want = TABLES[table]["rows"]
+    want = TABLES["T25_sigma3"]["rows"][3:] if table == "T25_sigma3_row4" else TABLES[table]["rows"]
     assert len(rows) <= len(want) and len(rows) >= 1
     for got, ref in zip(rows, want):
         for c in INT_COLS:
@@ -76,14 +76,18 @@ def test_level_loop_reproduces_published_row_with_the_stock_module_cpu(oracle):
 def test_gpu_path_reproduces_published_tables(gpu, tmp_path):
     """Everything on the device (K3 roots, numpy-FMA distance estimator, nearest matching, mollified histograms, KL / TV /
     overlap, GI flow) against the reference's published rows: integer columns and stop reasons exact, float columns to
-    1e-9 (the roots differ from LAPACK's in the 13th digit, KL by the last bit of log)."""
-    trk, args = _args("T25_sigma3", 128)
+    1e-9 (the roots differ from LAPACK's in the 13th digit, KL by the last bit of log); all 8 published rows."""
+    trk, args = _args("T25_sigma3", 512)
     rows, reason = trk.run(args, log=lambda *a: None)
-    assert len(rows) == 2
-    _compare(rows, "T25_sigma3", rtol=1e-9)
-    trk, args = _args("adaptive", 64)
+    assert len(rows) == 4
+    _compare(rows[:3], "T25_sigma3", rtol=1e-9)                # measured: <= 4.4e-15
+    # Lucas orders up to 1220: four near-tied matches decide the last digits; the reference's own re-run differs from its
+    # published row by 8.7e-5 here (DESIGN.md section 2), the device path by 6e-5
+    _compare(rows[3:], "T25_sigma3_row4", rtol=2e-4)
+    trk, args = _args("adaptive", 512)
     rows, reason = trk.run(args, log=lambda *a: None)
-    _compare(rows, "adaptive", rtol=1e-9)
+    assert len(rows) == 4
+    _compare(rows, "adaptive", rtol=1e-9)                      # measured: <= 1.6e-11, T_n = 87 / 103 / 106 / 109
     args.out_prefix = str(tmp_path / "t")
     csv_path, json_path = trk.write_outputs(args, rows, reason)
     head = open(csv_path).readline().strip().split(",")
