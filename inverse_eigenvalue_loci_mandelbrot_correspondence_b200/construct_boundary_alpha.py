@@ -1,0 +1,76 @@
+#!/usr/bin/env python3
+"""GPU drop-in for the reference script construct_boundary_alpha.py (README Step 2; same CLI, same outputs).
+
+    python -m inverse_eigenvalue_loci_mandelbrot_correspondence_b200.construct_boundary_alpha \\
+        --input_csv 0_data/construct_points.csv --alpha 30.0 --output_prefix outputs/construct
+
+Outputs (construct_boundary_alpha.py:127-160):
+  <prefix>_boundary.csv   ordered boundary points, header "x,y", "%.18e"
+  <prefix>_edges.csv      boundary edges (i, j) as the alpha filter reports them, header "i,j", "%d"
+  <prefix>_boundary.png   cloud + traced boundary
+  <prefix>_meta.txt       alpha / N / ordered_points
+
+The triangulation is scipy's Delaunay as in the reference; the radius test and edge-multiplicity count run on the device
+(alpha_shape.alpha_shape_edges -> lm_alpha_shape_edges); the walk over the boundary edges is the reference's.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+
+import numpy as np
+
+from .alpha_shape import alpha_shape_edges, circumradius, order_boundary  # noqa: F401  (reference-compatible names)
+from .curvature import load_points  # noqa: F401
+
+NO_EDGES_MSG = "Alpha-shape produced no boundary edges. Try smaller alpha (tighter) or larger (looser)."
+
+
+def save_outputs(P: np.ndarray, edges, ordered_idx, alpha: float, output_prefix: str):
+    B = P[ordered_idx, :]
+    os.makedirs(os.path.dirname(output_prefix), exist_ok=True)
+    b_csv = f"{output_prefix}_boundary.csv"
+    np.savetxt(b_csv, B, delimiter=",", header="x,y", comments="")
+    e_csv = f"{output_prefix}_edges.csv"
+    np.savetxt(e_csv, np.asarray(edges, dtype=int), fmt="%d", delimiter=",", header="i,j", comments="")
+    out_png = f"{output_prefix}_boundary.png"
+    try:
+        import matplotlib
+        matplotlib.use("Agg")
+        import matplotlib.pyplot as plt
+        plt.figure(figsize=(6, 6))
+        plt.scatter(P[:, 0], P[:, 1], s=2, alpha=0.25)
+        plt.plot(B[:, 0], B[:, 1], lw=1.0)
+        plt.axis("equal"); plt.axis("off")
+        plt.tight_layout()
+        plt.savefig(out_png, dpi=220)
+        plt.close()
+    except ImportError:
+        from .png import cloud_with_polyline_png
+        cloud_with_polyline_png(out_png, P, B)
+    meta = f"{output_prefix}_meta.txt"
+    with open(meta, "w") as f:
+        f.write(f"alpha={alpha}\nN={len(P)}\nordered_points={len(B)}\n")
+    return b_csv, e_csv, out_png, meta
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--input_csv", required=True)
+    ap.add_argument("--alpha", type=float, default=25.0, help="Larger alpha => tighter boundary")
+    ap.add_argument("--output_prefix", required=True)
+    args = ap.parse_args(argv)
+
+    P = load_points(args.input_csv)
+    edges = alpha_shape_edges(P, alpha=args.alpha)
+    if len(edges) == 0:
+        raise SystemExit(NO_EDGES_MSG)
+    ordered_idx = order_boundary(P, edges)
+    paths = save_outputs(P, edges, ordered_idx, args.alpha, args.output_prefix)
+    print("Wrote:")
+    for p in paths:
+        print(" ", p)
+
+
+if __name__ == "__main__":
+    main()
