@@ -48,11 +48,12 @@ def _compare(rows, table: str, rtol: float):
 
 
 @pytest.mark.skipif(not REF_MODULE.exists(), reason="needs the reference checkout (build container only)")
-def test_level_loop_reproduces_published_row_with_the_stock_module_cpu(oracle):
+def test_level_loop_reproduces_published_row_with_the_stock_module_cpu(oracle, monkeypatch):
     """The package's tracker driver (argument handling, level loop, bounds) run with the STOCK module and the numpy / scipy
     density functions of the oracle: the first row of the published table, every column, bit for bit."""
     for name in ("matplotlib", "matplotlib.pyplot"):                       # the stock module imports pyplot at the top
-        sys.modules.setdefault(name, types.ModuleType(name))
+        if name not in sys.modules:
+            monkeypatch.setitem(sys.modules, name, types.ModuleType(name))   # removed again when the test ends
     trk, args = _args("T25_sigma3", 64)
     args.module = str(REF_MODULE)
 
