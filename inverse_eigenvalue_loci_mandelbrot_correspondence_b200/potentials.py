@@ -102,3 +102,37 @@ def nearest_match(X, Y):
     global last_stats
     last_stats = st.as_dict()
     return idx, dist
+
+
+def sample_mandelbrot_boundary(nx: int = 120, ny: int = 80, max_iter: int = 200, threshold_low: float = 1e-6,
+                               threshold_high: float = 1e-1, nsamples: int = 800) -> np.ndarray:
+    """sample_mandelbrot_boundary of construct_stage1_clean.py:60-80: the scalar distance estimator on the
+    [-2.25, 1.25] x [-1.25, 1.25] grid (one device launch instead of nx*ny Python calls), candidates with
+    threshold_low < d < threshold_high in the reference's y-outer / x-inner order, and -- when there are more than
+    nsamples -- the same np.random.choice(len(cand), nsamples, replace=False, p=d / sum(d)) draw.  float [k, 2]."""
+    xs = np.linspace(-2.25, 1.25, nx)
+    ys = np.linspace(-1.25, 1.25, ny)
+    d, _ = distance_grid(xs, ys, int(max_iter), 1e6, 1e-16, DE_SCALAR)
+    jj, ii = np.nonzero((d > threshold_low) & (d < threshold_high))          # row-major = for y in ys: for x in xs
+    cand = np.column_stack([xs[ii], ys[jj]]).astype(float)
+    vals = d[jj, ii].astype(float)
+    if cand.size == 0:
+        return np.empty((0, 2), dtype=float)
+    if len(cand) <= nsamples:
+        return cand
+    probs = vals / np.sum(vals)
+    idx = np.random.choice(len(cand), size=nsamples, replace=False, p=probs)
+    return cand[idx]
+
+
+def mandelbrot_boundary_points(xmin: float = -2.25, xmax: float = 1.25, ymin: float = -1.75, ymax: float = 1.75,
+                               N: int = 600, dist_thresh: float = 0.002, max_iter: int = 500) -> np.ndarray:
+    """mandelbrot_boundary_points of variograms_construct_mandelbrot.py:90-104 (same in ...v2.py:97-111): escaped grid
+    points whose first-escape distance estimate (R = 4, eps = 1e-14) is <= dist_thresh, as a complex array in the row-major
+    order C[near] has."""
+    xs = np.linspace(xmin, xmax, N)
+    ys = np.linspace(ymin, ymax, N)
+    d, esc = distance_grid(xs, ys, int(max_iter), 4.0, 1e-14, DE_FIRST_ESCAPE)
+    jj, ii = np.nonzero(esc & (d <= dist_thresh))
+    return xs[ii] + 1j * ys[jj]
+

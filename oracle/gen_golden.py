@@ -281,6 +281,15 @@ def main() -> None:
     g["alpha_simplices"] = seen["simplices"].astype(np.int32)
     g["alpha_radius"] = np.array([ab["circumradius"](Pa[t[0]], Pa[t[1]], Pa[t[2]]) for t in seen["simplices"]])
 
+    # ---- the two grid samplers built on the distance estimators (construct_stage1_clean.py:60-80, seeded;
+    # variograms_construct_mandelbrot.py:90-104)
+    st1 = load_defs("construct_stage1_clean.py", ["mandelbrot_distance_estimator", "sample_mandelbrot_boundary"])
+    np.random.seed(11)
+    g["stage1_boundary_sample_seed11"] = st1["sample_mandelbrot_boundary"](nx=120, ny=80, max_iter=200, nsamples=300)
+    g["stage1_boundary_sample_all"] = st1["sample_mandelbrot_boundary"](nx=60, ny=40, max_iter=150, nsamples=10 ** 6)
+    vb = load_defs("variograms_construct_mandelbrot.py", ["mandelbrot_distance_estimator", "mandelbrot_boundary_points"])
+    g["vario_boundary_points_N160"] = vb["mandelbrot_boundary_points"](N=160, dist_thresh=0.01, max_iter=200)
+
     OUT.parent.mkdir(parents=True, exist_ok=True)
     np.savez_compressed(OUT, **g)
     print(f"wrote {OUT} ({OUT.stat().st_size / 1024:.1f} KiB, {len(g)} arrays)")

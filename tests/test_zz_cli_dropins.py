@@ -71,3 +71,37 @@ def test_cli_dropins_on_the_device(gpu, tmp_path):
     _check_curvature_outputs(out, rtol=1e-6)
     with pytest.raises(SystemExit):
         cb.main(["--input_csv", str(GOLD / "construct_points.csv"), "--alpha", "-1.0", "--output_prefix", str(out / "none")])
+
+
+def _check_samplers(pt, golden):
+    np.random.seed(11)
+    got = pt.sample_mandelbrot_boundary(nx=120, ny=80, max_iter=200, nsamples=300)
+    want = golden["stage1_boundary_sample_seed11"]
+    assert got.shape == want.shape == (300, 2)
+    # the seeded weighted draw: the same candidates in the same order, weights equal to ~1e-13 -> the same picks
+    assert np.array_equal(got, want)
+    got = pt.sample_mandelbrot_boundary(nx=60, ny=40, max_iter=150, nsamples=10 ** 6)       # no subsampling: every candidate
+    assert np.array_equal(got, golden["stage1_boundary_sample_all"])
+    got = pt.mandelbrot_boundary_points(N=160, dist_thresh=0.01, max_iter=200)
+    want = golden["vario_boundary_points_N160"]
+    # the reference iterates numpy complex ARRAYS (FMA multiply): a few pixels may escape one step apart
+    common = np.intersect1d(got, want).size
+    assert common >= 0.99 * max(got.size, want.size) and abs(got.size - want.size) <= 0.01 * want.size
+
+
+def test_grid_samplers_with_oracle_compute_cpu(oracle, golden, monkeypatch):
+    """sample_mandelbrot_boundary (construct_stage1_clean.py:60-80) and mandelbrot_boundary_points
+    (variograms_construct_mandelbrot.py:90-104): host logic around the distance-estimator grid, the device call replaced
+    by the oracle."""
+    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import potentials as pt
+
+    def grid(xs, ys, max_iter, bailout, eps, variant):
+        d, e = oracle.distance_grid(xs, ys, max_iter, bailout, eps, variant)
+        return d, e.astype(bool)
+    monkeypatch.setattr(pt, "distance_grid", grid)
+    _check_samplers(pt, golden)
+
+
+@pytest.mark.gpu
+def test_grid_samplers_on_the_device(gpu, golden):
+    _check_samplers(gpu.potentials, golden)
