@@ -37,17 +37,16 @@ def save_outputs(P: np.ndarray, edges, ordered_idx, alpha: float, output_prefix:
     try:
         import matplotlib
         matplotlib.use("Agg")
-        import matplotlib.pyplot as plt
-        plt.figure(figsize=(6, 6))
-        plt.scatter(P[:, 0], P[:, 1], s=2, alpha=0.25)
-        plt.plot(B[:, 0], B[:, 1], lw=1.0)
-        plt.axis("equal"); plt.axis("off")
-        plt.tight_layout()
-        plt.savefig(out_png, dpi=220)
-        plt.close()
+        from matplotlib import pyplot
     except ImportError:
         from .png import cloud_with_polyline_png
         cloud_with_polyline_png(out_png, P, B)
+    else:                                     # the reference's picture (:145-151): faint cloud, boundary line on top
+        fig, ax = pyplot.subplots(figsize=(6, 6))
+        ax.scatter(P[:, 0], P[:, 1], s=2, alpha=0.25)
+        ax.plot(B[:, 0], B[:, 1], lw=1.0)
+        ax.axis("equal"); ax.axis("off")
+        fig.tight_layout(); fig.savefig(out_png, dpi=220); pyplot.close(fig)
     meta = f"{output_prefix}_meta.txt"
     with open(meta, "w") as f:
         f.write(f"alpha={alpha}\nN={len(P)}\nordered_points={len(B)}\n")
@@ -57,7 +56,7 @@ def save_outputs(P: np.ndarray, edges, ordered_idx, alpha: float, output_prefix:
 def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--input_csv", required=True)
-    ap.add_argument("--alpha", type=float, default=25.0, help="Larger alpha => tighter boundary")
+    ap.add_argument("--alpha", type=float, default=25.0, help="triangles with circumradius >= 1/alpha are dropped (larger = tighter)")
     ap.add_argument("--output_prefix", required=True)
     args = ap.parse_args(argv)
 

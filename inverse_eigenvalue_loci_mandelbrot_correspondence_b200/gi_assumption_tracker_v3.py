@@ -52,30 +52,26 @@ def load_module(module_path, module_name: str = "tci_fixed_import"):
     return mod
 
 
+# (flag, type, default) of the reference's command line (gi_assumption_tracker_v3.py:154-186); dest = flag with "-" -> "_"
+CLI_OPTIONS = (
+    ("seed", int, 7), ("domain", str, "-2.2:1.2:-1.6:1.6"), ("alpha", float, 0.1),
+    ("bins-start", int, 64), ("bins-max", int, 1024),
+    ("construct-step", int, 20), ("construct-max-start", int, 300), ("construct-max-growth", float, 1.35),
+    ("mandelbrot-grid-start", int, 600), ("mandelbrot-grid-growth", float, 1.15),
+    ("mandelbrot-samples-start", int, 25000), ("mandelbrot-samples-growth", float, 1.35), ("mandelbrot-samples-max", int, 150000),
+    ("sigma-bins", float, 1.0), ("T-fixed", int, -1), ("kl-threshold", float, 1e-6), ("max-steps", int, 800), ("min-steps", int, 5),
+    ("compound-threshold", float, 1e-3), ("tv-threshold", float, 0.05), ("out-prefix", str, "gi_assumptions_v3"),
+)
+CLI_HELP = {"domain": "xmin:xmax:ymin:ymax (negative first value: write --domain=...)",
+            "sigma-bins": "blur width in histogram cells; 0 keeps the raw histogram",
+            "T-fixed": "a positive value runs exactly that many GI sweeps instead of stopping on --kl-threshold"}
+
+
 def build_parser() -> argparse.ArgumentParser:
     ap = argparse.ArgumentParser(description=__doc__.splitlines()[0])
-    ap.add_argument("--module", default=str(DEFAULT_MODULE), help="module with the tci_construct_mandelbrot_v002_fixed.py contract")
-    ap.add_argument("--seed", type=int, default=7)
-    ap.add_argument("--domain", type=str, default="-2.2:1.2:-1.6:1.6", help="xmin:xmax:ymin:ymax")
-    ap.add_argument("--alpha", type=float, default=0.1)
-    ap.add_argument("--bins-start", type=int, default=64)
-    ap.add_argument("--bins-max", type=int, default=1024)
-    ap.add_argument("--construct-step", type=int, default=20)
-    ap.add_argument("--construct-max-start", type=int, default=300)
-    ap.add_argument("--construct-max-growth", type=float, default=1.35)
-    ap.add_argument("--mandelbrot-grid-start", type=int, default=600)
-    ap.add_argument("--mandelbrot-grid-growth", type=float, default=1.15)
-    ap.add_argument("--mandelbrot-samples-start", type=int, default=25000)
-    ap.add_argument("--mandelbrot-samples-growth", type=float, default=1.35)
-    ap.add_argument("--mandelbrot-samples-max", type=int, default=150000)
-    ap.add_argument("--sigma-bins", type=float, default=1.0, help="Gaussian blur sigma in bins; 0 for the raw histogram")
-    ap.add_argument("--T-fixed", type=int, default=-1, help="if > 0, exactly T GI steps (no adaptive stopping)")
-    ap.add_argument("--kl-threshold", type=float, default=1e-6)
-    ap.add_argument("--max-steps", type=int, default=800)
-    ap.add_argument("--min-steps", type=int, default=5)
-    ap.add_argument("--compound-threshold", type=float, default=1e-3)
-    ap.add_argument("--tv-threshold", type=float, default=0.05)
-    ap.add_argument("--out-prefix", type=str, default="gi_assumptions_v3")
+    ap.add_argument("--module", default=str(DEFAULT_MODULE), help="script with the tci_construct_mandelbrot_v002_fixed.py contract")
+    for flag, kind, default in CLI_OPTIONS:
+        ap.add_argument("--" + flag, type=kind, default=default, help=CLI_HELP.get(flag))
     return ap
 
 
@@ -164,16 +160,18 @@ def write_outputs(args, rows: list[dict], reason: str) -> tuple[str, str]:
             w = csv.DictWriter(f, fieldnames=list(COLUMNS))
             w.writeheader()
             w.writerows(rows)
-    meta = {"module": args.module, "seed": int(args.seed), "domain": tuple(float(v) for v in args.domain.split(":")),
-            "alpha": float(args.alpha), "sigma_bins": float(args.sigma_bins), "bins_start": int(args.bins_start),
-            "bins_max": int(args.bins_max), "T_fixed": int(args.T_fixed), "kl_threshold": float(args.kl_threshold),
-            "max_steps": int(args.max_steps), "min_steps": int(args.min_steps), "compound_threshold": float(args.compound_threshold),
-            "tv_threshold": float(args.tv_threshold), "construct_step": int(args.construct_step),
-            "construct_max_start": int(args.construct_max_start), "construct_max_growth": float(args.construct_max_growth),
-            "mandelbrot_grid_start": int(args.mandelbrot_grid_start), "mandelbrot_grid_growth": float(args.mandelbrot_grid_growth),
-            "mandelbrot_samples_start": int(args.mandelbrot_samples_start),
-            "mandelbrot_samples_growth": float(args.mandelbrot_samples_growth),
-            "mandelbrot_samples_max": int(args.mandelbrot_samples_max), "global_stop_reason": reason, "rows": rows}
+    # the JSON header of the reference: its settings in its order (:305-330), then the rows
+    order = ("module", "seed", "domain", "alpha", "sigma_bins", "bins_start", "bins_max", "T_fixed", "kl_threshold", "max_steps",
+             "min_steps", "compound_threshold", "tv_threshold", "construct_step", "construct_max_start", "construct_max_growth",
+             "mandelbrot_grid_start", "mandelbrot_grid_growth", "mandelbrot_samples_start", "mandelbrot_samples_growth",
+             "mandelbrot_samples_max")
+    kinds = {flag.replace("-", "_"): kind for flag, kind, _ in CLI_OPTIONS}
+    meta = {}
+    for key in order:
+        value = getattr(args, key)
+        meta[key] = tuple(float(v) for v in value.split(":")) if key == "domain" else kinds.get(key, str)(value)
+    meta["global_stop_reason"] = reason
+    meta["rows"] = rows
     with open(json_path, "w", encoding="utf-8") as f:
         json.dump(meta, f, indent=2)
     return csv_path, json_path
