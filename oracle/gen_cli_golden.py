@@ -34,4 +34,16 @@ for f in ("construct_points.csv", "loop_boundary.csv"):
 for f in sorted(os.listdir(work + "/outputs")):
     if f.endswith((".csv", ".txt")):
         shutil.copy(work + "/outputs/" + f, out + "/" + f)
+# README step 2 as documented: construct_boundary_alpha_spyder_v2.py is a parameter-block script; run it with its three
+# parameters pointed at the fixture (alpha 12 gives one outer loop and eight holes on this cloud)
+import re
+src = open("/root/reference/construct_boundary_alpha_spyder_v2.py").read()
+src = re.sub(r'^input_csv\s*=.*$', f'input_csv = "{out}/construct_points.csv"', src, flags=re.M)
+src = re.sub(r'^alpha\s*=.*$', 'alpha = 12.0', src, flags=re.M)
+src = re.sub(r'^output_prefix\s*=.*$', f'output_prefix = "{work}/outputs/construct_v2"', src, flags=re.M)
+ns = {"__name__": "v2"}
+exec(compile(src, "construct_boundary_alpha_spyder_v2.py", "exec"), ns)
+for f in ("construct_v2_boundary.csv", "construct_v2_edges.csv", "construct_v2_meta.txt"):
+    shutil.copy(work + "/outputs/" + f, out + "/" + f)
+np.save(out + "/construct_v2_ordered_idx.npy", np.asarray(ns["ordered_idx"], dtype=np.int32))
 print(sorted(os.listdir(out)))

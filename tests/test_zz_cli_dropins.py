@@ -21,6 +21,11 @@ def _check_alpha_outputs(out: Path):
     assert (out / "construct_boundary.png").read_bytes()[:8] == b"\x89PNG\r\n\x1a\n"
 
 
+def _check_alpha_v2_outputs(out: Path):
+    for name in ("construct_v2_boundary.csv", "construct_v2_edges.csv", "construct_v2_meta.txt"):
+        assert (out / name).read_bytes() == (GOLD / name).read_bytes(), name
+
+
 def _check_curvature_outputs(out: Path, rtol: float):
     head, got = _read_csv(out / "loop_curvature.csv")
     head_ref, want = _read_csv(GOLD / "loop_curvature.csv")
@@ -52,6 +57,9 @@ def test_cli_file_formats_with_oracle_compute_cpu(oracle, tmp_path, monkeypatch)
     out = tmp_path / "outputs"
     cb.main(["--input_csv", str(GOLD / "construct_points.csv"), "--alpha", "6.0", "--output_prefix", str(out / "construct")])
     _check_alpha_outputs(out)
+    # the v2 behaviour (README step 2): nine components at alpha 12, the outer loop kept and resampled to 1500 points
+    cb.main(["--input_csv", str(GOLD / "construct_points.csv"), "--alpha", "12.0", "--output_prefix", str(out / "construct_v2"), "--main_loop"])
+    _check_alpha_v2_outputs(out)
     bc.main(["--input_csv", str(GOLD / "loop_boundary.csv"), "--output_prefix", str(out / "loop"), "--neighbors", "7"])
     _check_curvature_outputs(out, rtol=1e-7)
     with pytest.raises(SystemExit):                                       # too few points for the window: exit code 2
@@ -67,6 +75,8 @@ def test_cli_dropins_on_the_device(gpu, tmp_path):
     out = tmp_path / "outputs"
     cb.main(["--input_csv", str(GOLD / "construct_points.csv"), "--alpha", "6.0", "--output_prefix", str(out / "construct")])
     _check_alpha_outputs(out)
+    cb.main(["--input_csv", str(GOLD / "construct_points.csv"), "--alpha", "12.0", "--output_prefix", str(out / "construct_v2"), "--main_loop"])
+    _check_alpha_v2_outputs(out)
     bc.main(["--input_csv", str(GOLD / "loop_boundary.csv"), "--output_prefix", str(out / "loop"), "--neighbors", "7"])
     _check_curvature_outputs(out, rtol=1e-6)
     with pytest.raises(SystemExit):
