@@ -377,7 +377,7 @@ def run_ours(args):
             # through the host-buffer shard call (block returned to pinned host memory AND kept in HBM), shard-edge
             # rows all-gathered over NCCL straight from / into those blocks, K2 on them, records gathered and
             # linked on rank 0
-            lines = job.run(stream)
+            lines = job.run()
             return job.last_work_units, lines
 
         e2e_step()

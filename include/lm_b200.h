@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define LM_ABI_VERSION 1
+#define LM_ABI_VERSION 2
 
 /* ---- status codes -------------------------------------------------------------- */
 #define LM_OK           0
@@ -234,8 +234,9 @@ int32_t lm_contour_level_dev(const int32_t* dwell_dev, const double* xs_host, in
                              int64_t* line_offsets, int64_t cap_lines, int64_t* n_lines,
                              lm_stats* stats);
 
-/* After lm_contour_level[_dev] / lm_boundary_sample / lm_contour_link returned LM_E_CAP the
- * linked polylines are kept by the library; this copies them out (nothing is recomputed).   */
+/* After lm_contour_level[_dev] / lm_boundary_sample / lm_contour_link[_dev] returned LM_E_CAP the
+ * linked polylines stay on the device; this copies them out (nothing is recomputed).  Valid until the
+ * next contour call on the same device.                                                        */
 int32_t lm_contour_fetch_last(double* verts, int64_t cap_verts, int64_t* n_verts,
                               int64_t* line_offsets, int64_t cap_lines, int64_t* n_lines);
 
@@ -268,7 +269,7 @@ int32_t lm_boundary_sample_potential(const double* xs, int64_t nx, const double*
  * Multi-GPU building block: classify the quads of rows [0, ny-1) of a dwell block on the
  * device (ny rows including one halo row; ys_host holds the block's ny coordinates) and
  * return the compacted crossing-quad records, in raster order, to the host.  Records of
- * consecutive row blocks are concatenated and chained by lm_contour_link.
+ * consecutive row blocks are concatenated and chained by lm_contour_link[_dev].
  * A record is 8 x int64: {quad = (row_offset + j)*nx + i, SW | SE<<32, NW | NE<<32 (corner
  * dwell values), meta, exit vertex of segment 0 (x, y as binary64), exit vertex of
  * segment 1 (saddle quads)}; meta is described in csrc/lm_contour.cu.  A page-locked `records`
@@ -278,8 +279,29 @@ int32_t lm_contour_classify_dev(const int32_t* dwell_dev, const double* xs_host,
                                 const double* ys_host, int64_t ny, int64_t row_offset, double level,
                                 int64_t* records, int64_t cap_records, int64_t* n_records,
                                 void* stream);
-/* Host-only: chain raster-ordered records into mpl2014-ordered polylines (xs, ys: the full
- * grid coordinates).  Does not need a device.                                            */
+/* The same with the records left on the device, in the caller's device buffer `records_dev` (for the
+ * NCCL gather of the shards' records: nothing bounces through the host).  LM_E_CAP with *n_records set
+ * when the buffer is too small.                                                                   */
+int32_t lm_contour_records_dev(const int32_t* dwell_dev, const double* xs_host, int64_t nx,
+                               const double* ys_host, int64_t ny, int64_t row_offset, double level,
+                               int64_t* records_dev, int64_t cap_records, int64_t* n_records,
+                               void* stream);
+/*
+ * The ordered polylines of plt.contour (the line assembly of contourpy's mpl2014: lines(),
+ * get_start_edge, follow_interior; extract_contour, mandelbrot_boundary_sample.py:41-54) from
+ * raster-ordered records -- of one block or of consecutive row blocks concatenated -- ON THE DEVICE:
+ * successor table, pointer-jumping list ranking, scan over the line leaders, scatter of the vertices
+ * (csrc/lm_contour_link.cu).  xs, ys: the FULL grid coordinates (host).  lm_contour_link_dev takes the
+ * records in device memory, lm_contour_link uploads host records first; both need a device.
+ * LM_E_INVALID for records that are not in raster order or miss a neighbour.  Output and LM_E_CAP
+ * protocol as in lm_contour_level.
+ */
+int32_t lm_contour_link_dev(const int64_t* records_dev, int64_t n_records,
+                            const double* xs, int64_t nx, const double* ys, int64_t ny,
+                            double level,
+                            double* verts, int64_t cap_verts, int64_t* n_verts,
+                            int64_t* line_offsets, int64_t cap_lines, int64_t* n_lines,
+                            void* stream);
 int32_t lm_contour_link(const int64_t* records, int64_t n_records,
                         const double* xs, int64_t nx, const double* ys, int64_t ny,
                         double level,

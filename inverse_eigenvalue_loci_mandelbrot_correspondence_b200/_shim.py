@@ -30,7 +30,7 @@ EXPORTS = (
     "lm_dev_free", "lm_memcpy_h2d", "lm_memcpy_d2h", "lm_memcpy_d2d", "lm_stream_synchronize",
     "lm_escape_grid_f64", "lm_escape_grid_f64_dev", "lm_shard_escape", "lm_escape_grid_f32", "lm_escape_points_f64",
     "lm_distance_grid_f64",
-    "lm_contour_level", "lm_contour_level_dev", "lm_contour_classify_dev", "lm_contour_link", "lm_contour_fetch_last", "lm_boundary_sample", "lm_boundary_sample_potential",
+    "lm_contour_level", "lm_contour_level_dev", "lm_contour_classify_dev", "lm_contour_records_dev", "lm_contour_link", "lm_contour_link_dev", "lm_contour_fetch_last", "lm_boundary_sample", "lm_boundary_sample_potential",
     "lm_roots_batched", "lm_roots_batched_dev", "lm_cloud_compact_dev", "lm_cloud_append_dev", "lm_lucas_cloud_fields", "lm_lucas_cloud_fields_i8", "lm_escape_points_f64_dev",
     "lm_laplacian5_periodic", "lm_laplacian5_periodic_dev", "lm_smooth5_interior", "lm_smooth5_interior_dev",
     "lm_log_potential", "lm_log_potential_sums_dev", "lm_log_potential_finish_dev",
@@ -106,7 +106,9 @@ _SIGNATURES = {
     "lm_boundary_sample": (_i32, [_vp, _i64, _vp, _i64, _i32, _f64, _vp, _vp, _vp, _i64, _pi64, _vp, _i64, _pi64, _pStats]),
     "lm_boundary_sample_potential": (_i32, [_vp, _i64, _vp, _i64, _i32, _f64, _vp, _vp, _vp, _vp, _i64, _pi64, _vp, _i64, _pi64, _pStats]),
     "lm_contour_classify_dev": (_i32, [_vp, _vp, _i64, _vp, _i64, _i64, _f64, _vp, _i64, _pi64, _vp]),
+    "lm_contour_records_dev": (_i32, [_vp, _vp, _i64, _vp, _i64, _i64, _f64, _vp, _i64, _pi64, _vp]),
     "lm_contour_link": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _f64, _vp, _i64, _pi64, _vp, _i64, _pi64]),
+    "lm_contour_link_dev": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _f64, _vp, _i64, _pi64, _vp, _i64, _pi64, _vp]),
     "lm_roots_batched": (_i32, [_vp, _vp, _i64, _i32, _i32, _f64, _vp, _vp, _vp, _vp, _pStats]),
     "lm_roots_batched_dev": (_i32, [_vp, _vp, _i64, _i32, _i32, _f64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lm_cloud_compact_dev": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp]),

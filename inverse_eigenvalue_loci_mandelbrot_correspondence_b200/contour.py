@@ -5,7 +5,7 @@
 The reference calls plt.contour(xs, ys, Z, levels=[level_frac*max_iter]) and keeps the line
 with most vertices (cs.allsegs[0] semantics: one (N,2) array per connected line, closed loops
 repeat their first vertex).  Here the quads are classified and the vertices computed on the
-GPU (liblm_b200.so), the ordered chaining follows contourpy's mpl2014 rules.
+GPU (liblm_b200.so), and so is the ordered chaining of the lines (contourpy's mpl2014 rules).
 """
 from __future__ import annotations
 
@@ -150,18 +150,15 @@ def extract_contour(xs, ys, Z, max_iter: int, level_frac: float = 0.96):
     return longest(contour_lines(xs, ys, Z, target))
 
 
-def link_records(records: np.ndarray, xs, ys, level: float):
-    """Chain raster-ordered crossing records (lm_contour_classify_dev) into polylines (host only)."""
+def _link(fn_name: str, head_args: tuple, xs, ys, level: float, tail_args: tuple = ()) -> Polylines:
     xs = np.ascontiguousarray(xs, dtype=np.float64).ravel()
     ys = np.ascontiguousarray(ys, dtype=np.float64).ravel()
-    records = np.ascontiguousarray(records, dtype=np.int64).reshape(-1, 8)
-    n = records.shape[0]
     nv = C.c_int64(0); nl = C.c_int64(0)
     first = np.zeros(1, dtype=np.int64)
     lib = _shim.load()
     with _shim._lock:
-        rc = lib.lm_contour_link(_shim.ptr(records), n, _shim.ptr(xs), xs.size, _shim.ptr(ys), ys.size, float(level),
-                                 None, 0, C.byref(nv), _shim.ptr(first), 0, C.byref(nl))
+        rc = getattr(lib, fn_name)(*head_args, _shim.ptr(xs), xs.size, _shim.ptr(ys), ys.size, float(level),
+                                   None, 0, C.byref(nv), _shim.ptr(first), 0, C.byref(nl), *tail_args)
         if rc == _shim.LM_E_CAP:
             verts = np.empty((nv.value, 2), dtype=np.float64)
             offs = np.empty(nl.value + 1, dtype=np.int64)
@@ -171,3 +168,16 @@ def link_records(records: np.ndarray, xs, ys, level: float):
             offs = np.zeros(1, dtype=np.int64)
     _shim.check(rc)
     return Polylines(verts, offs)
+
+
+def link_records(records: np.ndarray, xs, ys, level: float) -> Polylines:
+    """Chain raster-ordered crossing records (lm_contour_classify_dev; of one block, or of consecutive row blocks
+    concatenated) into polylines in matplotlib's order.  The records are uploaded and linked on the GPU
+    (lm_contour_link); xs, ys are the full grid coordinates."""
+    records = np.ascontiguousarray(records, dtype=np.int64).reshape(-1, 8)
+    return _link("lm_contour_link", (_shim.ptr(records), records.shape[0]), xs, ys, level)
+
+
+def link_records_dev(records_dev_ptr: int, n_records: int, xs, ys, level: float, stream=None) -> Polylines:
+    """Same with the records already in device memory (lm_contour_records_dev / the NCCL gather of the shards)."""
+    return _link("lm_contour_link_dev", (C.c_void_p(records_dev_ptr), int(n_records)), xs, ys, level, tail_args=(stream,))

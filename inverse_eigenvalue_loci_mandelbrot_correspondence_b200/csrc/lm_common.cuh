@@ -43,7 +43,8 @@ enum WsSlot {
     WS_XS = 0, WS_YS, WS_OUT_I32, WS_OUT_F64, WS_FIELD, WS_COUNTERS, WS_IN_A, WS_IN_B,
     WS_IN_C, WS_OUT_A, WS_OUT_B, WS_OUT_C, WS_OUT_D, WS_RECORDS, WS_SCRATCH,
     WS_K1_WORK, WS_K2_MASK, WS_K2_COUNT, WS_K2_OFFSET, WS_K2_XS, WS_K2_YS,
-    WS_K1_SURVIVORS, WS_LOGPOT_PART, WS_ROOTS_PLAN, WS_ROOTS_INDEX, WS_CLOUD_SCAN, WS_CLOUD_A, WS_CLOUD_B, WS_CLOUD_C, WS_CLOUD_D, WS_NSLOTS
+    WS_K1_SURVIVORS, WS_LOGPOT_PART, WS_ROOTS_PLAN, WS_ROOTS_INDEX, WS_CLOUD_SCAN, WS_CLOUD_A, WS_CLOUD_B, WS_CLOUD_C, WS_CLOUD_D,
+    WS_LINK, WS_LINK_OUT, WS_NSLOTS
 };
 int32_t ws_get(WsSlot slot, size_t bytes, void** out);
 void    ws_release_all();
@@ -79,11 +80,19 @@ int32_t grid_host_begin(const double* xs, int64_t nx, const double* ys, int64_t 
                         int32_t field_mode, int32_t* dwell_i32, double* dwell_f64, double* field,
                         bool need_dev_dwell, int64_t extra_rows, GridHostJob* job);
 int32_t grid_host_finish(GridHostJob* job, lm_stats* stats);
-// K2 on a device-resident dwell grid -> polylines in host buffers (lm_contour.cu); enqueues on s
-// and synchronises s while fetching the records.
+// K2 on a device-resident dwell grid -> polylines in host buffers (lm_contour.cu + lm_contour_link.cu); enqueues
+// on s and synchronises s for the record count and the line sizes.
 int32_t contour_device_to_host(const int32_t* dwell_dev, const double* xs_host, int64_t nx, const double* ys_host,
                                int64_t ny, double level, double* verts, int64_t cap_verts, int64_t* n_verts,
                                int64_t* line_offsets, int64_t cap_lines, int64_t* n_lines,
                                float* kernel_ms, int* launches, cudaStream_t s);
+
+// raster-ordered crossing records on the device -> mpl2014-ordered polylines, kept on the device (lm_contour_link.cu)
+int32_t contour_link_device(const long long* rec_dev, long long n, const double* xs_host, long long nx,
+                            const double* ys_host, long long ny, double level, long long* nv, long long* nl,
+                            float* kernel_ms, cudaStream_t s);
+// the lines of the last contour_link_device on this device -> caller buffers (LM_E_CAP with the sizes if too small)
+int32_t contour_export(double* verts, long long cap_verts, long long* n_verts, long long* line_offsets,
+                       long long cap_lines, long long* n_lines, cudaStream_t s, const char* who);
 
 }  // namespace lm

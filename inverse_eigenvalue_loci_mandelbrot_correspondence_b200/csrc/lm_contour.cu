@@ -19,8 +19,10 @@
 //                      the four corners, derives the line segment(s) through it and their
 //                      exit vertices in the reference's exact arithmetic, and writes a 64-byte
 //                      record at its raster-order rank (ordered compaction, no sort needed).
-//   4. host link     : the records (~0.1-0.4 % of the quads) are chained into ordered
-//                      polylines following mpl2014's start/direction/saddle rules.
+//   4. link          : lm_contour_link.cu chains the records (~0.1-0.4 % of the quads) into ordered
+//                      polylines on the device (successor table, pointer-jumping list ranking, scan,
+//                      scatter) following mpl2014's start / direction / saddle rules; only the finished
+//                      lines are copied to the host.
 //
 // Record (8 x int64): [0] quad = j*nx + i (global row j), [1] SW | SE<<32, [2] NW | NE<<32
 // (corner dwell, uint32 each), [3] meta, [4..5] exit vertex of segment 0 (x, y as doubles),
@@ -32,14 +34,10 @@
 
 #include <cuda/ptx>
 
-#include <algorithm>
 #include <climits>
 #include <cmath>
-#include <cstring>
-#include <chrono>
 #include <cstdlib>
-#include <thread>
-#include <vector>
+#include <cstring>
 
 namespace {
 
@@ -543,15 +541,17 @@ __global__ void __launch_bounds__(MARK_WARPS * 32) contour_emit_kernel(
 }
 
 // ------------------------------------------------------------------------------------
-// device side driver: dwell block on the device -> ordered records on the host
+// device side driver: dwell block on the device -> raster-ordered records on the device
 // ------------------------------------------------------------------------------------
-// direct_dst / direct_cap: a caller buffer that is page-locked and large enough receives the records straight from
-// the device (no staging copy); *records_out then points at it.
+// The records land in dev_dst when the caller gives a device buffer that is large enough, otherwise in the
+// library's own workspace; *records_out points at them.  Synchronises s once (the record count sizes the buffer).
 int32_t classify_device(const int* dwell_dev, const double* xs_host, long long nx,
                         const double* ys_host, long long ny, long long row_offset, double level,
-                        const long long** records_out, long long* n_out, float* kernel_ms, cudaStream_t s,
-                        long long* direct_dst = nullptr, long long direct_cap = 0) {
+                        const long long** records_out, long long* n_out, float* kernel_ms, int* launches, cudaStream_t s,
+                        long long* dev_dst = nullptr, long long dev_cap = 0) {
     *records_out = nullptr; *n_out = 0;
+    if (launches) *launches = 0;
+    if (kernel_ms) *kernel_ms = 0.f;
     if (nx < 2 || ny < 2) return LM_OK;
     const long long nrows = ny - 1;
     const long long words_per_row = ((nx - 1 + STRIP - 1) / STRIP) * 4;
@@ -567,7 +567,7 @@ int32_t classify_device(const int* dwell_dev, const double* xs_host, long long n
     LM_CUDA_TRY(cudaMemsetAsync(dcount, 0, static_cast<size_t>(nrows) * sizeof(unsigned), s));
 
     lm::Timer tm;
-    if ((rc = tm.begin(s)) != LM_OK) return rc;
+    if (kernel_ms && (rc = tm.begin(s)) != LM_OK) return rc;
     // z > level  <=>  z > floor(level) for integer z (clamped to the int32 range)
     int ilevel;
     if (!(level >= -2147483648.0)) ilevel = INT_MIN;            // also NaN: nothing is above a NaN level
@@ -579,20 +579,20 @@ int32_t classify_device(const int* dwell_dev, const double* xs_host, long long n
     long long blocks = ((nrows + MARK_ROWS - 1) / MARK_ROWS) * ((strips_per_row + MARK_WARPS - 1) / MARK_WARPS);
     if (blocks > cap) blocks = cap;
     static const bool no_bulk = getenv("LM_K2_NO_BULK") != nullptr;      // tuning / A-B switch
+    int dev = 0;
+    LM_CUDA_TRY(cudaGetDevice(&dev));
+    const int di = (dev >= 0 && dev < 64) ? dev : 63;
     if (!no_bulk && nx % 4 == 0 && (reinterpret_cast<uintptr_t>(dwell_dev) & 15u) == 0) {
         const size_t smem = 2 * BULK_STAGE_INTS * sizeof(int) + 4 * sizeof(uint64_t) + MARK_WARPS * BULK_SCRATCH * sizeof(unsigned);
-        static bool attr_set = false;
-        if (!attr_set) {
+        static int per_sm[64] = {};                                                  // per device: attribute set, CTAs that fit
+        if (per_sm[di] == 0) {
             LM_CUDA_TRY(cudaFuncSetAttribute(contour_mark_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-            attr_set = true;
+            int v = 0;
+            LM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, contour_mark_bulk_kernel, MARK_WARPS * 32, smem));
+            per_sm[di] = v < 1 ? 1 : v;
         }
         long long bblocks = blocks;
-        static int per_sm = 0;                                                       // persistent: as many CTAs as fit (5 x 41 KB)
-        if (per_sm == 0) {
-            LM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, contour_mark_bulk_kernel, MARK_WARPS * 32, smem));
-            if (per_sm < 1) per_sm = 1;
-        }
-        const long long bcap = static_cast<long long>(lm::sm_count()) * per_sm;
+        const long long bcap = static_cast<long long>(lm::sm_count()) * per_sm[di];       // persistent: as many CTAs as fit
         if (bblocks > bcap) bblocks = bcap;
         contour_mark_bulk_kernel<<<static_cast<unsigned>(bblocks), MARK_WARPS * 32, smem, s>>>(
             dwell_dev, nx, ny, ilevel, static_cast<unsigned*>(dmask), words_per_row, static_cast<unsigned*>(dcount));
@@ -603,13 +603,16 @@ int32_t classify_device(const int* dwell_dev, const double* xs_host, long long n
     LM_CUDA_TRY(cudaGetLastError());
     contour_scan_kernel<<<1, 1024, 0, s>>>(static_cast<unsigned*>(dcount), nrows, static_cast<unsigned long long*>(doff));
     LM_CUDA_TRY(cudaGetLastError());
+    if (launches) *launches = 2;
     unsigned long long total = 0;
     LM_CUDA_TRY(cudaMemcpyAsync(&total, static_cast<unsigned long long*>(doff) + nrows, sizeof(total),
                                 cudaMemcpyDeviceToHost, s));
     LM_CUDA_TRY(cudaStreamSynchronize(s));
+    *n_out = static_cast<long long>(total);
     void* drec = nullptr;
     if (total) {
-        if ((rc = lm::ws_get(lm::WS_RECORDS, static_cast<size_t>(total) * REC_WORDS * sizeof(long long), &drec)) != LM_OK) return rc;
+        if (dev_dst && static_cast<long long>(total) <= dev_cap) drec = dev_dst;
+        else if ((rc = lm::ws_get(lm::WS_RECORDS, static_cast<size_t>(total) * REC_WORDS * sizeof(long long), &drec)) != LM_OK) return rc;
         long long eblocks = (nrows + MARK_WARPS - 1) / MARK_WARPS;
         if (eblocks > cap) eblocks = cap;
         contour_emit_kernel<<<static_cast<unsigned>(eblocks), MARK_WARPS * 32, 0, s>>>(
@@ -617,300 +620,10 @@ int32_t classify_device(const int* dwell_dev, const double* xs_host, long long n
             static_cast<unsigned*>(dmask), words_per_row, static_cast<unsigned*>(dcount),
             static_cast<unsigned long long*>(doff), static_cast<long long*>(drec));
         LM_CUDA_TRY(cudaGetLastError());
+        if (launches) *launches = 3;
     }
-    float ms = 0.f;
-    if ((rc = tm.end(s, &ms)) != LM_OK) return rc;
-    if (kernel_ms) *kernel_ms = ms;
-    if (total && direct_dst && static_cast<long long>(total) <= direct_cap) {
-        cudaPointerAttributes attr{};
-        if (cudaPointerGetAttributes(&attr, direct_dst) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
-            const size_t need = static_cast<size_t>(total) * REC_WORDS * sizeof(long long);
-            LM_CUDA_TRY(cudaMemcpyAsync(direct_dst, drec, need, cudaMemcpyDeviceToHost, s));
-            LM_CUDA_TRY(cudaStreamSynchronize(s));
-            *records_out = direct_dst;
-            *n_out = static_cast<long long>(total);
-            return LM_OK;
-        }
-        cudaGetLastError();           // pageable memory: not an error, take the staged path
-    }
-    if (total) {
-        // page-locked staging buffer, cached across calls (records are read by the host linker)
-        static long long* h_stage = nullptr;
-        static size_t h_cap = 0;
-        lm::register_release_hook([] { if (h_stage) { cudaFreeHost(h_stage); h_stage = nullptr; h_cap = 0; } });
-        const size_t need = static_cast<size_t>(total) * REC_WORDS * sizeof(long long);
-        if (need > h_cap) {
-            if (h_stage) cudaFreeHost(h_stage);
-            h_stage = nullptr; h_cap = 0;
-            const size_t want = need + need / 4;
-            if (cudaHostAlloc(reinterpret_cast<void**>(&h_stage), want, cudaHostAllocDefault) != cudaSuccess) {
-                cudaGetLastError();
-                return lm::fail(LM_E_NOMEM, "lm_contour: cudaHostAlloc(%zu) failed", want);
-            }
-            h_cap = want;
-        }
-        LM_CUDA_TRY(cudaMemcpyAsync(h_stage, drec, need, cudaMemcpyDeviceToHost, s));
-        LM_CUDA_TRY(cudaStreamSynchronize(s));
-        *records_out = h_stage;
-        *n_out = static_cast<long long>(total);
-    }
-    return LM_OK;
-}
-
-// ------------------------------------------------------------------------------------
-// 4. host link (mpl2014 order over the sparse records)
-// ------------------------------------------------------------------------------------
-struct Linker {
-    const long long* rec; long long n;
-    const double *xs, *ys; long long nx, ny; double level;
-    // per record, one 16-byte entry (one cache line access per step of the walk): the records reached through the exit
-    // edges of its (up to two) segments -- -1 = the line leaves the grid there, -2 = the neighbour record is
-    // missing (inconsistent input) -- and the visit flags: 1 visited, 2 saddle seen, 4 start-SW
-    struct alignas(16) Aux { int nxt[2]; int flags; int pad; };
-    std::vector<Aux> aux;
-    std::vector<double> verts;                 // x, y interleaved
-    std::vector<long long> offsets;            // line starts (+ end)
-
-    long long quad(long long k) const { return rec[k * REC_WORDS]; }
-    unsigned meta(long long k) const { return static_cast<unsigned>(rec[k * REC_WORDS + 3]); }
-    unsigned config(long long k) const { return meta(k) & 15u; }
-    bool is_saddle(long long k) const { const unsigned c = config(k); return c == 6u || c == 9u; }
-    int corner(long long k, int dj, int di) const {
-        const unsigned long long w = static_cast<unsigned long long>(rec[k * REC_WORDS + 1 + dj]);
-        return static_cast<int>(di ? (w >> 32) : (w & 0xffffffffu));
-    }
-    std::vector<long long> row_start;          // row_start[j] = first record of row >= j (size ny + 1)
-    void build_row_index() {
-        row_start.assign(static_cast<size_t>(ny) + 1, n);
-        long long k = 0;
-        for (long long j = 0; j <= ny; ++j) {
-            const long long first_quad = j * nx;            // quad(k) / nx < j  <=>  quad(k) < j * nx
-            while (k < n && quad(k) < first_quad) ++k;
-            row_start[static_cast<size_t>(j)] = k;
-        }
-    }
-    // record index of quad q, searching only inside its row; `hint` is the record we come from
-    long long find(long long q, long long hint) const {
-        if (hint + 1 < n && quad(hint + 1) == q) return hint + 1;     // east neighbour
-        if (hint > 0 && quad(hint - 1) == q) return hint - 1;         // west neighbour
-        const long long j = q / nx;
-        if (j < 0 || j >= ny) return -1;
-        long long lo = row_start[static_cast<size_t>(j)], hi = row_start[static_cast<size_t>(j) + 1];
-        while (lo < hi) {
-            const long long mid = (lo + hi) >> 1;
-            if (quad(mid) < q) lo = mid + 1; else hi = mid;
-        }
-        return (lo < n && quad(lo) == q) ? lo : -1;
-    }
-    bool is_boundary(long long q, int edge) const {
-        const long long i = q % nx, j = q / nx;
-        switch (edge) {
-            case EDGE_E: return i == nx - 2;
-            case EDGE_N: return j == ny - 2;
-            case EDGE_W: return i == 0;
-            default:     return j == 0;
-        }
-    }
-    // vertex on `edge` of record k from that edge's own orientation (host arithmetic, unfused:
-    // this translation unit is compiled with -ffp-contract=off)
-    void push_edge_vertex(long long k, int edge) {
-        int dj1, di1, dj2, di2;
-        edge_corners(edge, dj1, di1, dj2, di2);
-        const long long q = quad(k), i = q % nx, j = q / nx;
-        const double z1 = static_cast<double>(corner(k, dj1, di1)), z2 = static_cast<double>(corner(k, dj2, di2));
-        const double f = (z2 - level) / (z2 - z1);
-        const double g = 1.0 - f;
-        const double ax = xs[i + di1] * f, bx = xs[i + di2] * g;
-        const double ay = ys[j + dj1] * f, by = ys[j + dj2] * g;
-        verts.push_back(ax + bx);
-        verts.push_back(ay + by);
-    }
-    int start_edge(long long k) const {
-        const bool saddle = (aux[k].flags & 2) != 0, start_sw = (aux[k].flags & 4) != 0;
-        switch (config(k)) {
-            case 1: return EDGE_E;   case 2: return EDGE_S;   case 3: return EDGE_E;
-            case 4: return EDGE_N;   case 5: return EDGE_N;
-            case 6: return (!saddle || start_sw) ? EDGE_S : EDGE_N;
-            case 7: return EDGE_N;   case 8: return EDGE_W;
-            case 9: return (!saddle || !start_sw) ? EDGE_W : EDGE_E;
-            case 10: return EDGE_S;  case 11: return EDGE_E;  case 12: return EDGE_W;
-            case 13: return EDGE_W;  case 14: return EDGE_S;
-            default: return EDGE_NONE;
-        }
-    }
-    // record index of quad q in row j, coming from record `hint`
-    long long find_in_row(long long q, long long j, long long hint) const {
-        if (hint + 1 < n && quad(hint + 1) == q) return hint + 1;     // east neighbour
-        if (hint > 0 && quad(hint - 1) == q) return hint - 1;         // west neighbour
-        if (j < 0 || j >= ny) return -1;
-        long long lo = row_start[static_cast<size_t>(j)], hi = row_start[static_cast<size_t>(j) + 1];
-        while (lo < hi) {
-            const long long mid = (lo + hi) >> 1;
-            if (quad(mid) < q) lo = mid + 1; else hi = mid;
-        }
-        return (lo < n && quad(lo) == q) ? lo : -1;
-    }
-    // nxt[2k + s]: record reached through the exit edge of segment s of record k; -1 = the line leaves the
-    // grid there, -2 = the neighbour record is missing (inconsistent input).  Filled by all host threads
-    // before the (inherently sequential) walk, so the walk itself is pointer chasing.
-    void build_next_range(long long k_lo, long long k_hi) {
-        for (long long k = k_lo; k < k_hi; ++k) {
-            const unsigned m = meta(k);
-            const int nseg = static_cast<int>((m >> 16) & 3u);
-            const long long q = quad(k);
-            long long j = -1, i = -1;                      // row / column only when a vertical move needs them
-            for (int sg = 0; sg < 2; ++sg) {
-                long long r = -2;
-                if (sg < nseg) {
-                    const int ex = static_cast<int>((m >> (10 + 4 * sg)) & 3u);
-                    if (j < 0) { j = q / nx; i = q - j * nx; }
-                    switch (ex) {
-                        case EDGE_E: r = (i == nx - 2) ? -1 : ((k + 1 < n && quad(k + 1) == q + 1) ? k + 1 : -2); break;
-                        case EDGE_W: r = (i == 0) ? -1 : ((k > 0 && quad(k - 1) == q - 1) ? k - 1 : -2); break;
-                        case EDGE_N: r = (j == ny - 2) ? -1 : find_in_row(q + nx, j + 1, k); if (r < -1) r = -2; break;
-                        default:     r = (j == 0) ? -1 : find_in_row(q - nx, j - 1, k); if (r < -1) r = -2; break;
-                    }
-                    if ((ex == EDGE_N && j != ny - 2 && r == -1) || (ex == EDGE_S && j != 0 && r == -1)) r = -2;
-                }
-                aux[static_cast<size_t>(k)].nxt[sg] = static_cast<int>(r);
-            }
-        }
-    }
-    void build_next() {
-        aux.assign(static_cast<size_t>(n), Aux{{-2, -2}, 0, 0});
-        unsigned hw = std::thread::hardware_concurrency();
-        int nthreads = static_cast<int>(hw ? hw : 1);
-        if (nthreads > 16) nthreads = 16;
-        if (n < 20000) nthreads = 1;
-        if (nthreads <= 1) { build_next_range(0, n); return; }
-        std::vector<std::thread> pool;
-        for (int t = 0; t < nthreads; ++t) {
-            const long long lo = n * t / nthreads, hi = n * (t + 1) / nthreads;
-            pool.emplace_back([this, lo, hi] { build_next_range(lo, hi); });
-        }
-        for (auto& th : pool) th.join();
-    }
-    // returns false on an inconsistent record set (missing neighbour)
-    bool follow(long long k, int edge, bool want_initial, bool closed) {
-        const long long k0 = k; const int e0 = edge;
-        if (want_initial) push_edge_vertex(k, edge);
-        for (;;) {
-            const unsigned m = meta(k);
-            const unsigned cfg = m & 15u;
-            if (cfg == 6u || cfg == 9u) {
-                if (aux[k].flags & 2) aux[k].flags |= 1;
-                else { aux[k].flags |= 2; if (edge == EDGE_N || edge == EDGE_E) aux[k].flags |= 4; }
-            } else {
-                aux[k].flags |= 1;
-            }
-            const int nseg = static_cast<int>((m >> 16) & 3u);
-            int seg = -1;
-            for (int s = 0; s < nseg; ++s)
-                if (static_cast<int>((m >> (8 + 4 * s)) & 3u) == edge) seg = s;
-            if (seg < 0) return false;
-            const int ex = static_cast<int>((m >> (10 + 4 * seg)) & 3u);
-            double v[2];
-            memcpy(v, &rec[k * REC_WORDS + 4 + 2 * seg], sizeof(v));
-            verts.push_back(v[0]);
-            verts.push_back(v[1]);
-            const long long kn = aux[static_cast<size_t>(k)].nxt[seg];
-            if (kn == -1) return true;                      // left the grid
-            if (kn < 0) return false;
-            k = kn; edge = (ex + 2) & 3;                    // enter the neighbour through the opposite edge
-            if (closed && k == k0 && edge == e0) return true;
-        }
-    }
-    bool run() {
-        for (long long k = 1; k < n; ++k)
-            if (quad(k) <= quad(k - 1)) return false;       // records must be in raster order
-        const bool dbg = getenv("LM_LINK_DEBUG") != nullptr;
-        auto t0 = std::chrono::steady_clock::now();
-        build_row_index();
-        auto t1 = std::chrono::steady_clock::now();
-        build_next();
-        auto t2 = std::chrono::steady_clock::now();
-        if (dbg) fprintf(stderr, "[link] n=%lld row_index %.2f ms, next %.2f ms\n", n,
-                         std::chrono::duration<double, std::milli>(t1 - t0).count(),
-                         std::chrono::duration<double, std::milli>(t2 - t1).count());
-        struct Report { bool on; std::chrono::steady_clock::time_point t; ~Report() { if (on) fprintf(stderr, "[link] walk %.2f ms\n",
-                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count()); } } rep{dbg, t2};
-        verts.clear(); offsets.clear();
-        // lines that start and end on the boundary (edges tested S, W, N, E).  Only quads on the grid border can
-        // start one: every record of the first and last quad row, and the first / last record of the rows between
-        // (visited in raster order, like a scan over all records would).
-        verts.reserve(static_cast<size_t>(n) * 8 + 64);      // <= 2 segments per record + start / closing vertices per line
-        auto try_boundary_start = [&](long long k, long long i, long long j) -> bool {
-            if (aux[k].flags & 1) return true;
-            const unsigned c = config(k);
-            const bool nw = c & 8u, ne = c & 4u, sw = c & 2u, se = c & 1u;
-            const bool cond[4] = {i == nx - 2 && se && !ne, j == ny - 2 && ne && !nw, i == 0 && nw && !sw, j == 0 && sw && !se};
-            const int order[4] = {EDGE_S, EDGE_W, EDGE_N, EDGE_E};
-            for (int t = 0; t < 4; ++t) {
-                const int e = order[t];
-                if (!cond[e]) continue;
-                offsets.push_back(static_cast<long long>(verts.size() / 2));
-                if (!follow(k, e, true, false)) return false;
-                if (aux[k].flags & 1) break;
-            }
-            return true;
-        };
-        for (long long j = 0; j + 1 < ny; ++j) {
-            const long long a = row_start[static_cast<size_t>(j)], b = row_start[static_cast<size_t>(j) + 1];
-            if (a >= b) continue;
-            if (j == 0 || j == ny - 2) {
-                for (long long k = a; k < b; ++k)
-                    if (!try_boundary_start(k, quad(k) - j * nx, j)) return false;
-            } else {
-                const long long ia = quad(a) - j * nx, ib = quad(b - 1) - j * nx;
-                if (ia == 0 || ia == nx - 2) { if (!try_boundary_start(a, ia, j)) return false; }
-                if (b - 1 > a && (ib == 0 || ib == nx - 2)) { if (!try_boundary_start(b - 1, ib, j)) return false; }
-            }
-        }
-        // interior closed loops
-        for (long long k = 0; k < n; ++k) {
-            if (aux[k].flags & 1) continue;
-            const int se = start_edge(k);
-            if (se == EDGE_NONE) continue;
-            const bool ignore_first = (se == EDGE_N);
-            offsets.push_back(static_cast<long long>(verts.size() / 2));
-            const size_t first = verts.size();
-            if (!follow(k, se, !ignore_first, true)) return false;
-            if (ignore_first && verts.size() > first) {
-                const double fx = verts[first], fy = verts[first + 1];
-                verts.push_back(fx);
-                verts.push_back(fy);
-            }
-            if ((aux[k].flags & 2) && !(aux[k].flags & 1)) --k;      // second pass through the saddle
-        }
-        offsets.push_back(static_cast<long long>(verts.size() / 2));
-        return true;
-    }
-};
-
-// result of the most recent linking pass that did not fit the caller's buffers (lm_contour_fetch_last)
-std::vector<double> g_pending_verts;
-std::vector<long long> g_pending_offsets;
-
-int32_t link_and_export(const long long* records, long long n_records, const double* xs, long long nx,
-                        const double* ys, long long ny, double level,
-                        double* verts, long long cap_verts, long long* n_verts,
-                        long long* line_offsets, long long cap_lines, long long* n_lines) {
-    LM_REQUIRE(n_records < (1LL << 31), "lm_contour_link: more than 2^31 crossing records");
-    Linker L{records, n_records, xs, ys, nx, ny, level, {}, {}, {}, {}};
-    if (!L.run())
-        return lm::fail(LM_E_INVALID, "lm_contour_link: inconsistent crossing records (not in raster order, or a neighbour quad is missing)");
-    const long long nv = static_cast<long long>(L.verts.size() / 2);
-    const long long nl = static_cast<long long>(L.offsets.size()) - 1;
-    *n_verts = nv;
-    *n_lines = nl;
-    if (nv > cap_verts || nl > cap_lines) {
-        g_pending_verts.swap(L.verts);          // keep the result: the caller re-fetches it, nothing is recomputed
-        g_pending_offsets.swap(L.offsets);
-        return lm::fail(LM_E_CAP, "lm_contour: need room for %lld vertices and %lld lines (got %lld, %lld); "
-                        "call lm_contour_fetch_last with larger buffers", nv, nl, cap_verts, cap_lines);
-    }
-    if (nv) memcpy(verts, L.verts.data(), static_cast<size_t>(nv) * 2 * sizeof(double));
-    memcpy(line_offsets, L.offsets.data(), static_cast<size_t>(nl + 1) * sizeof(long long));
+    if (kernel_ms && (rc = tm.end(s, kernel_ms)) != LM_OK) return rc;
+    *records_out = static_cast<const long long*>(drec);
     return LM_OK;
 }
 
@@ -928,18 +641,25 @@ int32_t check_contour_args(const char* who, const void* dwell, const void* xs, i
 }  // namespace
 
 namespace lm {
+// K2 on a device-resident dwell grid: mark / scan / emit (records), build / rank (ordered lines), then the
+// lines -- and only the lines -- go back to the host.
 int32_t contour_device_to_host(const int32_t* dwell_dev, const double* xs_host, int64_t nx, const double* ys_host,
                                int64_t ny, double level, double* verts, int64_t cap_verts, int64_t* n_verts,
                                int64_t* line_offsets, int64_t cap_lines, int64_t* n_lines,
                                float* kernel_ms, int* launches, cudaStream_t s) {
     const long long* recs = nullptr;
     long long nrec = 0;
-    int32_t rc = classify_device(dwell_dev, xs_host, nx, ys_host, ny, 0, level, &recs, &nrec, kernel_ms, s);
+    float ms_a = 0.f, ms_b = 0.f;
+    int la = 0;
+    int32_t rc = classify_device(dwell_dev, xs_host, nx, ys_host, ny, 0, level, &recs, &nrec, kernel_ms ? &ms_a : nullptr, &la, s);
     if (rc != LM_OK) return rc;
-    if (launches) *launches = nrec ? 3 : 2;
-    return link_and_export(recs, nrec, xs_host, nx, ys_host, ny, level, verts, cap_verts,
-                           reinterpret_cast<long long*>(n_verts), reinterpret_cast<long long*>(line_offsets), cap_lines,
-                           reinterpret_cast<long long*>(n_lines));
+    long long nv = 0, nl = 0;
+    rc = contour_link_device(recs, nrec, xs_host, nx, ys_host, ny, level, &nv, &nl, kernel_ms ? &ms_b : nullptr, s);
+    if (rc != LM_OK) return rc;
+    if (kernel_ms) *kernel_ms = ms_a + ms_b;
+    if (launches) *launches = la + (nrec ? 2 : 0);
+    return contour_export(verts, cap_verts, reinterpret_cast<long long*>(n_verts), reinterpret_cast<long long*>(line_offsets),
+                          cap_lines, reinterpret_cast<long long*>(n_lines), s, "lm_contour");
 }
 }  // namespace lm
 
@@ -947,19 +667,12 @@ extern "C" {
 
 int32_t lm_contour_fetch_last(double* verts, int64_t cap_verts, int64_t* n_verts,
                               int64_t* line_offsets, int64_t cap_lines, int64_t* n_lines) {
+    int32_t rc = lm::require_device();
+    if (rc != LM_OK) return rc;
     LM_REQUIRE(n_verts && n_lines && line_offsets, "lm_contour_fetch_last: NULL argument");
-    LM_REQUIRE(!g_pending_offsets.empty(), "lm_contour_fetch_last: no pending result (the last call did not return LM_E_CAP)");
-    const long long nv = static_cast<long long>(g_pending_verts.size() / 2);
-    const long long nl = static_cast<long long>(g_pending_offsets.size()) - 1;
-    *n_verts = nv; *n_lines = nl;
-    if (nv > cap_verts || nl > cap_lines)
-        return lm::fail(LM_E_CAP, "lm_contour_fetch_last: need room for %lld vertices and %lld lines", nv, nl);
-    LM_REQUIRE(verts || nv == 0, "lm_contour_fetch_last: verts is NULL");
-    if (nv) memcpy(verts, g_pending_verts.data(), static_cast<size_t>(nv) * 2 * sizeof(double));
-    memcpy(line_offsets, g_pending_offsets.data(), static_cast<size_t>(nl + 1) * sizeof(long long));
-    std::vector<double>().swap(g_pending_verts);
-    std::vector<long long>().swap(g_pending_offsets);
-    return LM_OK;
+    LM_REQUIRE(cap_verts >= 0 && cap_lines >= 0, "lm_contour_fetch_last: negative capacity");
+    return lm::contour_export(verts, cap_verts, reinterpret_cast<long long*>(n_verts), reinterpret_cast<long long*>(line_offsets),
+                              cap_lines, reinterpret_cast<long long*>(n_lines), nullptr, "lm_contour_fetch_last");
 }
 
 int32_t lm_contour_classify_dev(const int32_t* dwell_dev, const double* xs_host, int64_t nx,
@@ -971,29 +684,74 @@ int32_t lm_contour_classify_dev(const int32_t* dwell_dev, const double* xs_host,
     LM_REQUIRE(nx >= 0 && ny >= 0 && cap_records >= 0, "lm_contour_classify_dev: negative size");
     const long long* recs = nullptr;
     long long n = 0;
-    rc = classify_device(dwell_dev, xs_host, nx, ys_host, ny, row_offset, level, &recs, &n, nullptr, lm::as_stream(stream),
-                         reinterpret_cast<long long*>(records), cap_records);
+    cudaStream_t s = lm::as_stream(stream);
+    rc = classify_device(dwell_dev, xs_host, nx, ys_host, ny, row_offset, level, &recs, &n, nullptr, nullptr, s);
     if (rc != LM_OK) return rc;
     *n_records = n;
     if (n > cap_records)
         return lm::fail(LM_E_CAP, "lm_contour_classify_dev: need room for %lld records (got %lld)", n,
                         static_cast<long long>(cap_records));
     LM_REQUIRE(records || n == 0, "lm_contour_classify_dev: records is NULL");
-    if (n && recs != reinterpret_cast<const long long*>(records))      // page-locked caller buffers were filled directly
-        memcpy(records, recs, static_cast<size_t>(n) * REC_WORDS * sizeof(long long));
+    if (n) {
+        LM_CUDA_TRY(cudaMemcpyAsync(records, recs, static_cast<size_t>(n) * REC_WORDS * sizeof(long long), cudaMemcpyDeviceToHost, s));
+        LM_CUDA_TRY(cudaStreamSynchronize(s));
+    }
     return LM_OK;
+}
+
+int32_t lm_contour_records_dev(const int32_t* dwell_dev, const double* xs_host, int64_t nx,
+                               const double* ys_host, int64_t ny, int64_t row_offset, double level,
+                               int64_t* records_dev, int64_t cap_records, int64_t* n_records, void* stream) {
+    int32_t rc = lm::require_device();
+    if (rc != LM_OK) return rc;
+    LM_REQUIRE(dwell_dev && xs_host && ys_host && n_records, "lm_contour_records_dev: NULL argument");
+    LM_REQUIRE(nx >= 0 && ny >= 0 && cap_records >= 0 && (records_dev || cap_records == 0), "lm_contour_records_dev: bad size / buffer");
+    const long long* recs = nullptr;
+    long long n = 0;
+    cudaStream_t s = lm::as_stream(stream);
+    rc = classify_device(dwell_dev, xs_host, nx, ys_host, ny, row_offset, level, &recs, &n, nullptr, nullptr, s,
+                         reinterpret_cast<long long*>(records_dev), cap_records);
+    if (rc != LM_OK) return rc;
+    *n_records = n;
+    if (n > cap_records)
+        return lm::fail(LM_E_CAP, "lm_contour_records_dev: need room for %lld records (got %lld)", n,
+                        static_cast<long long>(cap_records));
+    return LM_OK;
+}
+
+int32_t lm_contour_link_dev(const int64_t* records_dev, int64_t n_records, const double* xs, int64_t nx,
+                            const double* ys, int64_t ny, double level,
+                            double* verts, int64_t cap_verts, int64_t* n_verts,
+                            int64_t* line_offsets, int64_t cap_lines, int64_t* n_lines, void* stream) {
+    int32_t rc = lm::require_device();
+    if (rc != LM_OK) return rc;
+    LM_REQUIRE((records_dev || n_records == 0) && xs && ys && n_verts && n_lines && line_offsets, "lm_contour_link_dev: NULL argument");
+    LM_REQUIRE(n_records >= 0 && nx >= 0 && ny >= 0 && cap_verts >= 0 && cap_lines >= 0, "lm_contour_link_dev: negative size");
+    cudaStream_t s = lm::as_stream(stream);
+    long long nv = 0, nl = 0;
+    rc = lm::contour_link_device(reinterpret_cast<const long long*>(records_dev), n_records, xs, nx, ys, ny, level, &nv, &nl, nullptr, s);
+    if (rc != LM_OK) return rc;
+    return lm::contour_export(verts, cap_verts, reinterpret_cast<long long*>(n_verts), reinterpret_cast<long long*>(line_offsets),
+                              cap_lines, reinterpret_cast<long long*>(n_lines), s, "lm_contour_link_dev");
 }
 
 int32_t lm_contour_link(const int64_t* records, int64_t n_records, const double* xs, int64_t nx,
                         const double* ys, int64_t ny, double level,
                         double* verts, int64_t cap_verts, int64_t* n_verts,
                         int64_t* line_offsets, int64_t cap_lines, int64_t* n_lines) {
+    int32_t rc = lm::require_device();
+    if (rc != LM_OK) return rc;
     LM_REQUIRE((records || n_records == 0) && xs && ys && n_verts && n_lines && line_offsets,
                "lm_contour_link: NULL argument");
     LM_REQUIRE(n_records >= 0 && nx >= 0 && ny >= 0, "lm_contour_link: negative size");
-    return link_and_export(reinterpret_cast<const long long*>(records), n_records, xs, nx, ys, ny, level, verts, cap_verts,
-                           reinterpret_cast<long long*>(n_verts), reinterpret_cast<long long*>(line_offsets), cap_lines,
-                           reinterpret_cast<long long*>(n_lines));
+    void* drec = nullptr;
+    if (n_records) {
+        const size_t nb = static_cast<size_t>(n_records) * REC_WORDS * sizeof(long long);
+        if ((rc = lm::ws_get(lm::WS_RECORDS, nb, &drec)) != LM_OK) return rc;
+        LM_CUDA_TRY(cudaMemcpyAsync(drec, records, nb, cudaMemcpyHostToDevice, nullptr));
+    }
+    return lm_contour_link_dev(static_cast<const int64_t*>(drec), n_records, xs, nx, ys, ny, level, verts, cap_verts, n_verts,
+                               line_offsets, cap_lines, n_lines, nullptr);
 }
 
 int32_t lm_contour_level_dev(const int32_t* dwell_dev, const double* xs_host, int64_t nx,

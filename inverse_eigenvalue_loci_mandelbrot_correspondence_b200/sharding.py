@@ -94,28 +94,31 @@ def exchange_first_rows(first_row, group=None):
     return out
 
 
-def gather_records(records: np.ndarray, device, dst: int = 0, group=None):
-    """Gather the per-rank record arrays ([n, 8] int64, raster order inside a rank) to `dst`,
-    concatenated in rank order (= global raster order for contiguous row blocks)."""
+def gather_records(records, n_records: int, dst: int = 0, group=None):
+    """Gather the per-rank record arrays to `dst`, concatenated in rank order (= global raster order for
+    contiguous row blocks), WITHOUT leaving the device: `records` is a [cap, 8] int64 tensor (on the GPU for
+    NCCL, on the CPU for gloo) of which the first n_records rows count.  The counts are all-gathered, then every
+    rank sends exactly its rows and `dst` receives them at their offsets of one tensor (point-to-point over
+    NVLink; no padding, no host bounce).  Returns (tensor [total, 8], counts) on dst, (None, counts) elsewhere."""
     import torch
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    records = np.ascontiguousarray(records, dtype=np.int64).reshape(-1, 8)
-    counts = torch.zeros(world, dtype=torch.int64, device=device)
-    mine = torch.tensor([records.shape[0]], dtype=torch.int64, device=device)
+    counts = torch.zeros(world, dtype=torch.int64, device=records.device)
+    mine = torch.tensor([int(n_records)], dtype=torch.int64, device=records.device)
     dist.all_gather_into_tensor(counts, mine, group=group)
-    counts_h = counts.cpu().numpy()
-    cap = int(counts_h.max()) if world else 0
-    padded = torch.zeros((max(cap, 1), 8), dtype=torch.int64, device=device)
-    if records.shape[0]:
-        padded[: records.shape[0]] = torch.from_numpy(records).to(device)
-    if rank == dst:
-        bufs = [torch.empty_like(padded) for _ in range(world)]
-        dist.gather(padded, bufs, dst=dst, group=group)
-        parts = [bufs[r][: int(counts_h[r])].cpu().numpy() for r in range(world)]
-        return np.concatenate(parts) if parts else np.zeros((0, 8), dtype=np.int64)
-    dist.gather(padded, None, dst=dst, group=group)
-    return None
+    counts_h = [int(c) for c in counts.cpu().tolist()]
+    if rank != dst:
+        if n_records:
+            dist.send(records[:n_records].contiguous(), dst=dst, group=group)
+        return None, counts_h
+    offs = np.concatenate([[0], np.cumsum(counts_h)]).astype(np.int64)
+    out = torch.empty((int(offs[-1]), 8), dtype=torch.int64, device=records.device)
+    if n_records:
+        out[int(offs[rank]):int(offs[rank + 1])] = records[:n_records]
+    for r in range(world):
+        if r != dst and counts_h[r]:
+            dist.recv(out[int(offs[r]):int(offs[r + 1])], src=r, group=group)
+    return out, counts_h
 
 
 # ---- Lucas-Loci cloud (config 5): polynomials are independent -> contiguous slices, one all-reduce ----
@@ -183,8 +186,10 @@ class ShardedBoundary:
 
     Every rank computes K1 on its row block through the host-buffer shard call (the block comes back to a pinned
     host array AND stays in HBM with a halo slot), the first dwell row of every block is all-gathered over NCCL
-    straight from / into those blocks, K2 classifies each block on the device, the records are gathered to
-    rank 0 and linked once.  Cuts come from a coarse K1 pre-pass; `refine()` re-cuts from measured block times.
+    straight from / into those blocks, K2 classifies each block on the device, the records (device tensors) are
+    sent to rank 0's GPU over NCCL and chained there by the device linker; only the finished polylines go to the
+    host.  Cuts come from a coarse K1 pre-pass and a per-device cost model; `refine()` re-cuts from measured
+    block times.  All device work is enqueued on torch's CURRENT stream (the collectives order against it).
     Works with world size 1 too (then it is just the fused single-GPU call)."""
 
     def __init__(self, xs, ys, max_iter: int, level: float, device=None, with_potential: bool = False, cuts=None):
@@ -225,7 +230,7 @@ class ShardedBoundary:
         self._edge = torch.empty(nx, dtype=torch.int32, device=self.device)
         self._field = (torch.empty((self.rows, nx), dtype=torch.float64, device=self.device)
                        if (self.with_potential and self.world > 1) else None)
-        self._records = _shim.pinned_empty((max(int(0.002 * self.rows * nx) + 4096, 1 << 16), 8), np.int64)   # page-locked
+        self._records = torch.empty((max(int(0.002 * self.rows * nx) + 4096, 1 << 16), 8), dtype=torch.int64, device=self.device)
         self.full_potential = None
 
     def refine(self, rounds: int = 2):
@@ -248,10 +253,11 @@ class ShardedBoundary:
             self._set_cuts(refine_cuts(self.profile, self.cuts, t_all.cpu().numpy()))
         return self.cuts
 
-    def run(self, stream=None):
+    def run(self):
         """One pass.  Returns the polylines on rank 0 (None elsewhere); self.dwell / self.potential hold this rank's
         rows, self.full_potential the all-gathered field (device tensor) when asked for."""
         import ctypes as C
+        import torch
         from . import contour
         shim = self._shim
         nx = self.xs.size
@@ -260,6 +266,7 @@ class ShardedBoundary:
                                                 potential_out=self.potential)
             self.last_work_units = int(st["work_units"])
             return lines
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         st = shim.Stats()
         blk = C.c_void_p(); pblk = C.c_void_p()
         shim.call("lm_shard_escape", shim.ptr(self.xs), nx, shim.ptr(self.ys_rows), self.rows, self.max_iter,
@@ -276,18 +283,20 @@ class ShardedBoundary:
         n_rec = C.c_int64(0)
         lib = shim.load()
         while True:
-            rc = lib.lm_contour_classify_dev(blk, shim.ptr(self.xs), nx, shim.ptr(self.ys_block), self.ys_block.size, self.r0,
-                                             self.level, shim.ptr(self._records), self._records.shape[0], C.byref(n_rec), stream)
+            rc = lib.lm_contour_records_dev(blk, shim.ptr(self.xs), nx, shim.ptr(self.ys_block), self.ys_block.size, self.r0,
+                                            self.level, C.c_void_p(self._records.data_ptr()), self._records.shape[0],
+                                            C.byref(n_rec), stream)
             if rc == shim.LM_E_CAP:
-                self._records = shim.pinned_empty((n_rec.value + 1024, 8), np.int64)
+                self._records = torch.empty((n_rec.value + 1024, 8), dtype=torch.int64, device=self.device)
                 continue
             shim.check(rc)
             break
         self.n_records = int(n_rec.value)
-        allrec = gather_records(self._records[: n_rec.value], self.device, 0)
+        allrec, counts = gather_records(self._records, self.n_records, 0)
+        self.n_records_total = int(sum(counts))
         if self.rank != 0:
             return None
-        return contour.link_records(allrec, self.xs, self.ys, self.level)
+        return contour.link_records_dev(allrec.data_ptr(), allrec.shape[0], self.xs, self.ys, self.level, stream)
 
 
 def sharded_cloud_fields(toprows_local, deg_local, grid_x, grid_y, tol: float = 1e-12, eps: float = 1e-12, variant: int = 0,

@@ -122,7 +122,7 @@ static int start_edge(const Ctx* c, int64_t quad) {
         case 6: return (!saddle || start_sw) ? EDGE_S : EDGE_N;
         case 7: return EDGE_N;
         case 8: return EDGE_W;
-        case 9: return (!saddle || !start_sw) ? EDGE_W : EDGE_E;
+        case 9: return (!saddle || start_sw) ? EDGE_W : EDGE_E;
         case 10: return EDGE_S;
         case 11: return EDGE_E;
         case 12: return EDGE_W;

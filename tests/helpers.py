@@ -69,6 +69,86 @@ def records_from_dwell(dwell: np.ndarray, xs: np.ndarray, ys: np.ndarray, level:
     return np.stack(recs)
 
 
+def link_records_numpy(records: np.ndarray, xs: np.ndarray, ys: np.ndarray, level: float):
+    """numpy restatement of the DEVICE linker (csrc/lm_contour_link.cu): successor table, pointer jumping along the
+    predecessors (heads of the open chains / smallest node id of every cycle), list ranking from the leaders, scan
+    over the leaders (open lines first, then loops), scatter of the vertices.  Used to exercise the sharding
+    logic on the CPU (gloo tests) and, against the sequential mpl2014 restatement of the oracle, to pin the
+    ordering rule the kernels implement.  -> list of (N, 2) arrays."""
+    records = np.ascontiguousarray(records, dtype=np.int64).reshape(-1, 8)
+    nx, ny = xs.size, ys.size
+    n = records.shape[0]
+    if n == 0:
+        return []
+    quad = records[:, 0]
+    meta = records[:, 3].astype(np.uint64)
+    nseg = ((meta >> np.uint64(16)) & np.uint64(3)).astype(np.int64)
+    NS = 2 * n
+    ids = np.arange(NS)
+    k_of = ids >> 1; s_of = ids & 1
+    valid = s_of < nseg[k_of]
+    entry = ((meta[k_of] >> (8 + 4 * s_of).astype(np.uint64)) & np.uint64(3)).astype(np.int64)
+    exit_ = ((meta[k_of] >> (10 + 4 * s_of).astype(np.uint64)) & np.uint64(3)).astype(np.int64)
+    qi = (quad % nx)[k_of]; qj = (quad // nx)[k_of]
+
+    def on_border(e):
+        return ((e == E) & (qi == nx - 2)) | ((e == N) & (qj == ny - 2)) | ((e == W) & (qi == 0)) | ((e == S) & (qj == 0))
+
+    head = valid & on_border(entry)
+    leaves = on_border(exit_)
+    step = np.select([exit_ == E, exit_ == W, exit_ == N], [1, -1, nx], default=-nx)
+    q2 = quad[k_of] + step
+    k2 = np.searchsorted(quad, q2)
+    k2c = np.minimum(k2, n - 1)
+    found = valid & ~leaves & (quad[k2c] == q2)
+    want = (exit_ + 2) & 3
+    succ = np.full(NS, -1)
+    for s2 in range(2):
+        t = 2 * k2c + s2
+        ok = found & valid[t] & (entry[t] == want)
+        succ[ok] = t[ok]
+    if (valid & ~leaves & (succ < 0)).any():
+        raise ValueError("inconsistent crossing records")
+    pred = np.full(NS, -1)
+    src = ids[succ >= 0]
+    pred[succ[src]] = src
+    if (valid & ~head & (pred < 0)).any():
+        raise ValueError("inconsistent crossing records")
+    live = ids[valid]
+    rounds = max(int(np.ceil(np.log2(max(live.size, 2)))), 1)
+    p = np.where(head | ~valid, ids, pred); m = ids.copy()
+    for _ in range(rounds):
+        m = np.minimum(m, m[p]); p = p[p]
+    leader = np.where(head[p], p, m)
+    isl = valid & (leader == ids)
+    p = np.where(isl | ~valid, ids, pred); d = np.where(isl | ~valid, 0, 1)
+    for _ in range(rounds):
+        d = d + d[p]; p = p[p]
+    assert (p[live] == leader[live]).all()
+    nvl = np.zeros(NS, dtype=np.int64)
+    last = valid & ((succ == -1) | (succ == leader))
+    nvl[leader[last]] = d[last] + 2
+    order = np.concatenate([ids[isl & head], ids[isl & ~head]])
+    offs = np.concatenate([[0], np.cumsum(nvl[order])]).astype(np.int64)
+    base = np.zeros(NS, dtype=np.int64); base[order] = offs[:-1]
+    verts = np.full((offs[-1], 2), np.nan)
+    xy = records[:, 4:8].copy().view(np.float64).reshape(n, 2, 2)
+    nstart = np.zeros(NS, dtype=bool); nstart[order] = (~head[order]) & (entry[order] == N)
+    L = leader[live]
+    verts[base[L] + d[live] + np.where(nstart[L], 0, 1)] = xy[live >> 1, live & 1]
+    corners = records[:, 1:3].copy().view(np.uint32).view(np.int32).reshape(n, 2, 2)     # [k][dj][di]
+    for v in order:
+        if nstart[v]:
+            verts[base[v] + nvl[v] - 1] = xy[v >> 1, v & 1]
+        else:
+            k = v >> 1
+            dj1, di1, dj2, di2 = {E: (0, 1, 1, 1), N: (1, 1, 1, 0), W: (1, 0, 0, 0), S: (0, 0, 0, 1)}[int(entry[v])]
+            z1, z2 = np.float64(corners[k, dj1, di1]), np.float64(corners[k, dj2, di2])
+            f = (z2 - np.float64(level)) / (z2 - z1); g = np.float64(1.0) - f
+            verts[base[v]] = (xs[qi[v] + di1] * f + xs[qi[v] + di2] * g, ys[qj[v] + dj1] * f + ys[qj[v] + dj2] * g)
+    return [verts[offs[t]:offs[t + 1]] for t in range(offs.size - 1)]
+
+
 def lines_equal(a, b) -> bool:
     if len(a) != len(b):
         return False

@@ -1,5 +1,6 @@
 """CPU: the C-ABI library loads, exports every symbol include/lm_b200.h declares, fails loudly
-without a device, and its host-only logic (contour linker, PNG/CSV writers) is correct."""
+without a device, and the host-side logic (PNG/CSV writers) is correct; the ordering rule of the device
+contour linker is pinned against the sequential mpl2014 restatement through its numpy restatement."""
 import ctypes as C
 import re
 from pathlib import Path
@@ -7,7 +8,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from helpers import lines_equal, records_from_dwell
+from helpers import lines_equal, link_records_numpy, records_from_dwell
 
 ROOT = Path(__file__).resolve().parents[1]
 
@@ -26,7 +27,7 @@ def test_header_symbols_exported(shim):
     assert not missing, missing
     assert set(names) == set(shim.EXPORTS), set(names) ^ set(shim.EXPORTS)
     assert shim.missing_exports() == []
-    assert lib.lm_abi_version() == 1
+    assert lib.lm_abi_version() == 2
 
 
 def test_no_cpu_fallback(shim):
@@ -57,43 +58,49 @@ def test_product_does_not_import_oracle():
 
 @pytest.mark.parametrize("case", [(96, 500, (-2.1, 0.9), (-1.5, 1.5), 480.0), (120, 300, (-0.8, -0.7), (0.05, 0.15), 150.0),
                                   (75, 100, (-1.0, 0.5), (-0.3, 1.2), 3.0), (64, 60, (-0.755, -0.735), (0.10, 0.12), 57.6)])
-def test_contour_linker_matches_oracle(shim, oracle, case):
-    """lm_contour_link (host-only part of K2) against the dense mpl2014 restatement."""
-    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import contour
+def test_link_rule_matches_sequential_oracle(oracle, case):
+    """The ordering rule of the device linker (helpers.link_records_numpy restates csrc/lm_contour_link.cu: open
+    chains by head id, loops by smallest node id, list ranking) against the sequential mpl2014 restatement."""
     res, mi, xl, yl, lvl = case
     xs = np.linspace(*xl, res); ys = np.linspace(*yl, res + 7)
     d, _ = oracle.dwell_grid(xs, ys, mi)
     ref = oracle.contour_lines(xs, ys, d.astype(float), lvl)
-    got = contour.link_records(records_from_dwell(d, xs, ys, lvl), xs, ys, lvl)
-    assert lines_equal(ref, got)
+    assert lines_equal(ref, link_records_numpy(records_from_dwell(d, xs, ys, lvl), xs, ys, lvl))
 
 
-def test_contour_linker_random_fields(shim, oracle):
-    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import contour
+def test_link_rule_random_fields(oracle):
     rng = np.random.default_rng(1)
+    nlines = 0
     for _ in range(150):
         ny, nx = rng.integers(2, 14), rng.integers(2, 14)
         d = rng.integers(0, 6, size=(ny, nx)).astype(np.int32)
         xs = np.sort(rng.uniform(-1, 1, nx)); ys = np.sort(rng.uniform(-1, 1, ny))
         lvl = float(rng.choice([1.5, 2.0, 2.5, 3.0]))
         ref = oracle.contour_lines(xs, ys, d.astype(float), lvl)
-        got = contour.link_records(records_from_dwell(d, xs, ys, lvl), xs, ys, lvl)
-        assert lines_equal(ref, got)
+        assert lines_equal(ref, link_records_numpy(records_from_dwell(d, xs, ys, lvl), xs, ys, lvl))
+        nlines += len(ref)
+    assert nlines > 500
 
 
-def test_contour_linker_split_blocks(shim, oracle):
-    """Records of two row blocks (one halo row each side of the seam) concatenate to the single-block result."""
-    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import contour
-    xs = np.linspace(-2.1, 0.9, 90); ys = np.linspace(-1.5, 1.5, 80)
-    d, _ = oracle.dwell_grid(xs, ys, 200)
-    lvl = 192.0
-    whole = records_from_dwell(d, xs, ys, lvl)
-    cut = 37
-    top = records_from_dwell(d[: cut + 1], xs, ys[: cut + 1], lvl, row_offset=0)
-    bot = records_from_dwell(d[cut:], xs, ys[cut:], lvl, row_offset=cut)
-    both = np.concatenate([top, bot])
-    assert np.array_equal(whole, both)
-    assert lines_equal(contour.link_records(both, xs, ys, lvl), oracle.contour_lines(xs, ys, d.astype(float), lvl))
+def test_oracle_uses_every_segment_once(oracle):
+    """mpl2014 visits a saddle quad twice, once per segment.  On fields full of saddles the oracle's lines must use
+    every segment of every crossed quad exactly once: no duplicated and no missing pieces (this is what pins the
+    start edge of an already visited saddle: S/W when the first visit came in through N/E, else N/E)."""
+    rng = np.random.default_rng(11)
+    for _ in range(60):
+        ny, nx = rng.integers(3, 20), rng.integers(3, 20)
+        d = rng.integers(0, 3, size=(ny, nx)).astype(np.int32)
+        xs = np.arange(nx, dtype=float); ys = np.arange(ny, dtype=float)
+        lvl = 0.5
+        lines = oracle.contour_lines(xs, ys, d.astype(float), lvl)
+        nseg = int(((records_from_dwell(d, xs, ys, lvl)[:, 3] >> 16) & 3).sum())
+        assert sum(len(ln) - 1 for ln in lines) == nseg
+        pieces = set()
+        for ln in lines:
+            for a, b in zip(ln[:-1], ln[1:]):
+                key = (tuple(a), tuple(b))
+                assert key not in pieces
+                pieces.add(key)
 
 
 def test_contour_oracle_invariants(oracle):

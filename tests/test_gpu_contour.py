@@ -45,6 +45,73 @@ def test_records_match_numpy_restatement(gpu, oracle):
     assert np.array_equal(recs[: n.value], want)
 
 
+@pytest.mark.parametrize("case", [(96, 500, (-2.1, 0.9), (-1.5, 1.5), 480.0), (120, 300, (-0.8, -0.7), (0.05, 0.15), 150.0),
+                                  (75, 100, (-1.0, 0.5), (-0.3, 1.2), 3.0), (64, 60, (-0.755, -0.735), (0.10, 0.12), 57.6)])
+def test_contour_linker_matches_oracle(gpu, oracle, case):
+    """lm_contour_link (records uploaded, chained on the device) against the dense mpl2014 restatement."""
+    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import contour
+    res, mi, xl, yl, lvl = case
+    xs = np.linspace(*xl, res); ys = np.linspace(*yl, res + 7)
+    d, _ = oracle.dwell_grid(xs, ys, mi)
+    ref = oracle.contour_lines(xs, ys, d.astype(float), lvl)
+    got = contour.link_records(records_from_dwell(d, xs, ys, lvl), xs, ys, lvl)
+    assert lines_equal(ref, got)
+
+
+def test_contour_linker_random_fields(gpu, oracle):
+    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import contour
+    rng = np.random.default_rng(1)
+    for _ in range(150):
+        ny, nx = rng.integers(2, 14), rng.integers(2, 14)
+        d = rng.integers(0, 6, size=(ny, nx)).astype(np.int32)
+        xs = np.sort(rng.uniform(-1, 1, nx)); ys = np.sort(rng.uniform(-1, 1, ny))
+        lvl = float(rng.choice([1.5, 2.0, 2.5, 3.0]))
+        ref = oracle.contour_lines(xs, ys, d.astype(float), lvl)
+        got = contour.link_records(records_from_dwell(d, xs, ys, lvl), xs, ys, lvl)
+        assert lines_equal(ref, got)
+
+
+def test_contour_linker_split_blocks(gpu, oracle):
+    """Records of two row blocks (one halo row each side of the seam) concatenate to the single-block result."""
+    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import contour
+    xs = np.linspace(-2.1, 0.9, 90); ys = np.linspace(-1.5, 1.5, 80)
+    d, _ = oracle.dwell_grid(xs, ys, 200)
+    lvl = 192.0
+    whole = records_from_dwell(d, xs, ys, lvl)
+    cut = 37
+    top = records_from_dwell(d[: cut + 1], xs, ys[: cut + 1], lvl, row_offset=0)
+    bot = records_from_dwell(d[cut:], xs, ys[cut:], lvl, row_offset=cut)
+    both = np.concatenate([top, bot])
+    assert np.array_equal(whole, both)
+    assert lines_equal(contour.link_records(both, xs, ys, lvl), oracle.contour_lines(xs, ys, d.astype(float), lvl))
+
+
+
+
+def test_contour_linker_rejects_inconsistent_records(gpu, oracle):
+    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import contour
+    xs = np.linspace(-2.1, 0.9, 90); ys = np.linspace(-1.5, 1.5, 80)
+    d, _ = oracle.dwell_grid(xs, ys, 200)
+    recs = records_from_dwell(d, xs, ys, 192.0)
+    assert len(recs) > 50
+    with pytest.raises(ValueError, match="inconsistent"):
+        contour.link_records(np.delete(recs, len(recs) // 2, axis=0), xs, ys, 192.0)      # a neighbour quad is missing
+    with pytest.raises(ValueError, match="inconsistent"):
+        contour.link_records(recs[::-1], xs, ys, 192.0)                                     # not in raster order
+    assert len(contour.link_records(recs[:0], xs, ys, 192.0)) == 0
+
+
+def test_contour_link_dev_many_small_loops(gpu, oracle):
+    """A checkerboard-like field: thousands of 4-node loops and saddles, lines cut by every border."""
+    rng = np.random.default_rng(7)
+    d = rng.integers(0, 2, size=(257, 300)).astype(np.int32)
+    xs = np.linspace(0, 1, 300); ys = np.linspace(0, 1, 257)
+    want = oracle.contour_lines(xs, ys, d.astype(float), 0.5)
+    got = gpu.contour.contour_lines(xs, ys, d, 0.5)
+    assert len(want) > 3000
+    assert lines_equal(want, got)
+
+
 @pytest.mark.parametrize("shape", [(2, 2), (2, 300), (300, 2), (3, 129), (5, 130),
                                    # widths that are multiples of 4 take the bulk-copy mark kernel: tile / strip / row-group edges
                                    (2, 4), (3, 8), (6, 1024), (9, 1028), (5, 1032), (7, 2052), (4, 132), (11, 128), (13, 2048)])

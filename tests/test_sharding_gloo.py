@@ -70,9 +70,9 @@ def _worker(rank: int, world: int, port: int, q):
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
         import torch
         import torch.distributed as dist
-        from helpers import lines_equal, records_from_dwell
+        from helpers import lines_equal, link_records_numpy, records_from_dwell
         from oracle import oracle
-        from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import contour, sharding
+        from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import sharding
         dist.init_process_group("gloo", rank=rank, world_size=world)
         xs = np.linspace(-2.1, 0.9, 140); ys = np.linspace(-1.5, 1.5, 120)
         mi, lvl = 200, 192.0
@@ -88,15 +88,17 @@ def _worker(rank: int, world: int, port: int, q):
         has_halo = rank < world - 1
         block = np.vstack([mine, firsts[rank + 1].numpy()[None, :]]) if has_halo else mine
         recs = records_from_dwell(block, xs, ys[r0:r1 + (1 if has_halo else 0)], lvl, row_offset=r0, nx_global=xs.size)
-        allrec = sharding.gather_records(recs, torch.device("cpu"), 0)
-        ok = True
+        rec_t = torch.zeros((len(recs) + 5, 8), dtype=torch.int64)          # capacity > count, like the device buffer
+        rec_t[: len(recs)] = torch.from_numpy(recs)
+        allrec, counts = sharding.gather_records(rec_t, len(recs), 0)
+        ok = len(counts) == world and counts[rank] == len(recs)
         if rank == 0:
             full, _ = oracle.dwell_grid(xs, ys, mi)
-            ok = np.array_equal(allrec, records_from_dwell(full, xs, ys, lvl))
-            lines = contour.link_records(allrec, xs, ys, lvl)
+            ok = ok and np.array_equal(allrec.numpy(), records_from_dwell(full, xs, ys, lvl))
+            lines = link_records_numpy(allrec.numpy(), xs, ys, lvl)          # restates the device linker (no GPU here)
             ok = ok and lines_equal(lines, oracle.contour_lines(xs, ys, full.astype(float), lvl))
         else:
-            ok = allrec is None
+            ok = ok and allrec is None
         dist.barrier()
         dist.destroy_process_group()
         q.put((rank, bool(ok), ""))
