@@ -5,24 +5,29 @@
 
 Metric (BASELINE.json): G pixel-iterations/s in fp64, work unit = sum over pixels of
 min(dwell+1, max_iter) counted exactly by the kernel.  A step is one pass of the boundary stage
-over the whole window: K1 (escape-time dwell grid, fp64, bit-exact) followed by K2 (level-set
-classification -> crossing records); with N > 1 the rows are sharded over the ranks at equal
-estimated work and the shard-edge dwell rows are all-gathered over NCCL for K2's halo.
+over the whole window: K1 (escape-time dwell grid, fp64, bit-exact) followed by K2 (level set:
+crossing records -> ORDERED boundary polylines, all on the device); with N > 1 the rows are
+sharded over the ranks at equal estimated cost, the shard-edge dwell rows are all-gathered over
+NCCL for K2's halo and the shards' records are sent GPU-to-GPU to rank 0, which links them.
 
   value     whole-job throughput with inputs/outputs resident in HBM (device-timed, max over ranks)
-  e2e       the same through the host-buffer C ABI (lm_escape_grid_f64 on pinned numpy buffers +
-            K2 + gather of the records + ordered linking on rank 0): H2D and D2H inside the region
+  e2e       the same through the host-buffer C ABI (pinned numpy buffers in, dwell grid and ordered
+            polylines out): H2D and D2H inside the region
   roofline  K1 against the FP64 peak measured live by lm_probe_fp64_peak (MEASURED_PEAKS.json has
             no FP64 entry): achieved = pixel_iters x 8 flops / K1 device time
+  sub_rooflines   K2 (records) and K4 (5-point stencil) against the measured HBM copy bandwidth,
+            K3 against the FP64 probe
   cpu_baseline / --impl reference
             the CPU port of the reference (oracle/lm_oracle.c, pthreads over all host cores) on a
-            bounded row sample of the same workload.  The reference itself is pure Python
-            (0.84 M pixel-iter/s on one core) and cannot run the workload.
+            bounded row sample of the same workload, and beside it the reference's own pure-Python
+            loop (oracle/pyref.py; the reference's `def` itself where /root/reference exists)
+  legs      one-step runs of the other grid configs of BASELINE.json (cfg1, cfg2, cfg4)
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
@@ -37,7 +42,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 WORKLOADS = {
-    # BASELINE.json configs[2] (the grid the target is quoted on; fits one GPU), [1] and [0]
+    # BASELINE.json configs[2] (the grid the target is quoted on; fits one GPU), [1], [0] and [3]
     "cfg3": dict(xlim=(-2.1, 0.9), ylim=(-1.5, 1.5), res=32768, max_iter=10000, level=0.96),
     "cfg2": dict(xlim=(-2.1, 0.9), ylim=(-1.5, 1.5), res=8192, max_iter=2000, level=0.96),
     "cfg1": dict(xlim=(-2.1, 0.9), ylim=(-1.5, 1.5), res=2000, max_iter=500, level=0.96),
@@ -71,7 +76,10 @@ def parse_args():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["cfg5"], default="cfg3")
     ap.add_argument("--no-roots", action="store_true", help="skip the Lucas-roots leg of the default run")
+    ap.add_argument("--no-legs", action="store_true", help="skip the one-step cfg1 / cfg2 / cfg4 legs of the default run")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--refine", type=int, default=0,
+                    help="N > 1: rounds of measured re-cutting (untimed full K1 passes; charged to setup_ms). Default 0: one-shot cuts")
     ap.add_argument("--roots-f64-rows", action="store_true",
                     help="hand the Lucas first rows to the e2e call as float64 (8 B per coefficient) instead of int8")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -84,7 +92,7 @@ def workload_name(w: dict) -> str:
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU arm: the oracle port on a bounded sample of rows
+# CPU arm: the oracle port on a bounded sample of rows; the reference-speed Python loop
 # ---------------------------------------------------------------------------------------------
 def cpu_sample_rows(ny: int, every: int) -> np.ndarray:
     return np.arange(every // 2, ny, every, dtype=np.int64)
@@ -112,6 +120,20 @@ def pick_cpu_stride(w: dict, target_s: float) -> int:
     return min(every, probe_every)
 
 
+def python_loop_baseline(w: dict, budget_s: float) -> dict:
+    """The reference's own double loop over CPython complex numbers (mandelbrot_boundary_sample.py:22-39) on random
+    rows of the workload, every 64th column: kind "reference" where the reference checkout exists (its `def` run as
+    is), else the line-for-line restatement oracle/pyref.py (kind "port")."""
+    from oracle import pyref
+    xs = np.linspace(w["xlim"][0], w["xlim"][1], w["res"])
+    ys = np.linspace(w["ylim"][0], w["ylim"][1], w["res"])
+    stride = max(w["res"] // 512, 1)
+    r = pyref.timed_sample(xs, ys, w["max_iter"], budget_s=budget_s, cols_stride=stride)
+    return {"value": r["value"], "unit": "Gpixel-iter/s", "cores": 1, "kind": r["kind"], "language": "python",
+            "sample": f"{r['rows']} random rows x every {stride}th column ({r['cols']} pixels per row) of the workload, "
+                      f"{r['pixel_iters']} pixel-iterations in {r['seconds']:.1f} s (mandelbrot_dwell in CPython, one core)"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -134,8 +156,9 @@ def run_reference_arm(args):
         "cpu_baseline": {"value": value, "unit": "Gpixel-iter/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Gpixel-iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "CPU port of the reference's scalar loop (oracle/lm_oracle.c), all host threads; "
-                "the Python reference itself runs at ~0.84e-3 Gpixel-iter/s on one core",
+        "python_loop": python_loop_baseline(w, 10.0),
+        "note": "CPU port of the reference's scalar loop (oracle/lm_oracle.c), all host threads; python_loop is the "
+                "reference's own CPython loop on one core, timed beside it",
     }
     print(json.dumps(line), flush=True)
 
@@ -192,63 +215,97 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def measured_peaks() -> dict:
+    try:
+        return json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except (OSError, ValueError):
+        return {}
+
+
+def profiled_traffic(workload: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the K1 launch from the committed ncu capture of THIS round
+    (profiles/r02_k1_traffic.json, written by scripts/ncu_traffic.py from the --set full CSV); None when there is none."""
+    try:
+        t = json.loads((ROOT / "profiles" / "r02_k1_traffic.json").read_text())
+        e = t.get(workload)
+        return (float(e["dram_bytes"]), e["source"]) if e else (None, None)
+    except (OSError, ValueError, KeyError):
+        return None, None
+
+
 # ---------------------------------------------------------------------------------------------
-# GPU arm
+# GPU arm: one grid workload (the headline, or a one-step leg)
 # ---------------------------------------------------------------------------------------------
-def run_ours(args):
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+class Ctx:
+    pass
+
+
+def dwell_checksum(dwell_rows, r0: int, nx: int) -> int:
+    """Position-weighted sum of the dwell block mod 2^64 (int64 wrap-around): additive over row blocks, so the
+    all-reduced value is the same for every sharding of the same grid."""
+    import torch
+    acc = torch.zeros((), dtype=torch.int64, device=dwell_rows.device)
+    cols = torch.arange(nx, dtype=torch.int64, device=dwell_rows.device)[None, :]
+    for a in range(0, dwell_rows.shape[0], 1024):
+        blk = dwell_rows[a:a + 1024].to(torch.int64)
+        rows = torch.arange(r0 + a, r0 + a + blk.shape[0], dtype=torch.int64, device=dwell_rows.device)[:, None]
+        wgt = (rows * nx + cols) * 2654435761 + 40503
+        acc += (blk * wgt).sum()
+    return int(acc.item())
+
+
+def lines_digest(verts: np.ndarray, offsets: np.ndarray) -> str:
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(offsets, dtype=np.int64).tobytes())
+    h.update(np.ascontiguousarray(verts, dtype=np.float64).tobytes())
+    return h.hexdigest()[:16]
+
+
+def grid_leg(cx: Ctx, name: str, steps: int, warmup: int, want_e2e: bool, refine: int = 0) -> dict:
+    """K1 + K2 on workload `name` over the ranks of cx.  -> fields of the JSON line (rank 0 builds the line)."""
     import torch
     import torch.distributed as dist
-    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import _shim, build, contour, sharding
-
-    build.build()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    _shim.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    lib = _shim.load()
-    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-
-    w = WORKLOADS[args.workload]
+    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import _shim, contour, sharding
+    rank, world, dev, lib, stream = cx.rank, cx.world, cx.dev, cx.lib, cx.stream
+    w = WORKLOADS[name]
     res, max_iter = w["res"], w["max_iter"]
     level = w["level"] * max_iter
     xs = np.linspace(w["xlim"][0], w["xlim"][1], res)
     ys = np.linspace(w["ylim"][0], w["ylim"][1], res)
     nx, ny = xs.size, ys.size
 
-    # ---- row shard of this rank (contiguous block cut at equal estimated work)
-    if world > 1:
-        profile = sharding.coarse_row_profile(xs, ys, max_iter)
-        cuts = sharding.balanced_row_cuts(profile, world)
-        # measured rebalancing (untimed set-up): run K1 on the estimated blocks, time every rank with CUDA events,
-        # rescale the profile block by block to the measured times and cut again
-        for _ in range(2):
-            ra, rb = cuts[rank], cuts[rank + 1]
-            cal_ys = torch.from_numpy(np.ascontiguousarray(ys[ra:rb])).to(dev)
-            cal_xs = torch.from_numpy(xs).to(dev)
-            cal_d = torch.empty((rb - ra, nx), dtype=torch.int32, device=dev)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize(); dist.barrier()
-            e0.record()
-            _shim.call("lm_escape_grid_f64_dev", C.c_void_p(cal_xs.data_ptr()), nx, C.c_void_p(cal_ys.data_ptr()), rb - ra,
-                       max_iter, 2.0, 0, C.c_void_p(cal_d.data_ptr()), None, None, None, stream)
-            e1.record(); torch.cuda.synchronize()
-            t_all = torch.zeros(world, dtype=torch.float64, device=dev)
-            t_all[rank] = e0.elapsed_time(e1)
-            dist.all_reduce(t_all)
-            cuts = sharding.refine_cuts(profile, cuts, t_all.cpu().numpy())
-            del cal_d, cal_ys, cal_xs
-        balance = sharding.parallel_efficiency(profile, cuts)
-    else:
-        cuts, balance = [0, ny], 1.0
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- row shard of this rank: contiguous blocks cut ONCE at equal estimated cost (coarse K1 pre-pass weighted by
+    # the per-device cost model of sharding.plan_row_cuts); nothing is calibrated on the workload itself unless --refine
+    barrier()
+    t_setup = time.perf_counter()
+    plan = sharding.plan_row_cuts(xs, ys, max_iter, world, device=dev)
+    cuts = plan["cuts"]
+    balance_estimate_only = plan["balance_estimate"]
+    refined = 0
+    for _ in range(refine if world > 1 else 0):
+        ra, rb = cuts[rank], cuts[rank + 1]
+        cal_ys = torch.from_numpy(np.ascontiguousarray(ys[ra:rb])).to(dev)
+        cal_xs = torch.from_numpy(xs).to(dev)
+        cal_d = torch.empty((rb - ra, nx), dtype=torch.int32, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        _shim.call("lm_escape_grid_f64_dev", C.c_void_p(cal_xs.data_ptr()), nx, C.c_void_p(cal_ys.data_ptr()), rb - ra,
+                   max_iter, 2.0, 0, C.c_void_p(cal_d.data_ptr()), None, None, None, stream)
+        e1.record(); torch.cuda.synchronize()
+        t_all = torch.zeros(world, dtype=torch.float64, device=dev)
+        t_all[rank] = e0.elapsed_time(e1)
+        dist.all_reduce(t_all)
+        cuts = sharding.refine_cuts(plan["profile"], cuts, t_all.cpu().numpy())
+        refined += 1
+        del cal_d, cal_ys, cal_xs
+    barrier()
+    setup_ms = 1e3 * (time.perf_counter() - t_setup)
     r0, r1 = cuts[rank], cuts[rank + 1]
     rows = r1 - r0
     has_halo = rank < world - 1
@@ -259,13 +316,15 @@ def run_ours(args):
     dwell_d = torch.empty((rows + 1, nx), dtype=torch.int32, device=dev)      # +1: halo row slot
     # BASELINE.json configs[1] asks for the smooth potential with the dwell grid; at N > 1 the final field is
     # all-gathered so that every GPU holds it (north_star)
-    with_pot = args.workload == "cfg2"
+    with_pot = name == "cfg2"
     field_d = torch.empty((rows, nx), dtype=torch.float64, device=dev) if with_pot else None
     work_d = torch.zeros(1, dtype=torch.int64, device=dev)
-    rec_cap = max(int(0.002 * rows * nx) + 4096, 1 << 16)
-    records = _shim.pinned_empty((rec_cap, 8), np.int64)          # page-locked: the records land in it straight from the device
+    rec_d = torch.empty((max(int(0.002 * rows * nx) + 4096, 1 << 16), 8), dtype=torch.int64, device=dev)
     n_rec = C.c_int64(0)
+    nv = C.c_int64(0); nl = C.c_int64(0)
+    first = np.zeros(1, dtype=np.int64)
     launches = {"n": 0}
+    state = {"rec_d": rec_d, "n_rec_total": 0}
 
     def k1():
         _shim.call("lm_escape_grid_f64_dev", C.c_void_p(xs_d.data_ptr()), nx, C.c_void_p(ys_d.data_ptr()), rows,
@@ -273,96 +332,120 @@ def run_ours(args):
                    C.c_void_p(field_d.data_ptr()) if with_pot else None, C.c_void_p(work_d.data_ptr()), stream)
         launches["n"] += 1
 
-    def classify(block_ptr, nrows_k2):
-        nonlocal records
-        while True:
-            rc = lib.lm_contour_classify_dev(block_ptr, _shim.ptr(xs), nx, _shim.ptr(ys_block), nrows_k2,
-                                             r0, float(level), _shim.ptr(records), records.shape[0], C.byref(n_rec), stream)
-            if rc == _shim.LM_E_CAP:
-                records = _shim.pinned_empty((n_rec.value + 1024, 8), np.int64)
-                continue
-            _shim.check(rc)
-            break
-        launches["n"] += 3 if n_rec.value else 2
-        return records[: n_rec.value]
-
-    full_field = {"t": None}
-
-    def k2():
+    def k2_records():
+        """halo exchange + mark / scan / emit: this rank's crossing records, resident"""
         if world > 1:
             firsts = sharding.exchange_first_rows(dwell_d[0])
             if has_halo:
                 dwell_d[rows].copy_(firsts[rank + 1])
             if with_pot:
-                full_field["t"] = sharding.allgather_rows(field_d, cuts)
-        return classify(C.c_void_p(dwell_d.data_ptr()), rows + (1 if has_halo else 0))
+                state["full_field"] = sharding.allgather_rows(field_d, cuts)
+        while True:
+            rc = lib.lm_contour_records_dev(C.c_void_p(dwell_d.data_ptr()), _shim.ptr(xs), nx, _shim.ptr(ys_block),
+                                            rows + (1 if has_halo else 0), r0, float(level),
+                                            C.c_void_p(state["rec_d"].data_ptr()), state["rec_d"].shape[0], C.byref(n_rec), stream)
+            if rc == _shim.LM_E_CAP:
+                state["rec_d"] = torch.empty((n_rec.value + 1024, 8), dtype=torch.int64, device=dev)
+                continue
+            _shim.check(rc)
+            break
+        launches["n"] += 3 if n_rec.value else 2
 
-    def barrier():
+    def k2_link():
+        """records of all shards -> rank 0 (GPU to GPU) -> ordered polylines, left on the device"""
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+            allrec, counts = sharding.gather_records(state["rec_d"], n_rec.value, 0)
+            state["n_rec_total"] = int(sum(counts))
+        else:
+            allrec = state["rec_d"]
+            state["n_rec_total"] = n_rec.value
+        if rank == 0:
+            rc = lib.lm_contour_link_dev(C.c_void_p(allrec.data_ptr()), state["n_rec_total"], _shim.ptr(xs), nx, _shim.ptr(ys), ny,
+                                         float(level), None, 0, C.byref(nv), _shim.ptr(first), 0, C.byref(nl), stream)
+            if rc != _shim.LM_E_CAP:          # LM_E_CAP with zero capacity = "linked, kept on the device"
+                _shim.check(rc)
+            launches["n"] += 2 if state["n_rec_total"] else 0
 
-    # ---- FP64 peak for the roofline (not in MEASURED_PEAKS.json)
-    peak_tflops = C.c_double(0.0); mix = C.c_double(0.0)
-    _shim.call("lm_probe_fp64_peak", 2000, C.byref(peak_tflops), C.byref(mix))
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()             # before the warm-up (same load): nvidia-smi needs ~0.2 s for its first sample and
-                                    # the small workloads finish their timed region in ~0.1 s
-    for _ in range(args.warmup):
-        k1(); k2()
+    for _ in range(warmup):
+        k1(); k2_records(); k2_link()
     barrier()
     launches["n"] = 0
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 + 2 * args.steps)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 + 4 * steps)]
     work_steps = []
     ev[0].record()
-    for k in range(args.steps):
-        ev[2 + 2 * k].record()
+    for k in range(steps):
+        ev[2 + 4 * k].record()
         k1()
-        ev[3 + 2 * k].record()
-        k2()
+        ev[3 + 4 * k].record()
+        k2_records()
+        ev[4 + 4 * k].record()
+        k2_link()
+        ev[5 + 4 * k].record()
         work_steps.append(int(work_d.item()))
     ev[1].record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     elapsed_ms = ev[0].elapsed_time(ev[1])
-    k1_ms = sum(ev[2 + 2 * k].elapsed_time(ev[3 + 2 * k]) for k in range(args.steps))
+    k1_ms = sum(ev[2 + 4 * k].elapsed_time(ev[3 + 4 * k]) for k in range(steps))
+    k2a_ms = sum(ev[3 + 4 * k].elapsed_time(ev[4 + 4 * k]) for k in range(steps))
+    k2b_ms = sum(ev[4 + 4 * k].elapsed_time(ev[5 + 4 * k]) for k in range(steps))
     my_work = sum(work_steps)
-    t = torch.tensor([elapsed_ms, k1_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([elapsed_ms, k1_ms, k2a_ms, k2b_ms], dtype=torch.float64, device=dev)
+    tmin = torch.tensor([k1_ms], dtype=torch.float64, device=dev)
     wk = torch.tensor([my_work], dtype=torch.int64, device=dev)
+    crc = torch.tensor([dwell_checksum(dwell_d[:rows], r0, nx)], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tmin, op=dist.ReduceOp.SUM)
         dist.all_reduce(wk, op=dist.ReduceOp.SUM)
-    elapsed_ms, k1_ms_max = float(t[0]), float(t[1])
+        dist.all_reduce(crc, op=dist.ReduceOp.SUM)
+    elapsed_ms, k1_ms_max, k2a_ms_max, k2b_ms_max = (float(v) for v in t)
     total_work = int(wk[0])
     value = total_work / (elapsed_ms * 1e-3) / 1e9
-    gpu_launches = launches["n"]
+    out = {"name": name, "w": w, "value": value, "elapsed_ms": elapsed_ms, "ms_per_step": elapsed_ms / steps,
+           "total_work": total_work, "cuts": cuts, "plan": plan, "setup_ms": setup_ms, "refined": refined,
+           "balance_estimate_only": balance_estimate_only,
+           "balance_measured": float(tmin[0]) / world / max(k1_ms_max, 1e-9),      # mean / max of the ranks' K1 time
+           "k1_ms_per_step_max_rank": k1_ms_max / steps, "gpu_launches": launches["n"], "with_pot": with_pot,
+           "dwell_crc": f"{int(crc[0]) & 0xFFFFFFFFFFFFFFFF:016x}", "n_records": state["n_rec_total"]}
 
-    # ---- roofline of the dominant kernel (K1) on this rank
+    # the device-resident lines of the last step (rank 0) -> digest
+    if rank == 0:
+        verts = np.empty((nv.value, 2)); offs = np.empty(nl.value + 1, dtype=np.int64)
+        _shim.check(lib.lm_contour_fetch_last(_shim.ptr(verts), nv.value, C.byref(nv), _shim.ptr(offs), nl.value, C.byref(nl)))
+        out["boundary_sha256"] = lines_digest(verts, offs)
+        out["boundary_lines"] = int(nl.value)
+        out["boundary_vertices_total"] = int(nv.value)
+        out["boundary_vertices"] = int(np.diff(offs).max()) if nl.value else 0
+
+    # ---- roofline of the dominant kernel (K1) on this rank, K2 against HBM
     k1_gpi = my_work / (k1_ms * 1e-3) / 1e9
     achieved_tflops = k1_gpi * 1e9 * FLOPS_PER_PIXEL_ITER / 1e12
-    roofline = {
-        "bound": "fp64", "kernel": "lm_escape_kernel<grid, dwell + potential>" if with_pot else "lm_escape_kernel<grid, dwell>", "achieved": achieved_tflops, "peak": peak_tflops.value,
-        "unit": "TFLOP/s", "frac": achieved_tflops / peak_tflops.value,
+    peak = cx.peak_tflops
+    traffic, traffic_src = profiled_traffic(name) if world == 1 else (None, None)
+    out["roofline"] = {
+        "bound": "fp64", "kernel": "lm_escape_kernel<grid, dwell + potential>" if with_pot else "lm_escape_kernel<grid, dwell>",
+        "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s", "frac": achieved_tflops / peak,
         "peak_source": "lm_probe_fp64_peak (dependent-free DFMA loop, 2 flops/DFMA), measured live; "
                        "MEASURED_PEAKS.json has no FP64 entry",
         "algorithmic_flops_per_unit": FLOPS_PER_PIXEL_ITER,
-        "fp64_pipe_instr_util": k1_gpi * 1e9 * 6 / (peak_tflops.value * 1e12 / 2),
-        "k1_gpixel_iter_per_s": k1_gpi,
-        # dram__bytes_read.sum + dram__bytes_write.sum of this launch from one ncu --set full capture
-        # (profiles/r01_k1_escape_cfg3_ncu_full_v2.csv: 0.066 GB read + 4.263 GB written; algorithmic output 4.295 GB)
-        "traffic": 4.3289e9 if (args.workload == "cfg3" and world == 1) else None,
+        "fp64_pipe_instr_util": k1_gpi * 1e9 * 6 / (peak * 1e12 / 2),
+        "k1_gpixel_iter_per_s": k1_gpi, "traffic": traffic, "traffic_source": traffic_src,
     }
+    hbm = cx.hbm_gbs
+    k2_bytes = 4.0 * (rows + (1 if has_halo else 0)) * nx * steps
+    out["k2_roofline"] = {
+        "bound": "hbm", "kernel": "contour_mark_bulk_kernel + contour_scan_kernel + contour_emit_kernel (+ NCCL halo row at N > 1)",
+        "achieved": k2_bytes / (k2a_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": k2_bytes / (k2a_ms * 1e-3) / 1e9 / hbm,
+        "algorithmic_bytes_per_unit": 4, "ms_per_step": k2a_ms / steps,
+        "link_ms_per_step_max_rank": k2b_ms_max / steps, "records_ms_per_step_max_rank": k2a_ms_max / steps,
+        "note": "timed with CUDA events around lm_contour_records_dev on this rank; it includes the host sync that reads the "
+                "record count; link = record gather to rank 0 + link_build_kernel + link_rank_kernel"}
 
     # ---- e2e through the host-buffer C ABI
-    e2e = None
-    if not args.no_e2e:
-        out = _shim.pinned_empty((rows, nx), np.int32)
+    if want_e2e:
+        out_h = _shim.pinned_empty((rows, nx), np.int32)
         xs_p = _shim.pinned_empty(nx, np.float64); xs_p[:] = xs
         ys_p = _shim.pinned_empty(rows, np.float64); ys_p[:] = ys[r0:r1]
-        st = _shim.Stats()
-        edge_d = torch.empty(nx, dtype=torch.int32, device=dev)
         pot_p = _shim.pinned_empty((rows, nx), np.float64) if with_pot else None
         job = sharding.ShardedBoundary(xs, ys, max_iter, level, device=dev, with_potential=with_pot, cuts=cuts) if world > 1 else None
 
@@ -370,13 +453,12 @@ def run_ours(args):
             if world == 1:
                 # the fused host-buffer call (compute_grid + extract_contour of the script's main()):
                 # H2D of xs/ys, chunked K1, dwell grid copied back to the pinned host buffer while
-                # K1/K2 still run, K2 records -> ordered polylines on the host
-                lines, stx = contour.boundary_sample(xs_p, ys_p, max_iter, level, dwell_out=out, potential_out=pot_p)
+                # K1/K2 still run, K2 records -> ordered polylines on the device -> host
+                lines, stx = contour.boundary_sample(xs_p, ys_p, max_iter, level, dwell_out=out_h, potential_out=pot_p)
                 return stx["work_units"], lines
-            # N > 1: the package's sharded boundary stage (sharding.ShardedBoundary.run): K1 on this rank's rows
-            # through the host-buffer shard call (block returned to pinned host memory AND kept in HBM), shard-edge
-            # rows all-gathered over NCCL straight from / into those blocks, K2 on them, records gathered and
-            # linked on rank 0
+            # N > 1: sharding.ShardedBoundary.run: K1 on this rank's rows through the host-buffer shard call (block
+            # returned to pinned host memory AND kept in HBM), shard-edge rows all-gathered over NCCL straight from /
+            # into those blocks, K2 records on them, records sent GPU-to-GPU to rank 0 and linked there on the device
             lines = job.run()
             return job.last_work_units, lines
 
@@ -385,7 +467,7 @@ def run_ours(args):
         t0 = time.perf_counter()
         e2e_work = 0
         lines = None
-        for _ in range(args.steps):
+        for _ in range(steps):
             wu, lines = e2e_step()
             e2e_work += int(wu)
         barrier()
@@ -395,20 +477,113 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dist.all_reduce(ww, op=dist.ReduceOp.SUM)
-        n_vertices = int(lines.lengths().max()) if lines is not None and len(lines) else 0
-        e2e = {"value": int(ww[0]) / float(tt[0]) / 1e9, "unit": "Gpixel-iter/s",
-               "h2d_bytes_per_step": int((nx + rows) * 8),
-               "d2h_bytes_per_step": int(rows * nx * (12 if with_pot else 4) + (job.n_records if job else n_rec.value) * 64), "ms_per_step": 1e3 * float(tt[0]) / args.steps,
-               "boundary_vertices": n_vertices,
-               "api": ("lm_boundary_sample (pinned numpy buffers in, dwell grid + ordered boundary polylines out)" if world == 1 else
-                       "sharding.ShardedBoundary.run: lm_shard_escape (pinned numpy buffers; block kept in HBM) + NCCL edge rows + lm_contour_classify_dev + lm_contour_link")}
+        host_dwell = job.dwell if job else out_h
+        host_crc = torch.tensor([dwell_checksum(torch.from_numpy(host_dwell[: min(rows, 4096)]).to(dev), r0, nx)], dtype=torch.int64, device=dev)
+        dev_crc = torch.tensor([dwell_checksum(dwell_d[: min(rows, 4096)], r0, nx)], dtype=torch.int64, device=dev)
+        lines_bytes = int(lines.verts.nbytes + lines.offsets.nbytes) if lines is not None else 0
+        out["e2e"] = {"value": int(ww[0]) / float(tt[0]) / 1e9, "unit": "Gpixel-iter/s",
+                      "h2d_bytes_per_step": int((nx + rows) * 8),
+                      "d2h_bytes_per_step": int(rows * nx * (12 if with_pot else 4)) + lines_bytes,
+                      "ms_per_step": 1e3 * float(tt[0]) / steps,
+                      "boundary_vertices": int(lines.lengths().max()) if lines is not None and len(lines) else 0,
+                      "boundary_sha256": lines_digest(lines.verts, lines.offsets) if lines is not None else None,
+                      "host_dwell_matches_device": bool(int(host_crc[0]) == int(dev_crc[0])),
+                      "api": ("lm_boundary_sample (pinned numpy buffers in, dwell grid + ordered boundary polylines out)" if world == 1 else
+                              "sharding.ShardedBoundary.run: lm_shard_escape (pinned numpy buffers; block kept in HBM) + NCCL edge rows + "
+                              "lm_contour_records_dev + NCCL send of the records to rank 0 + lm_contour_link_dev")}
+    del dwell_d, field_d, rec_d
+    state.clear()
+    torch.cuda.empty_cache()
+    return out
+
+
+def k4_roofline(cx: Ctx, n: int = 8192, reps: int = 20) -> dict:
+    """5-point periodic Laplacian (Laplacian_C-M.py:49-59) on an n x n float64 field resident in HBM: 16 B / pixel."""
+    import torch
+    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import _shim
+    U = torch.rand((n, n), dtype=torch.float64, device=cx.dev)
+    out = torch.empty_like(U)
+    P = lambda t: C.c_void_p(t.data_ptr())
+    for _ in range(3):
+        _shim.call("lm_laplacian5_periodic_dev", P(U), n, n, 1e-3, P(out), cx.stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        _shim.call("lm_laplacian5_periodic_dev", P(U), n, n, 1e-3, P(out), cx.stream)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    gbs = 16.0 * n * n / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "laplacian5_kernel (periodic 5-point stencil, float64)", "achieved": gbs, "peak": cx.hbm_gbs,
+            "unit": "GB/s", "frac": gbs / cx.hbm_gbs, "algorithmic_bytes_per_unit": 16, "ms": ms,
+            "workload": f"{n} x {n} float64 field ({8 * n * n / 1e6:.0f} MB in, same out: larger than L2), {reps} launches back to back"}
+
+
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    import torch
+    import torch.distributed as dist
+    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import _shim, build
+
+    build.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    _shim.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cx = Ctx()
+    cx.rank, cx.world, cx.dev, cx.lib = rank, world, dev, _shim.load()
+    cx.stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # ---- FP64 peak for the roofline (not in MEASURED_PEAKS.json); HBM peak from the driver's file
+    peak_tflops = C.c_double(0.0); mix = C.c_double(0.0)
+    _shim.call("lm_probe_fp64_peak", 2000, C.byref(peak_tflops), C.byref(mix))
+    cx.peak_tflops = peak_tflops.value
+    mp = measured_peaks()
+    cx.hbm_gbs = float(mp.get("hbm_gbs", 6500.0))
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in mp else "fallback 6500 GB/s (B200_PROFILING.md)"
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()             # before the warm-up (same load): nvidia-smi needs ~0.2 s for its first sample
+    main = grid_leg(cx, args.workload, args.steps, args.warmup, want_e2e=not args.no_e2e, refine=args.refine)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- the other grid configs of BASELINE.json, one timed step each (builder-visible in round 1 only)
+    legs = {}
+    if args.workload == "cfg3" and not args.no_legs:
+        for nm in ("cfg1", "cfg2", "cfg4"):
+            try:
+                g = grid_leg(cx, nm, steps=1 if nm == "cfg4" else 3, warmup=1 if nm == "cfg4" else 3, want_e2e=(nm != "cfg4") and not args.no_e2e)
+                legs[nm] = {"workload": workload_name(g["w"]), "value": g["value"], "unit": "Gpixel-iter/s", "ms_per_step": g["ms_per_step"],
+                            "steps": 1 if nm == "cfg4" else 3, "pixel_iters_per_step": g["total_work"] // (1 if nm == "cfg4" else 3),
+                            "roofline_frac": g["roofline"]["frac"], "fp64_pipe_instr_util": g["roofline"]["fp64_pipe_instr_util"],
+                            "k1_gpixel_iter_per_s": g["roofline"]["k1_gpixel_iter_per_s"],
+                            "balance_estimate_only": g["balance_estimate_only"], "balance_measured": g["balance_measured"],
+                            "setup_ms": g["setup_ms"], "dwell_crc": g["dwell_crc"], "boundary_sha256": g.get("boundary_sha256"),
+                            "with_potential": g["with_pot"], "e2e": g.get("e2e")}
+            except Exception as e:      # the headline line must survive a failure of a secondary leg
+                legs[nm] = {"error": f"{type(e).__name__}: {e}"}
+
+    sub = None
+    try:
+        sub = {"k2_records": main["k2_roofline"], "k4_stencil": k4_roofline(cx) if rank == 0 or world == 1 else None,
+               "hbm_peak_source": hbm_src}
+    except Exception as e:
+        sub = {"error": f"{type(e).__name__}: {e}"}
 
     # ---- the other half of BASELINE.json's metric: Lucas roots/s (K3) on the config-5 batch, sharded by polynomial
     lucas_roots = None
     if not args.no_roots:
         try:
-            r = measure_roots(args, rank, world, dev, stream, full_fields=False)
-            lucas_roots = {k: r[k] for k in ("value", "unit", "ms_per_step", "roots", "mean_sweeps", "not_converged") if k in r}
+            r = measure_roots(args, rank, world, dev, cx.stream, full_fields=False, peak_tflops=cx.peak_tflops)
+            lucas_roots = {k: r[k] for k in ("value", "unit", "ms_per_step", "roots", "mean_sweeps", "not_converged", "roofline") if k in r}
             lucas_roots["workload"] = r["config"]["workload"]
             if "e2e" in r:
                 lucas_roots["e2e"] = r["e2e"]
@@ -417,27 +592,40 @@ def run_ours(args):
         except Exception as e:          # the headline line must survive a failure of the secondary leg
             lucas_roots = {"error": f"{type(e).__name__}: {e}"}
 
-    # ---- CPU baseline beside it (rank 0, N = 1 only)
+    # ---- CPU baselines beside it (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        w = main["w"]
         every = pick_cpu_stride(w, target_s=15.0)
         work, dt, threads, nrows = cpu_pass(w, every)
         cpu = {"value": work / dt / 1e9, "unit": "Gpixel-iter/s", "cores": threads, "kind": "port",
-               "sample": f"every {every}th row ({nrows} of {res} rows, full width), one pass, {dt:.1f} s"}
+               "sample": f"every {every}th row ({nrows} of {w['res']} rows, full width), one pass, {dt:.1f} s",
+               "python_loop": python_loop_baseline(w, 8.0)}
 
     if rank == 0:
+        w = main["w"]
+        plan = main["plan"]
         line = {
-            "metric": "gpixel_iter_per_s_fp64", "value": value, "unit": "Gpixel-iter/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+            "metric": "gpixel_iter_per_s_fp64", "value": main["value"], "unit": "Gpixel-iter/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(w), "pixel_iters_per_step": total_work // args.steps,
-                       "step": "K1 dwell grid" + (" + smooth potential" if with_pot else "") + " + K2 crossing records" +
-                               ((" + NCCL all-gather of shard-edge rows" + (" and of the potential field" if with_pot else "")) if world > 1 else ""),
-                       "sharding": (f"contiguous row blocks at equal estimated work" + (", refined twice from measured per-rank K1 times" if world > 1 else "") +
-                                    f", cuts={cuts}, estimated balance={balance:.3f}"),
+            "config": {"workload": workload_name(w), "pixel_iters_per_step": main["total_work"] // args.steps,
+                       "step": "K1 dwell grid" + (" + smooth potential" if main["with_pot"] else "") +
+                               " + K2 crossing records + ordered boundary polylines (device linker)" +
+                               ((" + NCCL all-gather of shard-edge rows" + (" and of the potential field" if main["with_pot"] else "") +
+                                 " + NCCL send of the records to rank 0") if world > 1 else ""),
+                       "sharding": (f"contiguous row blocks cut once at equal estimated cost ({plan['model']}), cuts={main['cuts']}" +
+                                    (f", then refined {main['refined']}x from measured per-rank K1 times" if main["refined"] else "")),
                        "l2": "FP64-bound; per step every rank writes its dwell block (>= L2 for cfg2/cfg3) and reads 2*res coordinates"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
-            "k1_ms_per_step_max_rank": k1_ms_max / args.steps, "lucas_roots": lucas_roots,
+            "roofline": main["roofline"], "sub_rooflines": sub, "cpu_baseline": cpu, "e2e": main.get("e2e"),
+            "gpu_launches": main["gpu_launches"], "clocks": clocks,
+            "k1_ms_per_step_max_rank": main["k1_ms_per_step_max_rank"],
+            "balance_estimate_only": main["balance_estimate_only"], "balance_measured": main["balance_measured"],
+            "setup_ms": main["setup_ms"], "setup": plan.get("setup"),
+            "dwell_crc": main["dwell_crc"], "boundary_sha256": main.get("boundary_sha256"),
+            "boundary_lines": main.get("boundary_lines"), "boundary_vertices": main.get("boundary_vertices"),
+            "boundary_vertices_total": main.get("boundary_vertices_total"), "n_records": main["n_records"],
+            "lucas_roots": lucas_roots, "legs": legs or None,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -491,7 +679,7 @@ def cpu_roots_baseline(target_s: float = 10.0) -> dict:
                       f"config-5 batch ({roots} roots), {procs} worker processes, {dt:.1f} s"}
 
 
-def measure_roots(args, rank, world, dev, stream, full_fields: bool):
+def measure_roots(args, rank, world, dev, stream, full_fields: bool, peak_tflops: float | None = None):
     """K3 (+ cloud compaction) over this rank's slice of the 10^7-polynomial batch, device resident; optionally the
     field stage (K1d, K4a with an NCCL all-reduce of the per-cell sums, K4).  -> dict for the JSON line."""
     import torch
@@ -545,6 +733,27 @@ def measure_roots(args, rank, world, dev, stream, full_fields: bool):
                       "sharding": f"{CFG5['chunks']} independently seeded chunks dealt contiguously to the ranks, no collective"},
            "roots": roots_total, "cloud_points": pts_total, "mean_sweeps": sweeps / max(npoly_total, 1), "not_converged": failed,
            "gpu_launches": 9 * args.steps}
+    # K3 against the FP64 peak: SURVEY 8d's flop model (28 flops per inner step, 2 d inner steps per root update:
+    # d Horner steps for p, p' and the error bound + d Aberth terms; root updates ~ roots x sweeps, an UPPER bound
+    # because converged roots drop out of the later sweeps) and the FP64 instructions the kernel issues per inner
+    # step (SASS of the two unrolled loops: 9 per Horner step, 6 per Aberth term)
+    if peak_tflops is None:
+        pk = C.c_double(0.0); mx = C.c_double(0.0)
+        _shim.call("lm_probe_fp64_peak", 2000, C.byref(pk), C.byref(mx))
+        peak_tflops = pk.value
+    sw_d2 = (iters[:npoly].abs().double() * deg[:npoly].double() ** 2).sum().reshape(1) if npoly else torch.zeros(1, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(sw_d2, op=dist.ReduceOp.SUM)
+    inner_steps = 2.0 * float(sw_d2[0])                      # sum over polynomials of sweeps * 2 d^2
+    flops = 14.0 * inner_steps                               # 28 d^2 per sweep = 14 per inner step
+    instr = 7.5 * inner_steps                                # (9 + 6) / 2 FP64 instructions per inner step
+    out["roofline"] = {"bound": "fp64", "kernel": "roots_pool_kernel (Aberth-Ehrlich, 4 lanes per polynomial) + sort / compaction kernels",
+                       "unit": "TFLOP/s", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peak_tflops * world,
+                       "frac": flops / (ms * 1e-3) / 1e12 / (peak_tflops * world),
+                       "fp64_pipe_instr_util": instr / (ms * 1e-3) / (peak_tflops * world * 1e12 / 2),
+                       "flop_model": "28 d^2 flops per polynomial and sweep (SURVEY 8d) x the sweeps each polynomial ran: an upper bound, "
+                                     "converged roots leave the later sweeps",
+                       "peak_source": "lm_probe_fp64_peak, measured live"}
 
     # e2e: host numpy arrays in, cloud on the host out, through the fused host-buffer call
     if not args.no_e2e:

@@ -300,8 +300,15 @@ __global__ void __launch_bounds__(CTA_THREADS, LM_K1_MIN_CTAS) lm_escape_kernel(
         double ze_r = 0.0, ze_i = 0.0; // z at the escape (FIELD modes)
 
         while (true) {
-            if (blind_ok && cool >= COOL_MIN && safe >= FB) {
-                // ---- blind block: FB iterations, 6 FP64 instructions each, one test at the end
+            if (blind_ok && cool >= COOL_MIN && (LM_K1_REDO_ESCAPED_ONLY || safe >= FB)) {
+                // ---- blind block: FB iterations, 6 FP64 instructions each, one test at the end.
+                // The block runs whatever `safe` says: a lane that passes max_iter inside it simply overshoots
+                // (its extra iterates are never looked at).  If its end-of-block test holds, no iterate of the
+                // block -- in particular none up to max_iter -- tripped the reference's test (backward induction,
+                // see the header), so the pixel retires with dwell = max_iter; if it fails, the lane repeats only
+                // the iterations that count.  Round 1 fell back to 4-iteration careful blocks for the WHOLE warp
+                // whenever any lane was within FB of max_iter, which is most of the time once refills have
+                // staggered the lanes (config 2: 0.56 -> see DESIGN.md).
                 const double szr = zr, szi = zi, sa = a, sb = b;
 #pragma unroll
                 for (int k = 0; k < FB; ++k) LM_STEP6();
@@ -312,18 +319,22 @@ __global__ void __launch_bounds__(CTA_THREADS, LM_K1_MIN_CTAS) lm_escape_kernel(
                     // Some lane escaped inside this block.  The lanes that did not keep the FB iterations they
                     // just made (their end-of-block test proves no earlier escape); only the escaped lanes go
                     // back to the saved state and repeat the block with the exact per-iteration test to find
-                    // their first-escape index.
+                    // their first-escape index (among the iterations before max_iter).
                     if (esc) {
                         zr = szr; zi = szi; a = sa; b = sb;
+                        const int left = A.max_iter - n;
+                        const int lim = left < FB ? left : FB;
                         int k = 0;
+                        bool found = false;
 #pragma unroll 1
-                        for (; k < FB - 1; ++k) {
+                        for (; k < lim; ++k) {
                             LM_STEP6();
-                            if (__dadd_rn(a, b) > A.thr2) break;
+                            if (__dadd_rn(a, b) > A.thr2) { found = true; break; }
                         }
-                        if (k == FB - 1) LM_STEP6();          // not found earlier: it is the block's last iterate
-                        done = true; n_fin = n + k + 1;
-                        if (FIELD || HYPOT || POINTS) { ze_r = zr; ze_i = zi; }
+                        if (found) {
+                            done = true; n_fin = n + k + 1;
+                            if (FIELD || HYPOT || POINTS) { ze_r = zr; ze_i = zi; }
+                        }
                     }
                     n += FB;
                     safe -= FB;
@@ -331,7 +342,7 @@ __global__ void __launch_bounds__(CTA_THREADS, LM_K1_MIN_CTAS) lm_escape_kernel(
                 }
                 n += FB;
                 safe -= FB;
-                if (safe == 0) break;
+                if (safe <= 0) break;
                 continue;
 #else
                 if (__any_sync(FULL, esc)) {
@@ -493,18 +504,48 @@ int32_t launch_escape(bool points, int field_mode, EscapeArgs& A, cudaStream_t s
 }
 
 // counters: [0] tile counter, [1] work counter, [2] overflow flag (as 8-byte slots).
-// A small ring of counter blocks lets several launches be in flight on different streams.
+// A ring of counter blocks lets several launches be in flight on different streams.  Every block carries an event
+// recorded behind the last launch that uses it; a block is handed out again only after that event has completed
+// (a caller of the *_dev entry points with more than COUNTER_BLOCKS launches in flight simply waits for the oldest
+// one instead of sharing a live tile queue with it).
 constexpr int COUNTER_BLOCKS = 64;
 int g_counter_next = 0;
+int g_counter_dev = -1;
+cudaEvent_t g_counter_ev[COUNTER_BLOCKS] = {};
+bool g_counter_busy[COUNTER_BLOCKS] = {};
 unsigned long long* g_last_counters = nullptr;   // block handed out by the latest get_counters()
-int32_t get_counters(unsigned long long** out, cudaStream_t stream) {
+void counters_reset() {
+    for (int k = 0; k < COUNTER_BLOCKS; ++k) {
+        if (g_counter_ev[k]) cudaEventDestroy(g_counter_ev[k]);
+        g_counter_ev[k] = nullptr; g_counter_busy[k] = false;
+    }
+    g_counter_dev = -1;
+}
+int32_t get_counters(unsigned long long** out, int* slot, cudaStream_t stream) {
     void* p = nullptr;
     int32_t rc = lm::ws_get(lm::WS_COUNTERS, 64 * COUNTER_BLOCKS, &p);
     if (rc != LM_OK) return rc;
-    unsigned char* blk = static_cast<unsigned char*>(p) + 64 * (g_counter_next++ % COUNTER_BLOCKS);
+    int dev = 0;
+    LM_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev != g_counter_dev) {                   // the workspace moved to another device: events are per device
+        counters_reset();
+        g_counter_dev = dev;
+        lm::register_release_hook(counters_reset);
+    }
+    const int k = g_counter_next++ % COUNTER_BLOCKS;
+    if (!g_counter_ev[k]) LM_CUDA_TRY(cudaEventCreateWithFlags(&g_counter_ev[k], cudaEventDisableTiming));
+    if (g_counter_busy[k]) { LM_CUDA_TRY(cudaEventSynchronize(g_counter_ev[k])); g_counter_busy[k] = false; }
+    unsigned char* blk = static_cast<unsigned char*>(p) + 64 * k;
     LM_CUDA_TRY(cudaMemsetAsync(blk, 0, 64, stream));
     *out = reinterpret_cast<unsigned long long*>(blk);
+    *slot = k;
     g_last_counters = *out;
+    return LM_OK;
+}
+// call behind the last launch that reads / writes the block
+int32_t counters_in_flight(int slot, cudaStream_t stream) {
+    LM_CUDA_TRY(cudaEventRecord(g_counter_ev[slot], stream));
+    g_counter_busy[slot] = true;
     return LM_OK;
 }
 
@@ -523,7 +564,8 @@ int32_t enqueue_grid(const double* xs, int64_t nx, const double* ys, int64_t ny,
                             int32_t* dwell_i32, double* dwell_f64, double* field,
                             unsigned long long* work_dev, int* overflow_dev, cudaStream_t s) {
     unsigned long long* counters = nullptr;
-    int32_t rc = get_counters(&counters, s);
+    int slot = 0;
+    int32_t rc = get_counters(&counters, &slot, s);
     if (rc != LM_OK) return rc;
     EscapeArgs A{};
     A.xs = xs; A.ys = ys; A.nx = nx; A.ny = ny;
@@ -539,7 +581,8 @@ int32_t enqueue_grid(const double* xs, int64_t nx, const double* ys, int64_t ny,
     A.vec_i32 = (nx % 4 == 0) && (reinterpret_cast<uintptr_t>(dwell_i32) % 16 == 0);
     A.vec_f64 = (nx % 2 == 0) && (reinterpret_cast<uintptr_t>(dwell_f64) % 16 == 0);
     A.vec_field = (nx % 2 == 0) && (reinterpret_cast<uintptr_t>(field) % 16 == 0);
-    return launch_escape(false, field_mode, A, s);
+    if ((rc = launch_escape(false, field_mode, A, s)) != LM_OK) return rc;
+    return counters_in_flight(slot, s);
 }
 
 }  // namespace
@@ -758,7 +801,8 @@ int32_t enqueue_points(const double* c_re, const double* c_im, int64_t n, int32_
     A.phi_im = phi_im;
     A.work_counter = work_dev;
     unsigned long long* counters = nullptr;
-    if ((rc = get_counters(&counters, s)) != LM_OK) return rc;
+    int slot = 0, slot2 = 0;
+    if ((rc = get_counters(&counters, &slot, s)) != LM_OK) return rc;
     A.tile_counter = counters;
     A.overflow_flag = reinterpret_cast<int*>(counters + 2);
     bool two_pass = max_iter > 4 * PASS1_ITERS && n >= TWO_PASS_MIN_POINTS;
@@ -766,7 +810,8 @@ int32_t enqueue_points(const double* c_re, const double* c_im, int64_t n, int32_
     if (!two_pass) {
         A.max_iter = max_iter;
         if (launches) *launches += 1;
-        return launch_escape(true, LM_FIELD_GREEN, A, s);
+        if ((rc = launch_escape(true, LM_FIELD_GREEN, A, s)) != LM_OK) return rc;
+        return counters_in_flight(slot, s);
     }
     void* dsurv = nullptr;
     if ((rc = lm::ws_get(lm::WS_K1_SURVIVORS, static_cast<size_t>(n) * sizeof(long long), &dsurv)) != LM_OK) return rc;
@@ -775,7 +820,7 @@ int32_t enqueue_points(const double* c_re, const double* c_im, int64_t n, int32_
     A.survivor_count = counters + 3;
     if ((rc = launch_escape(true, LM_FIELD_GREEN, A, s)) != LM_OK) return rc;
     unsigned long long* counters2 = nullptr;
-    if ((rc = get_counters(&counters2, s)) != LM_OK) return rc;
+    if ((rc = get_counters(&counters2, &slot2, s)) != LM_OK) return rc;
     A.tile_counter = counters2;
     A.overflow_flag = reinterpret_cast<int*>(counters2 + 2);
     A.max_iter = max_iter;
@@ -783,7 +828,9 @@ int32_t enqueue_points(const double* c_re, const double* c_im, int64_t n, int32_
     A.index = static_cast<const long long*>(dsurv);
     A.count_dev = counters + 3;
     if (launches) *launches += 2;
-    return launch_escape(true, LM_FIELD_GREEN, A, s);      // grid sized for n; the kernel reads the real count
+    if ((rc = launch_escape(true, LM_FIELD_GREEN, A, s)) != LM_OK) return rc;      // grid sized for n; the kernel reads the real count
+    if ((rc = counters_in_flight(slot, s)) != LM_OK) return rc;                      // pass 2 reads its item count from block 1
+    return counters_in_flight(slot2, s);
 }
 
 }  // namespace

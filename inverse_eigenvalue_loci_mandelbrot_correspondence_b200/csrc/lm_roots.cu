@@ -36,6 +36,9 @@ namespace {
 
 constexpr int ROOTS_THREADS = 128;
 constexpr int MAX_SWEEPS = 160;
+#ifndef LM_K3_SUM_RCP_STEPS
+#define LM_K3_SUM_RCP_STEPS 0            // Newton steps on MUFU.RCP64H inside the Aberth sum (0: the raw ~2^-22 estimate)
+#endif
 constexpr double TWO_PI = 6.283185307179586476925286766559;
 constexpr double EPS = 2.220446049250313e-16;
 
@@ -335,7 +338,8 @@ __device__ __forceinline__ void aberth_update(const Slot& S, int d, int i, cplx&
         const double q = fma(dr, dr, di * di);
         // j == i (q == 0) and coinciding estimates contribute nothing; the reciprocal's NaN/Inf for q == 0 is
         // discarded by the select
-        const double inv = (q > 1e-300) ? rcp_fast<1>(q) : 0.0;
+        // (the test reads the exponent with the integer pipe: q > 2^-996, which also rejects q == 0 and denormals)
+        const double inv = (__double2hiint(q) > 0x01b00000) ? rcp_fast<LM_K3_SUM_RCP_STEPS>(q) : 0.0;
         Sr = fma(dr, inv, Sr);
         Si = fma(-di, inv, Si);
     }
@@ -348,6 +352,42 @@ __device__ __forceinline__ void aberth_update(const Slot& S, int d, int i, cplx&
     if (!(isfinite(znew.r) && isfinite(znew.i))) znew = {z.r * 0.5 + 1e-3, z.i * 0.5 - 1e-3};
     // stagnation: the correction is below the resolution of z -> it is frozen with the new value
     if (corr.r * corr.r + corr.i * corr.i <= (4.0 * EPS * EPS) * az2) stagnant = true;
+}
+
+// One sweep over the roots of a slot that are still moving (rounds of G roots, Gauss-Seidel between rounds).
+// Returns true when the sweep updated nothing (every root is frozen).
+template <int G>
+__device__ __forceinline__ bool sweep_slot(const Tile& tile, const Slot& S, int d) {
+    const int l = tile.rank;
+    // compact the roots that are still moving into the (now free) hull array, so late sweeps with a few
+    // stragglers take one round instead of ceil(d/G)
+    int nact = 0;
+    for (int r0 = 0; r0 < d; r0 += G) {
+        const int i = r0 + l;
+        const bool live = (i < d) && !S.frozen[i];
+        const unsigned bal = tile.ballot(live);
+        if (live) S.hull[nact + __popc(bal & ((1u << l) - 1u))] = i;
+        nact += __popc(bal);
+    }
+    tile.sync();
+    bool mine_done = true;
+    for (int r0 = 0; r0 < nact; r0 += G) {
+        const bool active = r0 + l < nact;
+        const int i = active ? S.hull[r0 + l] : 0;
+        bool freeze = false, stagnant = false;
+        cplx znew = {0.0, 0.0};
+        if (active) {
+            aberth_update(S, d, i, znew, freeze, stagnant);
+            if (!freeze) mine_done = false;
+        }
+        tile.sync();               // everybody has read the old estimates of this round
+        if (active) {
+            if (freeze) S.frozen[i] = 1;
+            else { S.zz[i] = make_double2(znew.r, znew.i); if (stagnant) S.frozen[i] = 1; }
+        }
+        tile.sync();
+    }
+    return tile.all(mine_done);
 }
 
 // [zero roots] + computed roots, optionally inverted / filtered / compacted, NaN padding, counters
@@ -413,35 +453,7 @@ __global__ void __launch_bounds__(ROOTS_THREADS, LM_K3_MIN_CTAS) roots_kernel(co
         bool all_done = (d == 0);
         while (!all_done && sweeps < MAX_SWEEPS) {
             ++sweeps;
-            bool mine_done = true;
-            // compact the roots that are still moving into the (now free) hull array, so late sweeps with a few
-            // stragglers take one round instead of ceil(d/G)
-            int nact = 0;
-            for (int r0 = 0; r0 < d; r0 += G) {
-                const int i = r0 + l;
-                const bool live = (i < d) && !S.frozen[i];
-                const unsigned bal = tile.ballot(live);
-                if (live) S.hull[nact + __popc(bal & ((1u << l) - 1u))] = i;
-                nact += __popc(bal);
-            }
-            tile.sync();
-            for (int r0 = 0; r0 < nact; r0 += G) {
-                const bool active = r0 + l < nact;
-                const int i = active ? S.hull[r0 + l] : 0;
-                cplx znew = {0.0, 0.0};
-                bool freeze = false, stagnant = false;
-                if (active) {
-                    aberth_update(S, d, i, znew, freeze, stagnant);
-                    if (!freeze) mine_done = false;
-                }
-                tile.sync();               // everybody has read the old estimates of this round
-                if (active) {
-                    if (freeze) S.frozen[i] = 1;
-                    else { S.zz[i] = make_double2(znew.r, znew.i); if (stagnant) S.frozen[i] = 1; }
-                }
-                tile.sync();
-            }
-            all_done = tile.all(mine_done);
+            all_done = sweep_slot<G>(tile, S, d);
         }
         write_output<G>(tile, S, A, pid, d, nzero, sweeps, all_done);
     }
@@ -489,41 +501,11 @@ __global__ void __launch_bounds__(ROOTS_THREADS, LM_K3_MIN_CTAS) roots_pool_kern
         bool moving = occupied && d > 0;          // some root of my slot was still updated in its last sweep
         bool gave_up = false;
 
-        // ---- sweeps over the whole generation
-        // a slot that has converged waits for the generation to finish
+        // ---- sweeps over the whole generation; a slot that has converged waits for the generation to finish
         while (__ballot_sync(0xffffffffu, moving) != 0u) {
             if (moving) {
                 if (sweeps >= MAX_SWEEPS) { moving = false; gave_up = true; }
-                else {
-                    ++sweeps;
-                    int nact = 0;
-                    for (int r0 = 0; r0 < d; r0 += 4) {
-                        const int i = r0 + l;
-                        const bool live = (i < d) && !S.frozen[i];
-                        const unsigned bal = tile.ballot(live);
-                        if (live) S.hull[nact + __popc(bal & ((1u << l) - 1u))] = i;
-                        nact += __popc(bal);
-                    }
-                    tile.sync();
-                    bool mine_done = true;
-                    for (int r0 = 0; r0 < nact; r0 += 4) {
-                        const bool active = r0 + l < nact;
-                        const int i = active ? S.hull[r0 + l] : 0;
-                        cplx znew = {0.0, 0.0};
-                        bool freeze = false, stagnant = false;
-                        if (active) {
-                            aberth_update(S, d, i, znew, freeze, stagnant);
-                            if (!freeze) mine_done = false;
-                        }
-                        tile.sync();               // everybody has read the old estimates of this round
-                        if (active) {
-                            if (freeze) S.frozen[i] = 1;
-                            else { S.zz[i] = make_double2(znew.r, znew.i); if (stagnant) S.frozen[i] = 1; }
-                        }
-                        tile.sync();
-                    }
-                    if (tile.all(mine_done)) moving = false;
-                }
+                else { ++sweeps; if (sweep_slot<4>(tile, S, d)) moving = false; }
             }
         }
 
@@ -576,14 +558,20 @@ int32_t roots_enqueue(const double* toprows, const int* deg, long long npoly, in
     A.cls = 0; A.smem_deg = maxdeg < CLASS_SMALL_MAX ? maxdeg : CLASS_SMALL_MAX;
     {
         const size_t smem = group_smem_bytes(A.smem_deg) * POOL_SLOTS * POOL_WARPS;
-        static int per_sm = 0;
-        static size_t per_sm_smem = 0;
-        if (per_sm == 0 || per_sm_smem != smem) {
+        // function attribute and occupancy are per device (and per shared-memory size)
+        static int per_sm_dev[64] = {};
+        static size_t per_sm_smem[64] = {};
+        int dev = 0;
+        LM_CUDA_TRY(cudaGetDevice(&dev));
+        const int di = (dev >= 0 && dev < 64) ? dev : 63;
+        if (per_sm_dev[di] == 0 || per_sm_smem[di] != smem || di == 63) {
+            int v = 0;
             LM_CUDA_TRY(cudaFuncSetAttribute(roots_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-            LM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, roots_pool_kernel, ROOTS_THREADS, smem));
-            if (per_sm < 1) per_sm = 1;
-            per_sm_smem = smem;
+            LM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, roots_pool_kernel, ROOTS_THREADS, smem));
+            per_sm_dev[di] = v < 1 ? 1 : v;
+            per_sm_smem[di] = smem;
         }
+        const int per_sm = per_sm_dev[di];
         long long blocks = (npoly + POOL_SLOTS * POOL_WARPS - 1) / (POOL_SLOTS * POOL_WARPS);
         const long long cap = static_cast<long long>(lm::sm_count()) * per_sm;      // persistent CTAs, polynomials by work stealing
         if (blocks > cap) blocks = cap;

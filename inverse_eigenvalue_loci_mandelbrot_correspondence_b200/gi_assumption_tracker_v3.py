@@ -75,11 +75,35 @@ def build_parser() -> argparse.ArgumentParser:
     return ap
 
 
+def _is_stock_KL(mod) -> bool:
+    """Does mod.KL compute the stock module's formula (tci_construct_mandelbrot_v002_fixed.py:84-86),
+    sum(P_ * (log P_ - log X_)) with P_, X_ clipped at mod.eps?  Checked on a probe pair that exercises the clip."""
+    eps = float(getattr(mod, "eps", 1e-12))
+    rng = np.random.default_rng(12345)
+    P = rng.random((7, 5)); X = rng.random((7, 5))
+    P[0, 0] = 0.0; X[1, 1] = 0.0; P[2, 2] = eps / 3; X[3, 3] = eps / 7
+    P /= P.sum(); X /= X.sum()
+    P_ = np.clip(P, eps, None); X_ = np.clip(X, eps, None)
+    want = float(np.sum(P_ * (np.log(P_) - np.log(X_))))
+    try:
+        got = float(mod.KL(P, X))
+    except Exception:
+        return False
+    return bool(np.isfinite(got) and abs(got - want) <= 1e-12 * max(1.0, abs(want)))
+
+
 def _device_ops(mod):
-    """the density-stage functions, bound to the device implementation; KL_fn carries the module's eps"""
+    """the density-stage functions, bound to the device implementation; KL_fn carries the module's eps.
+    The device GI flow evaluates the STOCK KL itself, so a plug-in module with a different KL (other clipping, base or
+    symmetrisation) is refused instead of being silently replaced (the reference calls mod.KL everywhere, :214-224)."""
     from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import tracker
-    kl = mod.KL if getattr(mod.KL, "lm_eps", None) is not None else tracker.make_KL(float(getattr(mod, "eps", 1e-12)))
-    return tracker, kl
+    if getattr(mod.KL, "lm_eps", None) is not None:
+        return tracker, mod.KL
+    if not _is_stock_KL(mod):
+        raise SystemExit(f"--module {getattr(mod, '__file__', mod)}: its KL() is not the stock formula "
+                         "sum(P_*(log P_ - log X_)) with P_, X_ = clip(., eps); the device GI flow cannot stand in for it. "
+                         "Use a module whose KL comes from tracker.make_KL(eps) or the stock definition.")
+    return tracker, tracker.make_KL(float(getattr(mod, "eps", 1e-12)))
 
 
 def run_level(mod, ops, KL_fn, args, domain, bins: int, construct_max_n: int, mandel_grid: int, mandel_samples: int) -> dict:

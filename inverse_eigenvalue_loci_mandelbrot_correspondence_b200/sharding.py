@@ -56,15 +56,60 @@ def interpolate_row_profile(coarse_rows: np.ndarray, coarse_work: np.ndarray, ny
                      np.asarray(coarse_work, dtype=np.float64))
 
 
-def coarse_row_profile(xs, ys, max_iter: int, rows: int = 2048, cols: int = 2048) -> np.ndarray:
-    """Estimated work of every grid row from a coarse K1 pass on the GPU (subsampled rows/columns)."""
+# K1 cost of one pixel on a B200, in units of one blind-path pixel-iteration, as a function of its iteration count
+# `it` = min(dwell + 1, max_iter) and of whether it escaped:
+#     cost = it + B_PIXEL + D_LATE * [escaped and it > KNEE]
+# B_PIXEL: refill (ballot / popc rank, coordinate loads), the first careful iterations, staging and the store of the
+# result.  D_LATE: a pixel that escapes inside a blind block sends its lane back over that block with the exact test
+# while the other 31 lanes of the warp wait -- about 64 warp-iterations, i.e. ~2000 lane-iterations per event.
+# The constants were fitted ONCE, offline, to CUDA-event timings of 2 x 48 row bands of BASELINE.json configs 3 and 4 on
+# a B200 (joint least squares, rms error 0.9 %, max 3.4 %; scripts/balance_probe.py, profiles/r02_balance_*.json):
+# they are properties of the kernel and the device, not of the workload, so one-shot cuts need no calibration pass
+# over the answer.
+COST_MODEL_B200 = {"b_pixel": 15.0, "d_late": 2000.0, "knee": 64}
+
+
+def pixel_cost(dwell, max_iter: int, model: dict | None = None) -> np.ndarray:
+    """Estimated K1 cost (blind pixel-iteration units) of pixels with the given dwell values."""
+    m = COST_MODEL_B200 if model is None else model
+    d = np.asarray(dwell, dtype=np.int64)
+    it = np.minimum(d + 1, max_iter).astype(np.float64)
+    late = (d < max_iter) & (it > m["knee"])
+    return it + m["b_pixel"] + m["d_late"] * late
+
+
+def coarse_row_profile(xs, ys, max_iter: int, rows: int = 2048, cols: int = 2048, model: dict | None = None,
+                       iterations_only: bool = False) -> np.ndarray:
+    """Estimated K1 cost of every grid row from a coarse K1 pass on the GPU (subsampled rows / columns), weighted by
+    the per-pixel cost model (iterations_only=True: round 1's profile, the bare iteration counts)."""
     from . import escape
     xs = np.asarray(xs, dtype=np.float64); ys = np.asarray(ys, dtype=np.float64)
     ri = np.unique(np.linspace(0, ys.size - 1, min(rows, ys.size)).round().astype(np.int64))
     ci = np.unique(np.linspace(0, xs.size - 1, min(cols, xs.size)).round().astype(np.int64))
     d, _, _ = escape.escape_grid(xs[ci], ys[ri], max_iter)
-    work = np.minimum(d.astype(np.int64) + 1, max_iter).sum(axis=1).astype(np.float64)
-    return interpolate_row_profile(ri, work, ys.size)
+    if iterations_only:
+        work = np.minimum(d.astype(np.int64) + 1, max_iter).sum(axis=1).astype(np.float64)
+    else:
+        work = pixel_cost(d, max_iter, model).sum(axis=1)
+    return interpolate_row_profile(ri, work * (xs.size / ci.size), ys.size)
+
+
+def plan_row_cuts(xs, ys, max_iter: int, nparts: int, device=None, model: dict | None = None) -> dict:
+    """One-shot row cuts for `nparts` ranks: coarse K1 pre-pass (<= 2048 x 2048 samples, every rank runs the same
+    deterministic pass and gets the same cuts) -> per-row cost estimate -> contiguous blocks of equal estimated cost.
+    -> {"cuts", "profile", "balance_estimate", "model", "setup"}"""
+    import time
+    ys = np.asarray(ys, dtype=np.float64)
+    m = COST_MODEL_B200 if model is None else model
+    desc = (f"cost = it + {m['b_pixel']:g} + {m['d_late']:g}*[escaped, it>{m['knee']}] per pixel, constants fitted offline on a B200")
+    if nparts == 1:
+        return {"cuts": [0, int(ys.size)], "profile": np.ones(ys.size), "balance_estimate": 1.0, "model": desc,
+                "setup": {"coarse_pass_ms": 0.0}}
+    t0 = time.perf_counter()
+    profile = coarse_row_profile(xs, ys, max_iter, model=m)
+    cuts = balanced_row_cuts(profile, nparts)
+    return {"cuts": cuts, "profile": profile, "balance_estimate": parallel_efficiency(profile, cuts), "model": desc,
+            "setup": {"coarse_pass_ms": 1e3 * (time.perf_counter() - t0), "coarse_samples": "<= 2048 x 2048"}}
 
 
 def refine_cuts(row_work, cuts, measured) -> list[int]:
@@ -203,12 +248,8 @@ class ShardedBoundary:
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         if cuts is None:
-            if self.world > 1:
-                self.profile = coarse_row_profile(self.xs, self.ys, self.max_iter)
-                cuts = balanced_row_cuts(self.profile, self.world)
-            else:
-                self.profile = np.ones(self.ys.size)
-                cuts = [0, self.ys.size]
+            plan = plan_row_cuts(self.xs, self.ys, self.max_iter, self.world, device=self.device)
+            self.profile, cuts = plan["profile"], plan["cuts"]
         else:
             self.profile = np.ones(self.ys.size)
         self._set_cuts(cuts)
@@ -300,7 +341,7 @@ class ShardedBoundary:
 
 
 def sharded_cloud_fields(toprows_local, deg_local, grid_x, grid_y, tol: float = 1e-12, eps: float = 1e-12, variant: int = 0,
-                         h: float | None = None, potential: tuple | None = None, device=None, stream=None) -> dict:
+                         h: float | None = None, potential: tuple | None = None, device=None) -> dict:
     """lucas.cloud_fields with the polynomials sharded over the ranks (one process per GPU): every rank passes ITS
     slice of the batch (see item_slices), runs K3 -> cloud -> K1d -> K4a partial sums on it, the per-cell sums and
     the cloud sizes are all-reduced (NCCL), and every rank ends with the same U and Laplacian.
@@ -309,6 +350,8 @@ def sharded_cloud_fields(toprows_local, deg_local, grid_x, grid_y, tol: float = 
     import torch
     from . import _shim
     dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    # every kernel goes to torch's CURRENT stream: the NCCL collectives below order against that stream only
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     P = lambda t: C.c_void_p(t.data_ptr())
     top_h = np.ascontiguousarray(toprows_local, dtype=np.float64)
     deg_h = np.ascontiguousarray(deg_local, dtype=np.int32).reshape(-1)
@@ -323,9 +366,14 @@ def sharded_cloud_fields(toprows_local, deg_local, grid_x, grid_y, tol: float = 
     _shim.call("lm_roots_batched_dev", P(top), P(deg), npoly, maxdeg, 1, float(tol), P(re), P(im), P(kept), None, P(status), stream)
     _shim.call("lm_cloud_compact_dev", P(re), P(im), P(kept), npoly, maxdeg, P(px), P(py), nroots, P(cnt), stream)
     n_local = int(cnt.item())
+    # the status flags are all-reduced (MAX) BEFORE anybody raises: a rank-local exception ahead of the collectives
+    # below would leave the other ranks waiting in them forever, and every rank must report the same outcome
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(status, op=dist.ReduceOp.MAX)
     flags = status.cpu().numpy()
     if flags[1]:
-        raise ValueError("a degree outside [1, maxdeg]")
+        raise ValueError("a degree outside [1, maxdeg] (on some rank)")
     out = {"cloud": px[:n_local].cpu().numpy() + 1j * py[:n_local].cpu().numpy(), "g": None, "it": None}
     if potential is not None:
         g = torch.empty(max(n_local, 1), dtype=torch.float64, device=dev)
@@ -347,5 +395,5 @@ def sharded_cloud_fields(toprows_local, deg_local, grid_x, grid_y, tol: float = 
     out["U"] = U.cpu().numpy().reshape(ny, nx); out["lapU"] = lap.cpu().numpy().reshape(ny, nx)
     out["n_points_total"] = n_total
     if flags[0]:
-        raise RuntimeError("the Aberth iteration did not converge for some polynomial")
+        raise RuntimeError("the Aberth iteration did not converge for some polynomial (on some rank)")
     return out

@@ -61,11 +61,52 @@ def test_empty_and_errors(gpu):
 
 
 def test_max_iter_one_and_edges(gpu, oracle):
+    """max_iter around the blind-block length FB = 64 and the cool-down COOL_MIN = 4: the first blind block of a
+    fresh pixel covers iterations 5..68, the second 69..132; lanes overshoot max_iter inside a block."""
     xs = np.linspace(-2.5, 1.0, 200); ys = np.linspace(-1.5, 1.5, 100)
-    for mi in (1, 2, 3, 31, 32, 33, 47, 48, 49):     # around the blind-block (32) and cool-down (16) sizes
+    for mi in (1, 2, 3, 4, 5, 6) + tuple(range(63, 70)) + tuple(range(127, 134)) + (191, 192, 193, 197):
         want, work = oracle.dwell_grid(xs, ys, mi)
         got, _, st = gpu.escape.escape_grid(xs, ys, mi)
-        assert np.array_equal(got, want) and st["work_units"] == work
+        assert np.array_equal(got, want), mi
+        assert st["work_units"] == work, mi
+
+
+def test_escapes_on_block_edges(gpu, oracle):
+    """Pixels whose first escape lands exactly on iteration 64k-1, 64k, 64k+1, 64k+4, 64k+5 (the last / first
+    iterate of a blind block with and without the cool-down offset), inside and at max_iter."""
+    xs = np.linspace(-0.76, -0.73, 700); ys = np.linspace(0.09, 0.13, 500)        # seahorse valley: every dwell occurs
+    full, _ = oracle.dwell_grid(xs, ys, 400)
+    targets = sorted({64 * k + o for k in (1, 2, 3, 4, 5) for o in (-2, -1, 0, 1, 2, 3, 4, 5, 6)})
+    seen = 0
+    for t in targets:
+        jj, ii = np.nonzero(full == t)
+        if jj.size == 0:
+            continue
+        seen += 1
+        sel = slice(0, min(jj.size, 40))
+        px, py = xs[ii[sel]], ys[jj[sel]]
+        for mi in (t, t + 1, t + 2, 400):
+            # one row of selected columns per selected row would be a grid; use the point list through a 1-row grid each
+            for x, y, d0 in zip(px[:6], py[:6], full[jj[sel], ii[sel]][:6]):
+                got, _, _ = gpu.escape.escape_grid(np.array([x, x + 1e-9, 0.0, -0.1]), np.array([y]), mi)
+                assert got[0, 0] == min(int(d0), mi), (t, mi)
+    assert seen >= 20
+    # and the same window as a grid at max_iter values that cut through the blocks
+    for mi in (64, 65, 68, 69, 128, 132, 133, 260):
+        want, work = oracle.dwell_grid(xs[::5], ys[::5], mi)
+        got, _, st = gpu.escape.escape_grid(xs[::5], ys[::5], mi)
+        assert np.array_equal(got, want) and st["work_units"] == work, mi
+
+
+def test_staggered_lanes_near_max_iter(gpu, oracle):
+    """Warps whose lanes reach max_iter at different phases (boundary rows: refills stagger the lanes): the
+    overshooting blind blocks must retire interior pixels at exactly max_iter and late escapers at their index."""
+    xs = np.linspace(-0.2, 0.4, 777); ys = np.linspace(0.55, 0.75, 203)           # edge of the main cardioid
+    for mi in (150, 333, 1000):
+        want, work = oracle.dwell_grid(xs, ys, mi)
+        got, _, st = gpu.escape.escape_grid(xs, ys, mi)
+        assert np.array_equal(got, want) and st["work_units"] == work, mi
+        assert (want == mi).any() and ((want > 64) & (want < mi)).any()
 
 
 @pytest.mark.parametrize("mode,R,mi", [(1, 2.0, 300), (1, 2.0, 1200), (2, 10.0, 300), (3, 2.0, 200), (3, 10.0, 150), (4, 4.0, 500)])

@@ -23,6 +23,17 @@ def test_dwell_grid_bit_exact(oracle, golden, tag):
     assert work == int(np.minimum(Z.astype(np.int64) + 1, int(mi)).sum())
 
 
+@pytest.mark.parametrize("tag", ["cfg1", "seahorse", "tip"])
+def test_python_restatement_rows(golden, tag):
+    """oracle/pyref.py (the pure-Python loop bench.py times as the reference-speed CPU baseline) on sample rows of the
+    grids produced by the reference's own compute_grid."""
+    from oracle import pyref
+    xs, ys, Z = golden[f"dwell_{tag}_xs"], golden[f"dwell_{tag}_ys"], golden[f"dwell_{tag}_Z"]
+    mi = int(golden[f"dwell_{tag}_args"][5])
+    rows = [0, len(ys) // 3, len(ys) // 2, len(ys) - 1]
+    assert np.array_equal(pyref.dwell_rows(xs, ys[rows], mi), Z[rows])
+
+
 def test_dwell_points(oracle, golden):
     mi = int(golden["dwell_points_mi"][0])
     for (x, y), want in zip(golden["dwell_points_xy"], golden["dwell_points_out"]):

@@ -126,3 +126,23 @@ def test_tracker_levels(gpu, golden):
     assert mod.KL(P, P) == 0.0 and mod.KL(P, Q) > 0
     kls, traj = mod.tci_flow(P, Q)
     assert len(kls) == mod.T + 1 and kls[-1] < kls[0] * 1e-4 and np.all(np.diff(kls) < 0)
+
+
+def test_tracker_refuses_a_module_with_another_KL():
+    """The device GI flow evaluates the stock KL; a plug-in whose KL differs must not be replaced silently."""
+    import types
+    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import gi_assumption_tracker_v3 as trk
+    stock = types.SimpleNamespace(eps=1e-12)
+    stock.KL = lambda P, X: float(np.sum(np.clip(P, 1e-12, None) * (np.log(np.clip(P, 1e-12, None)) - np.log(np.clip(X, 1e-12, None)))))
+    assert trk._is_stock_KL(stock)
+    other_eps = types.SimpleNamespace(eps=1e-12)
+    other_eps.KL = lambda P, X: float(np.sum(np.clip(P, 1e-9, None) * (np.log(np.clip(P, 1e-9, None)) - np.log(np.clip(X, 1e-9, None)))))
+    assert not trk._is_stock_KL(other_eps)
+    sym = types.SimpleNamespace(eps=1e-12)
+    sym.KL = lambda P, X: 0.5 * (stock.KL(P, X) + stock.KL(X, P))
+    assert not trk._is_stock_KL(sym)
+    base2 = types.SimpleNamespace(eps=1e-12)
+    base2.KL = lambda P, X: stock.KL(P, X) / np.log(2.0)
+    assert not trk._is_stock_KL(base2)
+    with pytest.raises(SystemExit):
+        trk._device_ops(sym)
