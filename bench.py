@@ -371,7 +371,9 @@ def grid_leg(cx: Ctx, name: str, steps: int, warmup: int, want_e2e: bool, refine
     barrier()
     launches["n"] = 0
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 + 4 * steps)]
-    work_steps = []
+    work_steps_d = torch.zeros(steps, dtype=torch.int64, device=dev)     # per-step work counters, read after the timed region
+    _ = int(work_d.item())
+    barrier()
     ev[0].record()
     for k in range(steps):
         ev[2 + 4 * k].record()
@@ -381,14 +383,16 @@ def grid_leg(cx: Ctx, name: str, steps: int, warmup: int, want_e2e: bool, refine
         ev[4 + 4 * k].record()
         k2_link()
         ev[5 + 4 * k].record()
-        work_steps.append(int(work_d.item()))
+        work_steps_d[k:k + 1].copy_(work_d)
     ev[1].record()
     barrier()
     elapsed_ms = ev[0].elapsed_time(ev[1])
     k1_ms = sum(ev[2 + 4 * k].elapsed_time(ev[3 + 4 * k]) for k in range(steps))
     k2a_ms = sum(ev[3 + 4 * k].elapsed_time(ev[4 + 4 * k]) for k in range(steps))
     k2b_ms = sum(ev[4 + 4 * k].elapsed_time(ev[5 + 4 * k]) for k in range(steps))
-    my_work = sum(work_steps)
+    step_ms = [ev[2 + 4 * k].elapsed_time(ev[5 + 4 * k]) for k in range(steps)]
+    gap_ms = [ev[0].elapsed_time(ev[2])] + [ev[5 + 4 * k].elapsed_time(ev[6 + 4 * k]) for k in range(steps - 1)] + [ev[1 + 4 * steps].elapsed_time(ev[1])]
+    my_work = int(work_steps_d.sum().item())
     t = torch.tensor([elapsed_ms, k1_ms, k2a_ms, k2b_ms], dtype=torch.float64, device=dev)
     tmin = torch.tensor([k1_ms], dtype=torch.float64, device=dev)
     wk = torch.tensor([my_work], dtype=torch.int64, device=dev)
@@ -406,7 +410,8 @@ def grid_leg(cx: Ctx, name: str, steps: int, warmup: int, want_e2e: bool, refine
            "balance_estimate_only": balance_estimate_only,
            "balance_measured": float(tmin[0]) / world / max(k1_ms_max, 1e-9),      # mean / max of the ranks' K1 time
            "k1_ms_per_step_max_rank": k1_ms_max / steps, "gpu_launches": launches["n"], "with_pot": with_pot,
-           "dwell_crc": f"{int(crc[0]) & 0xFFFFFFFFFFFFFFFF:016x}", "n_records": state["n_rec_total"]}
+           "dwell_crc": f"{int(crc[0]) & 0xFFFFFFFFFFFFFFFF:016x}", "n_records": state["n_rec_total"],
+           "step_ms_rank0": step_ms, "gap_ms_rank0": gap_ms}
 
     # the device-resident lines of the last step (rank 0) -> digest
     if rank == 0:
@@ -550,7 +555,7 @@ def run_ours(args):
     hbm_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in mp else "fallback 6500 GB/s (B200_PROFILING.md)"
 
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("LM_BENCH_NO_SAMPLER"):
         sampler.start()             # before the warm-up (same load): nvidia-smi needs ~0.2 s for its first sample
     main = grid_leg(cx, args.workload, args.steps, args.warmup, want_e2e=not args.no_e2e, refine=args.refine)
     clocks = sampler.stop() if rank == 0 else None
@@ -625,6 +630,7 @@ def run_ours(args):
             "dwell_crc": main["dwell_crc"], "boundary_sha256": main.get("boundary_sha256"),
             "boundary_lines": main.get("boundary_lines"), "boundary_vertices": main.get("boundary_vertices"),
             "boundary_vertices_total": main.get("boundary_vertices_total"), "n_records": main["n_records"],
+            "step_ms_rank0": main["step_ms_rank0"], "gap_ms_rank0": main["gap_ms_rank0"],
             "lucas_roots": lucas_roots, "legs": legs or None,
         }
         print(json.dumps(line), flush=True)

@@ -181,11 +181,16 @@ int32_t lm_shard_escape(const double* xs, int64_t nx, const double* ys, int64_t 
                         int32_t* dwell_i32, double* potential, int64_t halo_rows,
                         int32_t** dwell_dev_out, double** potential_dev_out, lm_stats* stats);
 
-/* fp32 variant of the dwell grid (no reference counterpart; validated against the
- * fp64 kernel by mismatch fraction).                                                 */
+/* Optional single-precision variant of the dwell grid (BASELINE.json north_star, piece 1; no reference
+ * counterpart): the SAME persistent kernel -- work stealing, lane refill, blind blocks, staged 128-bit stores --
+ * instantiated in binary32 with unfused round-to-nearest operations.  Validated against the fp64 kernel by a stated
+ * dwell-mismatch / interior-mask tolerance (tests/test_gpu_escape.py::test_f32_*), never bit-exact.          */
 int32_t lm_escape_grid_f32(const double* xs, int64_t nx, const double* ys, int64_t ny,
                            int32_t max_iter, double bailout,
                            int32_t* dwell_i32, lm_stats* stats);
+int32_t lm_escape_grid_f32_dev(const double* xs, int64_t nx, const double* ys, int64_t ny,
+                               int32_t max_iter, double bailout, int32_t* dwell_i32,
+                               uint64_t* work_units_dev /* 1 counter, may be NULL */, void* stream);
 
 /* ---- K1d: escape-time at an arbitrary point list -------------------------------- */
 /*

@@ -28,7 +28,7 @@ EXPORTS = (
     "lm_abi_version", "lm_last_error", "lm_device_count", "lm_set_device", "lm_get_device_info",
     "lm_device_synchronize", "lm_release_workspace", "lm_host_alloc", "lm_host_free", "lm_dev_alloc",
     "lm_dev_free", "lm_memcpy_h2d", "lm_memcpy_d2h", "lm_memcpy_d2d", "lm_stream_synchronize",
-    "lm_escape_grid_f64", "lm_escape_grid_f64_dev", "lm_shard_escape", "lm_escape_grid_f32", "lm_escape_points_f64",
+    "lm_escape_grid_f64", "lm_escape_grid_f64_dev", "lm_shard_escape", "lm_escape_grid_f32", "lm_escape_grid_f32_dev", "lm_escape_points_f64",
     "lm_distance_grid_f64",
     "lm_contour_level", "lm_contour_level_dev", "lm_contour_classify_dev", "lm_contour_records_dev", "lm_contour_link", "lm_contour_link_dev", "lm_contour_fetch_last", "lm_boundary_sample", "lm_boundary_sample_potential",
     "lm_roots_batched", "lm_roots_batched_dev", "lm_cloud_compact_dev", "lm_cloud_append_dev", "lm_lucas_cloud_fields", "lm_lucas_cloud_fields_i8", "lm_escape_points_f64_dev",
@@ -98,6 +98,7 @@ _SIGNATURES = {
     "lm_escape_grid_f64": (_i32, [_vp, _i64, _vp, _i64, _i32, _f64, _i32, _vp, _vp, _vp, _pStats]),
     "lm_escape_grid_f64_dev": (_i32, [_vp, _i64, _vp, _i64, _i32, _f64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "lm_escape_grid_f32": (_i32, [_vp, _i64, _vp, _i64, _i32, _f64, _vp, _pStats]),
+    "lm_escape_grid_f32_dev": (_i32, [_vp, _i64, _vp, _i64, _i32, _f64, _vp, _vp, _vp]),
     "lm_escape_points_f64": (_i32, [_vp, _vp, _i64, _i32, _f64, _vp, _vp, _vp, _vp, _pStats]),
     "lm_distance_grid_f64": (_i32, [_vp, _i64, _vp, _i64, _i32, _f64, _f64, _i32, _vp, _vp, _pStats]),
     "lm_contour_level": (_i32, [_vp, _vp, _i64, _vp, _i64, _f64, _vp, _i64, _pi64, _vp, _i64, _pi64, _pStats]),

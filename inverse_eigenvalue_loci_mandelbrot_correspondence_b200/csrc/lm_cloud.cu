@@ -9,7 +9,7 @@
 //   K4   5-point periodic Laplacian of that field     laplacian, Laplacian_C-M.py:49-59
 // which is what the reference does through files (construct_points.csv -> Potentials.py /
 // Laplacian_C-M.py).  Built on the library's own _dev entry points.  The batch streams through the
-// device in chunks of 2^20 polynomials on three streams (upload of chunk c+1 | K3 + compaction of
+// device in chunks of 2^16..2^20 polynomials (at least ~8 per call) on three streams (upload of chunk c+1 | K3 + compaction of
 // chunk c | download of chunk c-1's cloud points), so with page-locked host buffers the PCIe
 // transfers hide behind the solver; the field stages follow on the compute stream, event-timed.
 #include "lm_common.cuh"
@@ -56,7 +56,11 @@ int32_t cloud_fields_impl(const double* toprows, const signed char* toprows_i8, 
     if (toprows_i8 && (rc = lm::ws_get(lm::WS_IN_C, ncoef, &dtop8)) != LM_OK) return rc;
     // the batch streams through the device in chunks: upload of chunk c+1, K3 + compaction of chunk c and the
     // download of chunk c-1's cloud points run on three streams
-    constexpr int64_t CHUNK = int64_t(1) << 20;
+    // chunk size: at most 2^20 polynomials, but at least ~8 chunks per call so that a rank's share of a sharded batch
+    // (1.25e6 polynomials at N = 8) still overlaps its transfers with the solver -- with 2^20-polynomial chunks such a
+    // slice was one big chunk plus a stub, and the download of 84 % of its cloud started only after 84 % of its compute
+    int64_t CHUNK = int64_t(1) << 20;
+    while (CHUNK > (int64_t(1) << 16) && npoly < 8 * CHUNK) CHUNK >>= 1;
     const int nchunks = static_cast<int>(npoly ? (npoly + CHUNK - 1) / CHUNK : 0);
     if ((rc = lm::ws_get(lm::WS_SCRATCH, 64 + 16 * static_cast<size_t>(nchunks + 1), &dstat)) != LM_OK) return rc;
     // the cloud has at most sum(deg) <= npoly * maxdeg points: the packed buffers are sized by that bound, and the

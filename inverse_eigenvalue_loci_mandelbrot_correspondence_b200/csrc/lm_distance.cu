@@ -101,31 +101,6 @@ __global__ void __launch_bounds__(256) distance_kernel(const double* __restrict_
     if (escaped) escaped[idx] = esc ? 1 : 0;
 }
 
-// fp32 dwell: same recurrence in binary32 (no reference counterpart)
-__global__ void __launch_bounds__(256) escape_f32_kernel(const double* __restrict__ xs, long long nx,
-                                                         const double* __restrict__ ys, long long ny, int max_iter,
-                                                         float bail2, int* __restrict__ dwell,
-                                                         unsigned long long* __restrict__ work) {
-    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    unsigned long long w = 0;
-    if (idx < nx * ny) {
-        const long long j = idx / nx, i = idx - j * nx;
-        const float cr = static_cast<float>(xs[i]), ci = static_cast<float>(ys[j]);
-        float zr = 0.f, zi = 0.f;
-        int n = 0;
-        for (; n < max_iter; ++n) {
-            const float a = __fmul_rn(zr, zr), b = __fmul_rn(zi, zi), p = __fmul_rn(zr, zi);
-            zr = __fadd_rn(__fsub_rn(a, b), cr);
-            zi = __fadd_rn(__fadd_rn(p, p), ci);
-            if (__fadd_rn(__fmul_rn(zr, zr), __fmul_rn(zi, zi)) > bail2) break;
-        }
-        dwell[idx] = n;
-        w = static_cast<unsigned long long>(n < max_iter ? n + 1 : max_iter);
-    }
-    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
-    if ((threadIdx.x & 31) == 0 && w) atomicAdd(work, w);
-}
-
 }  // namespace
 
 extern "C" {
@@ -176,40 +151,6 @@ int32_t lm_distance_grid_f64(const double* xs, int64_t nx, const double* ys, int
     if (escaped) LM_CUDA_TRY(cudaMemcpyAsync(escaped, de, npx, cudaMemcpyDeviceToHost, s));
     LM_CUDA_TRY(cudaStreamSynchronize(s));
     if (stats) { stats->items = npx; stats->kernel_ms = ms; stats->launches = 1; }
-    return LM_OK;
-}
-
-int32_t lm_escape_grid_f32(const double* xs, int64_t nx, const double* ys, int64_t ny,
-                           int32_t max_iter, double bailout, int32_t* dwell_i32, lm_stats* stats) {
-    int32_t rc = lm::require_device();
-    if (rc != LM_OK) return rc;
-    LM_REQUIRE(xs && ys && dwell_i32, "lm_escape_grid_f32: NULL buffer");
-    LM_REQUIRE(nx >= 0 && ny >= 0 && max_iter >= 1, "lm_escape_grid_f32: bad size");
-    if (stats) *stats = lm_stats{};
-    if (nx * ny == 0) return LM_OK;
-    cudaStream_t s = nullptr;
-    const size_t npx = static_cast<size_t>(nx) * ny;
-    void *dxs, *dys, *dd, *dw;
-    if ((rc = lm::ws_get(lm::WS_XS, nx * sizeof(double), &dxs)) != LM_OK) return rc;
-    if ((rc = lm::ws_get(lm::WS_YS, ny * sizeof(double), &dys)) != LM_OK) return rc;
-    if ((rc = lm::ws_get(lm::WS_OUT_I32, npx * sizeof(int), &dd)) != LM_OK) return rc;
-    if ((rc = lm::ws_get(lm::WS_SCRATCH, 64, &dw)) != LM_OK) return rc;
-    LM_CUDA_TRY(cudaMemcpyAsync(dxs, xs, nx * sizeof(double), cudaMemcpyHostToDevice, s));
-    LM_CUDA_TRY(cudaMemcpyAsync(dys, ys, ny * sizeof(double), cudaMemcpyHostToDevice, s));
-    LM_CUDA_TRY(cudaMemsetAsync(dw, 0, 64, s));
-    lm::Timer tm;
-    if ((rc = tm.begin(s)) != LM_OK) return rc;
-    escape_f32_kernel<<<static_cast<unsigned>((npx + 255) / 256), 256, 0, s>>>(
-        static_cast<double*>(dxs), nx, static_cast<double*>(dys), ny, max_iter,
-        static_cast<float>(bailout * bailout), static_cast<int*>(dd), static_cast<unsigned long long*>(dw));
-    LM_CUDA_TRY(cudaGetLastError());
-    float ms = 0.f;
-    if ((rc = tm.end(s, &ms)) != LM_OK) return rc;
-    uint64_t work = 0;
-    LM_CUDA_TRY(cudaMemcpyAsync(dwell_i32, dd, npx * sizeof(int), cudaMemcpyDeviceToHost, s));
-    LM_CUDA_TRY(cudaMemcpyAsync(&work, dw, sizeof(work), cudaMemcpyDeviceToHost, s));
-    LM_CUDA_TRY(cudaStreamSynchronize(s));
-    if (stats) { stats->items = npx; stats->work_units = work; stats->kernel_ms = ms; stats->launches = 1; }
     return LM_OK;
 }
 

@@ -94,15 +94,31 @@ struct EscapeArgs {
     unsigned long long* survivor_count;
 };
 
-// one unfused iteration z <- z*z + c given the squares a, b of the current z
+// Unfused, round-to-nearest arithmetic in the working precision R: double for the reference's semantics (bit-exact
+// dwell), float for the optional single-precision variant (same kernel, same scheduling; lm_escape_grid_f32).
+template <typename R> struct Ar;
+template <> struct Ar<double> {
+    static __device__ __forceinline__ double mul(double x, double y) { return __dmul_rn(x, y); }
+    static __device__ __forceinline__ double add(double x, double y) { return __dadd_rn(x, y); }
+    static __device__ __forceinline__ double sub(double x, double y) { return __dsub_rn(x, y); }
+    static __device__ __forceinline__ double twice_plus(double p, double c) { return __fma_rn(2.0, p, c); }   // == (p + p) + c exactly
+};
+template <> struct Ar<float> {
+    static __device__ __forceinline__ float mul(float x, float y) { return __fmul_rn(x, y); }
+    static __device__ __forceinline__ float add(float x, float y) { return __fadd_rn(x, y); }
+    static __device__ __forceinline__ float sub(float x, float y) { return __fsub_rn(x, y); }
+    static __device__ __forceinline__ float twice_plus(float p, float c) { return __fmaf_rn(2.0f, p, c); }
+};
+
+// one unfused iteration z <- z*z + c given the squares a, b of the current z (R = the kernel's working precision)
 #define LM_STEP6()                                   \
     do {                                             \
-        const double p__ = __dmul_rn(zr, zi);        \
-        const double t__ = __dsub_rn(a, b);          \
-        zr = __dadd_rn(t__, cr);                     \
-        zi = __fma_rn(2.0, p__, ci);                 \
-        a = __dmul_rn(zr, zr);                       \
-        b = __dmul_rn(zi, zi);                       \
+        const R p__ = Ar<R>::mul(zr, zi);            \
+        const R t__ = Ar<R>::sub(a, b);              \
+        zr = Ar<R>::add(t__, cr);                    \
+        zi = Ar<R>::twice_plus(p__, ci);             \
+        a = Ar<R>::mul(zr, zr);                      \
+        b = Ar<R>::mul(zi, zi);                      \
     } while (0)
 
 // field value at the end of an orbit.  iters = iterations performed (1-based escape index
@@ -141,9 +157,11 @@ __device__ __forceinline__ double field_value(double zr, double zi, int iters, b
 // FM             : LM_FIELD_* (LM_FIELD_NONE: dwell only)
 // HYPOT          : escape test is hypot(zr,zi) > R (the loop test is a slightly lowered
 //                  a+b threshold, confirmed with hypot in the handler)
-template <bool POINTS, int FM, bool HYPOT>
+// R              : working precision (double; float only for the dwell-only grid)
+template <bool POINTS, int FM, bool HYPOT, typename R>
 __global__ void __launch_bounds__(CTA_THREADS, LM_K1_MIN_CTAS) lm_escape_kernel(const EscapeArgs A) {
     constexpr bool FIELD = (FM != LM_FIELD_NONE);
+    const R thr2 = static_cast<R>(A.thr2), cfar2 = static_cast<R>(A.cfar2);
     constexpr int CB = HYPOT ? 1 : 4;          // iterations per careful block
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -167,7 +185,7 @@ __global__ void __launch_bounds__(CTA_THREADS, LM_K1_MIN_CTAS) lm_escape_kernel(
                       warp * (RING * TILE);
 
     // ---- lane state
-    double zr = 0.0, zi = 0.0, a = 0.0, b = 0.0, cr = 0.0, ci = 0.0;
+    R zr = 0, zi = 0, a = 0, b = 0, cr = 0, ci = 0;
     int n = 0;                       // iterations performed on the current pixel
     bool idle = true;                // lane holds no pixel
     bool far = false;                // |c| too large for the absorbing-escape argument
@@ -180,7 +198,7 @@ __global__ void __launch_bounds__(CTA_THREADS, LM_K1_MIN_CTAS) lm_escape_kernel(
     unsigned seq = 0;                // tiles acquired so far
     int cursor = 0, width = 0;       // next unassigned pixel of the current tile, its size
     long long base = 0, col0 = 0;    // flat index / first column of the current tile
-    double row_ci = 0.0;
+    R row_ci = 0;
     bool exhausted = false;
     int cool = 0;                    // careful iterations since the last refill / rollback
     unsigned long long pref = 0;     // prefetched tile id (valid in lane 0)
@@ -251,7 +269,7 @@ __global__ void __launch_bounds__(CTA_THREADS, LM_K1_MIN_CTAS) lm_escape_kernel(
                     const int slot = seq % RING;
                     if (seq >= RING) flush_slot(slot);
                     if (lane == 0) { s_base[warp][slot] = base; s_width[warp][slot] = width; }
-                    row_ci = __ldg(A.ys + row);
+                    row_ci = static_cast<R>(__ldg(A.ys + row));
                 }
                 cursor = 0;
                 ++seq;
@@ -266,14 +284,14 @@ __global__ void __launch_bounds__(CTA_THREADS, LM_K1_MIN_CTAS) lm_escape_kernel(
                 my_g = base + my_off;
                 if (POINTS) {
                     if (A.index) my_g = __ldg(A.index + my_g);
-                    cr = __ldg(A.xs + my_g);
-                    ci = __ldg(A.ys + my_g);
+                    cr = static_cast<R>(__ldg(A.xs + my_g));
+                    ci = static_cast<R>(__ldg(A.ys + my_g));
                 } else {
-                    cr = __ldg(A.xs + col0 + my_off);
+                    cr = static_cast<R>(__ldg(A.xs + col0 + my_off));
                     ci = row_ci;
                 }
-                zr = 0.0; zi = 0.0; a = 0.0; b = 0.0; n = 0;
-                far = !(cr * cr + ci * ci <= A.cfar2);
+                zr = 0; zi = 0; a = 0; b = 0; n = 0;
+                far = !(cr * cr + ci * ci <= cfar2);
                 idle = false;
                 need = false;
             }
@@ -283,7 +301,7 @@ __global__ void __launch_bounds__(CTA_THREADS, LM_K1_MIN_CTAS) lm_escape_kernel(
         if (need) {          // nothing left for this lane: spin on the origin, emit nothing
             idle = true;
             far = false;
-            cr = 0.0; ci = 0.0; zr = 0.0; zi = 0.0; a = 0.0; b = 0.0; n = 0;
+            cr = 0; ci = 0; zr = 0; zi = 0; a = 0; b = 0; n = 0;
         }
         if (assigned_any) cool = 0;
     };
@@ -297,7 +315,7 @@ __global__ void __launch_bounds__(CTA_THREADS, LM_K1_MIN_CTAS) lm_escape_kernel(
         const bool blind_ok = !HYPOT && !__any_sync(FULL, far);
         bool done = false;             // this lane escaped inside the current run
         int n_fin = 0;                 // iterations performed when it escaped
-        double ze_r = 0.0, ze_i = 0.0; // z at the escape (FIELD modes)
+        R ze_r = 0, ze_i = 0;          // z at the escape (FIELD modes)
 
         while (true) {
             if (blind_ok && cool >= COOL_MIN && (LM_K1_REDO_ESCAPED_ONLY || safe >= FB)) {
@@ -309,11 +327,11 @@ __global__ void __launch_bounds__(CTA_THREADS, LM_K1_MIN_CTAS) lm_escape_kernel(
                 // the iterations that count.  Round 1 fell back to 4-iteration careful blocks for the WHOLE warp
                 // whenever any lane was within FB of max_iter, which is most of the time once refills have
                 // staggered the lanes (config 2: 0.56 -> see DESIGN.md).
-                const double szr = zr, szi = zi, sa = a, sb = b;
+                const R szr = zr, szi = zi, sa = a, sb = b;
 #pragma unroll
                 for (int k = 0; k < FB; ++k) LM_STEP6();
-                const double m = __dadd_rn(a, b);
-                const bool esc = !(m <= A.thr2);
+                const R m = Ar<R>::add(a, b);
+                const bool esc = !(m <= thr2);
 #if LM_K1_REDO_ESCAPED_ONLY
                 if (__any_sync(FULL, esc)) {
                     // Some lane escaped inside this block.  The lanes that did not keep the FB iterations they
@@ -329,7 +347,7 @@ __global__ void __launch_bounds__(CTA_THREADS, LM_K1_MIN_CTAS) lm_escape_kernel(
 #pragma unroll 1
                         for (; k < lim; ++k) {
                             LM_STEP6();
-                            if (__dadd_rn(a, b) > A.thr2) { found = true; break; }
+                            if (Ar<R>::add(a, b) > thr2) { found = true; break; }
                         }
                         if (found) {
                             done = true; n_fin = n + k + 1;
@@ -363,8 +381,8 @@ __global__ void __launch_bounds__(CTA_THREADS, LM_K1_MIN_CTAS) lm_escape_kernel(
 #pragma unroll
                 for (int k = 0; k < CB; ++k) {
                     LM_STEP6();
-                    const double m = __dadd_rn(a, b);
-                    if (m > A.thr2) {
+                    const R m = Ar<R>::add(a, b);
+                    if (m > thr2) {
                         if ((FIELD || HYPOT || POINTS) && esc_bits == 0u) { ze_r = zr; ze_i = zi; }
                         esc_bits |= 1u << k;
                     }
@@ -374,8 +392,8 @@ __global__ void __launch_bounds__(CTA_THREADS, LM_K1_MIN_CTAS) lm_escape_kernel(
             } else {
                 // fewer than CB iterations left before some lane reaches max_iter: single step
                 LM_STEP6();
-                const double m = __dadd_rn(a, b);
-                if (m > A.thr2) {
+                const R m = Ar<R>::add(a, b);
+                if (m > thr2) {
                     done = true; n_fin = n + 1;
                     if (FIELD || HYPOT || POINTS) { ze_r = zr; ze_i = zi; }
                 }
@@ -390,7 +408,7 @@ __global__ void __launch_bounds__(CTA_THREADS, LM_K1_MIN_CTAS) lm_escape_kernel(
         // ---- handler: retire finished pixels, refill their lanes
         if (HYPOT && done) {
             // candidate only: the reference tests abs(z) > R  (CB == 1, so z is still ze)
-            if (!(hypot(ze_r, ze_i) > A.bailout)) done = false;
+            if (!(hypot(static_cast<double>(ze_r), static_cast<double>(ze_i)) > A.bailout)) done = false;
         }
         bool need = false;
         if (idle) {
@@ -404,7 +422,7 @@ __global__ void __launch_bounds__(CTA_THREADS, LM_K1_MIN_CTAS) lm_escape_kernel(
             const int dw = done ? n_fin - 1 : A.max_iter;
             work += static_cast<unsigned long long>(iters);
             double f = 0.0;
-            if (FIELD) f = field_value<FM>(done ? ze_r : zr, done ? ze_i : zi, iters, done, A.overflow_flag);
+            if (FIELD) f = field_value<FM>(static_cast<double>(done ? ze_r : zr), static_cast<double>(done ? ze_i : zi), iters, done, A.overflow_flag);
             if (POINTS) {
                 // lucas_equipotential_test_v3.py:140-151
                 if (A.field) A.field[my_g] = f;
@@ -414,8 +432,8 @@ __global__ void __launch_bounds__(CTA_THREADS, LM_K1_MIN_CTAS) lm_escape_kernel(
                     if (done) {
                         // phi = exp(log(z) * 2^-k), principal branch
                         const double s = scalbn(1.0, -iters);
-                        const double lr = __dmul_rn(log(hypot(ze_r, ze_i)), s);
-                        const double li = __dmul_rn(atan2(ze_i, ze_r), s);
+                        const double lr = __dmul_rn(log(hypot(static_cast<double>(ze_r), static_cast<double>(ze_i))), s);
+                        const double li = __dmul_rn(atan2(static_cast<double>(ze_i), static_cast<double>(ze_r)), s);
                         const double e = exp(lr);
                         double sn, cs;
                         sincos(li, &sn, &cs);
@@ -460,9 +478,9 @@ size_t smem_bytes(bool points, bool field) {
     return b;
 }
 
-template <bool POINTS, int FM, bool HYPOT>
+template <bool POINTS, int FM, bool HYPOT, typename R = double>
 int32_t launch_one(const EscapeArgs& A, cudaStream_t stream) {
-    auto kern = lm_escape_kernel<POINTS, FM, HYPOT>;
+    auto kern = lm_escape_kernel<POINTS, FM, HYPOT, R>;
     const size_t smem = smem_bytes(POINTS, FM != LM_FIELD_NONE);
     LM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int per_sm = 0;
@@ -478,7 +496,7 @@ int32_t launch_one(const EscapeArgs& A, cudaStream_t stream) {
     return LM_OK;
 }
 
-int32_t launch_escape(bool points, int field_mode, EscapeArgs& A, cudaStream_t stream) {
+int32_t launch_escape(bool points, int field_mode, EscapeArgs& A, cudaStream_t stream, bool single = false) {
     const bool hypot_test = !(field_mode == LM_FIELD_NONE || field_mode == LM_FIELD_GREEN);
     const double R = A.bailout;
     double thr2 = R * R;
@@ -488,6 +506,10 @@ int32_t launch_escape(bool points, int field_mode, EscapeArgs& A, cudaStream_t s
         // blind path precondition (see header): |c| <= R^2 - R - 0.05
         const double cmax = R * R - R - 0.05;
         A.cfar2 = (!hypot_test && cmax > 0.0 && cmax < 1e100) ? cmax * cmax : -1.0;
+    }
+    if (single) {
+        if (points || field_mode != LM_FIELD_NONE) return lm::fail(LM_E_INVALID, "the single-precision kernel produces the dwell grid only");
+        return launch_one<false, LM_FIELD_NONE, false, float>(A, stream);
     }
     if (points) {
         if (field_mode == LM_FIELD_GREEN) return launch_one<true, LM_FIELD_GREEN, false>(A, stream);
@@ -562,7 +584,7 @@ int32_t check_grid_args(const char* who, const void* xs, int64_t nx, const void*
 int32_t enqueue_grid(const double* xs, int64_t nx, const double* ys, int64_t ny,
                             int32_t max_iter, double bailout, int32_t field_mode,
                             int32_t* dwell_i32, double* dwell_f64, double* field,
-                            unsigned long long* work_dev, int* overflow_dev, cudaStream_t s) {
+                            unsigned long long* work_dev, int* overflow_dev, cudaStream_t s, bool single = false) {
     unsigned long long* counters = nullptr;
     int slot = 0;
     int32_t rc = get_counters(&counters, &slot, s);
@@ -581,7 +603,7 @@ int32_t enqueue_grid(const double* xs, int64_t nx, const double* ys, int64_t ny,
     A.vec_i32 = (nx % 4 == 0) && (reinterpret_cast<uintptr_t>(dwell_i32) % 16 == 0);
     A.vec_f64 = (nx % 2 == 0) && (reinterpret_cast<uintptr_t>(dwell_f64) % 16 == 0);
     A.vec_field = (nx % 2 == 0) && (reinterpret_cast<uintptr_t>(field) % 16 == 0);
-    if ((rc = launch_escape(false, field_mode, A, s)) != LM_OK) return rc;
+    if ((rc = launch_escape(false, field_mode, A, s, single)) != LM_OK) return rc;
     return counters_in_flight(slot, s);
 }
 
@@ -730,6 +752,54 @@ int32_t lm_escape_grid_f64_dev(const double* xs, int64_t nx, const double* ys, i
     if (nx == 0 || ny == 0) return LM_OK;
     return enqueue_grid(xs, nx, ys, ny, max_iter, bailout, field_mode, dwell_i32, dwell_f64, field,
                         reinterpret_cast<unsigned long long*>(work_units_dev), nullptr, s);
+}
+
+int32_t lm_escape_grid_f32_dev(const double* xs, int64_t nx, const double* ys, int64_t ny,
+                               int32_t max_iter, double bailout, int32_t* dwell_i32,
+                               uint64_t* work_units_dev, void* stream) {
+    int32_t rc = lm::require_device();
+    if (rc != LM_OK) return rc;
+    rc = check_grid_args("lm_escape_grid_f32_dev", xs, nx, ys, ny, max_iter, bailout);
+    if (rc != LM_OK) return rc;
+    LM_REQUIRE(bailout < 1e15, "lm_escape_grid_f32_dev: bailout out of the single-precision range");
+    cudaStream_t s = lm::as_stream(stream);
+    if (work_units_dev) LM_CUDA_TRY(cudaMemsetAsync(work_units_dev, 0, sizeof(uint64_t), s));
+    if (nx == 0 || ny == 0) return LM_OK;
+    return enqueue_grid(xs, nx, ys, ny, max_iter, bailout, LM_FIELD_NONE, dwell_i32, nullptr, nullptr,
+                        reinterpret_cast<unsigned long long*>(work_units_dev), nullptr, s, true);
+}
+
+int32_t lm_escape_grid_f32(const double* xs, int64_t nx, const double* ys, int64_t ny,
+                           int32_t max_iter, double bailout, int32_t* dwell_i32, lm_stats* stats) {
+    int32_t rc = lm::require_device();
+    if (rc != LM_OK) return rc;
+    rc = check_grid_args("lm_escape_grid_f32", xs, nx, ys, ny, max_iter, bailout);
+    if (rc != LM_OK) return rc;
+    LM_REQUIRE(dwell_i32 != nullptr, "lm_escape_grid_f32: dwell_i32 is NULL");
+    if (stats) *stats = lm_stats{};
+    if (nx == 0 || ny == 0) return LM_OK;
+    cudaStream_t s = nullptr;
+    const size_t npx = static_cast<size_t>(nx) * ny;
+    void *dxs, *dys, *dd, *dw;
+    if ((rc = lm::ws_get(lm::WS_XS, nx * sizeof(double), &dxs)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_YS, ny * sizeof(double), &dys)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_OUT_I32, npx * sizeof(int), &dd)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_K1_WORK, 64, &dw)) != LM_OK) return rc;
+    LM_CUDA_TRY(cudaMemcpyAsync(dxs, xs, nx * sizeof(double), cudaMemcpyHostToDevice, s));
+    LM_CUDA_TRY(cudaMemcpyAsync(dys, ys, ny * sizeof(double), cudaMemcpyHostToDevice, s));
+    lm::Timer tm;
+    if ((rc = tm.begin(s)) != LM_OK) return rc;
+    rc = lm_escape_grid_f32_dev(static_cast<double*>(dxs), nx, static_cast<double*>(dys), ny, max_iter, bailout,
+                                static_cast<int32_t*>(dd), static_cast<uint64_t*>(dw), s);
+    if (rc != LM_OK) return rc;
+    float ms = 0.f;
+    if ((rc = tm.end(s, &ms)) != LM_OK) return rc;
+    uint64_t work = 0;
+    LM_CUDA_TRY(cudaMemcpyAsync(dwell_i32, dd, npx * sizeof(int), cudaMemcpyDeviceToHost, s));
+    LM_CUDA_TRY(cudaMemcpyAsync(&work, dw, sizeof(work), cudaMemcpyDeviceToHost, s));
+    LM_CUDA_TRY(cudaStreamSynchronize(s));
+    if (stats) { stats->items = npx; stats->work_units = work; stats->kernel_ms = ms; stats->launches = 1; }
+    return LM_OK;
 }
 
 int32_t lm_escape_grid_f64(const double* xs, int64_t nx, const double* ys, int64_t ny,
