@@ -109,8 +109,10 @@ __host__ __device__ inline void edge_corners(int edge, int& dj1, int& di1, int& 
 //   X = (L ^ L') | (H ^ H') | (L ^ H),  L' / H' = the row words shifted by one column
 // (the funnel shift pulls in the first bit of the next chunk / the strip's edge column).
 // ------------------------------------------------------------------------------------
+// quad rows per tile: 8 rows re-read every 9th dwell row (measured on the 32768^2 grid, ncu: 4.50 GB read for 4.29 GB
+// of dwell values, 0.735 ms = 0.90 of the measured HBM peak; 4 rows: 4.84 GB, 0.822 ms -- profiles/r02_k2_mark_rows_ab.txt)
 #ifndef LM_K2_MARK_ROWS
-#define LM_K2_MARK_ROWS 4
+#define LM_K2_MARK_ROWS 8
 #endif
 constexpr int MARK_ROWS = LM_K2_MARK_ROWS;
 
@@ -255,7 +257,7 @@ __device__ __forceinline__ void mark_strip_tile(const int* __restrict__ strip0, 
             const bool in = SAFE || ((j0 + r < ny) && (c0 + 32 * k + lane < nx));
             const int z = in ? p[r * BULK_COLS + 32 * k] : INT_MIN;
             const unsigned b = __ballot_sync(FULL, z > ilevel);
-            if (lane == r * 4 + k) sm[r * 5 + k] = b;             // MARK_ROWS + 1 <= 8 rows: lane index < 32
+            if (lane == ((r * 4 + k) & 31)) sm[r * 5 + k] = b;    // any lane holds the (warp-uniform) ballot
         }
     }
     {
@@ -288,7 +290,7 @@ __device__ __forceinline__ void mark_strip_tile(const int* __restrict__ strip0, 
 __global__ void __launch_bounds__(MARK_WARPS * 32) contour_mark_bulk_kernel(
     const int* __restrict__ dwell, long long nx, long long ny, int ilevel,
     unsigned* __restrict__ mask, long long words_per_row, unsigned* __restrict__ row_count) {
-    static_assert(4 * (MARK_ROWS + 1) <= 32, "one lane per ballot word");
+    static_assert(4 * MARK_ROWS <= 32, "one lane per crossing word");
     extern __shared__ __align__(128) unsigned char bulk_smem[];
     int* tile = reinterpret_cast<int*>(bulk_smem);                                   // 2 stages
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(bulk_smem + 2 * BULK_STAGE_INTS * sizeof(int));

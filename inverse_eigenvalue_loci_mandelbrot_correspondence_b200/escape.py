@@ -48,6 +48,21 @@ def escape_grid(xs, ys, max_iter: int, bailout: float = 2.0, field_mode: int = F
     return (d32 if d32 is not None else d64), fld, last_stats
 
 
+def escape_grid_f32(xs, ys, max_iter: int, bailout: float = 2.0):
+    """The optional single-precision variant of K1 (no reference counterpart; BASELINE.json north_star piece 1): the same
+    persistent kernel instantiated in binary32.  Returns (dwell int32 [ny, nx], stats).  NOT bit-exact: measured against
+    the fp64 kernel, 0.2-0.3 % of the pixels of configs 1-3 differ (8-9 % in the deep zoom of config 4) and the
+    interior mask agrees on >= 99.97 % of the pixels (tests/test_gpu_escape.py::test_f32_variant_tolerance)."""
+    xs = _f64(xs).ravel(); ys = _f64(ys).ravel()
+    d32 = np.empty((ys.size, xs.size), dtype=np.int32)
+    st = Stats()
+    _shim.call("lm_escape_grid_f32", _shim.ptr(xs), xs.size, _shim.ptr(ys), ys.size, int(max_iter), float(bailout),
+               _shim.ptr(d32), C.byref(st))
+    global last_stats
+    last_stats = st.as_dict()
+    return d32, last_stats
+
+
 def compute_grid(xlim, ylim, res: int, max_iter: int):
     """Drop-in for compute_grid (mandelbrot_boundary_sample.py:32-39): -> (xs, ys, Z float64[res,res])."""
     xs = np.linspace(xlim[0], xlim[1], res)

@@ -179,16 +179,38 @@ def test_batch_potential_two_pass(gpu, oracle):
     assert np.array_equal(np.concatenate([p[0] for p in parts]), g)
 
 
-def test_f32_variant_tolerance(gpu, oracle):
-    """fp32 kernel (no reference counterpart): dwell mismatch fraction vs fp64 below 2 % on config 1's window."""
-    import ctypes as C
-    xs = np.linspace(-2.1, 0.9, 800); ys = np.linspace(-1.5, 1.5, 800)
-    want, _ = oracle.dwell_grid(xs, ys, 500)
-    out = np.empty((800, 800), dtype=np.int32)
-    st = gpu.shim.Stats()
-    gpu.shim.call("lm_escape_grid_f32", gpu.shim.ptr(xs), 800, gpu.shim.ptr(ys), 800, 500, 2.0, gpu.shim.ptr(out), C.byref(st))
-    assert (out != want).mean() < 0.02
-    assert ((out == 500) == (want == 500)).mean() > 0.999
+# the four grid windows of BASELINE.json (configs 1-4) at 1024^2 with their own max_iter; stated tolerances of the
+# single-precision variant against the fp64 kernel: (max dwell-mismatch fraction, min interior-mask agreement).
+# Measured on a B200 (profiles/r02_k1_f32_study.json): 0.0021-0.0029 / 0.9997-0.99996 on the full-set window,
+# 0.085-0.089 / 0.9997 in the seahorse zoom, where late escapers are chaotic in the last bits of c.
+F32_CASES = [((-2.1, 0.9), (-1.5, 1.5), 500, 0.005, 0.9995), ((-2.1, 0.9), (-1.5, 1.5), 2000, 0.005, 0.9995),
+             ((-2.1, 0.9), (-1.5, 1.5), 10000, 0.005, 0.9995), ((-0.755, -0.735), (0.10, 0.12), 100000, 0.12, 0.9995)]
+
+
+@pytest.mark.parametrize("xlim,ylim,mi,max_mismatch,min_mask", F32_CASES)
+def test_f32_variant_tolerance(gpu, xlim, ylim, mi, max_mismatch, min_mask):
+    """Optional fp32 variant (no reference counterpart): the same persistent kernel in binary32, validated against the
+    bit-exact fp64 kernel by the stated tolerances; its work count is that of its own dwell grid."""
+    xs = np.linspace(*xlim, 1024); ys = np.linspace(*ylim, 1024)
+    want, _, _ = gpu.escape.escape_grid(xs, ys, mi)
+    got, st = gpu.escape.escape_grid_f32(xs, ys, mi)
+    assert got.min() >= 0 and got.max() <= mi
+    assert (got != want).mean() < max_mismatch
+    assert ((got == mi) == (want == mi)).mean() > min_mask
+    assert st["work_units"] == int(np.minimum(got.astype(np.int64) + 1, mi).sum())
+
+
+def test_f32_variant_is_deterministic_and_ragged(gpu):
+    xs = np.linspace(-2.1, 0.9, 333); ys = np.linspace(-1.5, 1.5, 77)
+    a, _ = gpu.escape.escape_grid_f32(xs, ys, 300)
+    b, _ = gpu.escape.escape_grid_f32(xs, ys, 300)
+    assert np.array_equal(a, b)
+    # exactly representable coordinates well away from the boundary: fp32 and fp64 agree pixel for pixel
+    xs = np.arange(-16, 9) / 8.0; ys = np.arange(-12, 13) / 8.0
+    c, _ = gpu.escape.escape_grid_f32(xs, ys, 64)
+    d, _, _ = gpu.escape.escape_grid(xs, ys, 64)
+    far = (np.abs(xs[None, :] + 1j * ys[:, None]) > 2.2)
+    assert np.array_equal(c[far], d[far])
 
 
 def test_full_size_properties_config2(gpu):
