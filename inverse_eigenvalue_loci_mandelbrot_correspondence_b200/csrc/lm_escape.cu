@@ -59,6 +59,18 @@ namespace {
 #ifndef LM_K1_REDO_ESCAPED_ONLY
 #define LM_K1_REDO_ESCAPED_ONLY 1
 #endif
+// What happens when some lane escaped inside a blind block (LM_K1_REDO_ESCAPED_ONLY = 1):
+//   1  the escaped lanes repeat the block alone with the exact test while the other lanes of the warp wait
+//   2  the escaped lanes go back to the block's start and the WHOLE warp continues with careful blocks until they
+//      have retired: nobody waits, the other lanes pay 8 instead of 6 FP64 instructions for those iterations
+#ifndef LM_K1_ESC_MODE
+#define LM_K1_ESC_MODE 2
+#endif
+// cool-down (COOL_MIN careful iterations before the next blind block) after a refill only when a retiring pixel had
+// ESCAPED: lanes that retire at max_iter sit inside the set and their next pixels almost always do too
+#ifndef LM_K1_ADAPTIVE_COOL
+#define LM_K1_ADAPTIVE_COOL 1
+#endif
 
 constexpr int TILE = 128;          // pixels per tile (one int4 per lane)
 constexpr int WARPS = LM_K1_WARPS; // warps per CTA
@@ -189,6 +201,7 @@ __global__ void __launch_bounds__(CTA_THREADS, LM_K1_MIN_CTAS) lm_escape_kernel(
     int n = 0;                       // iterations performed on the current pixel
     bool idle = true;                // lane holds no pixel
     bool far = false;                // |c| too large for the absorbing-escape argument
+    bool redo = false;               // rolled back to the start of a blind block: escapes within the next FB iterations
     int my_off = 0;                  // offset of my pixel inside its tile
     unsigned my_seq = 0;             // sequence number (per warp) of my pixel's tile
     long long my_g = 0;              // flat output index of my pixel
@@ -242,7 +255,7 @@ __global__ void __launch_bounds__(CTA_THREADS, LM_K1_MIN_CTAS) lm_escape_kernel(
     };
 
     // hand pixels to the lanes that need one; acquire tiles as required
-    auto refill = [&](bool need) {
+    auto refill = [&](bool need, bool cool_down) {
         bool assigned_any = false;
         while (true) {
             const unsigned mask = __ballot_sync(FULL, need);
@@ -292,6 +305,7 @@ __global__ void __launch_bounds__(CTA_THREADS, LM_K1_MIN_CTAS) lm_escape_kernel(
                 }
                 zr = 0; zi = 0; a = 0; b = 0; n = 0;
                 far = !(cr * cr + ci * ci <= cfar2);
+                redo = false;
                 idle = false;
                 need = false;
             }
@@ -301,18 +315,19 @@ __global__ void __launch_bounds__(CTA_THREADS, LM_K1_MIN_CTAS) lm_escape_kernel(
         if (need) {          // nothing left for this lane: spin on the origin, emit nothing
             idle = true;
             far = false;
+            redo = false;
             cr = 0; ci = 0; zr = 0; zi = 0; a = 0; b = 0; n = 0;
         }
-        if (assigned_any) cool = 0;
+        if (assigned_any && cool_down) cool = 0;
     };
 
-    refill(true);
+    refill(true, true);
 
     while (true) {
         if (exhausted && __all_sync(FULL, idle)) break;
 
         int safe = __reduce_min_sync(FULL, A.max_iter - n);   // >= 1: iterations until the first lane hits max_iter
-        const bool blind_ok = !HYPOT && !__any_sync(FULL, far);
+        bool blind_ok = !HYPOT && !__any_sync(FULL, far || redo);
         bool done = false;             // this lane escaped inside the current run
         int n_fin = 0;                 // iterations performed when it escaped
         R ze_r = 0, ze_i = 0;          // z at the escape (FIELD modes)
@@ -332,7 +347,25 @@ __global__ void __launch_bounds__(CTA_THREADS, LM_K1_MIN_CTAS) lm_escape_kernel(
                 for (int k = 0; k < FB; ++k) LM_STEP6();
                 const R m = Ar<R>::add(a, b);
                 const bool esc = !(m <= thr2);
-#if LM_K1_REDO_ESCAPED_ONLY
+#if LM_K1_REDO_ESCAPED_ONLY && LM_K1_ESC_MODE == 2
+                if (__any_sync(FULL, esc)) {
+                    // Some lane escaped inside this block.  The lanes that did not keep the FB iterations they just
+                    // made (their end-of-block test proves no earlier escape); the escaped lanes go back to the saved
+                    // state, and the whole warp goes on with careful blocks -- which find their first-escape index
+                    // within the next FB iterations (or retire them at max_iter) -- while everybody else keeps
+                    // iterating: no lane waits for another one's repeat.
+                    if (esc) { zr = szr; zi = szi; a = sa; b = sb; redo = true; }
+                    else n += FB;
+                    safe -= FB;                                 // still a lower bound of every lane's remaining iterations
+                    blind_ok = false;                           // until the rolled-back lanes have retired
+                    if (safe <= 0) break;                       // somebody passed max_iter: retire it first
+                    continue;
+                }
+                n += FB;
+                safe -= FB;
+                if (safe <= 0) break;
+                continue;
+#elif LM_K1_REDO_ESCAPED_ONLY
                 if (__any_sync(FULL, esc)) {
                     // Some lane escaped inside this block.  The lanes that did not keep the FB iterations they
                     // just made (their end-of-block test proves no earlier escape); only the escaped lanes go
@@ -402,7 +435,7 @@ __global__ void __launch_bounds__(CTA_THREADS, LM_K1_MIN_CTAS) lm_escape_kernel(
             n += cnt;
             safe -= cnt;
             cool += cnt;
-            if (__any_sync(FULL, done) || safe == 0) break;
+            if (__any_sync(FULL, done) || safe <= 0) break;
         }
 
         // ---- handler: retire finished pixels, refill their lanes
@@ -457,7 +490,11 @@ __global__ void __launch_bounds__(CTA_THREADS, LM_K1_MIN_CTAS) lm_escape_kernel(
             }
             need = true;
         }
-        refill(need);
+#if LM_K1_ADAPTIVE_COOL
+        refill(need, __any_sync(FULL, done && !idle));
+#else
+        refill(need, true);
+#endif
     }
 
     if (!POINTS) {
