@@ -666,24 +666,31 @@ void GridHostJob::release_events() {
         }                                                                                      \
     } while (0)
 
-// Host-buffer K1.  Large outputs are produced in row chunks on one stream while a second
-// stream copies finished chunks back, so the PCIe transfer hides behind the FP64 work.
+// Host-buffer K1.  Large outputs are produced in row chunks while a copy stream returns finished chunks, so the PCIe
+// transfer hides behind the FP64 work.  The chunks alternate between TWO compute streams: a chunk's persistent CTAs
+// leave the SMs one by one as the tile queue drains (the last ones hold pixels that run to max_iter), and the next
+// chunk's CTAs move in behind them instead of waiting for the whole launch to end -- 16 serial launches cost 15 ms of
+// ramps and tails on the 32768^2 grid (626 ms against 611 ms for one launch).
 int32_t grid_host_begin(const double* xs, int64_t nx, const double* ys, int64_t ny, int32_t max_iter, double bailout,
                         int32_t field_mode, int32_t* dwell_i32, double* dwell_f64, double* field,
                         bool need_dev_dwell, int64_t extra_rows, GridHostJob* job) {
     int32_t rc;
     const size_t npx = static_cast<size_t>(nx) * static_cast<size_t>(ny);
     job->npx = npx;
-    static cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    static cudaStream_t s_compute = nullptr, s_compute2 = nullptr, s_copy = nullptr;
     static int s_dev = -1;
     lm::register_release_hook([] {
-        if (s_compute) { cudaStreamDestroy(s_compute); cudaStreamDestroy(s_copy); s_compute = s_copy = nullptr; s_dev = -1; }
+        if (s_compute) {
+            cudaStreamDestroy(s_compute); cudaStreamDestroy(s_compute2); cudaStreamDestroy(s_copy);
+            s_compute = s_compute2 = s_copy = nullptr; s_dev = -1;
+        }
     });
     int dev = 0;
     LM_CUDA_TRY(cudaGetDevice(&dev));
-    if (s_dev != dev) {      // (re)create the two pipeline streams on the current device
-        if (s_compute) { cudaStreamDestroy(s_compute); cudaStreamDestroy(s_copy); }
+    if (s_dev != dev) {      // (re)create the pipeline streams on the current device
+        if (s_compute) { cudaStreamDestroy(s_compute); cudaStreamDestroy(s_compute2); cudaStreamDestroy(s_copy); }
         LM_CUDA_TRY(cudaStreamCreateWithFlags(&s_compute, cudaStreamNonBlocking));
+        LM_CUDA_TRY(cudaStreamCreateWithFlags(&s_compute2, cudaStreamNonBlocking));
         LM_CUDA_TRY(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
         s_dev = dev;
     }
@@ -710,29 +717,35 @@ int32_t grid_host_begin(const double* xs, int64_t nx, const double* ys, int64_t 
 
     const size_t bytes_per_row = static_cast<size_t>(nx) * ((dwell_i32 ? 4 : 0) + (dwell_f64 ? 8 : 0) + (dfield ? 8 : 0));
     const size_t total_bytes = bytes_per_row * static_cast<size_t>(ny);
-    int64_t nchunks = static_cast<int64_t>((total_bytes + (size_t(256) << 20) - 1) / (size_t(256) << 20));
+    // ~128 MB of output per chunk (2.3 ms of PCIe): the copy of the LAST chunks is what remains after the compute ends
+    int64_t nchunks = static_cast<int64_t>((total_bytes + (size_t(128) << 20) - 1) / (size_t(128) << 20));
     if (nchunks < 1) nchunks = 1;
-    if (nchunks > 32) nchunks = 32;
+    if (nchunks > 64) nchunks = 64;
     if (nchunks > ny) nchunks = ny;
     const int64_t rows_per_chunk = (ny + nchunks - 1) / nchunks;
     job->ev_chunk.assign(static_cast<size_t>(nchunks), nullptr);
 
     LM_JOB_TRY(cudaEventCreate(&job->ev_begin));
     LM_JOB_TRY(cudaEventCreate(&job->ev_end));
-    LM_JOB_TRY(cudaEventRecord(job->ev_begin, s_compute));
+    LM_JOB_TRY(cudaEventRecord(job->ev_begin, s_compute));                 // behind the coordinate uploads and the counter reset
+    LM_JOB_TRY(cudaStreamWaitEvent(s_compute2, job->ev_begin, 0));
+    int64_t last_on_2 = -1;
     for (int64_t c = 0; c < nchunks; ++c) {
         const int64_t r0 = c * rows_per_chunk;
         const int64_t rows = (r0 + rows_per_chunk <= ny) ? rows_per_chunk : ny - r0;
         if (rows <= 0) break;
         const size_t off = static_cast<size_t>(r0) * nx;
+        cudaStream_t sc = (c & 1) ? s_compute2 : s_compute;
         rc = enqueue_grid(static_cast<double*>(dxs), nx, static_cast<double*>(dys) + r0, rows, max_iter, bailout, field_mode,
                           dd ? static_cast<int32_t*>(dd) + off : nullptr, df64 ? static_cast<double*>(df64) + off : nullptr,
-                          dfield ? static_cast<double*>(dfield) + off : nullptr, work_dev, overflow_dev, s_compute);
+                          dfield ? static_cast<double*>(dfield) + off : nullptr, work_dev, overflow_dev, sc);
         if (rc != LM_OK) { job->release_events(); cudaDeviceSynchronize(); return rc; }
         ++job->launches;
         LM_JOB_TRY(cudaEventCreateWithFlags(&job->ev_chunk[c], cudaEventDisableTiming));
-        LM_JOB_TRY(cudaEventRecord(job->ev_chunk[c], s_compute));
+        LM_JOB_TRY(cudaEventRecord(job->ev_chunk[c], sc));
+        if (c & 1) last_on_2 = c;
     }
+    if (last_on_2 >= 0) LM_JOB_TRY(cudaStreamWaitEvent(s_compute, job->ev_chunk[last_on_2], 0));   // join: K2 and ev_end follow on s_compute
     LM_JOB_TRY(cudaEventRecord(job->ev_end, s_compute));
     for (int64_t c = 0; c < nchunks; ++c) {
         if (!job->ev_chunk[c]) break;
