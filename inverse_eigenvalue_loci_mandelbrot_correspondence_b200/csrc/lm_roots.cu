@@ -87,6 +87,10 @@ __device__ __forceinline__ cplx cinv_fast(cplx a) {
     const double s = rcp_fast<2>(a.r * a.r + a.i * a.i);
     return {a.r * s, -a.i * s};
 }
+__device__ __forceinline__ cplx cinv_fast1(cplx a) {       // 2^-44: enough for a correction term
+    const double s = rcp_fast<1>(a.r * a.r + a.i * a.i);
+    return {a.r * s, -a.i * s};
+}
 __device__ __forceinline__ cplx cinv(cplx a) {
     const double s = 1.0 / (a.r * a.r + a.i * a.i);
     return {a.r * s, -a.i * s};
@@ -296,14 +300,17 @@ __device__ __forceinline__ void aberth_update(const Slot& S, int d, int i, cplx&
     const double2 zi2 = S.zz[i];
     const cplx z = {zi2.x, zi2.y};
     const double az2 = z.r * z.r + z.i * z.i;
-    const double az = sqrt(az2);
     // One Horner loop for both regimes, so lanes inside and outside the unit circle do not diverge:
     // |z| <= 1 evaluates p at w = z from coef[0] up;  |z| > 1 evaluates the reversed polynomial
     // q(w) = sum_k coef[k] w^k at w = 1/z from coef[d] down (p(z) = z^d q(1/z)).
-    const bool inside = az <= 1.0;
+    const bool inside = az2 <= 1.0;
     const double iz2 = rcp_fast<2>(inside ? 1.0 : az2);
     const cplx w = inside ? z : cplx{z.r * iz2, -z.i * iz2};
-    const double aw = inside ? az : az * iz2;
+    // |w| only scales the rounding-error bound of the evaluation: a single-precision square root rounded UP by
+    // 2^-20 is a valid (and 1e-6 tight) upper bound, and saves the ~20 instructions of the binary64 sqrt
+    // (binary32 covers |z|^2 in [1e-37, 1e37]; outside of it the double sqrt is taken)
+    const double aw2 = inside ? az2 : iz2;                       // |w|^2 (|1/z|^2 = 1/|z|^2)
+    const double aw = (aw2 > 1e-37) ? static_cast<double>(sqrtf(static_cast<float>(aw2))) * (1.0 + 9.5367431640625e-7) : sqrt(aw2);
     const int k_first = inside ? 0 : d, k_step = inside ? 1 : -1;
     cplx b = {S.coef[k_first], 0.0}, bp = {0.0, 0.0};
     double s = fabs(b.r);
@@ -329,7 +336,7 @@ __device__ __forceinline__ void aberth_update(const Slot& S, int d, int i, cplx&
     }
     const double dd = den.r * den.r + den.i * den.i;
     const cplx newton = (dd > 1e-290 && dd < 1e290) ? cmul(num, cinv_fast(den))
-                      : (dd > 0.0 ? cmul(num, cinv(den)) : cplx{1e-3 * (az + 1e-3), 1e-3 * (az + 1e-3)});
+                      : (dd > 0.0 ? cmul(num, cinv(den)) : cplx{1e-3 * (sqrt(az2) + 1e-3), 1e-3 * (sqrt(az2) + 1e-3)});
     double Sr = 0.0, Si = 0.0;
 #pragma unroll 4
     for (int j = 0; j < d; ++j) {
@@ -346,7 +353,7 @@ __device__ __forceinline__ void aberth_update(const Slot& S, int d, int i, cplx&
     const cplx ns = cmul(newton, cplx{Sr, Si});
     const cplx den2 = {1.0 - ns.r, -ns.i};
     const double d2 = den2.r * den2.r + den2.i * den2.i;
-    const cplx corr = (d2 > 1e-290 && d2 < 1e290) ? cmul(newton, cinv_fast(den2))
+    const cplx corr = (d2 > 1e-290 && d2 < 1e290) ? cmul(newton, cinv_fast1(den2))
                     : (d2 > 0.0 ? cmul(newton, cinv(den2)) : newton);
     znew = {z.r - corr.r, z.i - corr.i};
     if (!(isfinite(znew.r) && isfinite(znew.i))) znew = {z.r * 0.5 + 1e-3, z.i * 0.5 - 1e-3};

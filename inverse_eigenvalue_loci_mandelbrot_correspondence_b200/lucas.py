@@ -125,6 +125,69 @@ def compute_inverse_eigenvalues_family(family: str, n_min: int, n_max: int, tol:
     return _inverse_eigs_for_rows([family_toprow(family, n) for n in range(n_min, n_max + 1)], tol)
 
 
+def summarize_g(g: np.ndarray, label: str = "", quiet: bool = False) -> dict:
+    """summarize_g of lucas_equipotential_test_v3.py:168-184: counts and order statistics of the exterior potentials
+    (same keys, same numpy calls, same printed lines unless quiet)."""
+    g = np.asarray(g, dtype=np.float64)
+    outside = g > 0
+    has = bool(outside.any())
+    out = {
+        "count": int(len(g)),
+        "escaped": int(outside.sum()),
+        "escaped_frac": float(outside.mean()) if len(g) else float("nan"),
+        "g_median": float(np.median(g[outside])) if has else float("nan"),
+        "g_mean": float(np.mean(g[outside])) if has else float("nan"),
+        "g_std": float(np.std(g[outside])) if has else float("nan"),
+        "g_p10": float(np.quantile(g[outside], 0.10)) if has else float("nan"),
+        "g_p90": float(np.quantile(g[outside], 0.90)) if has else float("nan"),
+    }
+    if not quiet:
+        print(f"{label}escaped: {out['escaped']}/{out['count']}  ({out['escaped_frac']*100:.2f}%)")
+        if has:
+            print(f"{label}g median={out['g_median']:.6g}  mean={out['g_mean']:.6g}  std={out['g_std']:.6g}")
+            print(f"{label}g p10/p90={out['g_p10']:.6g}/{out['g_p90']:.6g}")
+    return out
+
+
+def _cloud_potentials_by_n(n_min: int, n_max: int, family: str | None, max_iter: int, escape_radius: float, tol: float):
+    """ONE K3 batch over n = n_min..n_max and ONE K1d pass over the whole cloud -> (g of every point, points per n).
+    The reference solves and re-evaluates per n (and, in cumulative_stats, re-evaluates the whole growing cloud for
+    every N: O(N^2) potential evaluations); g of a point does not depend on the other points, so one pass serves all."""
+    from . import escape
+    rows = [np.ones(n) if family is None else family_toprow(family, n) for n in range(n_min, n_max + 1)]
+    if not rows:
+        return np.zeros(0), np.zeros(0, dtype=np.int64)
+    maxdeg = max(r.shape[0] for r in rows)
+    tops = np.zeros((len(rows), maxdeg), dtype=np.float64)
+    deg = np.empty(len(rows), dtype=np.int32)
+    for k, r in enumerate(rows):
+        tops[k, : r.shape[0]] = r
+        deg[k] = r.shape[0]
+    vals, kept, _ = roots_batched(tops, deg, invert=True, tol=tol)
+    cloud = np.concatenate([vals[k, : kept[k]] for k in range(len(rows))]).astype(np.complex128)
+    g, _, _ = escape.batch_potential(cloud, max_iter=max_iter, escape_radius=escape_radius)
+    return g, kept.astype(np.int64)
+
+
+def per_n_stats(n_min: int, n_max: int, family: str | None = None, max_iter: int = 20000, escape_radius: float = 2.0,
+                tol: float = 1e-12, quiet: bool = False) -> list[dict]:
+    """per_n_stats of lucas_equipotential_test_v3.py:294-308 (MAX_ITER / ESCAPE_RADIUS / EIG_TOL of :41-44 as defaults):
+    one row {"n", count, escaped, escaped_frac, g_median, g_mean, g_std, g_p10, g_p90} per order n."""
+    g, counts = _cloud_potentials_by_n(n_min, n_max, family, max_iter, escape_radius, tol)
+    offs = np.concatenate([[0], np.cumsum(counts)])
+    return [{"n": n, **summarize_g(g[offs[k]:offs[k + 1]], label=f"[per-n n={n}] ", quiet=quiet)}
+            for k, n in enumerate(range(n_min, n_max + 1))]
+
+
+def cumulative_stats(n_min: int, n_max: int, family: str | None = None, max_iter: int = 20000, escape_radius: float = 2.0,
+                     tol: float = 1e-12, quiet: bool = False) -> list[dict]:
+    """cumulative_stats of lucas_equipotential_test_v3.py:310-327: row N summarises the cloud of orders n_min..N."""
+    g, counts = _cloud_potentials_by_n(n_min, n_max, family, max_iter, escape_radius, tol)
+    offs = np.concatenate([[0], np.cumsum(counts)])
+    return [{"N": N, **summarize_g(g[: offs[k + 1]], label=f"[cum N={N}] ", quiet=quiet)}
+            for k, N in enumerate(range(n_min, n_max + 1))]
+
+
 def construct_points(ns, tol: float = 1e-10) -> np.ndarray:
     """construct_points(ns) of tci_construct_mandelbrot.py:11-19 (tol 1e-10 there and in
     tci_construct_mandelbrot_v002_fixed.py:27-33; variograms_construct_mandelbrot.py:48-56 uses 1e-14)."""

@@ -79,6 +79,17 @@ def main() -> None:
     g["lucas_2_40_sorted_per_n"] = np.concatenate(
         [np.sort(lucas["compute_inverse_eigenvalues"](n, n, 1e-12)) for n in range(2, 41)])
     assert len(cloud) == len(g["lucas_2_40_sorted_per_n"])
+    # ---- per-n / cumulative statistics (lucas_equipotential_test_v3.py:168-184, 294-327), MAX_ITER lowered to 3000
+    stats = load_defs("lucas_equipotential_test_v3.py",
+                      ["generate_lucas_companion", "generate_companion_from_toprow", "family_toprow",
+                       "mandelbrot_parameter_potential", "batch_potential", "summarize_g", "per_n_stats", "cumulative_stats"],
+                      {"print": lambda *a, **k: None, "MAX_ITER": 3000, "ESCAPE_RADIUS": 2.0, "EIG_TOL": 1e-12})
+    cols = ["count", "escaped", "escaped_frac", "g_median", "g_mean", "g_std", "g_p10", "g_p90"]
+    for tag, fam in (("lucas", None), ("pell", "pell_like_all_twos")):
+        rows = stats["per_n_stats"](2, 30, family=fam)
+        g[f"per_n_stats_{tag}_2_30_mi3000"] = np.array([[r[c] for c in cols] for r in rows], dtype=np.float64)
+        rows = stats["cumulative_stats"](2, 30, family=fam)
+        g[f"cumulative_stats_{tag}_2_30_mi3000"] = np.array([[r[c] for c in cols] for r in rows], dtype=np.float64)
     tci = load_defs("tci_construct_mandelbrot.py", ["lucas_companion", "construct_points"])
     cp = tci["construct_points"](range(20, 301, 20))
     g["tci_construct_points_count"] = np.array([len(cp)])            # 2400, v3_T25_sigma3_dense.csv:2

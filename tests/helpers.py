@@ -161,3 +161,32 @@ def assert_columns_close(got, want, rtol: float, afrac: float, cols=None) -> Non
     for j in (range(want.shape[1]) if cols is None else cols):
         np.testing.assert_allclose(got[:, j], want[:, j], rtol=rtol, atol=afrac * float(np.abs(want[:, j]).max()),
                                    err_msg=f"column {j}")
+
+
+def true_roots_mp(top_row, digits: int = 60) -> np.ndarray:
+    """Roots of x^d - a_1 x^(d-1) - ... - a_d to ~`digits` digits (mpmath Durand-Kerner in extended precision), rounded to
+    complex128: the arbiter between two double-precision solvers on ill-conditioned (clustered) roots."""
+    import mpmath as mp
+    top_row = [float(v) for v in top_row]
+    d = len(top_row)
+    while d > 0 and top_row[d - 1] == 0.0:           # trailing zeros are roots at 0
+        d -= 1
+    nzero = len(top_row) - d
+    with mp.workdps(digits):
+        coeffs = [mp.mpf(1)] + [-mp.mpf(v) for v in top_row[:d]]
+        roots = mp.polyroots(coeffs, maxsteps=500, extraprec=4 * digits) if d > 0 else []
+        out = [complex(r) for r in roots]
+    return np.array(out + [0j] * nzero, dtype=np.complex128)
+
+
+def multiset_distance(a, b) -> float:
+    """Max relative distance after greedy nearest matching of two complex multisets (relative to the b values)."""
+    a = np.asarray(a, dtype=np.complex128).ravel(); b = np.asarray(b, dtype=np.complex128).ravel()
+    assert a.shape == b.shape
+    used = np.zeros(a.size, dtype=bool)
+    worst = 0.0
+    for v in b:
+        dist = np.abs(a - v); dist[used] = np.inf
+        k = int(np.argmin(dist)); used[k] = True
+        worst = max(worst, float(dist[k] / max(abs(v), 1e-300)))
+    return worst

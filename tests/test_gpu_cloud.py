@@ -175,3 +175,19 @@ def test_cloud_fields_int8_rows(gpu):
     assert np.array_equal(c["cloud"][0] + 1j * c["cloud"][1], a["cloud"][:n])
     with pytest.raises(RuntimeError):
         gpu.lucas.cloud_fields(top[:5000], deg[:5000], cloud_out=(cre[:n - 1], cim[:n - 1]))
+
+
+@pytest.mark.parametrize("tag,family", [("lucas", None), ("pell", "pell_like_all_twos")])
+def test_per_n_and_cumulative_stats_golden(gpu, golden, tag, family):
+    """per_n_stats / cumulative_stats (lucas_equipotential_test_v3.py:294-327) as ONE K3 batch + ONE K1d pass, against the
+    rows produced by the reference's own functions (MAX_ITER 3000, n = 2..30): counts exact, order statistics to 1e-9
+    (the roots agree with LAPACK's to 1e-10, the potential is a smooth function of the point)."""
+    cols = ["count", "escaped", "escaped_frac", "g_median", "g_mean", "g_std", "g_p10", "g_p90"]
+    for fn, key, xkey in ((gpu.lucas.per_n_stats, f"per_n_stats_{tag}_2_30_mi3000", "n"),
+                          (gpu.lucas.cumulative_stats, f"cumulative_stats_{tag}_2_30_mi3000", "N")):
+        rows = fn(2, 30, family=family, max_iter=3000, quiet=True)
+        want = golden[key]
+        assert [r[xkey] for r in rows] == list(range(2, 31))
+        got = np.array([[r[c] for c in cols] for r in rows], dtype=np.float64)
+        assert np.array_equal(got[:, :2], want[:, :2])                     # count, escaped
+        np.testing.assert_allclose(got[:, 2:], want[:, 2:], rtol=1e-9, atol=1e-12, equal_nan=True)

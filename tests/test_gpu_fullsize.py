@@ -65,6 +65,7 @@ def test_config5_lucas_cloud_full(gpu, oracle):
     named families x n = 2..25 (known answers), a random sample of the rest is checked by backward
     error and against numpy.linalg.eigvals."""
     from conftest import match_sorted_complex
+    from helpers import multiset_distance, true_roots_mp
     npoly, maxdeg = 10_000_000, 25
     rng = np.random.default_rng(0)
     deg = rng.integers(2, 26, size=npoly).astype(np.int32)
@@ -88,7 +89,7 @@ def test_config5_lucas_cloud_full(gpu, oracle):
             assert match_sorted_complex(vals[k, :kept[k]], ref) < 1e-10
             k += 1
     sample = rng.choice(npoly, size=400, replace=False)
-    loose = 0
+    arbitrated = 0
     for s in sample:
         d = int(deg[s]); lam = 1.0 / vals[s, :d]
         c = np.concatenate([[1.0], -top[s, :d]])
@@ -98,6 +99,11 @@ def test_config5_lucas_cloud_full(gpu, oracle):
             else:
                 be = abs(np.polyval(c[::-1], 1 / r)) / np.polyval(np.abs(c[::-1]), abs(1 / r))
             assert be < 1e-13
-        if match_sorted_complex(lam, oracle.eigvals_toprow(top[s, :d])) > 1e-10:
-            loose += 1
-    assert loose <= 8                                            # clustered roots only (see test_gpu_roots)
+        ref = oracle.eigvals_toprow(top[s, :d])
+        if match_sorted_complex(lam, ref) > 1e-10:
+            # clustered roots: a 60-digit solve arbitrates between the kernel and LAPACK (see test_gpu_roots)
+            truth = true_roots_mp(top[s, :d])
+            e_cuda, e_lapack = multiset_distance(lam, truth), multiset_distance(ref, truth)
+            assert e_cuda <= max(4.0 * e_lapack, 1e-10), (int(s), e_cuda, e_lapack)
+            arbitrated += 1
+    assert arbitrated <= 8

@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 from conftest import match_sorted_complex
+from helpers import multiset_distance, true_roots_mp
 
 pytestmark = pytest.mark.gpu
 
@@ -81,7 +82,7 @@ def test_random_batch_vs_numpy(gpu, oracle):
     vals, kept, iters = gpu.lucas.roots_batched(top, deg)
     assert (iters > 0).all() and (kept == deg).all()
     worst_rel, worst_back = 0.0, 0.0
-    loose = 0
+    arbitrated = []
     for k in range(npoly):
         mine = vals[k, : deg[k]]
         ref = oracle.eigvals_toprow(top[k, : deg[k]])
@@ -89,14 +90,20 @@ def test_random_batch_vs_numpy(gpu, oracle):
         worst_back = max(worst_back, be)
         rel = match_sorted_complex(mine, ref)
         if rel > RTOL_ROOTS:
-            # ill-conditioned (clustered) roots: LAPACK itself is only sqrt(eps)-accurate there;
-            # require that both are backward stable instead
-            loose += 1
-            assert be < 1e-13 and rel < 1e-5
+            # The two double-precision solvers disagree beyond the stated tolerance: clustered (ill-conditioned) roots,
+            # where ANY backward-stable solver is only ~eps^(1/m)-accurate.  A 60-digit solve arbitrates: the CUDA roots
+            # must be as close to the truth as LAPACK's (within a small factor), so the disagreement is LAPACK's
+            # conditioning, not an error of the kernel.
+            truth = true_roots_mp(top[k, : deg[k]])
+            e_cuda, e_lapack = multiset_distance(mine, truth), multiset_distance(ref, truth)
+            arbitrated.append((k, rel, e_cuda, e_lapack))
+            assert be < 1e-13
+            assert e_cuda <= max(4.0 * e_lapack, RTOL_ROOTS), (k, rel, e_cuda, e_lapack)
         else:
             worst_rel = max(worst_rel, rel)
     assert worst_back < 1e-13
-    assert loose < 0.01 * npoly
+    assert len(arbitrated) < 0.01 * npoly           # a handful of clustered cases, each one arbitrated above
+    print("arbitrated (poly, cuda-vs-lapack, cuda-vs-truth, lapack-vs-truth):", arbitrated)
 
 
 def test_invert_filter_and_zero_roots(gpu):

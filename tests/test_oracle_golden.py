@@ -232,3 +232,20 @@ def test_alpha_shape_edges(oracle, golden):
         keep, radius, edges = oracle.alpha_shape_edges(P, S, alpha)
         assert np.array_equal(radius, golden["alpha_radius"])
         assert np.array_equal(np.asarray(edges, dtype=np.int32).reshape(-1, 2), golden[f"alpha_{tag}_edges"])
+
+
+@pytest.mark.parametrize("tag,family", [("lucas", None), ("pell", "pell_like_all_twos")])
+def test_per_n_stats_composition(oracle, golden, tag, family):
+    """The oracle's eigvals + batch_potential composed like per_n_stats / cumulative_stats
+    (lucas_equipotential_test_v3.py:294-327) reproduces the rows of the reference's own functions."""
+    per, cum, acc = [], [], []
+    for n in range(2, 31):
+        top = np.ones(n) if family is None else oracle.family_toprow(family, n)
+        inv = oracle.inverse_eigenvalues_toprow(top, 1e-12)
+        acc.append(inv)
+        for rows, pts in ((per, inv), (cum, np.concatenate(acc))):
+            g, _, _ = oracle.batch_potential(pts, 3000, 2.0)
+            o = g > 0
+            rows.append([len(g), o.sum(), o.mean(), np.median(g[o]), np.mean(g[o]), np.std(g[o]), np.quantile(g[o], 0.1), np.quantile(g[o], 0.9)])
+    np.testing.assert_allclose(np.array(per, dtype=float), golden[f"per_n_stats_{tag}_2_30_mi3000"], rtol=1e-12, atol=0)
+    np.testing.assert_allclose(np.array(cum, dtype=float), golden[f"cumulative_stats_{tag}_2_30_mi3000"], rtol=1e-12, atol=0)
