@@ -141,7 +141,13 @@ __device__ __forceinline__ double field_value(double zr, double zi, int iters, b
     if (FM == LM_FIELD_GREEN) {
         // lucas_equipotential_test_v3.py:142-149: Re(log z) * exp2(-k), clamp
         if (!escaped) return 0.0;
-        double g = __dmul_rn(log(hypot(zr, zi)), scalbn(1.0, -iters));
+        // log|z| as log(zr^2 + zi^2) / 2: at the first escape |z|^2 <= (R^2 + |c|)^2, so nothing overflows and the
+        // ~35 instructions of hypot() are saved in this divergent path (only the retiring lanes run it); the value
+        // differs from log(hypot()) by < 3e-16 relative (|z|^2 > R^2 keeps the logarithm away from 0), well inside the
+        // 5e-15 parity bar of this field.  Escape radii near 1 (logarithm near 0) and huge ones (|z|^2 > 1e300) take hypot.
+        const double m2 = fma(zr, zr, zi * zi);
+        const double lg = (m2 >= 2.0 && m2 < 1e300) ? 0.5 * log(m2) : log(hypot(zr, zi));
+        double g = __dmul_rn(lg, scalbn(1.0, -iters));
         if (!(g >= 0.0) || isinf(g)) g = 0.0;
         return g;
     } else if (FM == LM_FIELD_POW2_ALWAYS) {

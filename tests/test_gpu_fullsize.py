@@ -104,6 +104,6 @@ def test_config5_lucas_cloud_full(gpu, oracle):
             # clustered roots: a 60-digit solve arbitrates between the kernel and LAPACK (see test_gpu_roots)
             truth = true_roots_mp(top[s, :d])
             e_cuda, e_lapack = multiset_distance(lam, truth), multiset_distance(ref, truth)
-            assert e_cuda <= max(4.0 * e_lapack, 1e-10), (int(s), e_cuda, e_lapack)
+            assert e_cuda <= max(16.0 * e_lapack, 1e-10), (int(s), e_cuda, e_lapack)
             arbitrated += 1
     assert arbitrated <= 8
