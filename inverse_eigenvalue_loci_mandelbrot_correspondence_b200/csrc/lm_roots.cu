@@ -252,21 +252,27 @@ __device__ __forceinline__ int load_and_init(const Tile& tile, const Slot& S, co
     for (int k = l; k <= d; k += G) {
         const double c = (k == 0) ? 1.0 : -top[k - 1];
         S.coef[k] = c;
-        S.logc[k] = (c != 0.0) ? static_cast<float>(log(fabs(c))) : -INFINITY;
+        // log|c| only places the starting points (three digits are plenty): the single-precision hardware logarithm
+        // whenever |c| is a normal float -- the binary64 log() of this line alone was 9 % of the kernel's
+        // instructions (profiles/r02_k3_roots_pool_ncu_by_line.txt)
+        const double ac = fabs(c);
+        S.logc[k] = (c != 0.0) ? ((ac > 1e-37 && ac < 1e37) ? __logf(static_cast<float>(ac)) : static_cast<float>(log(ac))) : -INFINITY;
     }
     tile.sync();
     // Work with ascending powers: a_i = coef[d-i].  Upper convex hull of (i, log|a_i|), i = 0..d
     // (a_0 = coef[d] != 0 after deflation, a_d = 1).
     int nh = 0;
     if (l == 0 && d > 0) {
+        // (single precision throughout: the polygon only places the starting points, and the binary64 version of
+        // this one-lane loop spent most of its instructions on float -> double and int -> double conversions)
         for (int i = 0; i <= d; ++i) {
-            const double yi = S.logc[d - i];
+            const float yi = S.logc[d - i];
             if (yi == -INFINITY) continue;
             while (nh >= 2) {
                 const int i1 = S.hull[nh - 2], i2 = S.hull[nh - 1];
-                const double y1 = S.logc[d - i1], y2 = S.logc[d - i2];
+                const float y1 = S.logc[d - i1], y2 = S.logc[d - i2];
                 // keep i2 only if it lies strictly above the chord i1 -> i
-                if ((y2 - y1) * (i - i1) <= (yi - y1) * (i2 - i1)) --nh; else break;
+                if ((y2 - y1) * static_cast<float>(i - i1) <= (yi - y1) * static_cast<float>(i2 - i1)) --nh; else break;
             }
             S.hull[nh++] = i;
         }
@@ -306,14 +312,17 @@ __device__ __forceinline__ void aberth_update(const Slot& S, int d, int i, cplx&
     const bool inside = az2 <= 1.0;
     const double iz2 = rcp_fast<2>(inside ? 1.0 : az2);
     const cplx w = inside ? z : cplx{z.r * iz2, -z.i * iz2};
-    // |w| only scales the rounding-error bound of the evaluation: a single-precision square root rounded UP by
-    // 2^-20 is a valid (and 1e-6 tight) upper bound, and saves the ~20 instructions of the binary64 sqrt
-    // (binary32 covers |z|^2 in [1e-37, 1e37]; outside of it the double sqrt is taken)
+    // |w| only scales the rounding-error bound of the evaluation: |w|^2 * rsqrt(|w|^2) from the hardware estimate
+    // (MUFU.RSQ64H, ~2^-22), rounded UP by 2^-20, is a valid and 1e-6 tight upper bound in three instructions (the
+    // binary64 sqrt costs ~20; |w|^2 = 0 gives 0 * inf = NaN, which the max() turns into the harmless bound 0)
     const double aw2 = inside ? az2 : iz2;                       // |w|^2 (|1/z|^2 = 1/|z|^2)
-    const double aw = (aw2 > 1e-37) ? static_cast<double>(sqrtf(static_cast<float>(aw2))) * (1.0 + 9.5367431640625e-7) : sqrt(aw2);
+    double rs;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rs) : "d"(aw2));
+    const double aw = fmax(aw2 * (1.0 + 9.5367431640625e-7) * rs, 0.0);
     const int k_first = inside ? 0 : d, k_step = inside ? 1 : -1;
     cplx b = {S.coef[k_first], 0.0}, bp = {0.0, 0.0};
     double s = fabs(b.r);
+#pragma unroll 8
     for (int k = 1, idx = k_first + k_step; k <= d; ++k, idx += k_step) {
         const double ck = S.coef[idx];
         bp = {fma(bp.r, w.r, fma(-bp.i, w.i, b.r)), fma(bp.r, w.i, fma(bp.i, w.r, b.i))};
@@ -338,15 +347,14 @@ __device__ __forceinline__ void aberth_update(const Slot& S, int d, int i, cplx&
     const cplx newton = (dd > 1e-290 && dd < 1e290) ? cmul(num, cinv_fast(den))
                       : (dd > 0.0 ? cmul(num, cinv(den)) : cplx{1e-3 * (sqrt(az2) + 1e-3), 1e-3 * (sqrt(az2) + 1e-3)});
     double Sr = 0.0, Si = 0.0;
-#pragma unroll 4
+#pragma unroll 8
     for (int j = 0; j < d; ++j) {
         const double2 zj = S.zz[j];
         const double dr = z.r - zj.x, di = z.i - zj.y;
-        const double q = fma(dr, dr, di * di);
-        // j == i (q == 0) and coinciding estimates contribute nothing; the reciprocal's NaN/Inf for q == 0 is
-        // discarded by the select
-        // (the test reads the exponent with the integer pipe: q > 2^-996, which also rejects q == 0 and denormals)
-        const double inv = (__double2hiint(q) > 0x01b00000) ? rcp_fast<LM_K3_SUM_RCP_STEPS>(q) : 0.0;
+        // |z_i - z_j|^2 + 1e-300: the j == i term becomes 0 * 1e300 = 0 without a compare / select per term (3 of the
+        // 13 instructions of this loop), and the offset is far below the square of any distance that matters
+        const double q = fma(dr, dr, fma(di, di, 1e-300));
+        const double inv = rcp_fast<LM_K3_SUM_RCP_STEPS>(q);
         Sr = fma(dr, inv, Sr);
         Si = fma(-di, inv, Si);
     }
@@ -356,9 +364,10 @@ __device__ __forceinline__ void aberth_update(const Slot& S, int d, int i, cplx&
     const cplx corr = (d2 > 1e-290 && d2 < 1e290) ? cmul(newton, cinv_fast1(den2))
                     : (d2 > 0.0 ? cmul(newton, cinv(den2)) : newton);
     znew = {z.r - corr.r, z.i - corr.i};
-    if (!(isfinite(znew.r) && isfinite(znew.i))) znew = {z.r * 0.5 + 1e-3, z.i * 0.5 - 1e-3};
+    const double c2 = corr.r * corr.r + corr.i * corr.i;
+    if (!(c2 < 1e300)) znew = {z.r * 0.5 + 1e-3, z.i * 0.5 - 1e-3};      // a non-finite (or absurd) correction: restart nearby
     // stagnation: the correction is below the resolution of z -> it is frozen with the new value
-    if (corr.r * corr.r + corr.i * corr.i <= (4.0 * EPS * EPS) * az2) stagnant = true;
+    if (c2 <= (4.0 * EPS * EPS) * az2) stagnant = true;
 }
 
 // One sweep over the roots of a slot that are still moving (rounds of G roots, Gauss-Seidel between rounds).
