@@ -454,6 +454,16 @@ int32_t lm_curvature_localpoly(const double* x, const double* y, int64_t n, int3
 int32_t lm_pair_histogram(const double* x, const double* y, const double* value, int64_t n,
                           const double* lo, const double* hi, int32_t nbins, int32_t weight_mode,
                           uint64_t* counts, double* sums, lm_stats* stats);
+/* The (v_i - w_j)^2 of the pairs (i in A, j in B) whose distance lies in [lo, hi), in row-major order of (i, j):
+ * dV2[np.where((D >= lo) & (D < hi) & ~diag)] of sample_semivariogram / sample_cross_semivariogram,
+ * variograms_construct_mandelbrot.py:178-315 -- needed for the one block per bin in which the reference draws a random
+ * subset of exactly this list (max_pairs_per_bin); all other blocks only need counts and sums (lm_pair_histogram).
+ * skip_diagonal != 0 drops the pairs with i == j (a block of a set against itself).  LM_E_CAP with *n_values set when
+ * `values` is too small.                                                                                       */
+int32_t lm_pair_select_sqdiff(const double* xa, const double* ya, const double* va, int64_t na,
+                              const double* xb, const double* yb, const double* vb, int64_t nb,
+                              double lo, double hi, int32_t skip_diagonal,
+                              double* values, int64_t cap_values, int64_t* n_values, lm_stats* stats);
 /* *dmax = max_{i<j} d_ij: the D.max() behind the default max_dist = 0.5 * D.max()
  * (Variogram-Mandelbrot-Construct.py:118-119, Iterative_Variogram_Laplacian.py:60-61).  0 for n < 2.          */
 int32_t lm_pair_max_distance(const double* x, const double* y, int64_t n, double* dmax, lm_stats* stats);

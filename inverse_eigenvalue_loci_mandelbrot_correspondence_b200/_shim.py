@@ -35,7 +35,7 @@ EXPORTS = (
     "lm_laplacian5_periodic", "lm_laplacian5_periodic_dev", "lm_smooth5_interior", "lm_smooth5_interior_dev",
     "lm_log_potential", "lm_log_potential_sums_dev", "lm_log_potential_finish_dev",
     "lm_nearest_match", "lm_weighted_log_sum", "lm_weighted_cauchy_sum", "lm_curvature_localpoly",
-    "lm_pair_histogram", "lm_pair_max_distance", "lm_alpha_shape_edges",
+    "lm_pair_histogram", "lm_pair_select_sqdiff", "lm_pair_max_distance", "lm_alpha_shape_edges",
     "lm_histogram2d", "lm_mollified_histogram", "lm_gaussian_filter_nearest", "lm_sum_pairwise", "lm_density_compare", "lm_gi_flow",
     "lm_probe_fp64_peak", "lm_probe_fp64_latency", "lm_probe_k1_loop", "lm_probe_hbm_copy",
 )
@@ -132,6 +132,7 @@ _SIGNATURES = {
     "lm_curvature_localpoly": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _pStats]),
     "lm_pair_histogram": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _pStats]),
     "lm_pair_max_distance": (_i32, [_vp, _vp, _i64, C.POINTER(C.c_double), _pStats]),
+    "lm_pair_select_sqdiff": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _f64, _f64, _i32, _vp, _i64, _pi64, _pStats]),
     "lm_histogram2d": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp, _i32, _vp, _pStats]),
     "lm_mollified_histogram": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp, _i32, _f64, _vp, _i32, _vp, _pStats]),
     "lm_gaussian_filter_nearest": (_i32, [_vp, _i64, _i64, _vp, _i32, _vp, _pStats]),

@@ -735,13 +735,23 @@ int32_t grid_host_begin(const double* xs, int64_t nx, const double* ys, int64_t 
     LM_JOB_TRY(cudaEventCreate(&job->ev_end));
     LM_JOB_TRY(cudaEventRecord(job->ev_begin, s_compute));                 // behind the coordinate uploads and the counter reset
     LM_JOB_TRY(cudaStreamWaitEvent(s_compute2, job->ev_begin, 0));
+    // Order of the chunks: from both ends of the row range towards the middle (0, n-1, 1, n-2, ...).  What remains after
+    // the compute ends is the copy of the chunks that finished last; the outer rows of a window around the set are
+    // the cheap ones (their copy takes longer than their compute), so they go first and the expensive middle chunks,
+    // whose copies hide behind their own compute, go last.  For other windows any order is as good as another.
+    std::vector<int64_t> order;
+    for (int64_t lo_c = 0, hi_c = nchunks - 1; lo_c <= hi_c; ++lo_c, --hi_c) {
+        order.push_back(lo_c);
+        if (hi_c != lo_c) order.push_back(hi_c);
+    }
     int64_t last_on_2 = -1;
-    for (int64_t c = 0; c < nchunks; ++c) {
+    for (size_t t = 0; t < order.size(); ++t) {
+        const int64_t c = order[t];
         const int64_t r0 = c * rows_per_chunk;
         const int64_t rows = (r0 + rows_per_chunk <= ny) ? rows_per_chunk : ny - r0;
-        if (rows <= 0) break;
+        if (rows <= 0) continue;
         const size_t off = static_cast<size_t>(r0) * nx;
-        cudaStream_t sc = (c & 1) ? s_compute2 : s_compute;
+        cudaStream_t sc = (t & 1) ? s_compute2 : s_compute;
         rc = enqueue_grid(static_cast<double*>(dxs), nx, static_cast<double*>(dys) + r0, rows, max_iter, bailout, field_mode,
                           dd ? static_cast<int32_t*>(dd) + off : nullptr, df64 ? static_cast<double*>(df64) + off : nullptr,
                           dfield ? static_cast<double*>(dfield) + off : nullptr, work_dev, overflow_dev, sc);
@@ -749,12 +759,13 @@ int32_t grid_host_begin(const double* xs, int64_t nx, const double* ys, int64_t 
         ++job->launches;
         LM_JOB_TRY(cudaEventCreateWithFlags(&job->ev_chunk[c], cudaEventDisableTiming));
         LM_JOB_TRY(cudaEventRecord(job->ev_chunk[c], sc));
-        if (c & 1) last_on_2 = c;
+        if (t & 1) last_on_2 = c;
     }
     if (last_on_2 >= 0) LM_JOB_TRY(cudaStreamWaitEvent(s_compute, job->ev_chunk[last_on_2], 0));   // join: K2 and ev_end follow on s_compute
     LM_JOB_TRY(cudaEventRecord(job->ev_end, s_compute));
-    for (int64_t c = 0; c < nchunks; ++c) {
-        if (!job->ev_chunk[c]) break;
+    for (size_t t = 0; t < order.size(); ++t) {
+        const int64_t c = order[t];
+        if (!job->ev_chunk[c]) continue;
         const int64_t r0 = c * rows_per_chunk;
         const int64_t rows = (r0 + rows_per_chunk <= ny) ? rows_per_chunk : ny - r0;
         const size_t off = static_cast<size_t>(r0) * nx, cnt = static_cast<size_t>(rows) * nx;

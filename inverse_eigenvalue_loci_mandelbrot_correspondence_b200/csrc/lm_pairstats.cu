@@ -265,6 +265,59 @@ unsigned launch_hist_mode(int weight_mode, const TileGrid& g, size_t smem, cudaS
     return launch_hist<LM_PAIR_W_DIST_SQ, PARTITION>(g, smem, s, a);
 }
 
+
+// ---------------------------------------------------------------------------------------
+// ordered selection: the (v_i - w_j)^2 of the pairs (i in A, j in B) whose distance falls into ONE bin, in row-major
+// order of (i, j) -- what dV2[np.where(m)] is in sample_semivariogram / sample_cross_semivariogram
+// (variograms_construct_mandelbrot.py:178-315) for the one block in which a bin crosses its max_pairs_per_bin cap and
+// the reference draws a random subset of exactly this list.  Distances are sqrt_rn(dx*dx + dy*dy) (np.linalg.norm
+// over the last axis) compared like the reference's mask (D >= lo) & (D < hi).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ bool pair_in_bin(double xa, double ya, double xb, double yb, double lo, double hi) {
+    const double dx = __dsub_rn(xa, xb), dy = __dsub_rn(ya, yb);
+    const double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+    return d >= lo && d < hi;
+}
+
+// one warp per row i of A: number of selected j
+__global__ void __launch_bounds__(256) pair_select_count_kernel(const double* __restrict__ xa, const double* __restrict__ ya, int na,
+                                                                const double* __restrict__ xb, const double* __restrict__ yb, int nb,
+                                                                double lo, double hi, int skip_diag, unsigned* __restrict__ row_count) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= na) return;
+    const double x = xa[i], y = ya[i];
+    unsigned c = 0;
+    for (int j = lane; j < nb; j += 32)
+        if (!(skip_diag && j == i) && pair_in_bin(x, y, xb[j], yb[j], lo, hi)) ++c;
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) row_count[i] = c;
+}
+
+// one warp per row: the selected values at row_offset[i] .. in ascending j (ballot compaction keeps the order)
+__global__ void __launch_bounds__(256) pair_select_write_kernel(const double* __restrict__ xa, const double* __restrict__ ya,
+                                                                const double* __restrict__ va, int na,
+                                                                const double* __restrict__ xb, const double* __restrict__ yb,
+                                                                const double* __restrict__ vb, int nb, double lo, double hi,
+                                                                int skip_diag, const unsigned long long* __restrict__ row_offset,
+                                                                double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= na) return;
+    const double x = xa[i], y = ya[i], v = va[i];
+    unsigned long long pos = row_offset[i];
+    for (int j0 = 0; j0 < nb; j0 += 32) {
+        const int j = j0 + lane;
+        const bool sel = j < nb && !(skip_diag && j == i) && pair_in_bin(x, y, xb[j], yb[j], lo, hi);
+        const unsigned bal = __ballot_sync(0xffffffffu, sel);
+        if (sel) {
+            const double dv = __dsub_rn(v, vb[j]);
+            out[pos + __popc(bal & ((1u << lane) - 1u))] = __dmul_rn(dv, dv);
+        }
+        pos += __popc(bal);
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -390,6 +443,65 @@ int32_t lm_pair_max_distance(const double* x, const double* y, int64_t n, double
         stats->kernel_ms = ms;
         stats->launches = 1;
     }
+    return LM_OK;
+}
+
+
+int32_t lm_pair_select_sqdiff(const double* xa, const double* ya, const double* va, int64_t na,
+                              const double* xb, const double* yb, const double* vb, int64_t nb,
+                              double lo, double hi, int32_t skip_diagonal,
+                              double* values, int64_t cap_values, int64_t* n_values, lm_stats* stats) {
+    int32_t rc = lm::require_device();
+    if (rc != LM_OK) return rc;
+    LM_REQUIRE(na >= 0 && nb >= 0 && na < (1 << 30) && nb < (1 << 30) && cap_values >= 0 && n_values, "lm_pair_select_sqdiff: bad sizes");
+    LM_REQUIRE((na == 0 || (xa && ya && va)) && (nb == 0 || (xb && yb && vb)), "lm_pair_select_sqdiff: NULL buffer");
+    if (stats) *stats = lm_stats{};
+    *n_values = 0;
+    if (na == 0 || nb == 0) return LM_OK;
+    cudaStream_t s = nullptr;
+    void *da, *db, *dcnt, *doff, *dout = nullptr;
+    if ((rc = lm::ws_get(lm::WS_IN_A, static_cast<size_t>(na) * 3 * sizeof(double), &da)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_IN_B, static_cast<size_t>(nb) * 3 * sizeof(double), &db)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_OUT_A, static_cast<size_t>(na) * sizeof(unsigned), &dcnt)) != LM_OK) return rc;
+    if ((rc = lm::ws_get(lm::WS_OUT_B, static_cast<size_t>(na) * sizeof(unsigned long long), &doff)) != LM_OK) return rc;
+    double* A = static_cast<double*>(da); double* B = static_cast<double*>(db);
+    LM_CUDA_TRY(cudaMemcpyAsync(A, xa, na * sizeof(double), cudaMemcpyHostToDevice, s));
+    LM_CUDA_TRY(cudaMemcpyAsync(A + na, ya, na * sizeof(double), cudaMemcpyHostToDevice, s));
+    LM_CUDA_TRY(cudaMemcpyAsync(A + 2 * na, va, na * sizeof(double), cudaMemcpyHostToDevice, s));
+    LM_CUDA_TRY(cudaMemcpyAsync(B, xb, nb * sizeof(double), cudaMemcpyHostToDevice, s));
+    LM_CUDA_TRY(cudaMemcpyAsync(B + nb, yb, nb * sizeof(double), cudaMemcpyHostToDevice, s));
+    LM_CUDA_TRY(cudaMemcpyAsync(B + 2 * nb, vb, nb * sizeof(double), cudaMemcpyHostToDevice, s));
+    lm::Timer tm;
+    if ((rc = tm.begin(s)) != LM_OK) return rc;
+    const unsigned blocks = static_cast<unsigned>((na + 7) / 8);
+    pair_select_count_kernel<<<blocks, 256, 0, s>>>(A, A + na, static_cast<int>(na), B, B + nb, static_cast<int>(nb), lo, hi,
+                                                    skip_diagonal != 0, static_cast<unsigned*>(dcnt));
+    LM_CUDA_TRY(cudaGetLastError());
+    std::vector<unsigned> cnt(static_cast<size_t>(na));
+    LM_CUDA_TRY(cudaMemcpyAsync(cnt.data(), dcnt, static_cast<size_t>(na) * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    LM_CUDA_TRY(cudaStreamSynchronize(s));
+    std::vector<unsigned long long> off(static_cast<size_t>(na));
+    unsigned long long total = 0;
+    for (int64_t i = 0; i < na; ++i) { off[static_cast<size_t>(i)] = total; total += cnt[static_cast<size_t>(i)]; }   // 4000-row blocks: a host scan
+    *n_values = static_cast<int64_t>(total);
+    if (static_cast<int64_t>(total) > cap_values)
+        return lm::fail(LM_E_CAP, "lm_pair_select_sqdiff: %llu pairs selected, room for %lld", total, static_cast<long long>(cap_values));
+    if (total) {
+        LM_REQUIRE(values != nullptr, "lm_pair_select_sqdiff: values is NULL");
+        if ((rc = lm::ws_get(lm::WS_OUT_C, static_cast<size_t>(total) * sizeof(double), &dout)) != LM_OK) return rc;
+        LM_CUDA_TRY(cudaMemcpyAsync(doff, off.data(), static_cast<size_t>(na) * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+        pair_select_write_kernel<<<blocks, 256, 0, s>>>(A, A + na, A + 2 * na, static_cast<int>(na), B, B + nb, B + 2 * nb,
+                                                        static_cast<int>(nb), lo, hi, skip_diagonal != 0,
+                                                        static_cast<unsigned long long*>(doff), static_cast<double*>(dout));
+        LM_CUDA_TRY(cudaGetLastError());
+    }
+    float ms = 0.f;
+    if ((rc = tm.end(s, &ms)) != LM_OK) return rc;
+    if (total) {
+        LM_CUDA_TRY(cudaMemcpyAsync(values, dout, static_cast<size_t>(total) * sizeof(double), cudaMemcpyDeviceToHost, s));
+        LM_CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    if (stats) { stats->items = static_cast<uint64_t>(na) * static_cast<uint64_t>(nb); stats->work_units = total; stats->kernel_ms = ms; stats->launches = total ? 2 : 1; }
     return LM_OK;
 }
 

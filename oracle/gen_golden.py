@@ -117,6 +117,26 @@ def main() -> None:
     vg = load_defs("variograms_construct_mandelbrot.py",
                    ["Grid", "make_grid", "log_potential_from_points", "mandelbrot_escape_potential",
                     "mandelbrot_distance_estimator"])
+    # ---- sub-sampled semivariograms (variograms_construct_mandelbrot.py:178-315) with a seeded global stream:
+    # an 84 x 80 grid (6720 pixels -> two chunks of 4000 / 2720 sampled points, three blocks) and caps that some
+    # bins reach and others do not, so that both the "take all" and the "draw a subset" branches are recorded
+    sv = load_defs("variograms_construct_mandelbrot.py",
+                   ["Grid", "make_grid", "sample_semivariogram", "sample_cross_semivariogram"])
+    sgrid = sv["make_grid"](-2.0, 1.0, -1.4, 1.4, 84, 80)
+    rng_f = np.random.default_rng(2024)
+    f1 = np.sin(3.0 * sgrid.X) * np.cos(2.0 * sgrid.Y) + 0.1 * rng_f.standard_normal(sgrid.X.shape)
+    f2 = np.cos(1.5 * sgrid.X + 0.3) * np.sin(2.5 * sgrid.Y) + 0.1 * rng_f.standard_normal(sgrid.X.shape)
+    g["semivario_field1"] = f1; g["semivario_field2"] = f2
+    g["semivario_grid_args"] = np.array([-2.0, 1.0, -1.4, 1.4, 84, 80], dtype=np.float64)
+    for tag, bins, cap in (("a", np.linspace(0.0, 2.0, 21), 20000), ("b", np.linspace(0.05, 3.5, 13), 150000)):
+        g[f"semivario_{tag}_bins"] = bins
+        g[f"semivario_{tag}_cap"] = np.array([cap])
+        np.random.seed(777)
+        rc, gam = sv["sample_semivariogram"](f1, sgrid, bins, max_pairs_per_bin=cap)
+        g[f"semivario_{tag}_centers"] = rc; g[f"semivario_{tag}_gamma"] = gam
+        np.random.seed(778)
+        rc, gam = sv["sample_cross_semivariogram"](f1, f2, sgrid, bins, max_pairs_per_bin=cap)
+        g[f"semivario_{tag}_cross_gamma"] = gam
     grid = vg["make_grid"](-2.25, 1.25, -1.75, 1.75, 30, 27)
     g["vario_grid_x"] = grid.x; g["vario_grid_y"] = grid.y
     g["vario_escape_potential_mi90"] = vg["mandelbrot_escape_potential"](grid, max_iter=90, R=4.0)

@@ -126,3 +126,43 @@ def test_tracker_cloud_full_size(ps):
     dx = P[:sub, None, 0] - P[None, :, 0]; dy = P[:sub, None, 1] - P[None, :, 1]
     D = np.sqrt(dx * dx + dy * dy)
     assert D.max() <= dmax
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_subsampled_semivariograms_golden(gpu, golden, tag):
+    """sample_semivariogram / sample_cross_semivariogram (variograms_construct_mandelbrot.py:178-315) with the seeded
+    global stream the reference was run with: per-block bin counts / sums from lm_pair_histogram, the ordered pair list
+    of the block that crosses a bin's cap from lm_pair_select_sqdiff, the reference's own np.random.choice draws on the
+    host.  gamma to 1e-12 against the reference's output (counts are exact, or the subsets would differ)."""
+    import types
+    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import pairstats
+    x0, x1, y0, y1, nx, ny = golden["semivario_grid_args"]
+    X, Y = np.meshgrid(np.linspace(x0, x1, int(nx)), np.linspace(y0, y1, int(ny)), indexing="xy")
+    grid = types.SimpleNamespace(X=X, Y=Y)
+    bins = golden[f"semivario_{tag}_bins"]; cap = int(golden[f"semivario_{tag}_cap"][0])
+    np.random.seed(777)
+    rc, gam = pairstats.sample_semivariogram(golden["semivario_field1"], grid, bins, max_pairs_per_bin=cap)
+    assert np.array_equal(rc, golden[f"semivario_{tag}_centers"])
+    np.testing.assert_allclose(gam, golden[f"semivario_{tag}_gamma"], rtol=1e-12, atol=0)
+    np.random.seed(778)
+    rc, gam = pairstats.sample_cross_semivariogram(golden["semivario_field1"], golden["semivario_field2"], grid, bins,
+                                                   max_pairs_per_bin=cap)
+    np.testing.assert_allclose(gam, golden[f"semivario_{tag}_cross_gamma"], rtol=1e-12, atol=0)
+
+
+def test_pair_select_matches_numpy(gpu):
+    """lm_pair_select_sqdiff: row-major order, diagonal exclusion, edge-inclusive lower bound (3-4-5 lattice)."""
+    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import pairstats
+    rng = np.random.default_rng(3)
+    xa = rng.integers(0, 12, 300).astype(float); ya = rng.integers(0, 12, 300).astype(float); va = rng.standard_normal(300)
+    xb = rng.integers(0, 12, 257).astype(float); yb = rng.integers(0, 12, 257).astype(float); vb = rng.standard_normal(257)
+    for lo, hi in ((5.0, 6.0), (0.0, 1.0), (4.999999, 5.0), (13.0, 1e9)):
+        D = np.sqrt((xa[:, None] - xb[None, :]) ** 2 + (ya[:, None] - yb[None, :]) ** 2)
+        m = (D >= lo) & (D < hi)
+        want = ((va[:, None] - vb[None, :]) ** 2)[np.where(m)]
+        got = pairstats._select_sqdiff((xa, ya, va), (xb, yb, vb), lo, hi, False, int(m.sum()))
+        assert np.array_equal(got, want)
+    D = np.sqrt((xa[:, None] - xa[None, :]) ** 2 + (ya[:, None] - ya[None, :]) ** 2)
+    m = (D >= 0.0) & (D < 2.0) & ~np.eye(300, dtype=bool)
+    got = pairstats._select_sqdiff((xa, ya, va), (xa, ya, va), 0.0, 2.0, True, int(m.sum()))
+    assert np.array_equal(got, ((va[:, None] - va[None, :]) ** 2)[np.where(m)])
