@@ -452,7 +452,8 @@ def grid_leg(cx: Ctx, name: str, steps: int, warmup: int, want_e2e: bool, refine
         xs_p = _shim.pinned_empty(nx, np.float64); xs_p[:] = xs
         ys_p = _shim.pinned_empty(rows, np.float64); ys_p[:] = ys[r0:r1]
         pot_p = _shim.pinned_empty((rows, nx), np.float64) if with_pot else None
-        job = sharding.ShardedBoundary(xs, ys, max_iter, level, device=dev, with_potential=with_pot, cuts=cuts) if world > 1 else None
+        job = (sharding.ShardedBoundary(xs, ys, max_iter, level, device=dev, with_potential=with_pot, cuts=cuts, profile=plan["profile"])
+               if world > 1 else None)
 
         def e2e_step():
             if world == 1:
@@ -493,6 +494,7 @@ def grid_leg(cx: Ctx, name: str, steps: int, warmup: int, want_e2e: bool, refine
                       "boundary_vertices": int(lines.lengths().max()) if lines is not None and len(lines) else 0,
                       "boundary_sha256": lines_digest(lines.verts, lines.offsets) if lines is not None else None,
                       "host_dwell_matches_device": bool(int(host_crc[0]) == int(dev_crc[0])),
+                      "phases_ms_rank0_last_step": (job.last_phases_ms if job else None),
                       "api": ("lm_boundary_sample (pinned numpy buffers in, dwell grid + ordered boundary polylines out)" if world == 1 else
                               "sharding.ShardedBoundary.run: lm_shard_escape (pinned numpy buffers; block kept in HBM) + NCCL edge rows + "
                               "lm_contour_records_dev + NCCL send of the records to rank 0 + lm_contour_link_dev")}

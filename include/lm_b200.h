@@ -176,9 +176,12 @@ int32_t lm_escape_grid_f64_dev(const double* xs, int64_t nx, const double* ys, i
  * lm_contour_classify_dev on it, so nothing is uploaded twice.  With potential != NULL the same pass
  * also produces the smooth potential (LM_FIELD_GREEN) of the shard's rows: returned to the host
  * buffer and kept in HBM (*potential_dev_out, [ny] x nx) for the all-gather of the final field.
+ * row_cost (may be NULL): ny estimates of the rows' relative cost -- the profile the shards were cut with; the
+ * row chunks are then computed cheapest first, so that the chunks finishing last are the ones whose copy to
+ * the host hides behind their own compute.
  */
 int32_t lm_shard_escape(const double* xs, int64_t nx, const double* ys, int64_t ny, int32_t max_iter,
-                        int32_t* dwell_i32, double* potential, int64_t halo_rows,
+                        int32_t* dwell_i32, double* potential, int64_t halo_rows, const double* row_cost,
                         int32_t** dwell_dev_out, double** potential_dev_out, lm_stats* stats);
 
 /* Optional single-precision variant of the dwell grid (BASELINE.json north_star, piece 1; no reference

@@ -94,7 +94,7 @@ _SIGNATURES = {
     "lm_memcpy_d2h": (_i32, [_vp, _vp, _sz, _vp]),
     "lm_memcpy_d2d": (_i32, [_vp, _vp, _sz, _vp]),
     "lm_stream_synchronize": (_i32, [_vp]),
-    "lm_shard_escape": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _i64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _pStats]),
+    "lm_shard_escape": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _i64, _vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _pStats]),
     "lm_escape_grid_f64": (_i32, [_vp, _i64, _vp, _i64, _i32, _f64, _i32, _vp, _vp, _vp, _pStats]),
     "lm_escape_grid_f64_dev": (_i32, [_vp, _i64, _vp, _i64, _i32, _f64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "lm_escape_grid_f32": (_i32, [_vp, _i64, _vp, _i64, _i32, _f64, _vp, _pStats]),

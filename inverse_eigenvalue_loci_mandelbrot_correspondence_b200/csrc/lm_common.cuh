@@ -78,7 +78,7 @@ struct GridHostJob {
 };
 int32_t grid_host_begin(const double* xs, int64_t nx, const double* ys, int64_t ny, int32_t max_iter, double bailout,
                         int32_t field_mode, int32_t* dwell_i32, double* dwell_f64, double* field,
-                        bool need_dev_dwell, int64_t extra_rows, GridHostJob* job);
+                        bool need_dev_dwell, int64_t extra_rows, GridHostJob* job, const double* row_cost = nullptr);
 int32_t grid_host_finish(GridHostJob* job, lm_stats* stats);
 // K2 on a device-resident dwell grid -> polylines in host buffers (lm_contour.cu + lm_contour_link.cu); enqueues
 // on s and synchronises s for the record count and the line sizes.

@@ -36,9 +36,11 @@
 // the kernel (lm_stats.work_units).
 #include "lm_common.cuh"
 
+#include <algorithm>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <utility>
 #include <vector>
 
 namespace {
@@ -679,7 +681,7 @@ void GridHostJob::release_events() {
 // ramps and tails on the 32768^2 grid (626 ms against 611 ms for one launch).
 int32_t grid_host_begin(const double* xs, int64_t nx, const double* ys, int64_t ny, int32_t max_iter, double bailout,
                         int32_t field_mode, int32_t* dwell_i32, double* dwell_f64, double* field,
-                        bool need_dev_dwell, int64_t extra_rows, GridHostJob* job) {
+                        bool need_dev_dwell, int64_t extra_rows, GridHostJob* job, const double* row_cost) {
     int32_t rc;
     const size_t npx = static_cast<size_t>(nx) * static_cast<size_t>(ny);
     job->npx = npx;
@@ -735,14 +737,27 @@ int32_t grid_host_begin(const double* xs, int64_t nx, const double* ys, int64_t 
     LM_JOB_TRY(cudaEventCreate(&job->ev_end));
     LM_JOB_TRY(cudaEventRecord(job->ev_begin, s_compute));                 // behind the coordinate uploads and the counter reset
     LM_JOB_TRY(cudaStreamWaitEvent(s_compute2, job->ev_begin, 0));
-    // Order of the chunks: from both ends of the row range towards the middle (0, n-1, 1, n-2, ...).  What remains after
-    // the compute ends is the copy of the chunks that finished last; the outer rows of a window around the set are
-    // the cheap ones (their copy takes longer than their compute), so they go first and the expensive middle chunks,
-    // whose copies hide behind their own compute, go last.  For other windows any order is as good as another.
+    // Order of the chunks.  What remains after the compute ends is the copy of the chunks that finished last, so the
+    // cheap chunks (their copy takes longer than their compute) should go first and the expensive ones, whose copies
+    // hide behind their own compute, last.  With a per-row cost estimate from the caller (the row profile the shards
+    // were cut with) the chunks are sorted by ascending estimated cost; without one they are taken from both ends of
+    // the row range towards the middle (0, n-1, 1, n-2, ...), which is that order for a window around the set.
     std::vector<int64_t> order;
-    for (int64_t lo_c = 0, hi_c = nchunks - 1; lo_c <= hi_c; ++lo_c, --hi_c) {
-        order.push_back(lo_c);
-        if (hi_c != lo_c) order.push_back(hi_c);
+    if (row_cost) {
+        std::vector<std::pair<double, int64_t>> est;
+        for (int64_t c = 0; c < nchunks; ++c) {
+            const int64_t r0 = c * rows_per_chunk, r1 = (r0 + rows_per_chunk <= ny) ? r0 + rows_per_chunk : ny;
+            double w = 0.0;
+            for (int64_t r = r0; r < r1; ++r) w += row_cost[r];
+            if (r1 > r0) est.emplace_back(w, c);
+        }
+        std::stable_sort(est.begin(), est.end(), [](const std::pair<double, int64_t>& a, const std::pair<double, int64_t>& b) { return a.first < b.first; });
+        for (const auto& e : est) order.push_back(e.second);
+    } else {
+        for (int64_t lo_c = 0, hi_c = nchunks - 1; lo_c <= hi_c; ++lo_c, --hi_c) {
+            order.push_back(lo_c);
+            if (hi_c != lo_c) order.push_back(hi_c);
+        }
     }
     int64_t last_on_2 = -1;
     for (size_t t = 0; t < order.size(); ++t) {
@@ -884,13 +899,13 @@ int32_t lm_escape_grid_f64(const double* xs, int64_t nx, const double* ys, int64
     if (stats) *stats = lm_stats{};
     if (nx == 0 || ny == 0) return LM_OK;
     lm::GridHostJob job;
-    rc = lm::grid_host_begin(xs, nx, ys, ny, max_iter, bailout, field_mode, dwell_i32, dwell_f64, field, false, 0, &job);
+    rc = lm::grid_host_begin(xs, nx, ys, ny, max_iter, bailout, field_mode, dwell_i32, dwell_f64, field, false, 0, &job, nullptr);
     if (rc != LM_OK) return rc;
     return lm::grid_host_finish(&job, stats);
 }
 
 int32_t lm_shard_escape(const double* xs, int64_t nx, const double* ys, int64_t ny, int32_t max_iter,
-                        int32_t* dwell_i32, double* potential, int64_t halo_rows,
+                        int32_t* dwell_i32, double* potential, int64_t halo_rows, const double* row_cost,
                         int32_t** dwell_dev_out, double** potential_dev_out, lm_stats* stats) {
     int32_t rc = lm::require_device();
     if (rc != LM_OK) return rc;
@@ -903,7 +918,7 @@ int32_t lm_shard_escape(const double* xs, int64_t nx, const double* ys, int64_t 
     if (nx == 0 || ny == 0) return LM_OK;
     lm::GridHostJob job;
     rc = lm::grid_host_begin(xs, nx, ys, ny, max_iter, 2.0, potential ? LM_FIELD_GREEN : LM_FIELD_NONE, dwell_i32, nullptr,
-                             potential, true, halo_rows, &job);
+                             potential, true, halo_rows, &job, row_cost);
     if (rc != LM_OK) return rc;
     *dwell_dev_out = job.dwell_dev;
     if (potential_dev_out) *potential_dev_out = job.field_dev;

@@ -237,7 +237,8 @@ class ShardedBoundary:
     block times.  All device work is enqueued on torch's CURRENT stream (the collectives order against it).
     Works with world size 1 too (then it is just the fused single-GPU call)."""
 
-    def __init__(self, xs, ys, max_iter: int, level: float, device=None, with_potential: bool = False, cuts=None):
+    def __init__(self, xs, ys, max_iter: int, level: float, device=None, with_potential: bool = False, cuts=None,
+                 profile=None):
         import torch
         import torch.distributed as dist
         from . import _shim
@@ -251,7 +252,7 @@ class ShardedBoundary:
             plan = plan_row_cuts(self.xs, self.ys, self.max_iter, self.world, device=self.device)
             self.profile, cuts = plan["profile"], plan["cuts"]
         else:
-            self.profile = np.ones(self.ys.size)
+            self.profile = np.ones(self.ys.size) if profile is None else np.asarray(profile, dtype=np.float64)
         self._set_cuts(cuts)
         self._shim = _shim
         self.last_work_units = 0
@@ -273,6 +274,11 @@ class ShardedBoundary:
                        if (self.with_potential and self.world > 1) else None)
         self._records = torch.empty((max(int(0.002 * self.rows * nx) + 4096, 1 << 16), 8), dtype=torch.int64, device=self.device)
         self.full_potential = None
+        # the row-cost profile of this rank's rows: lm_shard_escape computes its chunks cheapest first
+        self._row_cost = (np.ascontiguousarray(self.profile[self.r0:self.r1], dtype=np.float64)
+                          if np.asarray(self.profile).size == self.ys.size and np.ptp(self.profile) > 0 else None)
+        self._lines_buf = None           # rank 0: page-locked (verts, offsets) the linked lines are copied into
+        self.last_phases_ms = {}
 
     def refine(self, rounds: int = 2):
         """Measured rebalancing: time K1 on the current blocks on every rank, rescale the profile, cut again."""
@@ -287,7 +293,7 @@ class ShardedBoundary:
             blk = C.c_void_p(); pblk = C.c_void_p()
             dist.barrier()
             self._shim.call("lm_shard_escape", self._shim.ptr(self.xs), self.xs.size, self._shim.ptr(self.ys_rows), self.rows,
-                            self.max_iter, None, None, 1, C.byref(blk), C.byref(pblk), C.byref(st))
+                            self.max_iter, None, None, 1, None, C.byref(blk), C.byref(pblk), C.byref(st))
             t_all = torch.zeros(self.world, dtype=torch.float64, device=self.device)
             t_all[self.rank] = float(st.kernel_ms)
             dist.all_reduce(t_all)
@@ -307,11 +313,14 @@ class ShardedBoundary:
                                                 potential_out=self.potential)
             self.last_work_units = int(st["work_units"])
             return lines
+        import time
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         st = shim.Stats()
         blk = C.c_void_p(); pblk = C.c_void_p()
+        t0 = time.perf_counter()
         shim.call("lm_shard_escape", shim.ptr(self.xs), nx, shim.ptr(self.ys_rows), self.rows, self.max_iter,
-                  shim.ptr(self.dwell), shim.ptr(self.potential), 1, C.byref(blk), C.byref(pblk), C.byref(st))
+                  shim.ptr(self.dwell), shim.ptr(self.potential), 1, shim.ptr(self._row_cost), C.byref(blk), C.byref(pblk), C.byref(st))
+        t1 = time.perf_counter()
         self.last_work_units = int(st.work_units)
         if self.with_potential:     # final potential field on every GPU: all-gather straight from the resident block
             shim.call("lm_memcpy_d2d", C.c_void_p(self._field.data_ptr()), pblk, self.rows * nx * 8, stream)
@@ -332,12 +341,37 @@ class ShardedBoundary:
                 continue
             shim.check(rc)
             break
+        t2 = time.perf_counter()                 # includes waiting for the slowest rank's K1 in the all-gather
         self.n_records = int(n_rec.value)
         allrec, counts = gather_records(self._records, self.n_records, 0)
         self.n_records_total = int(sum(counts))
-        if self.rank != 0:
-            return None
-        return contour.link_records_dev(allrec.data_ptr(), allrec.shape[0], self.xs, self.ys, self.level, stream)
+        t3 = time.perf_counter()
+        lines = None
+        if self.rank == 0:
+            lines = self._link(allrec, stream)
+        t4 = time.perf_counter()
+        self.last_phases_ms = {"k1_host_call": 1e3 * (t1 - t0), "k1_kernels": float(st.kernel_ms),
+                               "halo_exchange_and_records": 1e3 * (t2 - t1), "record_gather": 1e3 * (t3 - t2),
+                               "link_and_fetch": 1e3 * (t4 - t3)}
+        return lines
+
+    def _link(self, allrec, stream):
+        """rank 0: chain all records on the device, copy the lines into a cached page-locked buffer (grown when
+        too small) and hand out exact-size copies."""
+        import ctypes as C
+        from . import contour
+        shim = self._shim
+        lib = shim.load()
+        n = int(allrec.shape[0])
+        if self._lines_buf is None or self._lines_buf[0].shape[0] < 2 * n + 16:
+            self._lines_buf = (shim.pinned_empty((4 * n + 64, 2), np.float64), shim.pinned_empty(2 * n + 65, np.int64))
+        verts, offs = self._lines_buf
+        nv = C.c_int64(0); nl = C.c_int64(0)
+        rc = lib.lm_contour_link_dev(C.c_void_p(allrec.data_ptr()), n, shim.ptr(self.xs), self.xs.size, shim.ptr(self.ys), self.ys.size,
+                                     float(self.level), shim.ptr(verts), verts.shape[0], C.byref(nv), shim.ptr(offs), offs.size - 1,
+                                     C.byref(nl), stream)
+        shim.check(rc)
+        return contour.Polylines(np.array(verts[: nv.value]), np.array(offs[: nl.value + 1]))
 
 
 def sharded_cloud_fields(toprows_local, deg_local, grid_x, grid_y, tol: float = 1e-12, eps: float = 1e-12, variant: int = 0,

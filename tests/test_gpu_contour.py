@@ -205,8 +205,9 @@ def test_shard_escape_keeps_block_for_halo_exchange(gpu):
         st = shim.Stats()
         ys_rows = np.ascontiguousarray(ys[r0:r1])
         pot = np.empty((rows, xs.size)); pblk = C.c_void_p()
+        cost = np.linspace(1.0, 3.0, rows) if has_halo else None        # a row-cost hint only reorders the chunks
         shim.call("lm_shard_escape", shim.ptr(xs), xs.size, shim.ptr(ys_rows), rows, mi, shim.ptr(out), shim.ptr(pot), 1,
-                  C.byref(blk), C.byref(pblk), C.byref(st))
+                  shim.ptr(cost), C.byref(blk), C.byref(pblk), C.byref(st))
         assert np.array_equal(out, full[r0:r1]) and blk.value and pblk.value
         back = np.empty_like(pot)
         shim.call("lm_memcpy_d2h", shim.ptr(back), pblk, back.nbytes, None); shim.call("lm_stream_synchronize", None)
