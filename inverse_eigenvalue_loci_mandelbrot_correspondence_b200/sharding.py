@@ -78,19 +78,45 @@ def pixel_cost(dwell, max_iter: int, model: dict | None = None) -> np.ndarray:
     return it + m["b_pixel"] + m["d_late"] * late
 
 
+def _sample_indices(n: int, k: int) -> np.ndarray:
+    return np.unique(np.linspace(0, n - 1, min(k, n)).round().astype(np.int64))
+
+
 def coarse_row_profile(xs, ys, max_iter: int, rows: int = 2048, cols: int = 2048, model: dict | None = None,
-                       iterations_only: bool = False) -> np.ndarray:
+                       iterations_only: bool = False, device=None) -> np.ndarray:
     """Estimated K1 cost of every grid row from a coarse K1 pass on the GPU (subsampled rows / columns), weighted by
-    the per-pixel cost model (iterations_only=True: round 1's profile, the bare iteration counts)."""
-    from . import escape
+    the per-pixel cost model (iterations_only=True: round 1's profile, the bare iteration counts).
+    With `device` (a torch CUDA device) the sampled dwell grid never leaves the GPU: K1 through the device-resident
+    entry point, the per-row cost sums in exact int64 arithmetic (identical on every rank), 16 KB back to the host;
+    without it the host-buffer API and numpy are used."""
     xs = np.asarray(xs, dtype=np.float64); ys = np.asarray(ys, dtype=np.float64)
-    ri = np.unique(np.linspace(0, ys.size - 1, min(rows, ys.size)).round().astype(np.int64))
-    ci = np.unique(np.linspace(0, xs.size - 1, min(cols, xs.size)).round().astype(np.int64))
-    d, _, _ = escape.escape_grid(xs[ci], ys[ri], max_iter)
-    if iterations_only:
-        work = np.minimum(d.astype(np.int64) + 1, max_iter).sum(axis=1).astype(np.float64)
+    ri = _sample_indices(ys.size, rows)
+    ci = _sample_indices(xs.size, cols)
+    m = COST_MODEL_B200 if model is None else model
+    if device is not None:
+        import ctypes as C
+        import torch
+        from . import _shim
+        xd = torch.from_numpy(np.ascontiguousarray(xs[ci])).to(device)
+        yd = torch.from_numpy(np.ascontiguousarray(ys[ri])).to(device)
+        d = torch.empty((ri.size, ci.size), dtype=torch.int32, device=device)
+        stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        _shim.call("lm_escape_grid_f64_dev", C.c_void_p(xd.data_ptr()), ci.size, C.c_void_p(yd.data_ptr()), ri.size,
+                   int(max_iter), 2.0, 0, C.c_void_p(d.data_ptr()), None, None, None, stream)
+        it = torch.clamp(d.to(torch.int64) + 1, max=int(max_iter))
+        if iterations_only:
+            work = it.sum(dim=1)
+        else:
+            late = ((d < int(max_iter)) & (it > int(m["knee"]))).to(torch.int64)
+            work = (it + int(round(m["b_pixel"])) + int(round(m["d_late"])) * late).sum(dim=1)
+        work = work.cpu().numpy().astype(np.float64)
     else:
-        work = pixel_cost(d, max_iter, model).sum(axis=1)
+        from . import escape
+        d, _, _ = escape.escape_grid(xs[ci], ys[ri], max_iter)
+        if iterations_only:
+            work = np.minimum(d.astype(np.int64) + 1, max_iter).sum(axis=1).astype(np.float64)
+        else:
+            work = pixel_cost(d, max_iter, m).sum(axis=1)
     return interpolate_row_profile(ri, work * (xs.size / ci.size), ys.size)
 
 
@@ -106,10 +132,11 @@ def plan_row_cuts(xs, ys, max_iter: int, nparts: int, device=None, model: dict |
         return {"cuts": [0, int(ys.size)], "profile": np.ones(ys.size), "balance_estimate": 1.0, "model": desc,
                 "setup": {"coarse_pass_ms": 0.0}}
     t0 = time.perf_counter()
-    profile = coarse_row_profile(xs, ys, max_iter, model=m)
+    profile = coarse_row_profile(xs, ys, max_iter, model=m, device=device)
     cuts = balanced_row_cuts(profile, nparts)
     return {"cuts": cuts, "profile": profile, "balance_estimate": parallel_efficiency(profile, cuts), "model": desc,
-            "setup": {"coarse_pass_ms": 1e3 * (time.perf_counter() - t0), "coarse_samples": "<= 2048 x 2048"}}
+            "setup": {"coarse_pass_ms": 1e3 * (time.perf_counter() - t0), "coarse_samples": "<= 2048 x 2048",
+                      "where": "device resident" if device is not None else "host-buffer API + numpy"}}
 
 
 def refine_cuts(row_work, cuts, measured) -> list[int]:

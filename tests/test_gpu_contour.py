@@ -242,3 +242,18 @@ def test_boundary_sample_with_potential(gpu, oracle):
     plain, _ = gpu.contour.boundary_sample(xs, ys, mi, 0.96 * mi)
     assert lines_equal(lines, plain)
     assert gpu.contour.longest(lines).shape == oracle.extract_contour(xs, ys, d_o.astype(float), mi, 0.96).shape
+
+
+def test_cost_profile_device_equals_host(gpu):
+    """sharding.coarse_row_profile: the device-resident path (exact int64 sums) and the host-buffer / numpy path give the
+    same per-row cost estimate, so every rank derives the same cuts whichever it uses."""
+    import torch
+    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import sharding
+    xs = np.linspace(-2.1, 0.9, 3000); ys = np.linspace(-1.5, 1.5, 2500)
+    dev = torch.device("cuda", 0)
+    a = sharding.coarse_row_profile(xs, ys, 700, rows=300, cols=400)
+    b = sharding.coarse_row_profile(xs, ys, 700, rows=300, cols=400, device=dev)
+    assert np.array_equal(a, b)
+    plan = sharding.plan_row_cuts(xs, ys, 700, 4, device=dev)
+    assert plan["cuts"][0] == 0 and plan["cuts"][-1] == ys.size and len(plan["cuts"]) == 5
+    assert plan["balance_estimate"] > 0.99
