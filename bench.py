@@ -593,6 +593,11 @@ def run_ours(args):
     cx.hbm_gbs = float(mp.get("hbm_gbs", 6500.0))
     hbm_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in mp else "fallback 6500 GB/s (B200_PROFILING.md)"
 
+    if world > 1:
+        # process warm-up: the first torch / NCCL kernels of a process load lazily (~150 ms); the plan below is timed
+        from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import sharding as _sh
+        _sh.plan_row_cuts(np.linspace(-2.0, 1.0, 64), np.linspace(-1.5, 1.5, 64), 50, world, device=dev)
+        dist.barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0 and not os.environ.get("LM_BENCH_NO_SAMPLER"):
         sampler.start()             # before the warm-up (same load): nvidia-smi needs ~0.2 s for its first sample

@@ -725,8 +725,9 @@ int32_t grid_host_begin(const double* xs, int64_t nx, const double* ys, int64_t 
 
     const size_t bytes_per_row = static_cast<size_t>(nx) * ((dwell_i32 ? 4 : 0) + (dwell_f64 ? 8 : 0) + (dfield ? 8 : 0));
     const size_t total_bytes = bytes_per_row * static_cast<size_t>(ny);
-    // ~128 MB of output per chunk (2.3 ms of PCIe): the copy of the LAST chunks is what remains after the compute ends
-    int64_t nchunks = static_cast<int64_t>((total_bytes + (size_t(128) << 20) - 1) / (size_t(128) << 20));
+    // ~64 MB of output per chunk (1.2 ms of PCIe, more when 8 ranks share the host): the copy of the LAST chunk is what
+    // remains after the compute ends; launches are free now that consecutive chunks overlap on two streams
+    int64_t nchunks = static_cast<int64_t>((total_bytes + (size_t(64) << 20) - 1) / (size_t(64) << 20));
     if (nchunks < 1) nchunks = 1;
     if (nchunks > 64) nchunks = 64;
     if (nchunks > ny) nchunks = ny;
