@@ -16,9 +16,11 @@ from __future__ import annotations
 import numpy as np
 
 
-def balanced_row_cuts(row_work, nparts: int) -> list[int]:
+def balanced_row_cuts(row_work, nparts: int, extra=None) -> list[int]:
     """Cut rows [0, ny) into `nparts` contiguous blocks of (nearly) equal cumulative work.
 
+    extra: optional fixed cost per block in the same units (e.g. the serial linking stage on the rank that also
+    chains the records): block k then receives row work T - extra[k], with T the common total per block.
     Returns nparts+1 increasing cut positions starting at 0 and ending at ny; every block has at
     least one row when ny >= nparts.
     """
@@ -30,9 +32,15 @@ def balanced_row_cuts(row_work, nparts: int) -> list[int]:
         raise ValueError(f"cannot cut {ny} rows into {nparts} non-empty blocks")
     w = np.maximum(w, 0.0) + 1e-12 * max(float(w.max(initial=0.0)), 1.0)     # keep the prefix strictly increasing
     cum = np.concatenate([[0.0], np.cumsum(w)])
+    ex = np.zeros(nparts) if extra is None else np.asarray(extra, dtype=np.float64).ravel()
+    if ex.size != nparts:
+        raise ValueError("one extra cost per block expected")
+    ex = np.clip(ex, 0.0, 0.5 * cum[-1] / nparts)        # a block keeps at least half of an even share of the row work
+    per_block = (cum[-1] + ex.sum()) / nparts
     cuts = [0]
+    target = 0.0
     for k in range(1, nparts):
-        target = cum[-1] * k / nparts
+        target += per_block - ex[k - 1]
         c = int(np.searchsorted(cum, target, side="left"))
         if c > 0 and abs(cum[c - 1] - target) <= abs(cum[min(c, ny)] - target):
             c -= 1
@@ -43,10 +51,12 @@ def balanced_row_cuts(row_work, nparts: int) -> list[int]:
     return cuts
 
 
-def parallel_efficiency(row_work, cuts) -> float:
-    """mean block work / max block work for the given cuts (1.0 = perfectly balanced)."""
+def parallel_efficiency(row_work, cuts, extra=None) -> float:
+    """mean block cost / max block cost for the given cuts (1.0 = perfectly balanced); extra as in balanced_row_cuts."""
     w = np.asarray(row_work, dtype=np.float64).ravel()
-    blocks = [w[a:b].sum() for a, b in zip(cuts[:-1], cuts[1:])]
+    blocks = np.array([w[a:b].sum() for a, b in zip(cuts[:-1], cuts[1:])])
+    if extra is not None:
+        blocks = blocks + np.asarray(extra, dtype=np.float64).ravel()
     return float(np.mean(blocks) / max(np.max(blocks), 1e-300))
 
 
@@ -66,7 +76,12 @@ def interpolate_row_profile(coarse_rows: np.ndarray, coarse_work: np.ndarray, ny
 # a B200 (joint least squares, rms error 0.9 %, max 3.4 %; scripts/balance_probe.py, profiles/r02_balance_*.json):
 # they are properties of the kernel and the device, not of the workload, so one-shot cuts need no calibration pass
 # over the answer.
-COST_MODEL_B200 = {"b_pixel": 15.0, "d_late": 2000.0, "knee": 64}
+COST_MODEL_B200 = {"b_pixel": 15.0, "d_late": 2000.0, "knee": 64,
+                   # absolute scale of one cost unit (2.96e12 blind pixel-iterations per second on a B200) and the
+                   # serial stage the linking rank runs after its K1 while the others wait for it in the next step:
+                   # record gather (NCCL recv from every rank) + device linker + its two host syncs, ~1.3 ms for the
+                   # 5.5e5 records of config 3 at N = 8 (`sub_rooflines.k2_records` of the bench line)
+                   "seconds_per_unit": 3.4e-13, "link_seconds": 1.3e-3}
 
 
 def pixel_cost(dwell, max_iter: int, model: dict | None = None) -> np.ndarray:
@@ -120,23 +135,32 @@ def coarse_row_profile(xs, ys, max_iter: int, rows: int = 2048, cols: int = 2048
     return interpolate_row_profile(ri, work * (xs.size / ci.size), ys.size)
 
 
-def plan_row_cuts(xs, ys, max_iter: int, nparts: int, device=None, model: dict | None = None) -> dict:
+def plan_row_cuts(xs, ys, max_iter: int, nparts: int, device=None, model: dict | None = None, linker_rank: int | None = 0) -> dict:
     """One-shot row cuts for `nparts` ranks: coarse K1 pre-pass (<= 2048 x 2048 samples, every rank runs the same
     deterministic pass and gets the same cuts) -> per-row cost estimate -> contiguous blocks of equal estimated cost.
-    -> {"cuts", "profile", "balance_estimate", "model", "setup"}"""
+    linker_rank: the rank that also gathers and chains the crossing records (rank 0 in ShardedBoundary); its block is
+    cut lighter by the model's estimate of that serial stage, so that the other ranks do not wait for it in the next
+    step's halo exchange (None: pure K1 balance).
+    -> {"cuts", "profile", "balance_estimate", "model", "setup", "extra"}"""
     import time
     ys = np.asarray(ys, dtype=np.float64)
     m = COST_MODEL_B200 if model is None else model
     desc = (f"cost = it + {m['b_pixel']:g} + {m['d_late']:g}*[escaped, it>{m['knee']}] per pixel, constants fitted offline on a B200")
     if nparts == 1:
         return {"cuts": [0, int(ys.size)], "profile": np.ones(ys.size), "balance_estimate": 1.0, "model": desc,
-                "setup": {"coarse_pass_ms": 0.0}}
+                "setup": {"coarse_pass_ms": 0.0}, "extra": None}
     t0 = time.perf_counter()
     profile = coarse_row_profile(xs, ys, max_iter, model=m, device=device)
-    cuts = balanced_row_cuts(profile, nparts)
-    return {"cuts": cuts, "profile": profile, "balance_estimate": parallel_efficiency(profile, cuts), "model": desc,
+    extra = None
+    if linker_rank is not None and m.get("link_seconds") and m.get("seconds_per_unit"):
+        extra = np.zeros(nparts)
+        extra[int(linker_rank)] = float(m["link_seconds"]) / float(m["seconds_per_unit"])
+        desc += f"; the linking rank {int(linker_rank)} is cut lighter by {1e3 * m['link_seconds']:.1f} ms of K1"
+    cuts = balanced_row_cuts(profile, nparts, extra)
+    return {"cuts": cuts, "profile": profile, "balance_estimate": parallel_efficiency(profile, cuts, extra), "model": desc,
             "setup": {"coarse_pass_ms": 1e3 * (time.perf_counter() - t0), "coarse_samples": "<= 2048 x 2048",
-                      "where": "device resident" if device is not None else "host-buffer API + numpy"}}
+                      "where": "device resident" if device is not None else "host-buffer API + numpy"},
+            "extra": None if extra is None else extra.tolist()}
 
 
 def refine_cuts(row_work, cuts, measured) -> list[int]:

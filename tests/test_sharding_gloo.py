@@ -236,3 +236,20 @@ def test_sharded_potential_field_gloo(oracle, world):
         p.join(timeout=60)
     for rank, ok, err in results:
         assert ok, f"rank {rank}: {err}"
+
+
+def test_balanced_row_cuts_with_a_serial_stage():
+    """The rank that also links the records gets less row work: block cost + extra is what is balanced."""
+    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import sharding
+    rng = np.random.default_rng(3)
+    w = rng.random(5000) + 0.05
+    extra = [40.0, 0.0, 0.0, 0.0, 0.0]
+    cuts = sharding.balanced_row_cuts(w, 5, extra)
+    tot = np.array([w[a:b].sum() for a, b in zip(cuts[:-1], cuts[1:])]) + np.array(extra)
+    assert cuts[0] == 0 and cuts[-1] == 5000 and all(b > a for a, b in zip(cuts[:-1], cuts[1:]))
+    assert tot.max() / tot.mean() < 1.002
+    assert sharding.parallel_efficiency(w, cuts, extra) > 0.998
+    assert sharding.balanced_row_cuts(w, 5, None) == sharding.balanced_row_cuts(w, 5, [0.0] * 5)
+    huge = sharding.balanced_row_cuts(w, 5, [1e12, 0, 0, 0, 0])            # capped: the block keeps half a share
+    first = w[: huge[1]].sum()
+    assert 0.35 * w.sum() / 5 < first < 0.65 * w.sum() / 5
