@@ -43,5 +43,15 @@ XT, T, kl0, klT = tracker.gi_flow_to_threshold(tracker.KL, PM, PC, 0.1, 1e-6, 20
 tv = tracker.tv_distance(PM, PC); sm = tracker.sum_pairwise(rng.standard_normal(12345))
 tri = alpha_shape.delaunay_simplices(P2)
 edges = alpha_shape.alpha_shape_edges(P2, 8.0, simplices=tri)
+# round 2: device linker on a field full of saddles / border-cut lines, fp32 K1, ordered pair selection, stats drop-ins
+fld = rng.integers(0, 3, size=(97, 130)).astype(np.int32)
+ll = contour.contour_lines(np.linspace(0, 1, 130), np.linspace(0, 1, 97), fld, 0.5)
+d32, _ = escape.escape_grid_f32(np.linspace(-2.1, 0.9, 301), ys, 120)
+grid = types.SimpleNamespace(X=np.meshgrid(np.linspace(-2, 1, 70), np.linspace(-1.4, 1.4, 66))[0],
+                             Y=np.meshgrid(np.linspace(-2, 1, 70), np.linspace(-1.4, 1.4, 66))[1])
+np.random.seed(5)
+rcs, gam = pairstats.sample_semivariogram(np.sin(grid.X) * np.cos(grid.Y), grid, np.linspace(0, 2, 11), max_pairs_per_bin=5000)
+rows = lucas.per_n_stats(2, 12, max_iter=300, quiet=True)
+print("round-2 rows ok:", len(ll), int(d32.sum()), float(gam.sum()), len(rows))
 print("new rows ok:", out8["n_points"], dm, T, klT, tv, len(edges))
 print("sanitize_small ok:", len(lines), len(l2), int(it.sum()), out["n_points"], hi.size, float(U.sum()), i[:3], float(w[0]))
