@@ -306,7 +306,9 @@ __global__ void __launch_bounds__(LINK_THREADS) link_rank_kernel(const LinkArgs 
         a.result[1] = n_lines;
     }
     grid.sync();
-    // ---- D. vertices
+    // ---- D. vertices.  For consistent records every position is < n_vertices <= 2 * NS (the allocated vertex slots);
+    // the bound is checked anyway, so that malformed input (flagged above, LM_E_INVALID) cannot write out of bounds.
+    const unsigned long long vcap = 2ull * static_cast<unsigned long long>(NS);
     for (int v = tid; v < NS; v += nth) {
         const unsigned f = a.info[v];
         if (!(f & NODE_VALID)) continue;
@@ -318,11 +320,13 @@ __global__ void __launch_bounds__(LINK_THREADS) link_rank_kernel(const LinkArgs 
         const int k = v >> 1, sg = v & 1;
         const longlong2 xyb = __ldg(reinterpret_cast<const longlong2*>(a.rec + static_cast<long long>(k) * REC_WORDS + 4 + 2 * sg));
         const double2 xy = make_double2(__longlong_as_double(xyb.x), __longlong_as_double(xyb.y));
-        a.verts[b + hi32(s) + (nstart ? 0u : 1u)] = xy;
+        const unsigned long long pos = b + hi32(s) + (nstart ? 0u : 1u);
+        if (pos < vcap) a.verts[pos] = xy;
         if (v == lead) {
             if (nstart) {
-                a.verts[b + __ldcg(a.len + v) - 1u] = xy;               // the loop closes on its first emitted vertex
-            } else {
+                const unsigned long long last = b + __ldcg(a.len + v) - 1u;
+                if (last < vcap) a.verts[last] = xy;                    // the loop closes on its first emitted vertex
+            } else if (b < vcap) {
                 // initial vertex: interp(edge start, edge end) on the ENTRY edge, in the reference's operation order
                 const int en = static_cast<int>((f >> 2) & 3u);
                 int dj1, di1, dj2, di2;
