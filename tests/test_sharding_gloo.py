@@ -79,8 +79,11 @@ def _worker(rank: int, world: int, port: int, q):
         # every rank derives the same cuts from the same (deterministic) coarse profile
         coarse_rows = np.arange(0, ys.size, 4)
         dc, _ = oracle.dwell_grid(xs[::2], ys[coarse_rows], mi)
-        prof = sharding.interpolate_row_profile(coarse_rows, np.minimum(dc.astype(np.int64) + 1, mi).sum(axis=1), ys.size)
-        cuts = sharding.balanced_row_cuts(prof, world)
+        # the product's plan on the CPU: per-pixel cost model on the coarse dwell samples, the linking rank cut lighter
+        prof = sharding.interpolate_row_profile(coarse_rows, sharding.pixel_cost(dc, mi).sum(axis=1) * 2.0, ys.size)
+        extra = np.zeros(world); extra[0] = 0.02 * prof.sum() / world
+        cuts = sharding.balanced_row_cuts(prof, world, extra)
+        assert sharding.parallel_efficiency(prof, cuts, extra) > 0.9
         r0, r1 = cuts[rank], cuts[rank + 1]
         mine, _ = oracle.dwell_grid(xs, ys[r0:r1], mi)                       # this rank's K1 rows
         firsts = sharding.exchange_first_rows(torch.from_numpy(mine[0].copy()))
@@ -253,3 +256,21 @@ def test_balanced_row_cuts_with_a_serial_stage():
     huge = sharding.balanced_row_cuts(w, 5, [1e12, 0, 0, 0, 0])            # capped: the block keeps half a share
     first = w[: huge[1]].sum()
     assert 0.35 * w.sum() / 5 < first < 0.65 * w.sum() / 5
+
+
+def test_pixel_cost_model():
+    """cost = it + b + d_late * [escaped and it > knee], it = min(dwell + 1, max_iter)."""
+    from inverse_eigenvalue_loci_mandelbrot_correspondence_b200 import sharding
+    m = sharding.COST_MODEL_B200
+    d = np.array([0, 3, 62, 63, 64, 500, 999, 1000])
+    c = sharding.pixel_cost(d, 1000)
+    it = np.minimum(d + 1, 1000)
+    late = (d < 1000) & (it > m["knee"])
+    assert np.array_equal(c, it + m["b_pixel"] + m["d_late"] * late)
+    assert list(late) == [False, False, False, False, True, True, True, False]      # interior pixels are not "late"
+    assert sharding.pixel_cost(np.array([1000]), 1000)[0] == 1000 + m["b_pixel"]
+    custom = {"b_pixel": 1.0, "d_late": 0.0, "knee": 64}
+    assert np.array_equal(sharding.pixel_cost(d, 1000, custom), it + 1.0)
+    # the one-rank plan needs no device
+    plan = sharding.plan_row_cuts(np.linspace(-2, 1, 10), np.linspace(-1, 1, 8), 50, 1)
+    assert plan["cuts"] == [0, 8] and plan["balance_estimate"] == 1.0
